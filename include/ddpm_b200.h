@@ -1,0 +1,174 @@
+/* ddpm_b200.h -- C-ABI of the B200-native DDPM hot path (libddpm_b200.so).
+ *
+ * Drop-in boundary for the compute that nereaqing/Polyp-Image-Generator reaches through
+ * diffusers/torch on its DDPM path.  The reference has NO native interface of its own (SURVEY.md §2.3:
+ * zero .cu/.cpp files); every entry point below therefore cites the *Python call site* whose
+ * third-party arithmetic it replaces.  All paths are relative to /root/reference/.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - the caller owns all buffers (incl. workspaces), kernels never allocate and never synchronise
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return 0 on success, <0 on error; ddpm_last_error() returns a thread-local message
+ *   - activations are NHWC bf16 with an explicit pixel stride `ld` (elements), so channel slices work
+ *   - conv/linear weights are bf16 [Cout][tap][Cin] (reduction index contiguous)
+ */
+#ifndef DDPM_B200_H_
+#define DDPM_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDPM_MAX_TAPS 9
+#define DDPM_ABI_VERSION 1
+
+const char* ddpm_last_error(void);
+int ddpm_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scheduler / loss elementwise kernels (fp32, single pass, HBM-bound)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* DDPMScheduler.add_noise -- generator_model/train_from_scratch.py:93
+ * out[b,i] = sqrt_ac[t[b]] * x0[b,i] + sqrt_1mac[t[b]] * noise[b,i]; each product rounded separately
+ * (no FMA contraction) so results are bit-identical to the torch expression.  t: int64[batch]. */
+int ddpm_add_noise(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
+                   const float* sqrt_1mac, float* out, int batch, long long per_sample, int num_train_timesteps,
+                   void* stream);
+
+/* F.mse_loss(pred, target) forward + backward -- generator_model/train_from_scratch.py:101,103
+ * loss_sum += sum((pred-target)^2) (caller zeroes it and divides by n), dpred = (2/n) * (pred-target). */
+int ddpm_mse_fwd_bwd(const float* pred, const float* target, float* loss_sum, float* dpred, long long n,
+                     void* stream);
+
+/* x *= *scale (device scalar): folds autograd's grad_output (e.g. GradScaler's scale) into dpred. */
+int ddpm_scale_by_device_scalar(float* x, const float* scale, long long n, void* stream);
+
+/* DDPMScheduler.step (fixed_small, epsilon, clip_sample) -- inside DDPMPipeline.__call__,
+ * generator_model/train_from_scratch.py:51-54.
+ *   x0 = clamp((x - sqrt_beta_prod*eps) / sqrt_alpha_prod, -clip, clip)   (clip<=0: no clamp)
+ *   prev = c0*x0 + ct*x (+ sigma*z when z != NULL)
+ * op order and rounding follow the torch expression.  pred_x0 may be NULL. */
+int ddpm_scheduler_step(const float* eps, const float* x, const float* z, float* prev, float* pred_x0, long long n,
+                        float sqrt_alpha_prod, float sqrt_beta_prod, float c0, float ct, float sigma, float clip,
+                        void* stream);
+
+/* Same step with z ~ N(0,1) drawn in-kernel (Philox4x32-10 + Box-Muller): 12 B/elem instead of 16. */
+int ddpm_scheduler_step_philox(const float* eps, const float* x, float* prev, long long n, float sqrt_alpha_prod,
+                               float sqrt_beta_prod, float c0, float ct, float sigma, float clip,
+                               unsigned long long seed, unsigned long long offset, void* stream);
+
+/* DDPMPipeline post-processing: (x/2+0.5).clamp(0,1) -> NHWC uint8 via round(x*255). x: NCHW fp32. */
+int ddpm_to_uint8_nhwc(const float* x, unsigned char* out, int n, int c, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * UNet2DModel forward / backward building blocks -- generator_model/train_from_scratch.py:100,103
+ * (model built at generator_model/PolypGeneratorModel.py:25-48)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Implicit-GEMM conv / linear on tcgen05 (fprop and dgrad; nn.Conv2d / nn.Linear forward and input grad).
+ *   out[pix, co] = bias[co] + temb[n, co] + res[pix, co] + sum_{tap, ci} X[pix + (dn,dh,dw)[tap], ci] * W[co][wk[tap] + ci]
+ * X may be the channel concat of two tensors (x0 | x1).  Out-of-range pixels read as zero (= padding). */
+typedef struct ddpm_conv_args {
+  const void* x0; int c0; long long ld0;     /* source 0: bf16 NHWC, c0 channels (multiple of 64) */
+  const void* x1; int c1; long long ld1;     /* optional source 1 (NULL / 0) */
+  int n, h, w;                               /* output pixel grid */
+  int src_n;                                 /* batch extent of the sources (0 -> n; 4n for space-to-depth) */
+  int ntaps;
+  int tap_dn[DDPM_MAX_TAPS], tap_dh[DDPM_MAX_TAPS], tap_dw[DDPM_MAX_TAPS], tap_wk[DDPM_MAX_TAPS];
+  const void* wgt; int cout; long long ldw; long long k_total; /* bf16 [cout][ldw]; k_total 0 -> ldw */
+  void* out; float* out_f32; long long ldo;  /* bf16 output, or fp32 output when out_f32 != NULL */
+  const float* bias;                         /* fp32 [cout] or NULL */
+  const float* temb; int ld_temb;            /* fp32 [n][ld_temb] or NULL: ResnetBlock2D time-embedding add */
+  const void* res; long long ldr;            /* bf16 NHWC residual or NULL */
+} ddpm_conv_args;
+int ddpm_conv_gemm(const ddpm_conv_args* args, void* stream);
+
+/* Conv / linear weight gradient on tcgen05:
+ *   dw[co][wk[tap] + ci] (+)= sum_pix dY[pix, co] * X[pix + (dn,dh,dw)[tap], ci]      (fp32, split-K) */
+typedef struct ddpm_wgrad_args {
+  const void* dy; long long ldy; int cout;   /* bf16 NHWC grad of the conv output (cout multiple of 64) */
+  const void* x0; int c0; long long ld0;
+  const void* x1; int c1; long long ld1;
+  int n, h, w; int src_n;
+  int ntaps;
+  int tap_dn[DDPM_MAX_TAPS], tap_dh[DDPM_MAX_TAPS], tap_dw[DDPM_MAX_TAPS], tap_wk[DDPM_MAX_TAPS];
+  float* dw; long long ldw;                  /* fp32 [cout][ldw] */
+  int accumulate;                            /* 1: add into dw, 0: dw must be zero-filled or splits==1 */
+  int splits;                                /* 0 = auto */
+} ddpm_wgrad_args;
+int ddpm_conv_wgrad(const ddpm_wgrad_args* args, void* stream);
+
+/* fp32 master weight [cout][taps][cin] -> bf16 fprop copy (same layout) and, if wd != NULL, the dgrad copy
+ * wd[ci][taps-1-tap][co] (taps flipped, in/out transposed). */
+int ddpm_prep_weight(const float* w, void* wf, long long ldwf, void* wd, long long ldwd, int cout, int taps, int cin,
+                     void* stream);
+
+/* conv_in (3 -> C, 3x3, pad 1): x NCHW fp32, w fp32 with element strides (w_sco, w_stap, w_sci), out NHWC bf16.
+ * Also used as conv_out's dgrad (with transposed strides and flip=1). */
+int ddpm_conv3_to_c(const float* x, const float* w, long long w_sco, long long w_stap, long long w_sci, int flip,
+                    const float* bias, void* out, long long ldo, int n, int h, int wd, int cin, int cout,
+                    void* stream);
+/* conv_out (C -> 3, 3x3, pad 1): a NHWC bf16, w fp32 [3][9][C], out NCHW fp32. */
+int ddpm_conv_c_to_3(const void* a, long long lda, const float* w, const float* bias, float* out, int n, int h,
+                     int wd, int cin, int cout, void* stream);
+/* weight grads of the two 3-channel convs:
+ *   dw[c*s_c + tap'*s_tap + k*s_k] += sum_pix big[pix, c] * small[n, k, pix + tap]   (tap' = flip ? 8-tap : tap)
+ *   big: NHWC bf16 [.., cbig]; small: NCHW fp32 [n][ksmall][h][w]; optional dbias_small[k] += sum small. */
+int ddpm_conv3_wgrad(const void* big, long long ldbig, int cbig, const float* small_, int ksmall, float* dw,
+                     long long s_c, long long s_tap, long long s_k, int flip, float* dbias_small, int n, int h,
+                     int wd, void* stream);
+
+/* GroupNorm statistics: stats[n][g] = (sum, sumsq) over the (possibly concatenated) channels of group g. */
+int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
+                  int groups, float* stats, void* stream);
+/* y = act(GroupNorm(x)) with act = SiLU (silu=1) or identity; y bf16 NHWC contiguous over c0+c1 channels. */
+int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
+                  int groups, const float* stats, float eps, const float* gamma, const float* beta, int silu,
+                  void* y, long long ldy, void* stream);
+/* GroupNorm(+SiLU) backward.  ws: fp32 workspace of n*(c0+c1)*2 + n*groups*2 floats.
+ *   dgamma/dbeta are accumulated (+=) when non-NULL.  dx = GN'(dy) + add0 + add1, written split over dx0|dx1. */
+int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
+                int groups, const float* stats, float eps, const float* gamma, const float* beta, int silu,
+                const void* dy, long long lddy, const void* add0, long long ldadd0, const void* add1,
+                long long ldadd1, void* dx0, long long lddx0, void* dx1, long long lddx1, float* dgamma,
+                float* dbeta, float* ws, void* stream);
+
+/* Self-attention core on fused qkv [b*t][3*heads*d] bf16 (AttnProcessor2_0's scaled_dot_product_attention). */
+int ddpm_attn_fwd(const void* qkv, long long ldqkv, void* o, long long ldo, float* lse, int b, int t, int heads,
+                  int d, float scale, void* stream);
+int ddpm_attn_bwd(const void* qkv, long long ldqkv, const void* o, long long ldo, const void* d_o, long long lddo,
+                  const float* lse, void* dqkv, long long lddqkv, int b, int t, int heads, int d, float scale,
+                  void* stream);
+
+/* Timesteps(128) sinusoid -> fp32 [b][dim]; t int64[b] (device). */
+int ddpm_timestep_embedding(const long long* t, float* out, int b, int dim, int flip_sin_to_cos, float freq_shift,
+                            void* stream);
+/* Small fp32 linears of the time-embedding path: y[m][n] = bias[n] + sum_k act(x[m][k]) * w[n][k]. */
+int ddpm_linear_f32(const float* x, const float* w, const float* bias, float* y, int m, int n, int k, int silu_in,
+                    void* stream);
+/* dw[n][k] += sum_m dy[m][n]*act(x[m][k]); db[n] += sum_m dy[m][n]  (db may be NULL) */
+int ddpm_linear_f32_wgrad(const float* x, const float* dy, float* dw, float* db, int m, int n, int k, int silu_in,
+                          void* stream);
+/* dx[m][k] (+)= act'(x[m][k]) * sum_n dy[m][n]*w[n][k] */
+int ddpm_linear_f32_dgrad(const float* dy, const float* w, const float* x, float* dx, int m, int n, int k,
+                          int silu_in, int accumulate, void* stream);
+
+/* out_nc[n][c] (=) sum_hw x[n,hw,c] and/or out_c[c] += sum_{n,hw} x[n,hw,c]; x bf16 NHWC. Either may be NULL. */
+int ddpm_reduce_hw(const void* x, long long ld, int n, int hw, int c, float* out_nc, long long ld_nc, float* out_c,
+                   void* stream);
+
+/* Layout helpers (bf16 NHWC, contiguous outputs). */
+int ddpm_space_to_depth(const void* x, long long ldx, void* out, int n, int h, int w, int c, int pad_lo,
+                        void* stream);                      /* out[(ph*2+pw)*n + b][h/2][w/2][c] */
+int ddpm_zero_insert2x(const void* dy, long long ldy, void* out, int n, int ho, int wo, int c, int h, int w,
+                       void* stream);                       /* out[b][2i][2j] = dy[b][i][j], else 0 */
+int ddpm_upsample2x(const void* x, long long ldx, void* out, int n, int h, int w, int c, void* stream);
+int ddpm_sumpool2x(const void* dy, long long ldy, const void* add, long long ldadd, void* out, int n, int h, int w,
+                   int c, void* stream);                    /* out[b][i][j] = sum 2x2 dy + add */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDPM_B200_H_ */

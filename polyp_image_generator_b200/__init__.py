@@ -1,0 +1,26 @@
+"""B200-native DDPM hot path: drop-in for the diffusers objects used by nereaqing/Polyp-Image-Generator.
+
+    from polyp_image_generator_b200 import UNet2DModel, DDPMScheduler, DDPMPipeline, LoraConfig
+
+All tensor arithmetic runs in hand-written sm_100a kernels behind the C-ABI in include/ddpm_b200.h
+(libddpm_b200.so, built in-tree by `python -m polyp_image_generator_b200.build`).  There is no CPU fallback.
+"""
+from .scheduler import DDPMScheduler, DDPMSchedulerOutput  # noqa: F401
+from .pipeline import DDPMPipeline, ImagePipelineOutput, randn_tensor  # noqa: F401
+
+
+def __getattr__(name):
+    # heavier modules are imported lazily so that `import polyp_image_generator_b200` stays cheap
+    if name in ("UNet2DModel", "UNet2DOutput"):
+        from . import unet
+        return getattr(unet, name)
+    if name in ("LoraConfig", "lora_state_dict", "recover_lora_modules"):
+        from . import lora
+        return getattr(lora, name)
+    if name in ("mse_loss", "fused_train_step"):
+        from . import training
+        return getattr(training, name)
+    if name in ("DistributedDataParallel",):
+        from . import ddp
+        return getattr(ddp, name)
+    raise AttributeError(name)

@@ -1,0 +1,666 @@
+// Implicit-GEMM convolution / linear kernels for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM.
+//
+// Replaces what diffusers' nn.Conv2d / nn.Linear layers dispatch to cuDNN / cuBLAS on the reference path
+// (UNet2DModel built at /root/reference/generator_model/PolypGeneratorModel.py:25-48, run at
+//  /root/reference/generator_model/train_from_scratch.py:100,103) -- SURVEY.md §2.3 rows K1/K2/K3/K7.
+//
+// Data layout: activations NHWC bf16 (channel stride given, so channel-slices of wider tensors work),
+// weights bf16 [Cout][tap][Cin] ("K-major": the reduction index is contiguous), accumulation fp32 in TMEM.
+//
+//  * conv_gemm_kernel (fprop and dgrad):  OUT[pixel, co] = sum_{tap, ci} X[pixel + tap_offset, ci] * Wt[co][tap][ci]
+//      A tile = 128 output pixels x 64 channels, fetched per tap as ONE shifted 4-D TMA box over (C, W, H, N);
+//      out-of-bounds rows/columns are zero-filled by TMA, which *is* the conv padding.  The channel dimension
+//      may be split over two source tensors (torch.cat([h, skip], 1) is never materialised).  Taps carry an
+//      arbitrary (dn, dh, dw) offset, so stride-2 convs (space-to-depth phases stacked along N), dgrad
+//      (flipped taps, transposed weights) and plain linears (1 tap, H = 1) all use the same kernel.
+//      Epilogue fuses bias, the per-(sample, channel) time-embedding add and the residual add.
+//  * conv_wgrad_kernel:  dW[co][tap][ci] += sum_{pixel} dY[pixel, co] * X[pixel + tap_offset, ci]
+//      both operands are "MN-major" straight out of NHWC (pixels are the reduction index), split-K over
+//      pixel tiles with fp32 red.global.add into the gradient buffer.
+#include "common.cuh"
+
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+#include <cstdlib>
+
+#include "../../include/ddpm_b200.h"
+
+namespace ddpm {
+
+constexpr int kBlockM = 128;   // output pixels per tile (UMMA M)
+constexpr int kBlockK = 64;    // bf16 channels per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kMaxTaps = DDPM_MAX_TAPS;
+constexpr int kGemmThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+struct TapTable {
+  int ntaps;
+  int dn[kMaxTaps], dh[kMaxTaps], dw[kMaxTaps], wk[kMaxTaps];
+};
+
+struct GemmParams {
+  int N, H, W;            // pixel grid
+  int kb0, kb1;           // 64-channel blocks from source 0 / 1
+  int Cout;
+  int wb, hb, nb;         // TMA box (pixels) = M tile shape
+  int tiles_w, tiles_h, tiles_n;
+  uint32_t a_bytes;       // bytes one A box delivers (wb*hb*nb*128)
+  __nv_bfloat16* out;
+  long long ldo;
+  float* out_f32;         // optional fp32 output instead of bf16 (same indexing, ldo)
+  const float* bias;
+  const float* temb;
+  int ld_temb;
+  const __nv_bfloat16* res;
+  long long ldr;
+  TapTable taps;
+};
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+// ---------------------------------------------------------------------------------------------
+// fprop / dgrad / linear
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+  using L = GemmSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates: blockIdx.x = cout tile (fastest, so CTAs sharing an A tile run together), y = pixel tile
+  const int nt = blockIdx.x;
+  int mt = blockIdx.y;
+  const int tw = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int th = mt % p.tiles_h;
+  const int tn = mt / p.tiles_h;
+  const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.kb1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int kbt = p.kb0 + p.kb1;
+  const int total_iters = p.taps.ntaps * kbt;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < p.taps.ntaps; ++t) {
+        const int cw = w0 + p.taps.dw[t], ch = h0 + p.taps.dh[t], cn = n0 + p.taps.dn[t], wk = p.taps.wk[t];
+        for (int kb = 0; kb < kbt; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[s], p.a_bytes + L::kBBytes);
+          if (kb < p.kb0)
+            tma_load_4d(sa, &tmA0, &full_bar[s], kb * kBlockK, cw, ch, cn);
+          else
+            tma_load_4d(sa, &tmA1, &full_bar[s], (kb - p.kb0) * kBlockK, cw, ch, cn);
+          tma_load_2d(sb, &tmB, &full_bar[s], wk + kb * kBlockK, nt * BLOCK_N);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, false, false);
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * kUmmaK * 2, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * kUmmaK * 2, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; one thread per output pixel (tile row)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rows_per_img = p.wb * p.hb;
+    const int ni = row / rows_per_img;
+    const int rem = row - ni * rows_per_img;
+    const int hi = rem / p.wb;
+    const int wi = rem - hi * p.wb;
+    const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
+    const bool valid = (ni < p.nb) && (n < p.N) && (h < p.H) && (w < p.W);
+    const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+    const int col0 = nt * BLOCK_N;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      const int col = col0 + c * 32;
+      if (valid && col < p.Cout) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (p.temb) {
+          const float* t = p.temb + static_cast<long long>(n) * p.ld_temb + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(t + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (p.res) {
+          const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + pix * p.ldr + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+            unpack8(rp[j], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[j * 8 + e] += f[e];
+          }
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldo + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          bf16x8* op = reinterpret_cast<bf16x8*>(p.out + pix * p.ldo + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad
+// ---------------------------------------------------------------------------------------------
+struct WgradParams {
+  int N, H, W;
+  int kb0, kb1;           // 64-channel blocks of X source 0 / 1
+  int Cout;               // multiple of 64
+  int wb, hb, nb, tiles_w, tiles_h, tiles_n;
+  uint32_t box_bytes;     // bytes of one 64-channel pixel box
+  int box_rows;           // wb*hb*nb
+  int ptiles;             // total pixel tiles
+  int ptiles_per_split;
+  int cin_tiles;          // ceil((kb0+kb1)*64 / BLOCK_N)
+  float* dw;              // fp32 [Cout][ldw]
+  long long ldw;
+  int atomic;             // 1: red.add (split-K or accumulate), 0: plain store
+  uint32_t lbo, sbo;      // MN-major descriptor strides (runtime so the bring-up test can probe them)
+  TapTable taps;
+};
+
+template <int BLOCK_N, int STAGES>
+struct WgradSmem {
+  static constexpr int kABytes = 2 * kBlockM * 128;             // two 64-cout boxes of 128 pixel rows
+  static constexpr int kBBytes = (BLOCK_N / 64) * kBlockM * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX0,
+                  const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ WgradParams p) {
+  using L = WgradSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tap = blockIdx.x / p.cin_tiles;
+  const int cit = blockIdx.x - tap * p.cin_tiles;
+  const int cot = blockIdx.y;
+  const int pt_begin = blockIdx.z * p.ptiles_per_split;
+  const int pt_end = min(p.ptiles, pt_begin + p.ptiles_per_split);
+  const int kbt = p.kb0 + p.kb1;
+  const int cb0 = cit * (BLOCK_N / 64);                 // first 64-channel block of this cin tile
+  const int ncb = min(BLOCK_N / 64, kbt - cb0);         // valid 64-channel blocks in this tile
+
+  // Pixel rows the TMA boxes never write (box_rows < 128) or channel blocks past Cin must read as zero.
+  if (p.box_rows < kBlockM || ncb < BLOCK_N / 64 || (cot * 2 + 1) * 64 >= p.Cout) {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < STAGES * L::kStageBytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmX0);
+    if (p.kb1 > 0) tma_prefetch_desc(&tmX1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int n_iters = pt_end - pt_begin;
+  const int nyb = ((cot * 2 + 1) * 64 < p.Cout) ? 2 : 1;  // 64-cout boxes actually present
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int dn = p.taps.dn[tap], dh = p.taps.dh[tap], dw = p.taps.dw[tap];
+      for (int it = 0; it < n_iters; ++it) {
+        int mt = pt_begin + it;
+        const int tw = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int tn = mt / p.tiles_h;
+        const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        mbar_expect_tx(&full_bar[s], p.box_bytes * (nyb + ncb));
+        for (int b = 0; b < nyb; ++b)
+          tma_load_4d(sa + b * (kBlockM * 128), &tmY, &full_bar[s], (cot * 2 + b) * 64, w0, h0, n0);
+        for (int b = 0; b < ncb; ++b) {
+          const int cb = cb0 + b;
+          if (cb < p.kb0)
+            tma_load_4d(sb + b * (kBlockM * 128), &tmX0, &full_bar[s], cb * 64, w0 + dw, h0 + dh, n0 + dn);
+          else
+            tma_load_4d(sb + b * (kBlockM * 128), &tmX1, &full_bar[s], (cb - p.kb0) * 64, w0 + dw, h0 + dh,
+                        n0 + dn);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, true, true);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockM / kUmmaK; ++k) {   // 128 pixel rows = 8 MMAs of K=16
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * kUmmaK * 128, p.lbo, p.sbo);
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * kUmmaK * 128, p.lbo, p.sbo);
+          umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;         // cout index within tile
+    const int co = cot * kBlockM + row;
+    const int cin_total = kbt * 64;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      const int ci = cit * BLOCK_N + c * 32;
+      if (co < p.Cout && ci < cin_total && n_iters > 0) {
+        float* dst = p.dw + static_cast<long long>(co) * p.ldw + p.taps.wk[tap] + ci;
+        if (p.atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                         "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map construction (cached) and launchers
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d[4];
+  uint64_t ld;
+  uint32_t box[4];
+  bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return static_cast<size_t>(h);
+  }
+};
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// NHWC bf16 activation view [n][h][w][c] with pixel stride ld (elements); box = (64, wb, hb, nb)
+static int make_act_map(CUtensorMap* out, const void* ptr, int c, long long ld, int n, int h, int w, int wb, int hb,
+                        int nb) {
+  MapKey k;
+  std::memset(&k, 0, sizeof(k));
+  k.ptr = ptr;
+  k.d[0] = c; k.d[1] = w; k.d[2] = h; k.d[3] = n;
+  k.ld = ld;
+  k.box[0] = 64; k.box[1] = wb; k.box[2] = hb; k.box[3] = nb;
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_maps.find(k);
+    if (it != g_maps.end()) { *out = it->second; return DDPM_OK; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point unavailable"); return DDPM_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) || (c % 8)) {
+    set_last_error("activation view not 16-byte aligned (ptr=%p ld=%lld c=%d)", ptr, ld, c);
+    return DDPM_ERR_INVALID;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * w, (cuuint64_t)ld * 2 * w * h};
+  cuuint32_t box[4] = {64, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(act c=%d w=%d h=%d n=%d ld=%lld box=%d,%d,%d) failed: %d", c, w, h, n, ld,
+                   wb, hb, nb, (int)r);
+    return DDPM_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(g_map_mu);
+  if (g_maps.size() > 65536) g_maps.clear();
+  g_maps.emplace(k, *out);
+  return DDPM_OK;
+}
+
+// K-major weight matrix [rows][ld] bf16; box = (64, box_rows)
+static int make_wgt_map(CUtensorMap* out, const void* ptr, long long k_total, long long ld, int rows, int box_rows) {
+  MapKey k;
+  std::memset(&k, 0, sizeof(k));
+  k.ptr = ptr;
+  k.d[0] = k_total; k.d[1] = rows; k.d[2] = 0; k.d[3] = 0xB;
+  k.ld = ld;
+  k.box[0] = 64; k.box[1] = box_rows;
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_maps.find(k);
+    if (it != g_maps.end()) { *out = it->second; return DDPM_OK; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point unavailable"); return DDPM_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) {
+    set_last_error("weight matrix not 16-byte aligned (ptr=%p ld=%lld)", ptr, ld);
+    return DDPM_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(wgt k=%lld rows=%d ld=%lld) failed: %d", k_total, rows, ld, (int)r);
+    return DDPM_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(g_map_mu);
+  g_maps.emplace(k, *out);
+  return DDPM_OK;
+}
+
+static void choose_box(int n, int h, int w, int* wb, int* hb, int* nb) {
+  *wb = w < kBlockM ? w : kBlockM;
+  int rem = kBlockM / *wb;
+  if (rem < 1) rem = 1;
+  *hb = h < rem ? h : rem;
+  rem = kBlockM / (*wb * *hb);
+  if (rem < 1) rem = 1;
+  *nb = n < rem ? n : rem;
+}
+
+static int fill_taps(TapTable* t, const ddpm_conv_args* a) {
+  if (a->ntaps < 1 || a->ntaps > kMaxTaps) { set_last_error("ntaps=%d out of range", a->ntaps); return DDPM_ERR_INVALID; }
+  t->ntaps = a->ntaps;
+  for (int i = 0; i < a->ntaps; ++i) {
+    t->dn[i] = a->tap_dn[i]; t->dh[i] = a->tap_dh[i]; t->dw[i] = a->tap_dw[i]; t->wk[i] = a->tap_wk[i];
+  }
+  return DDPM_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
+                       cudaStream_t stream) {
+  using L = GemmSmem<BLOCK_N, STAGES>;
+  static bool configured = false;
+  auto kern = conv_gemm_kernel<BLOCK_N, STAGES>;
+  if (!configured) {
+    DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  dim3 grid((p.Cout + BLOCK_N - 1) / BLOCK_N, p.tiles_w * p.tiles_h * p.tiles_n);
+  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(a0, a1, b, p);
+  return check_launch("conv_gemm_kernel");
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_wgrad(const CUtensorMap& y, const CUtensorMap& x0, const CUtensorMap& x1, const WgradParams& p,
+                        int splits, cudaStream_t stream) {
+  using L = WgradSmem<BLOCK_N, STAGES>;
+  static bool configured = false;
+  auto kern = conv_wgrad_kernel<BLOCK_N, STAGES>;
+  if (!configured) {
+    DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  dim3 grid(p.cin_tiles * p.taps.ntaps, (p.Cout + kBlockM - 1) / kBlockM, splits);
+  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(y, x0, x1, p);
+  return check_launch("conv_wgrad_kernel");
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+}  // namespace ddpm
+
+using namespace ddpm;
+
+extern "C" int ddpm_conv_gemm(const ddpm_conv_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPM_REQUIRE(a && a->x0 && a->wgt && (a->out || a->out_f32), "ddpm_conv_gemm: null pointer argument");
+  DDPM_REQUIRE(a->c0 > 0 && a->c0 % 64 == 0 && a->c1 >= 0 && a->c1 % 64 == 0,
+               "ddpm_conv_gemm: channel counts must be multiples of 64 (c0=%d c1=%d)", a->c0, a->c1);
+  DDPM_REQUIRE(a->c1 == 0 || a->x1, "ddpm_conv_gemm: c1>0 but x1 is null");
+  DDPM_REQUIRE(a->cout > 0 && a->cout % 32 == 0, "ddpm_conv_gemm: cout=%d must be a multiple of 32", a->cout);
+  DDPM_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0, "ddpm_conv_gemm: empty pixel grid");
+  DDPM_REQUIRE(a->ldo % 8 == 0 && (a->res == nullptr || a->ldr % 8 == 0), "ddpm_conv_gemm: ldo/ldr must be multiples of 8");
+  GemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  if (int e = fill_taps(&p.taps, a)) return e;
+  p.N = a->n; p.H = a->h; p.W = a->w;
+  p.kb0 = a->c0 / 64; p.kb1 = a->c1 / 64;
+  p.Cout = a->cout;
+  choose_box(a->n, a->h, a->w, &p.wb, &p.hb, &p.nb);
+  p.tiles_w = (a->w + p.wb - 1) / p.wb;
+  p.tiles_h = (a->h + p.hb - 1) / p.hb;
+  p.tiles_n = (a->n + p.nb - 1) / p.nb;
+  p.a_bytes = static_cast<uint32_t>(p.wb * p.hb * p.nb) * 128u;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.out_f32 = static_cast<float*>(a->out_f32);
+  p.ldo = a->ldo;
+  p.bias = a->bias; p.temb = a->temb; p.ld_temb = a->ld_temb;
+  p.res = static_cast<const __nv_bfloat16*>(a->res); p.ldr = a->ldr;
+  const int src_n = a->src_n > 0 ? a->src_n : a->n;
+
+  CUtensorMap ma0, ma1, mb;
+  if (int e = make_act_map(&ma0, a->x0, a->c0, a->ld0, src_n, a->h, a->w, p.wb, p.hb, p.nb)) return e;
+  if (a->c1 > 0) {
+    if (int e = make_act_map(&ma1, a->x1, a->c1, a->ld1, src_n, a->h, a->w, p.wb, p.hb, p.nb)) return e;
+  } else {
+    ma1 = ma0;
+  }
+  int block_n = env_int("DDPM_BLOCK_N", 0);
+  if (block_n == 0) {
+    const long long mtiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_n;
+    block_n = (a->cout % 256 == 0 && mtiles * (a->cout / 256) >= 2 * kNumSMs) ? 256 : 128;
+  }
+  long long k_total = a->k_total > 0 ? a->k_total : a->ldw;
+  if (block_n == 256) {
+    if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 256)) return e;
+    return launch_gemm<256, 4>(ma0, ma1, mb, p, stream);
+  }
+  if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 128)) return e;
+  return launch_gemm<128, 3>(ma0, ma1, mb, p, stream);
+}
+
+extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPM_REQUIRE(a && a->dy && a->x0 && a->dw, "ddpm_conv_wgrad: null pointer argument");
+  DDPM_REQUIRE(a->c0 > 0 && a->c0 % 64 == 0 && a->c1 >= 0 && a->c1 % 64 == 0,
+               "ddpm_conv_wgrad: channel counts must be multiples of 64 (c0=%d c1=%d)", a->c0, a->c1);
+  DDPM_REQUIRE(a->cout > 0 && a->cout % 64 == 0, "ddpm_conv_wgrad: cout=%d must be a multiple of 64", a->cout);
+  DDPM_REQUIRE(a->ldw % 4 == 0, "ddpm_conv_wgrad: ldw must be a multiple of 4");
+  WgradParams p;
+  std::memset(&p, 0, sizeof(p));
+  if (a->ntaps < 1 || a->ntaps > kMaxTaps) { set_last_error("ntaps=%d out of range", a->ntaps); return DDPM_ERR_INVALID; }
+  p.taps.ntaps = a->ntaps;
+  for (int i = 0; i < a->ntaps; ++i) {
+    p.taps.dn[i] = a->tap_dn[i]; p.taps.dh[i] = a->tap_dh[i]; p.taps.dw[i] = a->tap_dw[i]; p.taps.wk[i] = a->tap_wk[i];
+  }
+  p.N = a->n; p.H = a->h; p.W = a->w;
+  p.kb0 = a->c0 / 64; p.kb1 = a->c1 / 64;
+  p.Cout = a->cout;
+  choose_box(a->n, a->h, a->w, &p.wb, &p.hb, &p.nb);
+  p.tiles_w = (a->w + p.wb - 1) / p.wb;
+  p.tiles_h = (a->h + p.hb - 1) / p.hb;
+  p.tiles_n = (a->n + p.nb - 1) / p.nb;
+  p.box_rows = p.wb * p.hb * p.nb;
+  p.box_bytes = static_cast<uint32_t>(p.box_rows) * 128u;
+  p.ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.dw = a->dw; p.ldw = a->ldw;
+  p.lbo = static_cast<uint32_t>(env_int("DDPM_WGRAD_LBO", kBlockM * 128));
+  p.sbo = static_cast<uint32_t>(env_int("DDPM_WGRAD_SBO", 1024));
+  const int src_n = a->src_n > 0 ? a->src_n : a->n;
+  const int kbt = p.kb0 + p.kb1;
+
+  int block_n = (kbt % 2 == 0 && kbt >= 4) ? 128 : (kbt >= 2 ? 128 : 64);
+  block_n = env_int("DDPM_WGRAD_BLOCK_N", block_n);
+  p.cin_tiles = (kbt * 64 + block_n - 1) / block_n;
+  const long long out_tiles = static_cast<long long>(p.cin_tiles) * a->ntaps * ((a->cout + kBlockM - 1) / kBlockM);
+  int splits = a->splits;
+  if (splits <= 0) {
+    // aim for ~2 waves of CTAs, but keep >= 8 pixel tiles per CTA so the red.add epilogue is amortised
+    long long want = (2LL * kNumSMs + out_tiles - 1) / out_tiles;
+    long long cap = p.ptiles / 8;
+    if (cap < 1) cap = 1;
+    splits = static_cast<int>(want < cap ? want : cap);
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.ptiles) splits = p.ptiles;
+  p.ptiles_per_split = (p.ptiles + splits - 1) / splits;
+  splits = (p.ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
+  p.atomic = (splits > 1 || a->accumulate) ? 1 : 0;
+
+  CUtensorMap my, mx0, mx1;
+  if (int e = make_act_map(&my, a->dy, a->cout, a->ldy, a->n, a->h, a->w, p.wb, p.hb, p.nb)) return e;
+  if (int e = make_act_map(&mx0, a->x0, a->c0, a->ld0, src_n, a->h, a->w, p.wb, p.hb, p.nb)) return e;
+  if (a->c1 > 0) {
+    DDPM_REQUIRE(a->x1, "ddpm_conv_wgrad: c1>0 but x1 is null");
+    if (int e = make_act_map(&mx1, a->x1, a->c1, a->ld1, src_n, a->h, a->w, p.wb, p.hb, p.nb)) return e;
+  } else {
+    mx1 = mx0;
+  }
+  if (block_n == 64) return launch_wgrad<64, 4>(my, mx0, mx1, p, splits, stream);
+  if (block_n == 128) return launch_wgrad<128, 3>(my, mx0, mx1, p, splits, stream);
+  set_last_error("ddpm_conv_wgrad: unsupported block_n=%d", block_n);
+  return DDPM_ERR_UNSUPPORTED;
+}

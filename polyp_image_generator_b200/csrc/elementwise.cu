@@ -1,0 +1,306 @@
+// Single-pass fp32 elementwise kernels of the DDPM path: add_noise, MSE fwd+bwd, scheduler step, uint8
+// post-processing.  HBM-bound; 16-byte vector accesses, grid sized to the problem (streaming, no reuse).
+// Replaces ~6 / ~3 / ~30 TensorIterator launches of the reference.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/ddpm_b200.h"
+
+namespace ddpm {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return DDPM_ERR_CUDA;
+  }
+  return DDPM_OK;
+}
+
+constexpr int kEwThreads = 256;
+
+static inline int ew_blocks(long long work_items) {
+  long long b = (work_items + kEwThreads - 1) / kEwThreads;
+  const long long cap = static_cast<long long>(kNumSMs) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// ---- add_noise ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
+                 const float* __restrict__ sa_tab, const float* __restrict__ sb_tab, float* __restrict__ out,
+                 long long per_sample, long long total_vec, int vec_per_sample_ok, int T) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  if (vec_per_sample_ok) {
+    const long long vps = per_sample >> 2;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+      const long long b = i / vps;
+      long long tt = t[b];
+      tt = tt < 0 ? 0 : (tt >= T ? T - 1 : tt);
+      const float a = sa_tab[tt], s = sb_tab[tt];
+      const float4 x = reinterpret_cast<const float4*>(x0)[i];
+      const float4 z = reinterpret_cast<const float4*>(noise)[i];
+      float4 o;
+      o.x = __fadd_rn(__fmul_rn(a, x.x), __fmul_rn(s, z.x));
+      o.y = __fadd_rn(__fmul_rn(a, x.y), __fmul_rn(s, z.y));
+      o.z = __fadd_rn(__fmul_rn(a, x.z), __fmul_rn(s, z.z));
+      o.w = __fadd_rn(__fmul_rn(a, x.w), __fmul_rn(s, z.w));
+      reinterpret_cast<float4*>(out)[i] = o;
+    }
+  } else {
+    const long long total = total_vec;  // scalar count in this mode
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const long long b = i / per_sample;
+      long long tt = t[b];
+      tt = tt < 0 ? 0 : (tt >= T ? T - 1 : tt);
+      out[i] = __fadd_rn(__fmul_rn(sa_tab[tt], x0[i]), __fmul_rn(sb_tab[tt], noise[i]));
+    }
+  }
+}
+
+// ---- MSE forward + backward ----------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss_sum,
+                   float* __restrict__ dpred, long long n, float two_over_n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = n >> 2;
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 p = reinterpret_cast<const float4*>(pred)[i];
+    const float4 q = reinterpret_cast<const float4*>(target)[i];
+    float4 d = make_float4(p.x - q.x, p.y - q.y, p.z - q.z, p.w - q.w);
+    acc += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+    if (dpred) reinterpret_cast<float4*>(dpred)[i] = make_float4(d.x * two_over_n, d.y * two_over_n, d.z * two_over_n, d.w * two_over_n);
+  }
+  for (long long i = (nvec << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = pred[i] - target[i];
+    acc += d * d;
+    if (dpred) dpred[i] = d * two_over_n;
+  }
+  __shared__ float red[kEwThreads / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kEwThreads / 32 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+scale_by_scalar_kernel(float* __restrict__ x, const float* __restrict__ scale, long long n) {
+  const float s = *scale;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = n >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  for (long long i = (nvec << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    x[i] *= s;
+}
+
+// ---- scheduler step --------------------------------------------------------------------------------
+struct StepCoef {
+  float sa, sb, c0, ct, sigma, clip;
+};
+
+__device__ __forceinline__ float step_one(float e, float x, float z, bool has_z, const StepCoef& k, float* x0_out) {
+  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sb, e)), k.sa);
+  if (k.clip > 0.f) x0 = fminf(fmaxf(x0, -k.clip), k.clip);
+  *x0_out = x0;
+  float mu = __fadd_rn(__fmul_rn(k.c0, x0), __fmul_rn(k.ct, x));
+  if (has_z) mu = __fadd_rn(mu, __fmul_rn(k.sigma, z));
+  return mu;
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+scheduler_step_kernel(const float* __restrict__ eps, const float* __restrict__ x, const float* __restrict__ z,
+                      float* __restrict__ prev, float* __restrict__ pred_x0, long long n, StepCoef k) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = n >> 2;
+  const bool has_z = z != nullptr;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 e = reinterpret_cast<const float4*>(eps)[i];
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_z) zv = reinterpret_cast<const float4*>(z)[i];
+    float4 o, p0;
+    o.x = step_one(e.x, xv.x, zv.x, has_z, k, &p0.x);
+    o.y = step_one(e.y, xv.y, zv.y, has_z, k, &p0.y);
+    o.z = step_one(e.z, xv.z, zv.z, has_z, k, &p0.z);
+    o.w = step_one(e.w, xv.w, zv.w, has_z, k, &p0.w);
+    reinterpret_cast<float4*>(prev)[i] = o;
+    if (pred_x0) reinterpret_cast<float4*>(pred_x0)[i] = p0;
+  }
+  for (long long i = (nvec << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float p0;
+    prev[i] = step_one(eps[i], x[i], has_z ? z[i] : 0.f, has_z, k, &p0);
+    if (pred_x0) pred_x0[i] = p0;
+  }
+}
+
+// Philox4x32-10, counter = (element-quad index, offset), key = seed
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  const float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+scheduler_step_philox_kernel(const float* __restrict__ eps, const float* __restrict__ x, float* __restrict__ prev,
+                             long long n, StepCoef k, unsigned long long seed, unsigned long long offset) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = (n + 3) >> 2;
+  const bool has_z = k.sigma != 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (has_z) {
+      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32),
+                                               static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32)),
+                                    make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+      const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+      zz[0] = g0.x; zz[1] = g0.y; zz[2] = g1.x; zz[3] = g1.y;
+    }
+    const long long base = i << 2;
+    if (base + 3 < n) {
+      const float4 e = reinterpret_cast<const float4*>(eps)[i];
+      const float4 xv = reinterpret_cast<const float4*>(x)[i];
+      float4 o;
+      float p0;
+      o.x = step_one(e.x, xv.x, zz[0], has_z, k, &p0);
+      o.y = step_one(e.y, xv.y, zz[1], has_z, k, &p0);
+      o.z = step_one(e.z, xv.z, zz[2], has_z, k, &p0);
+      o.w = step_one(e.w, xv.w, zz[3], has_z, k, &p0);
+      reinterpret_cast<float4*>(prev)[i] = o;
+    } else {
+      for (int j = 0; j < 4 && base + j < n; ++j) {
+        float p0;
+        prev[base + j] = step_one(eps[base + j], x[base + j], zz[j], has_z, k, &p0);
+      }
+    }
+  }
+}
+
+// ---- uint8 post-processing -----------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+to_uint8_nhwc_kernel(const float* __restrict__ x, unsigned char* __restrict__ out, int n, int c, int h, int w) {
+  const long long total = static_cast<long long>(n) * h * w * c;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long hw = static_cast<long long>(h) * w;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int ch = static_cast<int>(i % c);
+    const long long pix = i / c;
+    const long long b = pix / hw, p = pix - b * hw;
+    float v = x[(b * c + ch) * hw + p];
+    v = __fadd_rn(__fdiv_rn(v, 2.0f), 0.5f);
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    out[i] = static_cast<unsigned char>(rintf(__fmul_rn(v, 255.0f)));
+  }
+}
+
+}  // namespace ddpm
+
+using namespace ddpm;
+
+extern "C" const char* ddpm_last_error(void) { return g_err; }
+extern "C" int ddpm_abi_version(void) { return DDPM_ABI_VERSION; }
+
+extern "C" int ddpm_add_noise(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
+                              const float* sqrt_1mac, float* out, int batch, long long per_sample,
+                              int num_train_timesteps, void* stream) {
+  DDPM_REQUIRE(x0 && noise && t && sqrt_ac && sqrt_1mac && out, "ddpm_add_noise: null pointer argument");
+  DDPM_REQUIRE(batch >= 0 && per_sample >= 0 && num_train_timesteps > 0, "ddpm_add_noise: bad sizes");
+  const long long total = static_cast<long long>(batch) * per_sample;
+  if (total == 0) return DDPM_OK;
+  const bool vec_ok = (per_sample % 4 == 0) && ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(noise) |
+                                                 reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  const long long items = vec_ok ? total / 4 : total;
+  add_noise_kernel<<<ew_blocks(items), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x0, noise, t, sqrt_ac, sqrt_1mac, out, per_sample, items, vec_ok ? 1 : 0, num_train_timesteps);
+  return check_launch("add_noise_kernel");
+}
+
+extern "C" int ddpm_mse_fwd_bwd(const float* pred, const float* target, float* loss_sum, float* dpred, long long n,
+                                void* stream) {
+  DDPM_REQUIRE(pred && target && loss_sum, "ddpm_mse_fwd_bwd: null pointer argument");
+  DDPM_REQUIRE(n > 0, "ddpm_mse_fwd_bwd: n must be positive");
+  DDPM_REQUIRE((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) |
+                reinterpret_cast<uintptr_t>(dpred)) % 16 == 0, "ddpm_mse_fwd_bwd: pointers must be 16-byte aligned");
+  mse_fwd_bwd_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, target, loss_sum, dpred, n, 2.0f / static_cast<float>(n));
+  return check_launch("mse_fwd_bwd_kernel");
+}
+
+extern "C" int ddpm_scale_by_device_scalar(float* x, const float* scale, long long n, void* stream) {
+  DDPM_REQUIRE(x && scale && n >= 0, "ddpm_scale_by_device_scalar: bad argument");
+  DDPM_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0, "ddpm_scale_by_device_scalar: x must be 16-byte aligned");
+  if (n == 0) return DDPM_OK;
+  scale_by_scalar_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, scale, n);
+  return check_launch("scale_by_scalar_kernel");
+}
+
+extern "C" int ddpm_scheduler_step(const float* eps, const float* x, const float* z, float* prev, float* pred_x0,
+                                   long long n, float sqrt_alpha_prod, float sqrt_beta_prod, float c0, float ct,
+                                   float sigma, float clip, void* stream) {
+  DDPM_REQUIRE(eps && x && prev && n >= 0, "ddpm_scheduler_step: bad argument");
+  DDPM_REQUIRE((reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z) |
+                reinterpret_cast<uintptr_t>(prev) | reinterpret_cast<uintptr_t>(pred_x0)) % 16 == 0,
+               "ddpm_scheduler_step: pointers must be 16-byte aligned");
+  if (n == 0) return DDPM_OK;
+  StepCoef k{sqrt_alpha_prod, sqrt_beta_prod, c0, ct, sigma, clip};
+  scheduler_step_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(eps, x, z, prev,
+                                                                                                  pred_x0, n, k);
+  return check_launch("scheduler_step_kernel");
+}
+
+extern "C" int ddpm_scheduler_step_philox(const float* eps, const float* x, float* prev, long long n,
+                                          float sqrt_alpha_prod, float sqrt_beta_prod, float c0, float ct,
+                                          float sigma, float clip, unsigned long long seed,
+                                          unsigned long long offset, void* stream) {
+  DDPM_REQUIRE(eps && x && prev && n >= 0, "ddpm_scheduler_step_philox: bad argument");
+  DDPM_REQUIRE((reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(prev)) % 16 == 0,
+               "ddpm_scheduler_step_philox: pointers must be 16-byte aligned");
+  if (n == 0) return DDPM_OK;
+  StepCoef k{sqrt_alpha_prod, sqrt_beta_prod, c0, ct, sigma, clip};
+  scheduler_step_philox_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      eps, x, prev, n, k, seed, offset);
+  return check_launch("scheduler_step_philox_kernel");
+}
+
+extern "C" int ddpm_to_uint8_nhwc(const float* x, unsigned char* out, int n, int c, int h, int w, void* stream) {
+  DDPM_REQUIRE(x && out && n >= 0 && c > 0 && h > 0 && w > 0, "ddpm_to_uint8_nhwc: bad argument");
+  if (n == 0) return DDPM_OK;
+  to_uint8_nhwc_kernel<<<ew_blocks(static_cast<long long>(n) * c * h * w), kEwThreads, 0,
+                         static_cast<cudaStream_t>(stream)>>>(x, out, n, c, h, w);
+  return check_launch("to_uint8_nhwc_kernel");
+}

@@ -1,0 +1,367 @@
+// Small supporting kernels of the UNet path: timestep sinusoid, the fp32 time-embedding linears (tiny M),
+// per-(sample, channel) reductions (bias / time-embedding gradients), bf16 weight preparation and the
+// layout helpers for stride-2 / upsampling convs.  SURVEY.md §2.3 rows K5, K7 (time MLP part).
+#include "common.cuh"
+
+#include "../../include/ddpm_b200.h"
+
+namespace ddpm {
+
+constexpr int kThreads = 256;
+
+static int blocks_for(long long items, int threads = kThreads) {
+  long long b = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(kNumSMs) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// ---- Timesteps(dim): diffusers get_timestep_embedding -------------------------------------------------
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, float* __restrict__ out, int b, int dim,
+                                          int flip, float freq_shift) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b * half) return;
+  const int row = i / half, j = i - row * half;
+  // exponent = -ln(10000) * j / (half - shift); emb = exp(exponent) * t   (fp32, same op order as torch)
+  const float expo = __fdiv_rn(__fmul_rn(-9.210340371976184f, static_cast<float>(j)),
+                               static_cast<float>(half) - freq_shift);
+  const float arg = __fmul_rn(static_cast<float>(t[row]), expf(expo));
+  const float sv = sinf(arg), cv = cosf(arg);
+  float* o = out + static_cast<long long>(row) * dim;
+  if (flip) {
+    o[j] = cv;
+    o[half + j] = sv;
+  } else {
+    o[j] = sv;
+    o[half + j] = cv;
+  }
+}
+
+// ---- fp32 linear, tiny M: one warp per output element column-block --------------------------------------
+// y[m][n] = bias[n] + sum_k act(x[m][k]) * w[n][k];  grid (ceil(n/8), m), block 256 = 8 warps, warp -> one n
+__global__ void __launch_bounds__(kThreads)
+linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, int M, int N, int K, int silu_in) {
+  extern __shared__ float xs[];  // act(x[m][:])
+  const int m = blockIdx.y;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = x[static_cast<long long>(m) * K + k];
+    xs[k] = silu_in ? silu_f(v) : v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (kThreads / 32) + warp;
+  if (n >= N) return;
+  const float* wr = w + static_cast<long long>(n) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc += xs[k] * wr[k];
+  acc = warp_sum(acc);
+  if (lane == 0) y[static_cast<long long>(m) * N + n] = acc + (bias ? bias[n] : 0.f);
+}
+
+// dw[n][k] += sum_m dy[m][n] * act(x[m][k]);  db[n] += sum_m dy[m][n].  thread per (n, k), M small.
+__global__ void __launch_bounds__(kThreads)
+linear_f32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                        float* __restrict__ db, int M, int N, int K, int silu_in) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
+  float acc = 0.f, accb = 0.f;
+  for (int m = 0; m < M; ++m) {
+    float xv = x[static_cast<long long>(m) * K + k];
+    if (silu_in) xv = silu_f(xv);
+    const float d = dy[static_cast<long long>(m) * N + n];
+    acc += d * xv;
+    accb += d;
+  }
+  dw[i] += acc;
+  if (db && k == 0) db[n] += accb;
+}
+
+// dx[m][k] (+)= act'(x[m][k]) * sum_n dy[m][n] * w[n][k];  grid (ceil(K/256), M)
+__global__ void __launch_bounds__(kThreads)
+linear_f32_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ x,
+                        float* __restrict__ dx, int M, int N, int K, int silu_in, int accumulate) {
+  extern __shared__ float dys[];
+  const int m = blockIdx.y;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) dys[n] = dy[static_cast<long long>(m) * N + n];
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) acc += dys[n] * w[static_cast<long long>(n) * K + k];
+  if (silu_in) acc *= silu_grad_f(x[static_cast<long long>(m) * K + k]);
+  float* o = dx + static_cast<long long>(m) * K + k;
+  *o = accumulate ? *o + acc : acc;
+}
+
+// ---- per-(n, c) sums over hw of a bf16 NHWC tensor -------------------------------------------------------
+// grid (chunks, N); block V*ppb; out_nc atomically accumulated (caller-zeroed by the launcher)
+__global__ void __launch_bounds__(kThreads)
+reduce_hw_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int hw, int C, float* __restrict__ out_nc,
+                 long long ld_nc, float* __restrict__ out_c, int pix_per_block, int V) {
+  extern __shared__ float smc[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) smc[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(hw, p_begin + pix_per_block);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int p = p_begin + pl; p < p_end; p += ppb) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + (static_cast<long long>(n) * hw + p) * ld + v * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) atomicAdd(&smc[v * 8 + e], acc[e]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    if (out_nc) atomicAdd(&out_nc[static_cast<long long>(n) * ld_nc + i], smc[i]);
+    if (out_c) atomicAdd(&out_c[i], smc[i]);
+  }
+}
+
+// ---- weight preparation -----------------------------------------------------------------------------------
+// wf[co][tap][ci] = bf16(w[co][tap][ci]);  wd[ci][T-1-tap][co] = bf16(w[co][tap][ci])
+// grid (ceil(cin/32), ceil(cout/32), taps), block (32, 8)
+__global__ void prep_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, long long ldwf,
+                                   __nv_bfloat16* __restrict__ wd, long long ldwd, int cout, int taps, int cin) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    float v = 0.f;
+    if (co < cout && ci < cin) {
+      v = w[(static_cast<long long>(co) * taps + tap) * cin + ci];
+      if (wf) wf[static_cast<long long>(co) * ldwf + static_cast<long long>(tap) * cin + ci] = __float2bfloat16(v);
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  if (!wd) return;
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < cin && co < cout)
+      wd[static_cast<long long>(ci) * ldwd + static_cast<long long>(taps - 1 - tap) * cout + co] =
+          __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+// ---- layout helpers (one 16-byte vector per thread) ----------------------------------------------------------
+// out[(ph*2+pw)*N + b][i][j][c] = x[b][2i+ph-pad_lo][2j+pw-pad_lo][c]  (zero outside); output grid (H2, W2)
+__global__ void space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                      __nv_bfloat16* __restrict__ out, int N, int H, int W, int C, int H2, int W2,
+                                      int pad_lo, long long total_vec) {
+  const int V = C / 8;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int v = static_cast<int>(i % V);
+    long long r = i / V;
+    const int j = static_cast<int>(r % W2); r /= W2;
+    const int ii = static_cast<int>(r % H2); r /= H2;
+    const int b = static_cast<int>(r % N);
+    const int phase = static_cast<int>(r / N);
+    const int h = 2 * ii + (phase >> 1) - pad_lo, w = 2 * j + (phase & 1) - pad_lo;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (h >= 0 && h < H && w >= 0 && w < W)
+      val = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * H + h) * W + w) * ldx + v * 8);
+    reinterpret_cast<uint4*>(out)[i] = val;
+  }
+}
+
+// out[b][h][w][c] = (h,w both even and h/2<Ho, w/2<Wo) ? dy[b][h/2][w/2][c] : 0 ; output grid (H, W)
+__global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
+                                     __nv_bfloat16* __restrict__ out, int N, int Ho, int Wo, int C, int H, int W,
+                                     long long total_vec) {
+  const int V = C / 8;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int v = static_cast<int>(i % V);
+    long long r = i / V;
+    const int w = static_cast<int>(r % W); r /= W;
+    const int h = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
+      val = *reinterpret_cast<const uint4*>(dy + ((static_cast<long long>(b) * Ho + (h >> 1)) * Wo + (w >> 1)) * ldy + v * 8);
+    reinterpret_cast<uint4*>(out)[i] = val;
+  }
+}
+
+// out[b][h][w][c] = x[b][h/2][w/2][c]; output grid (2H, 2W)
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out,
+                                  int N, int H, int W, int C, long long total_vec) {
+  const int V = C / 8;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int v = static_cast<int>(i % V);
+    long long r = i / V;
+    const int w = static_cast<int>(r % (2 * W)); r /= (2 * W);
+    const int h = static_cast<int>(r % (2 * H));
+    const int b = static_cast<int>(r / (2 * H));
+    reinterpret_cast<uint4*>(out)[i] =
+        *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * H + (h >> 1)) * W + (w >> 1)) * ldx + v * 8);
+  }
+}
+
+// out[b][i][j][c] = sum_{a,b in 0..1} dy[b][2i+a][2j+b][c] (+ add); output grid (H, W), dy grid (2H, 2W)
+__global__ void sumpool2x_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
+                                 const __nv_bfloat16* __restrict__ add, long long ldadd,
+                                 __nv_bfloat16* __restrict__ out, int N, int H, int W, int C, long long total_vec) {
+  const int V = C / 8;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int v = static_cast<int>(i % V);
+    long long r = i / V;
+    const int j = static_cast<int>(r % W); r /= W;
+    const int ii = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(
+                    dy + ((static_cast<long long>(b) * 2 * H + 2 * ii + a) * 2 * W + 2 * j + bb) * ldy + v * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    if (add) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(add + ((static_cast<long long>(b) * H + ii) * W + j) * ldadd + v * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    reinterpret_cast<bf16x8*>(out)[i] = pack8(acc);
+  }
+}
+
+}  // namespace ddpm
+
+using namespace ddpm;
+
+extern "C" int ddpm_timestep_embedding(const long long* t, float* out, int b, int dim, int flip_sin_to_cos,
+                                       float freq_shift, void* stream) {
+  DDPM_REQUIRE(t && out && b > 0 && dim > 0 && dim % 2 == 0, "ddpm_timestep_embedding: bad argument");
+  const int items = b * (dim / 2);
+  timestep_embedding_kernel<<<(items + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, b, dim,
+                                                                                               flip_sin_to_cos,
+                                                                                               freq_shift);
+  return check_launch("timestep_embedding_kernel");
+}
+
+extern "C" int ddpm_linear_f32(const float* x, const float* w, const float* bias, float* y, int m, int n, int k,
+                               int silu_in, void* stream) {
+  DDPM_REQUIRE(x && w && y && m > 0 && n > 0 && k > 0 && k <= 8192, "ddpm_linear_f32: bad argument");
+  linear_f32_kernel<<<dim3((n + 7) / 8, m), kThreads, k * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      x, w, bias, y, m, n, k, silu_in);
+  return check_launch("linear_f32_kernel");
+}
+
+extern "C" int ddpm_linear_f32_wgrad(const float* x, const float* dy, float* dw, float* db, int m, int n, int k,
+                                     int silu_in, void* stream) {
+  DDPM_REQUIRE(x && dy && dw && m > 0 && n > 0 && k > 0, "ddpm_linear_f32_wgrad: bad argument");
+  const long long items = static_cast<long long>(n) * k;
+  linear_f32_wgrad_kernel<<<static_cast<int>((items + kThreads - 1) / kThreads), kThreads, 0,
+                            static_cast<cudaStream_t>(stream)>>>(x, dy, dw, db, m, n, k, silu_in);
+  return check_launch("linear_f32_wgrad_kernel");
+}
+
+extern "C" int ddpm_linear_f32_dgrad(const float* dy, const float* w, const float* x, float* dx, int m, int n, int k,
+                                     int silu_in, int accumulate, void* stream) {
+  DDPM_REQUIRE(dy && w && dx && m > 0 && n > 0 && k > 0 && n <= 12288, "ddpm_linear_f32_dgrad: bad argument");
+  DDPM_REQUIRE(!silu_in || x, "ddpm_linear_f32_dgrad: silu_in needs x");
+  static bool configured = false;
+  if (!configured) {
+    DDPM_CUDA(cudaFuncSetAttribute(linear_f32_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4));
+    configured = true;
+  }
+  linear_f32_dgrad_kernel<<<dim3((k + kThreads - 1) / kThreads, m), kThreads, n * sizeof(float),
+                            static_cast<cudaStream_t>(stream)>>>(dy, w, x, dx, m, n, k, silu_in, accumulate);
+  return check_launch("linear_f32_dgrad_kernel");
+}
+
+extern "C" int ddpm_reduce_hw(const void* x, long long ld, int n, int hw, int c, float* out_nc, long long ld_nc,
+                              float* out_c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPM_REQUIRE(x && n > 0 && hw > 0 && c > 0 && c % 8 == 0 && c <= 2048 && ld % 8 == 0 && (out_nc || out_c),
+               "ddpm_reduce_hw: bad argument");
+  const int V = c / 8;
+  int ppb = kThreads / V;
+  if (ppb < 1) ppb = 1;
+  const int threads = V * ppb;
+  long long want = (4LL * kNumSMs + n - 1) / n;
+  long long ppblk = (hw + want - 1) / want;
+  if (ppblk < ppb * 8LL) ppblk = ppb * 8LL;
+  if (ppblk > hw) ppblk = hw;
+  const int chunks = static_cast<int>((hw + ppblk - 1) / ppblk);
+  if (out_nc) {
+    if (ld_nc == c) {
+      DDPM_CUDA(cudaMemsetAsync(out_nc, 0, sizeof(float) * n * c, stream));
+    } else {
+      DDPM_CUDA(cudaMemset2DAsync(out_nc, ld_nc * sizeof(float), 0, c * sizeof(float), n, stream));
+    }
+  }
+  reduce_hw_kernel<<<dim3(chunks, n), threads, c * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(x), ld, hw, c, out_nc, ld_nc, out_c, static_cast<int>(ppblk), V);
+  return check_launch("reduce_hw_kernel");
+}
+
+extern "C" int ddpm_prep_weight(const float* w, void* wf, long long ldwf, void* wd, long long ldwd, int cout, int taps,
+                                int cin, void* stream) {
+  DDPM_REQUIRE(w && (wf || wd) && cout > 0 && taps > 0 && cin > 0, "ddpm_prep_weight: bad argument");
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32, taps);
+  prep_weight_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(wf), ldwf, static_cast<__nv_bfloat16*>(wd), ldwd, cout, taps, cin);
+  return check_launch("prep_weight_kernel");
+}
+
+extern "C" int ddpm_space_to_depth(const void* x, long long ldx, void* out, int n, int h, int w, int c, int pad_lo,
+                                   void* stream) {
+  DDPM_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && ldx % 8 == 0, "ddpm_space_to_depth: bad argument");
+  // phase grid covers input rows 2i+ph-pad_lo for i in [0, H2): H2 = ceil((h + pad_lo) / 2) (+1 row of zeros if needed)
+  const int h2 = (h + pad_lo + 1) / 2, w2 = (w + pad_lo + 1) / 2;
+  const long long total_vec = 4LL * n * h2 * w2 * (c / 8);
+  space_to_depth_kernel<<<blocks_for(total_vec), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), n, h, w, c, h2, w2, pad_lo,
+      total_vec);
+  return check_launch("space_to_depth_kernel");
+}
+
+extern "C" int ddpm_zero_insert2x(const void* dy, long long ldy, void* out, int n, int ho, int wo, int c, int h, int w,
+                                  void* stream) {
+  DDPM_REQUIRE(dy && out && n > 0 && ho > 0 && wo > 0 && c % 8 == 0 && ldy % 8 == 0, "ddpm_zero_insert2x: bad argument");
+  const long long total_vec = static_cast<long long>(n) * h * w * (c / 8);
+  zero_insert2x_kernel<<<blocks_for(total_vec), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), ldy, static_cast<__nv_bfloat16*>(out), n, ho, wo, c, h, w, total_vec);
+  return check_launch("zero_insert2x_kernel");
+}
+
+extern "C" int ddpm_upsample2x(const void* x, long long ldx, void* out, int n, int h, int w, int c, void* stream) {
+  DDPM_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && c % 8 == 0 && ldx % 8 == 0, "ddpm_upsample2x: bad argument");
+  const long long total_vec = 4LL * n * h * w * (c / 8);
+  upsample2x_kernel<<<blocks_for(total_vec), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), n, h, w, c, total_vec);
+  return check_launch("upsample2x_kernel");
+}
+
+extern "C" int ddpm_sumpool2x(const void* dy, long long ldy, const void* add, long long ldadd, void* out, int n, int h,
+                              int w, int c, void* stream) {
+  DDPM_REQUIRE(dy && out && n > 0 && h > 0 && w > 0 && c % 8 == 0 && ldy % 8 == 0 && (!add || ldadd % 8 == 0),
+               "ddpm_sumpool2x: bad argument");
+  const long long total_vec = static_cast<long long>(n) * h * w * (c / 8);
+  sumpool2x_kernel<<<blocks_for(total_vec), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), ldy, static_cast<const __nv_bfloat16*>(add), ldadd,
+      static_cast<__nv_bfloat16*>(out), n, h, w, c, total_vec);
+  return check_launch("sumpool2x_kernel");
+}

@@ -1,0 +1,369 @@
+"""Thin torch-tensor front end of the C-ABI kernels (include/ddpm_b200.h).
+
+Every function launches hand-written sm_100a kernels on torch's current CUDA stream; PyTorch is used only for
+device memory and streams.  There is NO fallback: a non-CUDA tensor or a missing library raises.
+
+Activation tensors are "NHWC views": shape [N, H, W, C] bf16 with stride(3) == 1 and a pixel stride
+ld == stride(2) (so channel slices of wider tensors are valid inputs and outputs).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+
+Tap = Tuple[int, int, int, int]  # (dn, dh, dw, wk)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("polyp_image_generator_b200 kernels need CUDA tensors (no CPU fallback exists)")
+    return t.data_ptr()
+
+
+def _nhwc(t: torch.Tensor, what: str) -> Tuple[int, int, int, int, int]:
+    """-> (n, h, w, c, ld) of an NHWC bf16 view."""
+    if t.dtype != torch.bfloat16 or t.dim() != 4:
+        raise ValueError(f"{what}: expected a 4-d bf16 NHWC view, got {tuple(t.shape)} {t.dtype}")
+    n, h, w, c = t.shape
+    ld = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if n > 1 else c))
+    if c > 1 and t.stride(3) != 1:
+        raise ValueError(f"{what}: channel stride must be 1")
+    if (w > 1 and t.stride(2) != ld) or (h > 1 and t.stride(1) != w * ld) or (n > 1 and t.stride(0) != h * w * ld):
+        raise ValueError(f"{what}: not a dense-pixel NHWC view, shape {tuple(t.shape)} strides {t.stride()}")
+    return n, h, w, c, ld
+
+
+def taps_3x3(cin_total: int, pad: int = 1) -> List[Tap]:
+    return [(0, r - pad, s - pad, (r * 3 + s) * cin_total) for r in range(3) for s in range(3)]
+
+
+def taps_1x1() -> List[Tap]:
+    return [(0, 0, 0, 0)]
+
+
+def taps_s2d(cin_total: int, n: int, pad: int) -> List[Tap]:
+    """3x3 stride-2 conv over a space-to-depth tensor whose phase p = (row parity)*2 + (col parity) lives at
+    batch offset p*n.  pad = 1 (diffusers default) or 0 (downsample_padding=0, i.e. F.pad(x, (0,1,0,1)))."""
+    out = []
+    for r in range(3):
+        for s in range(3):
+            ir, ic = r - pad, s - pad          # input row = 2*ho + ir
+            ph, dh = ir % 2, (ir - ir % 2) // 2
+            pw, dw = ic % 2, (ic - ic % 2) // 2
+            out.append(((ph * 2 + pw) * n, dh, dw, (r * 3 + s) * cin_total))
+    return out
+
+
+class CudaOps:
+    """The product backend: every method is one (or a few) C-ABI calls."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _capi.load()
+        self.launches = 0  # kernels launched through this object (bench.py reports it)
+
+    # ---- scheduler / loss ----------------------------------------------------------------------------
+    def add_noise(self, x0, noise, t, sqrt_ac, sqrt_1mac):
+        out = torch.empty_like(x0)
+        b = x0.shape[0]
+        per = x0.numel() // max(b, 1)
+        _capi.check(self.lib.ddpm_add_noise(_ptr(x0), _ptr(noise), _ptr(t), _ptr(sqrt_ac), _ptr(sqrt_1mac), _ptr(out),
+                                            b, per, sqrt_ac.numel(), _stream()), "ddpm_add_noise")
+        self.launches += 1
+        return out
+
+    def mse_fwd_bwd(self, pred, target, want_grad=True):
+        loss_sum = torch.zeros(1, device=pred.device, dtype=torch.float32)
+        dpred = torch.empty_like(pred) if want_grad else None
+        _capi.check(self.lib.ddpm_mse_fwd_bwd(_ptr(pred), _ptr(target), _ptr(loss_sum), _ptr(dpred), pred.numel(),
+                                              _stream()), "ddpm_mse_fwd_bwd")
+        self.launches += 1
+        return loss_sum, dpred
+
+    def scale_by_device_scalar(self, x, scale):
+        _capi.check(self.lib.ddpm_scale_by_device_scalar(_ptr(x), _ptr(scale), x.numel(), _stream()),
+                    "ddpm_scale_by_device_scalar")
+        self.launches += 1
+        return x
+
+    def scheduler_step(self, eps, x, z, sa, sb, c0, ct, sigma, clip, want_x0=False):
+        prev = torch.empty_like(x)
+        x0 = torch.empty_like(x) if want_x0 else None
+        _capi.check(self.lib.ddpm_scheduler_step(_ptr(eps), _ptr(x), _ptr(z), _ptr(prev), _ptr(x0), x.numel(), sa, sb,
+                                                 c0, ct, sigma, clip, _stream()), "ddpm_scheduler_step")
+        self.launches += 1
+        return prev, x0
+
+    def scheduler_step_philox(self, eps, x, sa, sb, c0, ct, sigma, clip, seed, offset):
+        prev = torch.empty_like(x)
+        _capi.check(self.lib.ddpm_scheduler_step_philox(_ptr(eps), _ptr(x), _ptr(prev), x.numel(), sa, sb, c0, ct,
+                                                        sigma, clip, seed, offset, _stream()),
+                    "ddpm_scheduler_step_philox")
+        self.launches += 1
+        return prev
+
+    def to_uint8_nhwc(self, x):
+        n, c, h, w = x.shape
+        out = torch.empty((n, h, w, c), device=x.device, dtype=torch.uint8)
+        _capi.check(self.lib.ddpm_to_uint8_nhwc(_ptr(x), _ptr(out), n, c, h, w, _stream()), "ddpm_to_uint8_nhwc")
+        self.launches += 1
+        return out
+
+    # ---- tcgen05 conv / linear -------------------------------------------------------------------------
+    def conv_gemm(self, x0, x1, taps: Sequence[Tap], wgt, cout: int, grid: Tuple[int, int, int], bias=None,
+                  temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0):
+        """out[n,h,w,co] = bias + temb[n] + res + sum_taps X[pix+tap] . wgt[co, wk:wk+cin]; see ddpm_conv_gemm."""
+        n, h, w = grid
+        _, _, _, c0, ld0 = _nhwc(x0, "x0")
+        a = _capi.ConvArgs()
+        a.x0, a.c0, a.ld0 = _ptr(x0), c0, ld0
+        if x1 is not None:
+            _, _, _, c1, ld1 = _nhwc(x1, "x1")
+            a.x1, a.c1, a.ld1 = _ptr(x1), c1, ld1
+        a.n, a.h, a.w, a.src_n = n, h, w, src_n
+        a.ntaps = len(taps)
+        for i, (dn, dh, dw, wk) in enumerate(taps):
+            a.tap_dn[i], a.tap_dh[i], a.tap_dw[i], a.tap_wk[i] = dn, dh, dw, wk
+        if wgt.dtype != torch.bfloat16 or wgt.dim() != 2 or wgt.stride(1) != 1:
+            raise ValueError("wgt must be a bf16 [cout, K] matrix with unit inner stride")
+        a.wgt, a.cout, a.ldw, a.k_total = _ptr(wgt), cout, wgt.stride(0), wgt.shape[1]
+        if out is None:
+            out = torch.empty((n, h, w, cout), device=x0.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+        if out_f32:
+            a.out_f32, a.ldo = _ptr(out), out.stride(2) if w > 1 else out.shape[3]
+        else:
+            a.out, a.ldo = _ptr(out), _nhwc(out, "out")[4]
+        a.bias = _ptr(bias)
+        if temb is not None:
+            a.temb, a.ld_temb = _ptr(temb), temb.stride(0)
+        if res is not None:
+            a.res, a.ldr = _ptr(res), _nhwc(res, "res")[4]
+        _capi.check(self.lib.ddpm_conv_gemm(C.byref(a), _stream()), "ddpm_conv_gemm")
+        self.launches += 1
+        return out
+
+    def conv_wgrad(self, dy, x0, x1, taps: Sequence[Tap], dw, grid: Tuple[int, int, int], accumulate: bool = True,
+                   src_n: int = 0, splits: int = 0):
+        """dw[co, wk+ci] (+)= sum_pix dy[pix, co] * X[pix+tap, ci]; dw: fp32 [cout, K] matrix view."""
+        n, h, w = grid
+        a = _capi.WgradArgs()
+        _, _, _, cout, ldy = _nhwc(dy, "dy")
+        a.dy, a.ldy, a.cout = _ptr(dy), ldy, cout
+        _, _, _, c0, ld0 = _nhwc(x0, "x0")
+        a.x0, a.c0, a.ld0 = _ptr(x0), c0, ld0
+        if x1 is not None:
+            _, _, _, c1, ld1 = _nhwc(x1, "x1")
+            a.x1, a.c1, a.ld1 = _ptr(x1), c1, ld1
+        a.n, a.h, a.w, a.src_n = n, h, w, src_n
+        a.ntaps = len(taps)
+        for i, (dn, dh, dw_, wk) in enumerate(taps):
+            a.tap_dn[i], a.tap_dh[i], a.tap_dw[i], a.tap_wk[i] = dn, dh, dw_, wk
+        if dw.dtype != torch.float32 or dw.dim() != 2 or dw.stride(1) != 1:
+            raise ValueError("dw must be an fp32 [cout, K] matrix with unit inner stride")
+        a.dw, a.ldw = _ptr(dw), dw.stride(0)
+        a.accumulate, a.splits = int(accumulate), splits
+        _capi.check(self.lib.ddpm_conv_wgrad(C.byref(a), _stream()), "ddpm_conv_wgrad")
+        self.launches += 1
+        return dw
+
+    def prep_weight(self, w, wf, wd, cout: int, taps: int, cin: int):
+        """w: fp32 [cout][taps][cin] (physical); wf: bf16 [cout, taps*cin] or None; wd: bf16 [cin, taps*cout] or None."""
+        _capi.check(self.lib.ddpm_prep_weight(_ptr(w), _ptr(wf), wf.stride(0) if wf is not None else 0, _ptr(wd),
+                                              wd.stride(0) if wd is not None else 0, cout, taps, cin, _stream()),
+                    "ddpm_prep_weight")
+        self.launches += 1
+
+    # ---- 3-channel convs ---------------------------------------------------------------------------------
+    def conv3_to_c(self, x, w, strides: Tuple[int, int, int], flip: bool, bias, cout: int, out=None):
+        """x: NCHW fp32 [n, cin<=4, h, w] -> NHWC bf16 [n, h, w, cout]."""
+        n, cin, h, wd = x.shape
+        if out is None:
+            out = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_conv3_to_c(_ptr(x), _ptr(w), strides[0], strides[1], strides[2], int(flip),
+                                             _ptr(bias), _ptr(out), _nhwc(out, "out")[4], n, h, wd, cin, cout,
+                                             _stream()), "ddpm_conv3_to_c")
+        self.launches += 1
+        return out
+
+    def conv_c_to_3(self, a, w, bias, cout: int):
+        """a: NHWC bf16 -> NCHW fp32 [n, cout<=4, h, w]; w fp32 [cout][9][cin]."""
+        n, h, wd, cin, lda = _nhwc(a, "a")
+        out = torch.empty((n, cout, h, wd), device=a.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_conv_c_to_3(_ptr(a), lda, _ptr(w), _ptr(bias), _ptr(out), n, h, wd, cin, cout,
+                                              _stream()), "ddpm_conv_c_to_3")
+        self.launches += 1
+        return out
+
+    def conv3_wgrad(self, big, small, dw, strides: Tuple[int, int, int], flip: bool, dbias_small=None):
+        n, h, wd, cbig, ldbig = _nhwc(big, "big")
+        ks = small.shape[1]
+        _capi.check(self.lib.ddpm_conv3_wgrad(_ptr(big), ldbig, cbig, _ptr(small), ks, _ptr(dw), strides[0],
+                                              strides[1], strides[2], int(flip), _ptr(dbias_small), n, h, wd,
+                                              _stream()), "ddpm_conv3_wgrad")
+        self.launches += 1
+
+    # ---- GroupNorm ---------------------------------------------------------------------------------------
+    def gn_stats(self, x0, x1, groups: int):
+        n, h, w, c0, ld0 = _nhwc(x0, "x0")
+        c1, ld1 = 0, 0
+        if x1 is not None:
+            _, _, _, c1, ld1 = _nhwc(x1, "x1")
+        stats = torch.empty((n, groups, 2), device=x0.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_gn_stats(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats),
+                                           _stream()), "ddpm_gn_stats")
+        self.launches += 2
+        return stats
+
+    def gn_apply(self, x0, x1, groups: int, stats, eps: float, gamma, beta, silu: bool, out=None):
+        n, h, w, c0, ld0 = _nhwc(x0, "x0")
+        c1, ld1 = 0, 0
+        if x1 is not None:
+            _, _, _, c1, ld1 = _nhwc(x1, "x1")
+        if out is None:
+            out = torch.empty((n, h, w, c0 + c1), device=x0.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_gn_apply(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats), eps,
+                                           _ptr(gamma), _ptr(beta), int(silu), _ptr(out), _nhwc(out, "out")[4],
+                                           _stream()), "ddpm_gn_apply")
+        self.launches += 1
+        return out
+
+    def gn_bwd(self, x0, x1, groups: int, stats, eps: float, gamma, beta, silu: bool, dy, add0=None, add1=None,
+               dgamma=None, dbeta=None, need_dx1: bool = True):
+        """-> (dx0, dx1).  dgamma / dbeta are accumulated in place."""
+        n, h, w, c0, ld0 = _nhwc(x0, "x0")
+        c1, ld1 = 0, 0
+        if x1 is not None:
+            _, _, _, c1, ld1 = _nhwc(x1, "x1")
+        C_ = c0 + c1
+        dx0 = torch.empty((n, h, w, c0), device=x0.device, dtype=torch.bfloat16)
+        dx1 = torch.empty((n, h, w, c1), device=x0.device, dtype=torch.bfloat16) if (c1 and need_dx1) else None
+        ws = torch.empty(n * C_ * 2 + n * groups * 2, device=x0.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_gn_bwd(
+            _ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats), eps, _ptr(gamma), _ptr(beta),
+            int(silu), _ptr(dy), _nhwc(dy, "dy")[4],
+            _ptr(add0), _nhwc(add0, "add0")[4] if add0 is not None else 0,
+            _ptr(add1), _nhwc(add1, "add1")[4] if add1 is not None else 0,
+            _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream()), "ddpm_gn_bwd")
+        self.launches += 4
+        return dx0, dx1
+
+    # ---- attention core ----------------------------------------------------------------------------------
+    def attn_fwd(self, qkv, b: int, t: int, heads: int, d: int, scale: float):
+        """qkv: bf16 [b*t, 3*heads*d] -> (o bf16 [b*t, heads*d], lse fp32 [b, heads, t])."""
+        o = torch.empty((b * t, heads * d), device=qkv.device, dtype=torch.bfloat16)
+        lse = torch.empty((b, heads, t), device=qkv.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_attn_fwd(_ptr(qkv), qkv.stride(0), _ptr(o), o.stride(0), _ptr(lse), b, t, heads, d,
+                                           scale, _stream()), "ddpm_attn_fwd")
+        self.launches += 1
+        return o, lse
+
+    def attn_bwd(self, qkv, o, d_o, lse, b: int, t: int, heads: int, d: int, scale: float):
+        dqkv = torch.empty_like(qkv)
+        _capi.check(self.lib.ddpm_attn_bwd(_ptr(qkv), qkv.stride(0), _ptr(o), o.stride(0), _ptr(d_o), d_o.stride(0),
+                                           _ptr(lse), _ptr(dqkv), dqkv.stride(0), b, t, heads, d, scale, _stream()),
+                    "ddpm_attn_bwd")
+        self.launches += 1
+        return dqkv
+
+    # ---- time embedding path ---------------------------------------------------------------------------------
+    def timestep_embedding(self, t, dim: int, flip_sin_to_cos: bool, freq_shift: float):
+        out = torch.empty((t.numel(), dim), device=t.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_timestep_embedding(_ptr(t), _ptr(out), t.numel(), dim, int(flip_sin_to_cos),
+                                                     float(freq_shift), _stream()), "ddpm_timestep_embedding")
+        self.launches += 1
+        return out
+
+    def linear_f32(self, x, w, bias, silu_in: bool):
+        m, k = x.shape
+        n = w.shape[0]
+        y = torch.empty((m, n), device=x.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_linear_f32(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), m, n, k, int(silu_in), _stream()),
+                    "ddpm_linear_f32")
+        self.launches += 1
+        return y
+
+    def linear_f32_wgrad(self, x, dy, dw, db, silu_in: bool):
+        m, k = x.shape
+        n = dy.shape[1]
+        _capi.check(self.lib.ddpm_linear_f32_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), m, n, k, int(silu_in),
+                                                   _stream()), "ddpm_linear_f32_wgrad")
+        self.launches += 1
+
+    def linear_f32_dgrad(self, dy, w, x, silu_in: bool, dx=None):
+        m, n = dy.shape
+        k = w.shape[1]
+        acc = dx is not None
+        if dx is None:
+            dx = torch.empty((m, k), device=dy.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_linear_f32_dgrad(_ptr(dy), _ptr(w), _ptr(x), _ptr(dx), m, n, k, int(silu_in),
+                                                   int(acc), _stream()), "ddpm_linear_f32_dgrad")
+        self.launches += 1
+        return dx
+
+    def reduce_hw(self, x, out_nc=None, out_c=None):
+        """out_nc[n, c] = sum_hw x (overwritten); out_c[c] += sum_{n,hw} x."""
+        n, h, w, c, ld = _nhwc(x, "x")
+        _capi.check(self.lib.ddpm_reduce_hw(_ptr(x), ld, n, h * w, c, _ptr(out_nc),
+                                            out_nc.stride(0) if out_nc is not None else 0, _ptr(out_c), _stream()),
+                    "ddpm_reduce_hw")
+        self.launches += 1
+
+    # ---- layout helpers ----------------------------------------------------------------------------------------
+    def space_to_depth(self, x):
+        n, h, w, c, ld = _nhwc(x, "x")
+        out = torch.empty((4 * n, (h + 1) // 2, (w + 1) // 2, c), device=x.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_space_to_depth(_ptr(x), ld, _ptr(out), n, h, w, c, 0, _stream()),
+                    "ddpm_space_to_depth")
+        self.launches += 1
+        return out
+
+    def zero_insert2x(self, dy, h: int, w: int):
+        n, ho, wo, c, ld = _nhwc(dy, "dy")
+        out = torch.empty((n, h, w, c), device=dy.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_zero_insert2x(_ptr(dy), ld, _ptr(out), n, ho, wo, c, h, w, _stream()),
+                    "ddpm_zero_insert2x")
+        self.launches += 1
+        return out
+
+    def upsample2x(self, x):
+        n, h, w, c, ld = _nhwc(x, "x")
+        out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_upsample2x(_ptr(x), ld, _ptr(out), n, h, w, c, _stream()), "ddpm_upsample2x")
+        self.launches += 1
+        return out
+
+    def sumpool2x(self, dy, add=None):
+        n, h2, w2, c, ld = _nhwc(dy, "dy")
+        out = torch.empty((n, h2 // 2, w2 // 2, c), device=dy.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_sumpool2x(_ptr(dy), ld, _ptr(add), _nhwc(add, "add")[4] if add is not None else 0,
+                                            _ptr(out), n, h2 // 2, w2 // 2, c, _stream()), "ddpm_sumpool2x")
+        self.launches += 1
+        return out
+
+
+_backend = None
+
+
+def get():
+    """The active op backend.  Product code only ever gets CudaOps; tests may inject a checker via set_backend."""
+    global _backend
+    if _backend is None:
+        _backend = CudaOps()
+    return _backend
+
+
+def set_backend(b) -> None:
+    """Test hook (tests/emu_ops.py verifies the host-side graph wiring on CPU).  Never called by product code."""
+    global _backend
+    _backend = b

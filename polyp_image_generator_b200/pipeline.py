@@ -1,0 +1,102 @@
+"""Drop-in `DDPMPipeline` (diffusers 0.33.1 semantics): the 1000-step reverse-diffusion sampling loop.
+
+Call sites replaced (paths relative to /root/reference/):
+  generator_model/train_from_scratch.py:121    DDPMPipeline(unet=model, scheduler=noise_scheduler)
+  generator_model/train_from_scratch.py:51-54  pipeline(batch_size=..., generator=torch.Generator('cpu').manual_seed(s)).images
+  generator_model/train_from_scratch.py:130    pipeline.save_pretrained(path)
+RNG contract: with a CPU generator every draw happens on the CPU generator in diffusers'
+order (one draw for x_T, one per step with t > 0) and is copied to the device, so sampled images are reproducible
+against the reference.  With generator=None the per-step noise is drawn inside the step kernel instead.
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Union
+
+import torch
+
+from . import ops as _ops
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None):
+    """diffusers.utils.torch_utils.randn_tensor: a CPU generator with a CUDA device draws on CPU, then moves."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    rand_device = device
+    if generator is not None:
+        gen_device_type = generator.device.type
+        if gen_device_type != device.type and gen_device_type == "cpu":
+            rand_device = torch.device("cpu")
+        elif gen_device_type != device.type and gen_device_type == "cuda":
+            raise ValueError(f"Cannot generate a {device} tensor from a generator of type {gen_device_type}.")
+    return torch.randn(tuple(shape), generator=generator, device=rand_device, dtype=dtype).to(device)
+
+
+@dataclass
+class ImagePipelineOutput:
+    images: Union[List, "object"]
+
+
+class DDPMPipeline:
+    def __init__(self, unet, scheduler):
+        self.unet = unet
+        self.scheduler = scheduler
+
+    @property
+    def device(self):
+        return self.unet.device
+
+    def to(self, device):
+        self.unet.to(device)
+        return self
+
+    @torch.no_grad()
+    def __call__(self, batch_size: int = 1, generator=None, num_inference_steps: int = 1000,
+                 output_type: Optional[str] = "pil", return_dict: bool = True):
+        s = self.unet.config.sample_size
+        hw = (s, s) if isinstance(s, int) else tuple(s)
+        image_shape = (batch_size, self.unet.config.in_channels, *hw)
+        image = randn_tensor(image_shape, generator=generator, device=self.device, dtype=torch.float32)
+        self.scheduler.set_timesteps(num_inference_steps)
+        for t in self.scheduler._ts_list:
+            model_output = self.unet(image, t).sample
+            image = self.scheduler.step(model_output, t, image, generator=generator,
+                                        want_pred_original_sample=False).prev_sample
+        if output_type == "pt_raw":           # extension: raw x_0 in [-1, 1] on the device
+            return ImagePipelineOutput(images=image) if return_dict else (image,)
+        u8 = _ops.get().to_uint8_nhwc(image.contiguous())  # (x/2+0.5).clamp(0,1)*255 rounded, NHWC uint8
+        if output_type == "uint8":            # extension: device uint8 NHWC
+            images = u8
+        else:
+            arr = u8.cpu().numpy()
+            if output_type == "pil":
+                from PIL import Image
+                images = [Image.fromarray(a.squeeze() if a.shape[-1] == 1 else a) for a in arr]
+            else:                              # "np"/"numpy": float32 NHWC in [0, 1] quantised to 1/255 steps
+                images = arr.astype("float32") / 255.0
+        if not return_dict:
+            return (images,)
+        return ImagePipelineOutput(images=images)
+
+    # ---- diffusers-compatible on-disk layout --------------------------------------
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = True):
+        os.makedirs(os.path.join(save_directory, "unet"), exist_ok=True)
+        os.makedirs(os.path.join(save_directory, "scheduler"), exist_ok=True)
+        with open(os.path.join(save_directory, "model_index.json"), "w") as f:
+            json.dump({"_class_name": "DDPMPipeline", "_diffusers_version": "0.33.1",
+                       "scheduler": ["diffusers", "DDPMScheduler"], "unet": ["diffusers", "UNet2DModel"]}, f, indent=2)
+        self.unet.save_pretrained(os.path.join(save_directory, "unet"), safe_serialization=safe_serialization)
+        cfg = dict(vars(self.scheduler.config))
+        cfg.update({"_class_name": "DDPMScheduler", "_diffusers_version": "0.33.1"})
+        with open(os.path.join(save_directory, "scheduler", "scheduler_config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+
+    @classmethod
+    def from_pretrained(cls, directory: str):
+        from .scheduler import DDPMScheduler
+        from .unet import UNet2DModel
+        unet = UNet2DModel.from_pretrained(os.path.join(directory, "unet"))
+        with open(os.path.join(directory, "scheduler", "scheduler_config.json")) as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        return cls(unet=unet, scheduler=DDPMScheduler(**cfg))
