@@ -142,9 +142,10 @@ int ddpm_attn_bwd(const void* qkv, long long ldqkv, const void* o, long long ldo
                   const float* lse, void* dqkv, long long lddqkv, int b, int t, int heads, int d, float scale,
                   void* stream);
 
-/* Timesteps(128) sinusoid -> fp32 [b][dim]; t int64[b] (device). */
-int ddpm_timestep_embedding(const long long* t, float* out, int b, int dim, int flip_sin_to_cos, float freq_shift,
-                            void* stream);
+/* Timesteps(128) sinusoid -> fp32 [b][dim]; t int64[b] (device); freqs fp32[dim/2] (device) =
+ * exp(-ln(10000) * j / (dim/2 - freq_shift)) tabulated by the host. */
+int ddpm_timestep_embedding(const long long* t, const float* freqs, float* out, int b, int dim,
+                            int flip_sin_to_cos, void* stream);
 /* Small fp32 linears of the time-embedding path: y[m][n] = bias[n] + sum_k act(x[m][k]) * w[n][k]. */
 int ddpm_linear_f32(const float* x, const float* w, const float* bias, float* y, int m, int n, int k, int silu_in,
                     void* stream);

@@ -18,16 +18,15 @@ static int blocks_for(long long items, int threads = kThreads) {
 }
 
 // ---- Timesteps(dim): diffusers get_timestep_embedding -------------------------------------------------
-__global__ void timestep_embedding_kernel(const long long* __restrict__ t, float* __restrict__ out, int b, int dim,
-                                          int flip, float freq_shift) {
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, const float* __restrict__ freqs,
+                                          float* __restrict__ out, int b, int dim, int flip) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b * half) return;
   const int row = i / half, j = i - row * half;
-  // exponent = -ln(10000) * j / (half - shift); emb = exp(exponent) * t   (fp32, same op order as torch)
-  const float expo = __fdiv_rn(__fmul_rn(-9.210340371976184f, static_cast<float>(j)),
-                               static_cast<float>(half) - freq_shift);
-  const float arg = __fmul_rn(static_cast<float>(t[row]), expf(expo));
+  // freqs[j] = exp(-ln(10000) * j / (half - shift)) is tabulated by the host exactly as diffusers computes it;
+  // emb = t * freqs (one rounded product), then sin / cos
+  const float arg = __fmul_rn(static_cast<float>(t[row]), freqs[j]);
   const float sv = sinf(arg), cv = cosf(arg);
   float* o = out + static_cast<long long>(row) * dim;
   if (flip) {
@@ -250,13 +249,12 @@ __global__ void sumpool2x_kernel(const __nv_bfloat16* __restrict__ dy, long long
 
 using namespace ddpm;
 
-extern "C" int ddpm_timestep_embedding(const long long* t, float* out, int b, int dim, int flip_sin_to_cos,
-                                       float freq_shift, void* stream) {
-  DDPM_REQUIRE(t && out && b > 0 && dim > 0 && dim % 2 == 0, "ddpm_timestep_embedding: bad argument");
+extern "C" int ddpm_timestep_embedding(const long long* t, const float* freqs, float* out, int b, int dim,
+                                       int flip_sin_to_cos, void* stream) {
+  DDPM_REQUIRE(t && freqs && out && b > 0 && dim > 0 && dim % 2 == 0, "ddpm_timestep_embedding: bad argument");
   const int items = b * (dim / 2);
-  timestep_embedding_kernel<<<(items + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, b, dim,
-                                                                                               flip_sin_to_cos,
-                                                                                               freq_shift);
+  timestep_embedding_kernel<<<(items + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, freqs, out, b, dim,
+                                                                                               flip_sin_to_cos);
   return check_launch("timestep_embedding_kernel");
 }
 

@@ -64,6 +64,15 @@ def taps_s2d(cin_total: int, n: int, pad: int) -> List[Tap]:
     return out
 
 
+def timestep_freqs(dim: int, freq_shift: float, max_period: int = 10000) -> torch.Tensor:
+    """Host-side frequency table of diffusers' get_timestep_embedding (fp32, same op order)."""
+    import math
+    half = dim // 2
+    exponent = -math.log(max_period) * torch.arange(0, half, dtype=torch.float32)
+    exponent = exponent / (half - freq_shift)
+    return torch.exp(exponent)
+
+
 class CudaOps:
     """The product backend: every method is one (or a few) C-ABI calls."""
 
@@ -72,6 +81,7 @@ class CudaOps:
     def __init__(self):
         self.lib = _capi.load()
         self.launches = 0  # kernels launched through this object (bench.py reports it)
+        self._freqs = {}
 
     # ---- scheduler / loss ----------------------------------------------------------------------------
     def add_noise(self, x0, noise, t, sqrt_ac, sqrt_1mac):
@@ -278,9 +288,14 @@ class CudaOps:
 
     # ---- time embedding path ---------------------------------------------------------------------------------
     def timestep_embedding(self, t, dim: int, flip_sin_to_cos: bool, freq_shift: float):
+        key = (dim, float(freq_shift), str(t.device))
+        freqs = self._freqs.get(key)
+        if freqs is None:
+            freqs = timestep_freqs(dim, freq_shift).to(t.device)
+            self._freqs[key] = freqs
         out = torch.empty((t.numel(), dim), device=t.device, dtype=torch.float32)
-        _capi.check(self.lib.ddpm_timestep_embedding(_ptr(t), _ptr(out), t.numel(), dim, int(flip_sin_to_cos),
-                                                     float(freq_shift), _stream()), "ddpm_timestep_embedding")
+        _capi.check(self.lib.ddpm_timestep_embedding(_ptr(t), _ptr(freqs), _ptr(out), t.numel(), dim,
+                                                     int(flip_sin_to_cos), _stream()), "ddpm_timestep_embedding")
         self.launches += 1
         return out
 

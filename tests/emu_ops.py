@@ -1,0 +1,281 @@
+"""CPU emulation of the op contracts in include/ddpm_b200.h -- TEST INFRASTRUCTURE ONLY.
+
+Implements every method of polyp_image_generator_b200.ops.CudaOps with plain torch on the CPU (fp32 by default,
+optionally rounding activations to bf16 like the kernels do).  It exists so the `-m "not gpu"` suite can verify the
+HOST LOGIC of the product (the UNet forward/backward programs, tap tables, arena layout, LoRA wiring, DDP bucketing)
+against the oracle without a GPU.  It is injected explicitly with ops.set_backend(EmuOps()) by tests; the product
+never imports this file and never falls back to it.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+class EmuOps:
+    name = "emu"
+
+    def __init__(self, act_dtype=torch.float32):
+        self.act = act_dtype           # dtype of "bf16" activation tensors
+        self.operand_dtype = act_dtype  # dtype of the tensor-core operand arena
+        self.launches = 0
+
+    def _a(self, t):
+        return t.to(self.act)
+
+    # ---- scheduler / loss -------------------------------------------------------------------------------
+    def add_noise(self, x0, noise, t, sa, sb):
+        shape = (-1,) + (1,) * (x0.dim() - 1)
+        return sa[t].view(shape) * x0 + sb[t].view(shape) * noise
+
+    def mse_fwd_bwd(self, pred, target, want_grad=True):
+        d = pred - target
+        return (d * d).sum().reshape(1), (d * (2.0 / pred.numel())) if want_grad else None
+
+    def scale_by_device_scalar(self, x, scale):
+        x.mul_(scale.reshape(()))
+        return x
+
+    def scheduler_step(self, eps, x, z, sa, sb, c0, ct, sigma, clip, want_x0=False):
+        f = lambda v: torch.tensor(v, dtype=torch.float32)
+        x0 = (x - f(sb) * eps) / f(sa)
+        if clip > 0:
+            x0 = x0.clamp(-clip, clip)
+        prev = f(c0) * x0 + f(ct) * x
+        if z is not None:
+            prev = prev + f(sigma) * z
+        return prev, (x0 if want_x0 else None)
+
+    def scheduler_step_philox(self, eps, x, sa, sb, c0, ct, sigma, clip, seed, offset):
+        g = torch.Generator().manual_seed((seed + offset) & 0x7FFFFFFF)
+        z = torch.randn(x.shape, generator=g) if sigma != 0 else None
+        return self.scheduler_step(eps, x, z, sa, sb, c0, ct, sigma, clip)[0]
+
+    def to_uint8_nhwc(self, x):
+        return ((x / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8)
+
+    # ---- conv / linear -------------------------------------------------------------------------------------
+    @staticmethod
+    def _shift(X, dn, dh, dw, n, h, w):
+        """out[i,j,k] = X[i+dn, j+dh, k+dw] (zero outside X)."""
+        SN, H, W, C = X.shape
+        out = X.new_zeros((n, h, w, C))
+        i0, i1 = max(0, -dn), min(n, SN - dn)
+        j0, j1 = max(0, -dh), min(h, H - dh)
+        k0, k1 = max(0, -dw), min(w, W - dw)
+        if i1 > i0 and j1 > j0 and k1 > k0:
+            out[i0:i1, j0:j1, k0:k1] = X[i0 + dn:i1 + dn, j0 + dh:j1 + dh, k0 + dw:k1 + dw]
+        return out
+
+    def conv_gemm(self, x0, x1, taps, wgt, cout, grid, bias=None, temb=None, res=None, out=None, out_f32=False,
+                  src_n=0):
+        n, h, w = grid
+        X = x0 if x1 is None else torch.cat([x0, x1], -1)
+        X = X.float()
+        C = X.shape[-1]
+        acc = torch.zeros((n, h, w, cout), dtype=torch.float32)
+        Wm = wgt.float()
+        for (dn, dh, dw, wk) in taps:
+            acc += self._shift(X, dn, dh, dw, n, h, w) @ Wm[:cout, wk:wk + C].t()
+        if bias is not None:
+            acc += bias
+        if temb is not None:
+            acc += temb[:, None, None, :cout]
+        if res is not None:
+            acc += res.float()
+        r = acc if out_f32 else self._a(acc)
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+
+    def conv_wgrad(self, dy, x0, x1, taps, dw, grid, accumulate=True, src_n=0, splits=0):
+        n, h, w = grid
+        X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
+        C = X.shape[-1]
+        dyf = dy.float().reshape(-1, dy.shape[-1])
+        if not accumulate:
+            dw.zero_()
+        for (dn, dh, dw_, wk) in taps:
+            xs = self._shift(X, dn, dh, dw_, n, h, w).reshape(-1, C)
+            dw[:, wk:wk + C] += dyf.t() @ xs
+        return dw
+
+    def prep_weight(self, w, wf, wd, cout, taps, cin):
+        w3 = w.reshape(cout, taps, cin)
+        if wf is not None:
+            wf.copy_(w3.reshape(cout, taps * cin).to(wf.dtype))
+        if wd is not None:
+            wd.copy_(w3.flip(1).permute(2, 1, 0).reshape(cin, taps * cout).to(wd.dtype))
+
+    # ---- 3-channel convs -------------------------------------------------------------------------------------
+    @staticmethod
+    def _w_from_strides(w, strides, flip, cout, cin):
+        """dense [cout][9][cin] view of w[co*s0 + tap'*s1 + ci*s2], tap' = 8-tap when flip."""
+        flat = w.reshape(-1)
+        co = torch.arange(cout).view(-1, 1, 1)
+        tap = torch.arange(9).view(1, -1, 1)
+        ci = torch.arange(cin).view(1, 1, -1)
+        tp = 8 - tap if flip else tap
+        return flat[co * strides[0] + tp * strides[1] + ci * strides[2]]
+
+    def conv3_to_c(self, x, w, strides, flip, bias, cout, out=None):
+        n, cin, h, wd = x.shape
+        w3 = self._w_from_strides(w, strides, flip, cout, cin)            # [cout][9][cin]
+        w4 = w3.reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        y = F.conv2d(x, w4, bias, padding=1).permute(0, 2, 3, 1)
+        r = self._a(y)
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r.contiguous()
+
+    def conv_c_to_3(self, a, w, bias, cout):
+        cin = a.shape[-1]
+        w4 = w.reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        return F.conv2d(a.float().permute(0, 3, 1, 2), w4, bias, padding=1).contiguous()
+
+    def conv3_wgrad(self, big, small, dw, strides, flip, dbias_small=None):
+        n, h, wd, cbig = big.shape
+        ks = small.shape[1]
+        bigf = big.float().reshape(-1, cbig)
+        X = small.permute(0, 2, 3, 1)                                      # [n,h,w,ks]
+        flat = dw.reshape(-1)
+        for tap in range(9):
+            xs = self._shift(X, 0, tap // 3 - 1, tap % 3 - 1, n, h, wd).reshape(-1, ks)
+            contrib = bigf.t() @ xs                                        # [cbig, ks]
+            tp = 8 - tap if flip else tap
+            idx = (torch.arange(cbig).view(-1, 1) * strides[0] + tp * strides[1] + torch.arange(ks).view(1, -1) * strides[2])
+            flat.index_add_(0, idx.reshape(-1), contrib.reshape(-1))
+        if dbias_small is not None:
+            dbias_small += small.sum((0, 2, 3))
+
+    # ---- GroupNorm -------------------------------------------------------------------------------------------
+    def gn_stats(self, x0, x1, groups):
+        X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
+        n, h, w, C = X.shape
+        xg = X.reshape(n, h * w, groups, C // groups)
+        return torch.stack([xg.sum((1, 3)), (xg * xg).sum((1, 3))], -1)   # [n, groups, 2]
+
+    @staticmethod
+    def _mean_rstd(stats, m, eps):
+        mean = stats[..., 0] / m
+        var = (stats[..., 1] / m - mean * mean).clamp_min(0)
+        return mean, torch.rsqrt(var + eps)
+
+    def _gn_fwd_f32(self, X, groups, stats, eps, gamma, beta, silu):
+        n, h, w, C = X.shape
+        cpg = C // groups
+        mean, rstd = self._mean_rstd(stats, cpg * h * w, eps)
+        mean = mean.repeat_interleave(cpg, 1)[:, None, None, :]
+        rstd = rstd.repeat_interleave(cpg, 1)[:, None, None, :]
+        z = (X - mean) * rstd * gamma + beta
+        return F.silu(z) if silu else z
+
+    def gn_apply(self, x0, x1, groups, stats, eps, gamma, beta, silu, out=None):
+        X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
+        r = self._a(self._gn_fwd_f32(X, groups, stats, eps, gamma, beta, silu))
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+
+    def gn_bwd(self, x0, x1, groups, stats, eps, gamma, beta, silu, dy, add0=None, add1=None, dgamma=None,
+               dbeta=None, need_dx1=True):
+        X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
+        c0 = x0.shape[-1]
+        with torch.enable_grad():
+            Xr = X.detach().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            g = gamma.detach().clone().requires_grad_(True)
+            b = beta.detach().clone().requires_grad_(True)
+            y = F.group_norm(Xr, groups, g, b, eps)
+            if silu:
+                y = F.silu(y)
+            y.backward(dy.float().permute(0, 3, 1, 2))
+        dx = Xr.grad.permute(0, 2, 3, 1)
+        if add0 is not None:
+            dx = dx + add0.float()
+        if add1 is not None:
+            dx = dx + add1.float()
+        if dgamma is not None:
+            dgamma += g.grad
+        if dbeta is not None:
+            dbeta += b.grad
+        dx = self._a(dx)
+        dx0 = dx[..., :c0].contiguous()
+        dx1 = dx[..., c0:].contiguous() if (x1 is not None and need_dx1) else None
+        return dx0, dx1
+
+    # ---- attention ----------------------------------------------------------------------------------------------
+    def _split(self, qkv, b, t, heads, d):
+        C = heads * d
+        return [z.reshape(b, t, heads, d).transpose(1, 2) for z in qkv.float().split(C, 1)]
+
+    def attn_fwd(self, qkv, b, t, heads, d, scale):
+        q, k, v = self._split(qkv, b, t, heads, d)
+        s = (q @ k.transpose(-1, -2)) * scale
+        lse = torch.logsumexp(s, -1) * 1.4426950408889634
+        o = torch.softmax(s, -1) @ v
+        return self._a(o.transpose(1, 2).reshape(b * t, heads * d)), lse
+
+    def attn_bwd(self, qkv, o, d_o, lse, b, t, heads, d, scale):
+        with torch.enable_grad():
+            qr = qkv.detach().float().clone().requires_grad_(True)
+            q, k, v = self._split(qr, b, t, heads, d)
+            out = F.scaled_dot_product_attention(q, k, v, scale=scale).transpose(1, 2).reshape(b * t, heads * d)
+            out.backward(d_o.float())
+        return self._a(qr.grad)
+
+    # ---- time embedding path ---------------------------------------------------------------------------------------
+    def timestep_embedding(self, t, dim, flip_sin_to_cos, freq_shift):
+        from polyp_image_generator_b200.ops import timestep_freqs
+        arg = t[:, None].float() * timestep_freqs(dim, freq_shift)[None, :]
+        s, c = torch.sin(arg), torch.cos(arg)
+        return torch.cat([c, s], -1) if flip_sin_to_cos else torch.cat([s, c], -1)
+
+    def linear_f32(self, x, w, bias, silu_in):
+        return F.linear(F.silu(x) if silu_in else x, w, bias)
+
+    def linear_f32_wgrad(self, x, dy, dw, db, silu_in):
+        xa = F.silu(x) if silu_in else x
+        dw += dy.t() @ xa
+        if db is not None:
+            db += dy.sum(0)
+
+    def linear_f32_dgrad(self, dy, w, x, silu_in, dx=None):
+        r = dy @ w
+        if silu_in:
+            s = torch.sigmoid(x)
+            r = r * (s * (1 + x * (1 - s)))
+        if dx is not None:
+            dx += r
+            return dx
+        return r
+
+    def reduce_hw(self, x, out_nc=None, out_c=None):
+        s = x.float().sum((1, 2))
+        if out_nc is not None:
+            out_nc.copy_(s)
+        if out_c is not None:
+            out_c += s.sum(0)
+
+    # ---- layout helpers -----------------------------------------------------------------------------------------------
+    def space_to_depth(self, x):
+        n, h, w, c = x.shape
+        return torch.cat([x[:, ph::2, pw::2] for ph in (0, 1) for pw in (0, 1)], 0).contiguous()
+
+    def zero_insert2x(self, dy, h, w):
+        n, ho, wo, c = dy.shape
+        out = dy.new_zeros((n, h, w, c))
+        out[:, 0:2 * ho:2, 0:2 * wo:2] = dy
+        return out
+
+    def upsample2x(self, x):
+        return x.repeat_interleave(2, 1).repeat_interleave(2, 2)
+
+    def sumpool2x(self, dy, add=None):
+        n, h2, w2, c = dy.shape
+        r = dy.float().reshape(n, h2 // 2, 2, w2 // 2, 2, c).sum((2, 4))
+        if add is not None:
+            r = r + add.float()
+        return self._a(r)
