@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- DDPM UNet training throughput (img/s @128^2) on N B200s, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--size S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): UNet2DModel 128x128 train_from_scratch DDPM step, bf16 tensor-core compute,
+batch 64 per GPU, data-parallel over N GPUs.  One "step" = add_noise -> UNet forward -> MSE -> backward ->
+(gradient all-reduce) -> clip_grad_norm_(1.0) -> AdamW -> zero_grad, i.e. the loop body of
+/root/reference/generator_model/train_from_scratch.py:83-116 over the drop-in objects.
+
+Prints ONE JSON line (rank 0).  `value`: inputs already resident in HBM.  `e2e`: same step through the public API
+with the batch coming from pinned host memory every step and the loss read back (loss.item()) every step.
+`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv fprop/dgrad) timed live with CUDA events inside the
+timed region.  `cpu_baseline` / --impl reference: the oracle (pure-PyTorch restatement of the reference's
+diffusers path) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch
+
+METRIC = "ddpm_unet_train_images_per_sec_128px"
+UNIT = "img/s"
+FWD_GFLOP_PER_IMG = {64: 31.035, 128: 124.138, 256: 497.028}   # SURVEY.md §8(d), algorithmic
+
+
+def synthetic_polyp_batch(n: int, size: int, seed: int) -> torch.Tensor:
+    """Polyp-shaped synthetic RGB in [-1, 1]: mucosa base colour + low-frequency noise, one bright
+    shaded ellipse with specular dots, dark endoscope vignette, random horizontal flip; fp32 NCHW."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, size), torch.linspace(0, 1, size), indexing="ij")
+    base = torch.tensor([0.75, 0.35, 0.30]).view(1, 3, 1, 1)
+    low = torch.nn.functional.interpolate(torch.randn(n, 3, 8, 8, generator=g), size=(size, size), mode="bilinear",
+                                          align_corners=False) * 0.06
+    img = base + low
+    cx, cy = torch.rand(n, generator=g) * 0.4 + 0.3, torch.rand(n, generator=g) * 0.4 + 0.3
+    ax, ay = torch.rand(n, generator=g) * 0.2 + 0.1, torch.rand(n, generator=g) * 0.2 + 0.1
+    th = torch.rand(n, generator=g) * 3.14159
+    dx, dy = xx[None] - cx.view(-1, 1, 1), yy[None] - cy.view(-1, 1, 1)
+    u = dx * torch.cos(th).view(-1, 1, 1) + dy * torch.sin(th).view(-1, 1, 1)
+    v = -dx * torch.sin(th).view(-1, 1, 1) + dy * torch.cos(th).view(-1, 1, 1)
+    r2 = (u / ax.view(-1, 1, 1)) ** 2 + (v / ay.view(-1, 1, 1)) ** 2
+    bump = torch.clamp(1 - r2, min=0).sqrt()
+    img = img + 0.25 * bump[:, None] * torch.tensor([1.0, 0.8, 0.7]).view(1, 3, 1, 1)
+    for _ in range(3):
+        sx, sy = cx + (torch.rand(n, generator=g) - 0.5) * ax, cy + (torch.rand(n, generator=g) - 0.5) * ay
+        d2 = (xx[None] - sx.view(-1, 1, 1)) ** 2 + (yy[None] - sy.view(-1, 1, 1)) ** 2
+        img = img + 0.5 * torch.exp(-d2 / 2e-4)[:, None]
+    vign = ((xx - 0.5) ** 2 + (yy - 0.5) ** 2).sqrt()
+    img = img * torch.clamp(1.15 - 1.6 * vign, 0, 1)[None, None]
+    flip = torch.rand(n, generator=g) < 0.5
+    img[flip] = img[flip].flip(-1)
+    return ((img.clamp(0, 1) - 0.5) / 0.5).contiguous()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_oracle_train(size: int, batch: int, steps: int, warmup: int, budget_s: float = 30.0):
+    """Reference CPU path = oracle restatement of the diffusers graph driven by train_from_scratch.py:83-116
+    (bf16 CPU autocast exactly as the reference does at :95, no GradScaler effect on CPU timing)."""
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = oracle.UNet2DModel(**oracle.polyp_unet_config(size))
+    sched = oracle.DDPMScheduler(num_train_timesteps=1000)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    clean = synthetic_polyp_batch(batch, size, 1234)
+    g = torch.Generator().manual_seed(4321)
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        noise = torch.randn(clean.shape, generator=g)
+        t = torch.randint(0, 1000, (batch,), generator=g, dtype=torch.int64)
+        t0 = time.perf_counter()
+        noisy = sched.add_noise(clean, noise, t)
+        with torch.amp.autocast("cpu"):
+            pred = model(noisy, t, return_dict=False)[0]
+            loss = torch.nn.functional.mse_loss(pred, noise)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        _ = loss.item()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return {"value": batch / (ms / 1e3), "ms_per_step": ms, "steps": len(times), "cores": cores,
+            "sample": f"{len(times)} step(s) of batch {batch} at {size}x{size} (bf16 CPU autocast, AdamW, clip 1.0)"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = cpu_oracle_train(args.size, args.cpu_batch, max(1, min(args.steps, 3)), 1, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(r["value"], 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": 1, "ms_per_step": round(r["ms_per_step"], 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"UNet2DModel {args.size}x{args.size} DDPM train step (train_from_scratch.py:83-116)",
+                   "per_gpu_batch": args.batch, "note": "CPU arm runs a bounded sample: batch "
+                   f"{args.cpu_batch} per step on the host cores (oracle port of the reference's diffusers path; "
+                   "diffusers itself is not installable offline)"},
+        "cpu_baseline": {"value": round(r["value"], 4), "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": round(r["value"], 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+def conv_gemm_flops(args_tuple):
+    taps, cin, cout, grid = args_tuple
+    n, h, w = grid
+    return 2.0 * n * h * w * cout * cin * taps
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from polyp_image_generator_b200 import DDPMScheduler, UNet2DModel
+    from polyp_image_generator_b200 import ops as ops_mod
+    from polyp_image_generator_b200.training import mse_loss
+    import oracle  # only for polyp_unet_config (the reference's constructor kwargs) and the CPU baseline leg
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    S, B = args.size, args.batch
+    torch.manual_seed(0)
+    model = UNet2DModel(**oracle.polyp_unet_config(S)).to(dev)
+    model.train()
+    sched = DDPMScheduler(num_train_timesteps=1000)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    net = model
+    if world > 1:
+        from polyp_image_generator_b200.ddp import DistributedDataParallel
+        net = DistributedDataParallel(model)
+    ops = ops_mod.get()
+
+    clean_host = synthetic_polyp_batch(B, S, 1234 + rank).pin_memory()
+    clean_dev = clean_host.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    noise_dev = torch.randn(clean_dev.shape, device=dev, generator=gen)
+    t_dev = torch.randint(0, 1000, (B,), device=dev, dtype=torch.int64, generator=gen)
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def step(clean, noise, t):
+        noisy = sched.add_noise(clean, noise, t)
+        pred = net(noisy, t, return_dict=False)[0]
+        loss = mse_loss(pred, noise)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- instrument the dominant kernel (conv_gemm) with CUDA events on the launch stream ----
+    prof = {"on": False, "ev": [], "flops": 0.0}
+    orig_conv_gemm = ops.conv_gemm
+
+    def conv_gemm_timed(x0, x1, taps, wgt, cout, grid, **kw):
+        if not prof["on"]:
+            return orig_conv_gemm(x0, x1, taps, wgt, cout, grid, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_conv_gemm(x0, x1, taps, wgt, cout, grid, **kw)
+        e1.record()
+        cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+        prof["ev"].append((e0, e1))
+        prof["flops"] += conv_gemm_flops((len(taps), cin, cout, grid))
+        return out
+
+    ops.conv_gemm = conv_gemm_timed
+
+    for _ in range(args.warmup):
+        step(clean_dev, noise_dev, t_dev)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launches
+    prof["on"] = True
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_begin.record()
+    for _ in range(args.steps):
+        loss = step(clean_dev, noise_dev, t_dev)
+    e_end.record()
+    barrier()
+    prof["on"] = False
+    clocks = sampler.stop()
+    launches = ops.launches - l0
+    ms_total = e_begin.elapsed_time(e_end)
+    gemm_ms = sum(a.elapsed_time(b) for a, b in prof["ev"])
+    gemm_launches = len(prof["ev"])
+    gemm_flops = prof["flops"]
+    final_loss = float(loss.item())
+
+    # ---- timed region 2: end to end (pinned host batch in, loss out, every step) ----
+    barrier()
+    e2_begin, e2_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2_begin.record()
+    for _ in range(args.steps):
+        clean = clean_host.to(dev, non_blocking=True)                  # train_from_scratch.py:84
+        noise = torch.randn(clean.shape, device=dev)                   # :85
+        t = torch.randint(0, 1000, (B,), device=dev, dtype=torch.int64)  # :88-91
+        loss = step(clean, noise, t)
+        _ = loss.item()                                                # :115
+    e2_end.record()
+    barrier()
+    ms_e2e = e2_begin.elapsed_time(e2_end)
+
+    tt = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(tt[0]), float(tt[1])
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained")
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    if peak_tf is None:
+        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+    step_gflop = 3.0 * FWD_GFLOP_PER_IMG.get(S, 0.0) * B
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_oracle_train(S, args.cpu_batch, 1, 1, budget_s=60.0)
+        cpu = {"value": round(r["value"], 4), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"UNet2DModel {S}x{S} train_from_scratch DDPM step, bf16 tensor-core compute, "
+                        f"batch {B}/GPU, {'DDP dp%d' % world if world > 1 else 'single GPU'}",
+            "per_gpu_batch": B, "global_batch": B * world, "image_size": S, "num_train_timesteps": 1000,
+            "params": 113673219, "optimizer": "torch AdamW(fused) + clip_grad_norm_(1.0)",
+            "l2": "per-step working set (activations + 455 MB weights/grads) is far larger than the 126 MB L2",
+            "algorithmic_gflop_per_step": round(step_gflop, 1), "final_loss": round(final_loss, 5),
+        },
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": clean_host.numel() * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": launches,
+        "roofline": {
+            "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv/linear fprop+dgrad)", "bound": "tensor",
+            "achieved": round(achieved_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": round(achieved_tf / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+            "launches_timed": gemm_launches, "kernel_ms_per_step": round(gemm_ms / args.steps, 3),
+            "share_of_step": round(gemm_ms / ms_total, 4),
+            "whole_step_tflops": round(step_gflop / ms_step, 2),
+        },
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (BASELINE configs[1]: 64)")
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""Training-step pieces of the DDPM hot path that sit next to the UNet: the fused MSE loss and the step recipe.
+
+Call sites replaced (paths relative to /root/reference/):
+  generator_model/train_from_scratch.py:101   loss = F.mse_loss(noise_pred, noise)
+  generator_model/train_from_scratch.py:103   scaler.scale(loss).backward()
+  generator_model/train_from_scratch.py:83-116 (train_step below restates the loop body over the drop-in objects)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops as _ops
+
+
+class _MSELoss(torch.autograd.Function):
+    """mean((pred - target)^2) with the gradient produced in the same pass (ddpm_mse_fwd_bwd)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        ops = _ops.get()
+        need = pred.requires_grad
+        loss_sum, dpred = ops.mse_fwd_bwd(pred.contiguous(), target.contiguous(), want_grad=need)
+        ctx.dpred = dpred
+        ctx.used = False
+        return (loss_sum / pred.numel()).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.used:
+            raise RuntimeError("mse_loss backward ran twice; the fused kernel keeps a single gradient buffer")
+        ctx.used = True
+        dpred = ctx.dpred
+        ctx.dpred = None
+        if dpred is None:
+            return None, None
+        # grad_output is a device scalar (1.0, or GradScaler's scale): fold it in without a host sync
+        _ops.get().scale_by_device_scalar(dpred, g.to(torch.float32).reshape(1).contiguous())
+        return dpred, None
+
+
+def mse_loss(pred: torch.Tensor, target: torch.Tensor, reduction: str = "mean") -> torch.Tensor:
+    """Drop-in for F.mse_loss(pred, target) on the DDPM path (fp32, reduction='mean')."""
+    if reduction != "mean":
+        raise NotImplementedError("only reduction='mean' is on the DDPM hot path")
+    if pred.shape != target.shape:
+        raise ValueError("mse_loss: pred and target must have the same shape")
+    if pred.dtype != torch.float32 or target.dtype != torch.float32:
+        pred, target = pred.float(), target.float()
+    return _MSELoss.apply(pred, target.detach())
+
+
+def train_step(model, noise_scheduler, optimizer, clean_images: torch.Tensor, noise: Optional[torch.Tensor] = None,
+               timesteps: Optional[torch.Tensor] = None, lr_scheduler=None, max_grad_norm: Optional[float] = 1.0,
+               scaler=None) -> torch.Tensor:
+    """One iteration of train_from_scratch.py::train_loop (lines 84-113) over the drop-in objects.
+
+    noise / timesteps may be supplied (parity tests feed both implementations the same tensors); otherwise they are
+    drawn on the device as the reference does (:85, :88-91).  Returns the (detached) loss tensor; no host sync.
+    """
+    device = clean_images.device
+    if noise is None:
+        noise = torch.randn(clean_images.shape, device=device)
+    if timesteps is None:
+        timesteps = torch.randint(0, noise_scheduler.config.num_train_timesteps, (clean_images.shape[0],),
+                                  device=device, dtype=torch.int64)
+    noisy = noise_scheduler.add_noise(clean_images, noise, timesteps)
+    pred = model(noisy, timesteps, return_dict=False)[0]
+    loss = mse_loss(pred, noise)
+    if scaler is not None:
+        scaler.scale(loss).backward()
+    else:
+        loss.backward()
+    params = [p for p in model.parameters() if p.requires_grad]
+    if max_grad_norm is not None:
+        torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+    if scaler is not None:
+        scaler.step(optimizer)
+        scaler.update()
+    else:
+        optimizer.step()
+    optimizer.zero_grad()
+    if lr_scheduler is not None:
+        lr_scheduler.step()
+    return loss.detach()
+
+
+def get_cosine_schedule_with_warmup(optimizer, num_warmup_steps: int, num_training_steps: int,
+                                    num_cycles: float = 0.5, last_epoch: int = -1):
+    """diffusers.optimization.get_cosine_schedule_with_warmup (train_from_scratch.py:274-278); host-side scalar."""
+    import math
+
+    def lr_lambda(current_step):
+        if current_step < num_warmup_steps:
+            return float(current_step) / float(max(1, num_warmup_steps))
+        progress = float(current_step - num_warmup_steps) / float(max(1, num_training_steps - num_warmup_steps))
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
+
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda, last_epoch)

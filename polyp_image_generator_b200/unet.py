@@ -758,6 +758,7 @@ class UNet2DModel(nn.Module):
                           dgamma=self._gview(G, no.g_off, (c0,)) if tr else None,
                           dbeta=self._gview(G, no.b_off, (c0,)) if tr else None)
 
+        prog = getattr(self, "_grad_progress_hook", None)
         for i in range(len(tape.steps) - 1, first_needed - 1, -1):
             kind, rec, s = tape.steps[i]
             if kind == "resnet":
@@ -768,6 +769,8 @@ class UNet2DModel(nn.Module):
                 g = self._down_bwd(st, rec, s, g)
             else:
                 g = self._up_bwd(st, rec, s, g)
+            if prog is not None:   # DDP: weight grads at arena offsets >= this step's first layer are final
+                prog(G, rec.conv1.w_off if kind == "resnet" else (rec.qkv.w_off if kind == "attn" else rec.conv.w_off))
 
         if first_needed == 0 and self._head_trainable():
             # g is now the gradient of conv_in's output (skip 0 already folded in by the first resnet)
@@ -937,10 +940,10 @@ class _UNetFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         model = ctx.model
         G, st = model._run_backward(ctx.tape, d_out)
-        hook = getattr(model, "_grad_ready_hook", None)
-        if hook is not None:
-            hook(G)                       # DDP: all-reduce the flat gradient arena
         views = model._grad_views(G, st)
+        hook = getattr(model, "_grad_ready_hook", None)
+        if hook is not None:              # DDP: all-reduce the flat gradient arena (+ LoRA grads)
+            hook(G, [g for gobj in model._plan.gemms if gobj.lora is not None for g in gobj.lora.grads.values()])
         grads = tuple(views.get(id(p)) for p in ctx.params)
         ctx.tape = None
         return (None, None, None, None) + grads

@@ -1,0 +1,247 @@
+"""Host-side logic of the product on CPU: C-ABI surface, scheduler tables, tap tables, arena layout, and the UNet
+forward/backward *programs* verified against the oracle through the CPU emulation of the op contracts
+(tests/emu_ops.py).  No CUDA compute happens here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "ddpm_b200.h")).read()
+    declared = set(re.findall(r"\b(ddpm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"ddpm_conv_args", "ddpm_wgrad_args"}
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(str(built_lib))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/ddpm_b200.h but not exported"
+    from polyp_image_generator_b200 import _capi
+    assert set(_capi.SIGNATURES) | {"ddpm_last_error"} == declared
+    assert _capi.load().ddpm_abi_version() == 1
+
+
+def test_capi_argument_validation_without_gpu(built_lib):
+    """Entry points reject bad arguments before touching the device (error string, negative rc)."""
+    from polyp_image_generator_b200 import _capi
+    lib = _capi.load()
+    assert lib.ddpm_add_noise(None, None, None, None, None, None, 1, 1, 1000, None) < 0
+    assert "null pointer" in _capi.last_error()
+    a = _capi.ConvArgs()
+    assert lib.ddpm_conv_gemm(ctypes.byref(a), None) < 0
+    assert lib.ddpm_attn_fwd(1, 8, 1, 8, 1, 1, 4, 1, 7, 1.0, None) < 0
+    assert "head_dim=7" in _capi.last_error()
+
+
+def test_product_refuses_cpu_tensors(built_lib):
+    from polyp_image_generator_b200 import DDPMScheduler, UNet2DModel, ops as ops_mod
+    assert ops_mod._backend is None or ops_mod._backend.name == "cuda"
+    s = DDPMScheduler()
+    x = torch.zeros(1, 3, 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        s.add_noise(x, x, torch.tensor([1]))
+    cfg = oracle.polyp_unet_config(32)
+    cfg["block_out_channels"] = (64, 64, 64, 64, 64, 64)
+    m = UNet2DModel(**cfg)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 32, 32), 1)
+
+
+def test_scheduler_tables_and_timesteps_match_oracle():
+    from polyp_image_generator_b200 import DDPMScheduler
+    for T in (1000, 2000):
+        a, b = DDPMScheduler(num_train_timesteps=T), oracle.DDPMScheduler(num_train_timesteps=T)
+        assert torch.equal(a.alphas_cumprod, b.alphas_cumprod) and torch.equal(a.betas, b.betas)
+        assert torch.equal(a.timesteps, b.timesteps)
+        assert a.config.num_train_timesteps == T and a.init_noise_sigma == 1.0
+    a, b = DDPMScheduler(), oracle.DDPMScheduler()
+    for n in (1000, 250, 50, 7):
+        a.set_timesteps(n)
+        b.set_timesteps(n)
+        assert torch.equal(a.timesteps, b.timesteps)
+        for t in a.timesteps.tolist()[:5] + a.timesteps.tolist()[-3:]:
+            assert a.previous_timestep(t) == int(b.previous_timestep(torch.tensor(t)))
+    with pytest.raises(ValueError, match="cannot be larger"):
+        a.set_timesteps(1001)
+    with pytest.raises(NotImplementedError):
+        DDPMScheduler(beta_schedule="squaredcos_cap_v2")
+
+
+def test_scheduler_step_and_add_noise_through_emulation(emu_backend):
+    from polyp_image_generator_b200 import DDPMScheduler
+    a, b = DDPMScheduler(), oracle.DDPMScheduler()
+    a.set_timesteps(1000)
+    b.set_timesteps(1000)
+    torch.manual_seed(0)
+    x, e, z = torch.randn(2, 3, 8, 8), torch.randn(2, 3, 8, 8), torch.randn(2, 3, 8, 8)
+    t = torch.tensor([3, 998])
+    assert torch.allclose(a.add_noise(x, e, t), b.add_noise(x, e, t), rtol=1e-6, atol=1e-7)
+    for tt in (999, 500, 1, 0):
+        pa = a.step(e, tt, x, variance_noise=z).prev_sample
+        pb = b.step(e, torch.tensor(tt), x, variance_noise=z).prev_sample
+        assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-6)
+    ga, gb = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+    pa = a.step(e, 10, x, generator=ga).prev_sample
+    pb = b.step(e, torch.tensor(10), x, generator=gb).prev_sample
+    assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-6)   # consumes the CPU generator like randn_tensor
+
+
+def test_tap_tables():
+    from polyp_image_generator_b200.ops import taps_3x3, taps_s2d
+    t = taps_3x3(128)
+    assert t[0] == (0, -1, -1, 0) and t[4] == (0, 0, 0, 4 * 128) and t[8] == (0, 1, 1, 8 * 128)
+    n = 5
+    for pad in (0, 1):
+        for (dn, dh, dw, wk), (r, s) in zip(taps_s2d(64, n, pad), [(r, s) for r in range(3) for s in range(3)]):
+            phase = dn // n
+            ph, pw = phase // 2, phase % 2
+            assert 2 * dh + ph == r - pad and 2 * dw + pw == s - pad and wk == (r * 3 + s) * 64
+
+
+def _small_cfg(S=32, **kw):
+    cfg = oracle.polyp_unet_config(S)
+    cfg["block_out_channels"] = (64, 64, 128, 128, 128, 128)
+    cfg.update(kw)
+    return cfg
+
+
+def test_unet_state_dict_and_arena(emu_backend):
+    from polyp_image_generator_b200 import UNet2DModel
+    m = UNet2DModel(**oracle.polyp_unet_config(64))
+    om = oracle.UNet2DModel(**oracle.polyp_unet_config(64))
+    sd, osd = m.state_dict(), om.state_dict()
+    assert list(sd.keys()) == list(osd.keys())
+    assert all(sd[k].shape == osd[k].shape for k in sd)
+    assert sum(p.numel() for p in m.parameters()) == 113_673_219
+    m.load_state_dict(osd)
+    m._ensure_arena()
+    P = m._plan
+    assert P.temb_total == 9984
+    base = m._arena.data_ptr()
+    for p, off, phys in P.layout:
+        assert p.data_ptr() == base + 4 * off
+    # parameters are views into the arena with unchanged logical values; conv weights are channels_last
+    assert torch.equal(m.conv_in.weight.detach(), osd["conv_in.weight"])
+    w = m.down_blocks[2].resnets[0].conv1.weight
+    assert w.shape == (256, 128, 3, 3) and w.stride() == (9 * 128, 1, 3 * 128, 128)
+    assert torch.equal(w.detach(), osd["down_blocks.2.resnets.0.conv1.weight"])
+    # q, k, v weights (and biases) are adjacent so the fused qkv GEMM / wgrad see one matrix
+    a = m.mid_block.attentions[0]
+    assert a.to_k.weight.data_ptr() == a.to_q.weight.data_ptr() + 4 * 512 * 512
+    assert a.to_v.bias.data_ptr() == a.to_q.bias.data_ptr() + 4 * 1024
+    # .to()/state_dict round trip keeps values and re-flattens lazily
+    m2 = UNet2DModel(**oracle.polyp_unet_config(64))
+    m2.load_state_dict(m.state_dict())
+    assert torch.equal(m2.conv_out.weight, m.conv_out.weight)
+
+
+@pytest.mark.parametrize("variant", ["polyp", "celebahq"])
+def test_unet_forward_backward_programs_match_oracle(emu_backend, variant):
+    from polyp_image_generator_b200 import UNet2DModel
+    if variant == "polyp":
+        cfg, S = _small_cfg(32), 32
+    else:
+        cfg = oracle.celebahq_unet_config(64)
+        cfg["block_out_channels"] = (64, 64, 128, 128, 128, 128)
+        cfg["attention_head_dim"] = 16
+        S = 64
+    torch.manual_seed(0)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    x, t = torch.randn(2, 3, S, S), torch.tensor([10, 700])
+    y, yo = m(x, t).sample, om(x, t).sample
+    assert ((y - yo).norm() / yo.norm()).item() < 1e-5
+    tgt = torch.randn_like(y)
+    torch.nn.functional.mse_loss(y, tgt).backward()
+    torch.nn.functional.mse_loss(yo, tgt).backward()
+    og = dict(om.named_parameters())
+    tot = sum(p.grad.norm() ** 2 for p in om.parameters()) ** 0.5
+    for n, p in m.named_parameters():
+        g = og[n].grad
+        assert p.grad is not None, n
+        assert ((p.grad - g).norm() / (g.norm() + 1e-6 * tot)).item() < 1e-3, n
+    # python-int and 0-dim timesteps, return_dict=False, no_grad path
+    with torch.no_grad():
+        y1 = m(x, 37, return_dict=False)[0]
+        y2 = m(x, torch.tensor(37)).sample
+        yo1 = om(x, 37).sample
+    assert torch.equal(y1, y2) and ((y1 - yo1).norm() / yo1.norm()).item() < 1e-5
+
+
+def test_unet_errors_mirror_reference_behaviour():
+    from polyp_image_generator_b200 import UNet2DModel
+    with pytest.raises(ValueError, match="same number"):
+        UNet2DModel(down_block_types=("DownBlock2D",), up_block_types=("UpBlock2D", "UpBlock2D"),
+                    block_out_channels=(64,))
+    with pytest.raises(NotImplementedError):
+        UNet2DModel(**_small_cfg(), time_embedding_type="fourier")
+    m = UNet2DModel(**_small_cfg())
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 3, 32, 32), 1, encoder_hidden_states=None)   # train_from_scratch.py:98 dead branch
+
+
+def test_train_step_recipe_matches_oracle_loop(emu_backend):
+    """One full iteration of train_from_scratch.py:83-116 (add_noise, UNet, MSE, clip, AdamW) vs the oracle."""
+    from polyp_image_generator_b200 import DDPMScheduler, UNet2DModel
+    from polyp_image_generator_b200.training import train_step
+    cfg = _small_cfg(32)
+    torch.manual_seed(0)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    opt, oopt = torch.optim.AdamW(m.parameters(), lr=1e-4), torch.optim.AdamW(om.parameters(), lr=1e-4)
+    x0, noise, t = torch.randn(2, 3, 32, 32).clamp(-1, 1), torch.randn(2, 3, 32, 32), torch.tensor([5, 900])
+    loss = train_step(m, DDPMScheduler(), opt, x0, noise, t)
+    osch = oracle.DDPMScheduler()
+    pred = om(osch.add_noise(x0, noise, t), t, return_dict=False)[0]
+    oloss = torch.nn.functional.mse_loss(pred, noise)
+    oloss.backward()
+    torch.nn.utils.clip_grad_norm_(om.parameters(), 1.0)
+    oopt.step()
+    assert loss.item() == pytest.approx(oloss.item(), rel=1e-5)
+    osd = om.state_dict()
+    # Adam's first update is lr*sign(g) wherever |g| >> eps, so elements whose gradient is numerically zero may
+    # land on either side: every weight moves by at most lr, and all but a sliver of them identically.
+    diffs = torch.cat([(v - osd[k]).abs().reshape(-1) for k, v in m.state_dict().items()])
+    assert diffs.max().item() <= 2.0 * 1e-4 * 1.01 + 1e-7
+    assert (diffs > 2e-6).float().mean().item() < 2e-3
+    assert all(p.grad is None for p in m.parameters())   # zero_grad(set_to_none)
+
+
+def test_sampling_shards_cover_single_gpu_image_set():
+    from polyp_image_generator_b200.ddp import shard_sampling_batches
+    for total, bs, world in ((256, 32, 8), (1024, 20, 8), (100, 20, 3), (7, 20, 4)):
+        seen = []
+        for r in range(world):
+            seen += shard_sampling_batches(total, bs, r, world)
+        seen.sort()
+        assert [b for b, _, _ in seen] == list(range(len(seen)))
+        assert sum(c for _, _, c in seen) == total
+        assert all(s == b * bs for b, s, _ in seen)
+
+
+def test_pipeline_matches_oracle_pipeline(emu_backend):
+    """DDPMPipeline RNG contract: x_T and every step's z come from the CPU generator in diffusers' order."""
+    from polyp_image_generator_b200 import DDPMPipeline, DDPMScheduler, UNet2DModel
+    cfg = _small_cfg(32)
+    cfg["block_out_channels"] = (64, 64, 64, 64, 64, 64)
+    torch.manual_seed(0)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    pa = DDPMPipeline(unet=m, scheduler=DDPMScheduler())
+    pb = oracle.DDPMPipeline(unet=om, scheduler=oracle.DDPMScheduler())
+    ia = pa(batch_size=2, generator=torch.Generator("cpu").manual_seed(3), num_inference_steps=4, output_type="np").images
+    ib = pb(batch_size=2, generator=torch.Generator("cpu").manual_seed(3), num_inference_steps=4, output_type="np").images
+    assert ia.shape == (2, 32, 32, 3)
+    assert abs(ia - ib).max() <= 1.0 / 255 + 1e-6
+    pil = pa(batch_size=1, generator=torch.Generator("cpu").manual_seed(3), num_inference_steps=2).images
+    assert len(pil) == 1 and pil[0].size == (32, 32)
+    with pytest.raises(ValueError):
+        pa(batch_size=1, num_inference_steps=1001)

@@ -1,0 +1,139 @@
+"""Pins the CPU oracle against the closed-form known answers of SURVEY.md Appendix E and the structural
+invariants of the reference architecture (the reference itself ships no golden vectors: "parity unpinned")."""
+import json
+import math
+import os
+
+import pytest
+import torch
+
+import oracle
+from oracle.unet2d import get_timestep_embedding
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_alphas_cumprod_kat():
+    s = oracle.DDPMScheduler(num_train_timesteps=1000)
+    ac = s.alphas_cumprod
+    assert ac.dtype == torch.float32
+    for i, want in ((0, 0.9998999834), (1, 0.9997800589), (499, 7.8587234020e-02), (999, 4.0358303522e-05)):
+        assert ac[i].item() == pytest.approx(want, rel=2e-7)
+    assert ac.double().sum().item() == pytest.approx(275.513195, abs=2e-6)
+    s2 = oracle.DDPMScheduler(num_train_timesteps=2000)
+    assert s2.alphas_cumprod[999].item() == pytest.approx(6.1605386436e-03, rel=2e-7)
+    assert s2.alphas_cumprod[1999].item() == pytest.approx(1.6288478344e-09, rel=2e-6)
+
+
+@pytest.mark.parametrize("t,want", [
+    (999, (6.352818571e-03, 9.999797940e-01, 1.283513702e-04, 9.899486899e-01, 1.414212286e-01)),
+    (500, (2.789205015e-01, 9.603142142e-01, 3.058036556e-03, 9.941043854e-01, 1.002560183e-01)),
+    (1, (9.998900294e-01, 1.483041234e-02, 5.452302098e-01, 4.547152817e-01, 7.384767756e-03)),
+    (0, (9.999499917e-01, 1.000082958e-02, 1.0, 0.0, None)),
+])
+def test_step_coefficients_kat(t, want):
+    from polyp_image_generator_b200.scheduler import step_coefficients
+    s = oracle.DDPMScheduler()
+    c = step_coefficients(s.alphas_cumprod, t, t - 1)
+    got = (c["sa"], c["sb"], c["c0"], c["ct"], c["sigma"])
+    for g, w in zip(got, want):
+        if w is None:
+            assert g == 0.0
+        else:
+            assert g == pytest.approx(w, rel=3e-7, abs=1e-12)
+
+
+def test_oracle_step_matches_closed_form():
+    s = oracle.DDPMScheduler()
+    s.set_timesteps(1000)
+    torch.manual_seed(0)
+    x, e, z = torch.randn(2, 3, 8, 8), torch.randn(2, 3, 8, 8), torch.randn(2, 3, 8, 8)
+    out = s.step(e, torch.tensor(500), x, variance_noise=z)
+    sa, sb, c0, ct, sg = 2.789205015e-01, 9.603142142e-01, 3.058036556e-03, 9.941043854e-01, 1.002560183e-01
+    x0 = ((x - sb * e) / sa).clamp(-1, 1)
+    want = c0 * x0 + ct * x + sg * z
+    assert torch.allclose(out.prev_sample, want, rtol=1e-5, atol=1e-6)
+    out0 = s.step(e, torch.tensor(0), x)
+    assert torch.allclose(out0.prev_sample, out0.pred_original_sample)
+
+
+def test_set_timesteps_and_errors():
+    s = oracle.DDPMScheduler()
+    s.set_timesteps(1000)
+    assert s.timesteps[0].item() == 999 and s.timesteps[-1].item() == 0 and len(s.timesteps) == 1000
+    s.set_timesteps(50)
+    assert s.timesteps.tolist() == list(range(980, -1, -20))
+    with pytest.raises(ValueError):
+        s.set_timesteps(1001)
+
+
+def test_timestep_embedding_kat():
+    e = get_timestep_embedding(torch.tensor([500]), 128, True, 0)[0]
+    for i, w in ((0, -0.88384926), (1, 0.84850687), (63, 0.99833357), (64, -0.46777180), (65, -0.52918434),
+                 (127, 0.05770700)):
+        assert e[i].item() == pytest.approx(w, abs=2e-6)
+    assert e.double().sum().item() == pytest.approx(26.608001, abs=1e-4)
+    e = get_timestep_embedding(torch.tensor([500]), 128, False, 1)[0]
+    for i, w in ((0, -0.46777180), (1, -0.99968141), (63, 0.04997916), (64, -0.88384926), (127, 0.99875027)):
+        assert e[i].item() == pytest.approx(w, abs=2e-6)
+
+
+def test_cosine_schedule_kat():
+    from polyp_image_generator_b200.training import get_cosine_schedule_with_warmup
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1.0)
+    sch = get_cosine_schedule_with_warmup(opt, 500, 10000)
+    f = sch.lr_lambdas[0]
+    for step, want in ((0, 0.0), (250, 0.5), (500, 1.0), (5250, 0.5), (10000, 0.0)):
+        assert f(step) == pytest.approx(want, abs=1e-9)
+
+
+def test_unet_structure():
+    m = oracle.UNet2DModel(**oracle.polyp_unet_config(64))
+    assert sum(p.numel() for p in m.parameters()) == 113_673_219
+    sd = m.state_dict()
+    assert len(sd) == 450
+    for k in ("conv_in.weight", "time_embedding.linear_1.weight", "down_blocks.4.attentions.1.to_out.0.bias",
+              "down_blocks.2.resnets.0.conv_shortcut.weight", "mid_block.attentions.0.group_norm.weight",
+              "up_blocks.1.attentions.2.to_q.weight", "up_blocks.4.upsamplers.0.conv.weight", "conv_norm_out.bias",
+              "down_blocks.4.downsamplers.0.conv.weight", "conv_out.bias"):
+        assert k in sd, k
+    assert "down_blocks.5.downsamplers.0.conv.weight" not in sd
+    shortcuts = [k for k in sd if k.endswith("conv_shortcut.weight")]
+    assert len(shortcuts) == 20
+    assert sd["up_blocks.0.resnets.0.conv1.weight"].shape == (512, 1024, 3, 3)
+    assert sd["up_blocks.3.resnets.2.conv1.weight"].shape == (256, 384, 3, 3)
+    c = oracle.UNet2DModel(**oracle.celebahq_unet_config(256))
+    assert sum(p.numel() for p in c.parameters()) == 113_673_219
+    assert c.mid_block.attentions[0].heads == 1 and c.mid_block.attentions[0].dim_head == 512
+
+
+def test_lora_structure_and_key_grammar():
+    m = oracle.UNet2DModel(**oracle.polyp_unet_config(64))
+    cfg = oracle.LoraConfig(r=8, lora_alpha=8, target_modules=["to_q", "to_k", "to_v", "to_out.0"], lora_dropout=0.3,
+                            init_lora_weights="gaussian")
+    wrapped = oracle.add_adapter(m, cfg)
+    assert len(wrapped) == 24
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 196_608
+    sd = oracle.lora_state_dict(m)
+    assert len(sd) == 48
+    assert "mid_block.attentions.0.to_q.lora_A.default.weight" in sd
+    assert sd["mid_block.attentions.0.to_q.lora_A.default.weight"].shape == (8, 512)
+    assert sd["mid_block.attentions.0.to_out.0.lora_B.default.weight"].shape == (512, 8)
+    mods = oracle.recover_lora_modules(sd)
+    assert len(mods) == 24 and "up_blocks.1.attentions.2.to_out.0" in mods
+    assert "mid_block.attentions.0.to_q.base_layer.weight" in m.state_dict()
+
+
+def test_golden_vectors_reproduce():
+    """tests/golden/*.pt were written by tests/golden/make_golden.py from this oracle; re-derive and compare."""
+    path = os.path.join(GOLD, "unet32_fwd_bwd.pt")
+    if not os.path.exists(path):
+        pytest.skip("golden fixture not generated")
+    from golden.make_golden import small_case
+    g = torch.load(path)
+    case = small_case()
+    assert torch.allclose(case["pred"], g["pred"], rtol=1e-4, atol=1e-5)
+    assert case["loss"] == pytest.approx(g["loss"], rel=1e-5)
+    for k, v in g["grad_norms"].items():
+        assert case["grad_norms"][k] == pytest.approx(v, rel=1e-3, abs=1e-9)
