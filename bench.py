@@ -289,6 +289,34 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     ms_e2e = e2_begin.elapsed_time(e2_end)
 
+    # ---- optional per-op breakdown (after the timed regions; CUDA events around every C-ABI op) ----
+    if args.breakdown and rank == 0:
+        ops.conv_gemm = orig_conv_gemm
+        pr = ops_mod.OpProfiler(ops).start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(2):
+            step(clean_dev, noise_dev, t_dev)
+        ev1.record()
+        table = pr.stop()
+        wall = ev0.elapsed_time(ev1) / 2
+        rows = sorted(table.items(), key=lambda kv: -kv[1]["ms"])
+        acc = sum(v["ms"] for _, v in rows) / 2
+        out = {"ms_per_step_profiled": wall, "ms_in_ops": acc, "ops": {}}
+        print(f"[breakdown] step {wall:.2f} ms, in C-ABI ops {acc:.2f} ms (rest = torch optimizer/clip/alloc)",
+              file=sys.stderr)
+        for name, v in rows:
+            ms = v["ms"] / 2
+            tf = v["flops"] / 2 / (ms * 1e-3) / 1e12 if v["flops"] and ms > 0 else None
+            gb = v["bytes"] / 2 / (ms * 1e-3) / 1e9 if v["bytes"] and ms > 0 else None
+            out["ops"][name] = {"calls": v["calls"] // 2, "ms": round(ms, 3), "tflops": tf and round(tf, 1),
+                                "gbps": gb and round(gb, 1)}
+            print(f"[breakdown] {name:24s} calls {v['calls'] // 2:5d}  {ms:8.3f} ms  "
+                  f"{'%.1f TFLOP/s' % tf if tf else ''}{'%.0f GB/s' % gb if gb else ''}", file=sys.stderr)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as f:
+            json.dump(out, f, indent=1)
+
     tt = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -356,6 +384,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="after timing, print a per-op CUDA-event breakdown")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

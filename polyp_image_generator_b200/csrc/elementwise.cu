@@ -304,3 +304,56 @@ extern "C" int ddpm_to_uint8_nhwc(const float* x, unsigned char* out, int n, int
                          static_cast<cudaStream_t>(stream)>>>(x, out, n, c, h, w);
   return check_launch("to_uint8_nhwc_kernel");
 }
+
+// ---- LoRA dropout (peft lora_dropout on the adapter branch; train_with_lora_all_classes.py:316-322) ----------
+// The keep mask is a pure function of (seed, offset, element index): Philox4x32-10 yields eight 16-bit lanes per
+// 8-element vector, element kept iff lane >= p*65536.  Nothing is stored; backward regenerates the same mask.
+namespace ddpm {
+__device__ __forceinline__ void dropout_mask8(long long vec_idx, unsigned long long seed, unsigned long long offset,
+                                              uint32_t thresh, float keep_scale, float* m) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(vec_idx), static_cast<uint32_t>(vec_idx >> 32),
+                                           static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32)),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[2 * i] = (w[i] & 0xFFFFu) >= thresh ? keep_scale : 0.f;
+    m[2 * i + 1] = (w[i] >> 16) >= thresh ? keep_scale : 0.f;
+  }
+}
+
+// out = (add ? add : 0) + x * mask / (1 - p)     (forward: add == NULL; backward: x = dy, add = upstream grad)
+__global__ void __launch_bounds__(kEwThreads)
+dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ add,
+               __nv_bfloat16* __restrict__ out, long long nvec, uint32_t thresh, float keep_scale,
+               unsigned long long seed, unsigned long long offset) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float f[8], m[8];
+    unpack8(reinterpret_cast<const bf16x8*>(x)[i], f);
+    dropout_mask8(i, seed, offset, thresh, keep_scale, m);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= m[e];
+    if (add) {
+      float a[8];
+      unpack8(reinterpret_cast<const bf16x8*>(add)[i], a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += a[e];
+    }
+    reinterpret_cast<bf16x8*>(out)[i] = pack8(f);
+  }
+}
+}  // namespace ddpm
+
+extern "C" int ddpm_dropout(const void* x, const void* add, void* out, long long n, float p, unsigned long long seed,
+                            unsigned long long offset, void* stream) {
+  DDPM_REQUIRE(x && out && n >= 0 && n % 8 == 0 && p >= 0.f && p < 1.f, "ddpm_dropout: bad argument (n %% 8, 0<=p<1)");
+  DDPM_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+               "ddpm_dropout: pointers must be 16-byte aligned");
+  if (n == 0) return DDPM_OK;
+  const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+  dropout_kernel<<<ew_blocks(n / 8), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(out),
+      n / 8, thresh, 1.0f / (1.0f - p), seed, offset);
+  return check_launch("dropout_kernel");
+}

@@ -334,6 +334,16 @@ class CudaOps:
                     "ddpm_reduce_hw")
         self.launches += 1
 
+    def dropout(self, x, p: float, seed: int, offset: int, add=None):
+        """out = (add or 0) + x * keep/(1-p); keep is a pure function of (seed, offset, index).  bf16, contiguous."""
+        if not x.is_contiguous() or (add is not None and not add.is_contiguous()):
+            raise ValueError("dropout needs contiguous tensors")
+        out = torch.empty_like(x)
+        _capi.check(self.lib.ddpm_dropout(_ptr(x), _ptr(add), _ptr(out), x.numel(), float(p), seed, offset, _stream()),
+                    "ddpm_dropout")
+        self.launches += 1
+        return out
+
     # ---- layout helpers ----------------------------------------------------------------------------------------
     def space_to_depth(self, x):
         n, h, w, c, ld = _nhwc(x, "x")
@@ -365,6 +375,88 @@ class CudaOps:
                                             _ptr(out), n, h2 // 2, w2 // 2, c, _stream()), "ddpm_sumpool2x")
         self.launches += 1
         return out
+
+
+class OpProfiler:
+    """CUDA-event timing of every C-ABI op, recorded on the launching stream (bench.py roofline, profiles/).
+
+        prof = OpProfiler(ops.get()); prof.start(); ...; table = prof.stop()
+    `table[name] = {"calls": n, "ms": total_ms, "flops": algorithmic_flops, "bytes": algorithmic_bytes}`.
+    """
+
+    def __init__(self, backend: "CudaOps"):
+        self.b = backend
+        self._orig = {}
+        self.records = []          # (name, e0, e1, flops, bytes)
+
+    @staticmethod
+    def _algorithmic(name, args, kwargs, out):
+        """Algorithmic FLOPs / bytes of one call; 0 when not modelled."""
+        try:
+            if name == "conv_gemm":
+                x0, x1, taps, wgt, cout, grid = args[:6]
+                cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+                n, h, w = grid
+                return 2.0 * n * h * w * cout * cin * len(taps), 0.0
+            if name == "conv_wgrad":
+                dy, x0, x1, taps, dw, grid = args[:6]
+                cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+                n, h, w = grid
+                return 2.0 * n * h * w * dy.shape[-1] * cin * len(taps), 0.0
+            if name == "gn_apply":
+                return 0.0, 4.0 * out.numel()                 # bf16 read + bf16 write
+            if name == "gn_stats":
+                x0, x1 = args[0], args[1]
+                return 0.0, 2.0 * (x0.numel() + (x1.numel() if x1 is not None else 0))
+            if name == "gn_bwd":
+                x0, x1 = args[0], args[1]
+                return 0.0, 6.0 * (x0.numel() + (x1.numel() if x1 is not None else 0))   # x, dy read + dx write
+            if name in ("add_noise", "mse_fwd_bwd"):
+                return 0.0, 12.0 * args[0].numel()
+            if name == "scheduler_step":
+                return 0.0, (16.0 if args[2] is not None else 12.0) * args[1].numel()
+            if name == "scheduler_step_philox":
+                return 0.0, 12.0 * args[1].numel()
+        except Exception:  # noqa: BLE001
+            pass
+        return 0.0, 0.0
+
+    def start(self):
+        for name in dir(self.b):
+            fn = getattr(self.b, name)
+            if name.startswith("_") or not callable(fn) or name in ("lib",):
+                continue
+            self._orig[name] = fn
+
+            def wrapped(*a, __fn=fn, __name=name, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = __fn(*a, **k)
+                e1.record()
+                fl, by = self._algorithmic(__name, a, k, out)
+                self.records.append((__name, e0, e1, fl, by))
+                return out
+
+            setattr(self.b, name, wrapped)
+        return self
+
+    def stop(self):
+        for name in self._orig:
+            try:
+                delattr(self.b, name)      # drop the instance attribute -> class method is visible again
+            except AttributeError:
+                pass
+        self._orig = {}
+        torch.cuda.synchronize()
+        table = {}
+        for name, e0, e1, fl, by in self.records:
+            t = table.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            t["calls"] += 1
+            t["ms"] += e0.elapsed_time(e1)
+            t["flops"] += fl
+            t["bytes"] += by
+        self.records = []
+        return table
 
 
 _backend = None

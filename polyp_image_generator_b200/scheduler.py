@@ -134,6 +134,8 @@ class DDPMScheduler:
         t = timesteps.to(device=original_samples.device, dtype=torch.int64).flatten().contiguous()
         if t.numel() != original_samples.shape[0]:
             raise ValueError("timesteps must have one entry per sample")
+        if original_samples.numel() == 0:
+            return torch.empty_like(original_samples)
         return _ops.get().add_noise(original_samples.contiguous(), noise.contiguous(), t, sa, sb)
 
     # ---- reverse step ---------------------------------------------------------------------------------------

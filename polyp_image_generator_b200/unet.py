@@ -366,7 +366,12 @@ class UNet2DModel(nn.Module):
             rec.norm = norm(name + ".group_norm", a.group_norm)
             rec.qkv = gemm(name + ".to_qkv", [a.to_q, a.to_k, a.to_v], 1, c, c)
             rec.out = gemm(name + ".to_out.0", [a.to_out[0]], 1, c, c)
-            rec.lora_mods = [a.to_q, a.to_k, a.to_v, a.to_out[0]]
+            from .lora import LORA_K, GemmLora, LoraLinear
+            lm = [m if isinstance(m, LoraLinear) else None for m in (a.to_q, a.to_k, a.to_v)]
+            if any(m is not None for m in lm):
+                rec.qkv.lora, rec.qkv.extra_k = GemmLora(lm, c, c), LORA_K
+            if isinstance(a.to_out[0], LoraLinear):
+                rec.out.lora, rec.out.extra_k = GemmLora([a.to_out[0]], c, c), LORA_K
             return rec
 
         P.down = []
@@ -672,12 +677,12 @@ class UNet2DModel(nn.Module):
         stats = ops.gn_stats(x, None, at.norm.groups)
         xn = ops.gn_apply(x, None, at.norm.groups, stats, at.norm.eps, gam, bet, False)
         xn2 = xn.view(1, 1, N * T, C)
-        lora_qkv = at.qkv.lora.forward_extra(ops, xn2, st.tape is not None and self.training) if at.qkv.lora else None
+        lora_qkv = at.qkv.lora.forward_extra(ops, xn2, self.training) if (at.qkv.lora and at.qkv.lora.active) else None
         qkv = ops.conv_gemm(xn2, lora_qkv.u if lora_qkv else None, self._lin_taps(at.qkv), at.qkv.wf, 3 * C,
                             (1, 1, N * T), bias=self._bias(at.qkv))
         o, lse = ops.attn_fwd(qkv.view(N * T, 3 * C), N, T, at.heads, at.d, at.d ** -0.5)
         o2 = o.view(1, 1, N * T, C)
-        lora_o = at.out.lora.forward_extra(ops, o2, st.tape is not None and self.training) if at.out.lora else None
+        lora_o = at.out.lora.forward_extra(ops, o2, self.training) if (at.out.lora and at.out.lora.active) else None
         out = ops.conv_gemm(o2, lora_o.u if lora_o else None, self._lin_taps(at.out), at.out.wf, C, (1, 1, N * T),
                             bias=self._bias(at.out), res=x.view(1, 1, N * T, C)).view(N, H, W, C)
         if st.tape is not None:
@@ -868,7 +873,7 @@ class UNet2DModel(nn.Module):
         if at.out.trainable:
             ops.conv_wgrad(g2, o2, None, taps_1x1(), dWo, (1, 1, M))
         d_o = ops.conv_gemm(g2, None, taps_1x1(), at.out.wd, C, (1, 1, M))
-        if at.out.lora is not None:
+        if s.lora_o is not None:
             d_o = at.out.lora.backward(ops, s.lora_o, o2, g2, d_o)
         dqkv = ops.attn_bwd(s.qkv.view(M, 3 * C), s.o, d_o.view(M, C), s.lse, N, T, at.heads, at.d, at.d ** -0.5)
         dq2 = dqkv.view(1, 1, M, 3 * C)
@@ -879,7 +884,7 @@ class UNet2DModel(nn.Module):
         if at.qkv.trainable:
             ops.conv_wgrad(dq2, xn2, None, taps_1x1(), dWq, (1, 1, M))
         d_xn = ops.conv_gemm(dq2, None, taps_1x1(), at.qkv.wd, C, (1, 1, M))
-        if at.qkv.lora is not None:
+        if s.lora_qkv is not None:
             d_xn = at.qkv.lora.backward(ops, s.lora_qkv, xn2, dq2, d_xn)
         extra = st.skip_grads.pop(s.in_skip, None) if s.in_skip is not None else None
         gam, bet = self._norm_params(at.norm)

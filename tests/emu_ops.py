@@ -259,6 +259,14 @@ class EmuOps:
         if out_c is not None:
             out_c += s.sum(0)
 
+    def dropout(self, x, p, seed, offset, add=None):
+        g = torch.Generator().manual_seed((seed * 1000003 + offset) & 0x7FFFFFFFFFFF)
+        keep = (torch.rand(x.shape, generator=g) >= p).float() / (1.0 - p)
+        r = x.float() * keep
+        if add is not None:
+            r = r + add.float()
+        return self._a(r)
+
     # ---- layout helpers -----------------------------------------------------------------------------------------------
     def space_to_depth(self, x):
         n, h, w, c = x.shape

@@ -254,6 +254,71 @@ def test_pipeline_sampling_vs_oracle(dev):
     assert dev_noise.dtype == torch.uint8 and dev_noise.shape == (2, 32, 32, 3)
 
 
+def test_lora_forward_backward_and_merge_vs_oracle(dev):
+    """configs[3]-style LoRA (r=8, alpha=8, to_q/to_k/to_v/to_out.0), dropout off for parity."""
+    from polyp_image_generator_b200 import LoraConfig, UNet2DModel
+    from polyp_image_generator_b200.lora import lora_state_dict, merge_adapter
+    from polyp_image_generator_b200.training import mse_loss
+    cfg = _small_cfg(32)
+    torch.manual_seed(7)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    tg = ["to_q", "to_k", "to_v", "to_out.0"]
+    oracle.add_adapter(om, oracle.LoraConfig(r=8, lora_alpha=8, target_modules=tg, init_lora_weights="gaussian"))
+    m.add_adapter(LoraConfig(r=8, lora_alpha=8, target_modules=tg, init_lora_weights="gaussian"))
+    sd = {k: torch.randn_like(v) * 0.05 for k, v in oracle.lora_state_dict(om).items()}
+    om.load_state_dict(sd, strict=False)
+    m.load_state_dict(sd, strict=False)
+    m.to(dev).train()
+    x, t, nz = torch.randn(3, 3, 32, 32), torch.tensor([4, 400, 900]), torch.randn(3, 3, 32, 32)
+    pred = m(x.to(dev), t.to(dev)).sample
+    pred_o = om(x, t).sample
+    assert rel(pred, pred_o) < 2e-2
+    mse_loss(pred, nz.to(dev)).backward()
+    F.mse_loss(pred_o, nz).backward()
+    og = dict(om.named_parameters())
+    tot = sum(p.grad.norm() ** 2 for p in om.parameters() if p.grad is not None) ** 0.5
+    num = den = 0.0
+    for n, p in m.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        g = og[n].grad
+        num += (p.grad.cpu() - g).norm().item() ** 2
+        den += g.norm().item() ** 2
+        assert ((p.grad.cpu() - g).norm() / (g.norm() + 2e-2 * tot)).item() < 5e-2, n
+    assert (num / den) ** 0.5 < 2e-2
+    assert len(lora_state_dict(m)) == 48
+    merge_adapter(m)
+    oracle.merge_adapter(om)
+    for (n, p), (_, po) in zip(m.named_parameters(), om.named_parameters()):
+        assert torch.allclose(p.detach().cpu(), po, rtol=0, atol=1e-5), n      # merged weights within 1e-5
+    m.eval()
+    with torch.no_grad():
+        assert rel(m(x.to(dev), t.to(dev)).sample, pred) < 1e-2
+
+
+def test_lora_dropout_kernel(dev):
+    """Keep-rate, scaling, determinism in (seed, offset), and forward/backward mask agreement."""
+    from polyp_image_generator_b200 import ops
+    o = ops.get()
+    x = torch.ones(1 << 20, device=dev, dtype=torch.bfloat16)
+    y = o.dropout(x, 0.3, 11, 5)
+    y2 = o.dropout(x, 0.3, 11, 5)
+    y3 = o.dropout(x, 0.3, 11, 6)
+    assert torch.equal(y, y2) and not torch.equal(y, y3)
+    kept = (y != 0).float().mean().item()
+    assert abs(kept - 0.7) < 5e-3
+    assert torch.allclose(y[y != 0].float(), torch.tensor(1 / 0.7), rtol=1e-2)
+    g = torch.randn(1 << 20, device=dev).to(torch.bfloat16)
+    add = torch.randn(1 << 20, device=dev).to(torch.bfloat16)
+    back = o.dropout(g, 0.3, 11, 5, add=add)
+    want = add.float() + g.float() * (y != 0).float() / 0.7
+    assert rel(back, want) < 5e-3
+    assert torch.equal(o.dropout(x, 0.0, 1, 1), x)
+
+
 def test_full_size_properties_128(dev):
     """BASELINE configs[1] size (128x128, full model): properties that need no CPU oracle run -- finite output,
     batch independence (sample i's eps does not depend on its batch mates), run-to-run stability."""
