@@ -2,8 +2,11 @@
 // Replaces at::native::group_norm + a separate silu kernel per site (71 sites per UNet forward), and folds
 // torch.cat([h, skip], 1) into the load path: the input may be split over two tensors along channels.
 //
-// All kernels are HBM-bound streamers: one 16-byte vector (8 channels) per thread per pixel, coalesced along
-// the channel dimension, warp-shuffle / shared-memory reductions, fp32 atomics for the cross-CTA combine.
+// All kernels are HBM-bound streamers.  Thread mapping (all four kernels): a CTA owns a chunk of pixels of ONE
+// sample; thread (v, pl) owns the 8-channel vector v (one 16-byte access) and walks pixels pl, pl+ppb, ... of the
+// chunk.  Per-channel parameters (gamma, beta, mean, rstd, group coefficients) therefore live in registers for the
+// whole loop, the inner loop is 16-byte loads -> 8 FMAs (+ SiLU) -> 16-byte store with kUnroll pixels in flight,
+// and all index arithmetic is 32-bit.  Cross-CTA combines use fp32 atomics on tiny [N][groups] / [N][C] buffers.
 #include "common.cuh"
 
 #include "../../include/ddpm_b200.h"
@@ -12,6 +15,7 @@ namespace ddpm {
 
 constexpr int kGnThreads = 256;
 constexpr int kMaxC = 2048;
+constexpr int kUnroll = 4;
 
 struct GnSrc {
   const __nv_bfloat16* x0;
@@ -20,10 +24,26 @@ struct GnSrc {
   int c0, c1;
 };
 
-__device__ __forceinline__ bf16x8 gn_load(const GnSrc& s, long long pix, int c) {
-  if (c < s.c0) return *reinterpret_cast<const bf16x8*>(s.x0 + pix * s.ld0 + c);
-  return *reinterpret_cast<const bf16x8*>(s.x1 + pix * s.ld1 + (c - s.c0));
+// pointer to this thread's 8-channel vector at pixel 0 of sample n, and its pixel stride (elements)
+__device__ __forceinline__ const __nv_bfloat16* gn_base(const GnSrc& s, int n, int hw, int c, long long* ld) {
+  if (c < s.c0) {
+    *ld = s.ld0;
+    return s.x0 + static_cast<long long>(n) * hw * s.ld0 + c;
+  }
+  *ld = s.ld1;
+  return s.x1 + static_cast<long long>(n) * hw * s.ld1 + (c - s.c0);
 }
+
+__device__ __forceinline__ void gn_mean_rstd(const float* stats, int n, int g, int groups, float inv_m, float eps,
+                                             float* mean, float* rstd) {
+  const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<long long>(n) * groups + g) * 2);
+  const float mu = st.x * inv_m;
+  const float var = fmaxf(st.y * inv_m - mu * mu, 0.f);
+  *mean = mu;
+  *rstd = rsqrtf(var + eps);
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // ---- statistics ------------------------------------------------------------------------------------
 // grid (chunks, N); block = V * ppb threads (V = C/8 vectors per pixel, ppb pixels in flight)
@@ -36,65 +56,76 @@ gn_stats_kernel(GnSrc s, int hw, int cpg, int groups, float* __restrict__ stats,
   const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(hw, p_begin + pix_per_block);
+  long long ld;
+  const __nv_bfloat16* xp = gn_base(s, n, hw, v * 8, &ld);
   float sum[8], sq[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) sum[e] = sq[e] = 0.f;
-  if (pl < ppb) {
-    for (int p = p_begin + pl; p < p_end; p += ppb) {
+  int p = p_begin + pl;
+  for (; p + (kUnroll - 1) * ppb < p_end; p += kUnroll * ppb) {
+    bf16x8 raw[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) raw[u] = *reinterpret_cast<const bf16x8*>(xp + (p + u * ppb) * ld);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
       float f[8];
-      unpack8(gn_load(s, static_cast<long long>(n) * hw + p, v * 8), f);
+      unpack8(raw[u], f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         sum[e] += f[e];
-        sq[e] += f[e] * f[e];
+        sq[e] = fmaf(f[e], f[e], sq[e]);
       }
     }
-    // fold the 8 channels into their groups (a vector spans at most two groups for cpg >= 4)
-    int g_prev = (v * 8) / cpg;
-    float a = 0.f, b = 0.f;
+  }
+  for (; p < p_end; p += ppb) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(xp + p * ld), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int g = (v * 8 + e) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&sm[g_prev * 2], a);
-        atomicAdd(&sm[g_prev * 2 + 1], b);
-        a = b = 0.f;
-        g_prev = g;
-      }
-      a += sum[e];
-      b += sq[e];
+      sum[e] += f[e];
+      sq[e] = fmaf(f[e], f[e], sq[e]);
     }
-    atomicAdd(&sm[g_prev * 2], a);
-    atomicAdd(&sm[g_prev * 2 + 1], b);
   }
+  // fold the 8 channels into their groups
+  int g_prev = (v * 8) / cpg;
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int g = (v * 8 + e) / cpg;
+    if (g != g_prev) {
+      atomicAdd(&sm[g_prev * 2], a);
+      atomicAdd(&sm[g_prev * 2 + 1], b);
+      a = b = 0.f;
+      g_prev = g;
+    }
+    a += sum[e];
+    b += sq[e];
+  }
+  atomicAdd(&sm[g_prev * 2], a);
+  atomicAdd(&sm[g_prev * 2 + 1], b);
   __syncthreads();
   for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
     atomicAdd(&stats[static_cast<long long>(n) * groups * 2 + i], sm[i]);
 }
 
-__device__ __forceinline__ void gn_mean_rstd(const float* stats, int n, int g, int groups, float inv_m, float eps,
-                                             float* mean, float* rstd) {
-  const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<long long>(n) * groups + g) * 2);
-  const float mu = st.x * inv_m;
-  const float var = fmaxf(st.y * inv_m - mu * mu, 0.f);
-  *mean = mu;
-  *rstd = rsqrtf(var + eps);
-}
-
 // ---- forward apply -----------------------------------------------------------------------------------
+// y = act(x * a + b) with a = rstd*gamma, b = beta - mean*rstd*gamma (per channel, in registers)
+template <bool SILU>
 __global__ void __launch_bounds__(kGnThreads)
-gn_apply_kernel(GnSrc s, int hw, long long total_vec, int cpg, int groups, const float* __restrict__ stats, float eps,
-                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                __nv_bfloat16* __restrict__ y, long long ldy, int V) {
+gn_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                long long ldy, int pix_per_block, int V) {
   const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
-    const int v = static_cast<int>(i % V);
-    const long long pix = i / V;
-    const int n = static_cast<int>(pix / hw);
-    const int c = v * 8;
-    float f[8];
-    unpack8(gn_load(s, pix, c), f);
+  const int n = blockIdx.y;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = v * 8;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(hw, p_begin + pix_per_block);
+  long long ld;
+  const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
+  __nv_bfloat16* yp = y + static_cast<long long>(n) * hw * ldy + c;
+  float ka[8], kb[8];
+  {
     int g_prev = -1;
     float mean = 0.f, rstd = 0.f;
 #pragma unroll
@@ -104,18 +135,53 @@ gn_apply_kernel(GnSrc s, int hw, long long total_vec, int cpg, int groups, const
         gn_mean_rstd(stats, n, g, groups, inv_m, eps, &mean, &rstd);
         g_prev = g;
       }
-      float z = (f[e] - mean) * rstd * gamma[c + e] + beta[c + e];
-      f[e] = silu ? silu_f(z) : z;
+      ka[e] = rstd * gamma[c + e];
+      kb[e] = beta[c + e] - mean * ka[e];
     }
-    *reinterpret_cast<bf16x8*>(y + pix * ldy + c) = pack8(f);
   }
+  int p = p_begin + pl;
+  for (; p + (kUnroll - 1) * ppb < p_end; p += kUnroll * ppb) {
+    bf16x8 raw[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) raw[u] = *reinterpret_cast<const bf16x8*>(xp + (p + u * ppb) * ld);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float z = fmaf(f[e], ka[e], kb[e]);
+        f[e] = SILU ? z * fast_sigmoid(z) : z;
+      }
+      *reinterpret_cast<bf16x8*>(yp + (p + u * ppb) * ldy) = pack8(f);
+    }
+  }
+  for (; p < p_end; p += ppb) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(xp + p * ld), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float z = fmaf(f[e], ka[e], kb[e]);
+      f[e] = SILU ? z * fast_sigmoid(z) : z;
+    }
+    *reinterpret_cast<bf16x8*>(yp + p * ldy) = pack8(f);
+  }
+}
+
+// dz = dy * act'(z) with z = xhat*gamma + beta
+template <bool SILU>
+__device__ __forceinline__ float gn_dz(float dy, float z) {
+  if (!SILU) return dy;
+  const float sg = fast_sigmoid(z);
+  return dy * sg * fmaf(z, 1.0f - sg, 1.0f);
 }
 
 // ---- backward pass 1: per-(n, c) sums of dz and dz*xhat ---------------------------------------------------
 // grid (chunks, N); dynamic smem: C*2 floats
+template <bool SILU>
 __global__ void __launch_bounds__(kGnThreads)
 gn_bwd_reduce_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
-                     const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
                      const __nv_bfloat16* __restrict__ dy, long long lddy, float* __restrict__ sums /*[N][C][2]*/,
                      int pix_per_block, int V) {
   extern __shared__ float smc[];
@@ -128,34 +194,69 @@ gn_bwd_reduce_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restri
   const int c = v * 8;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(hw, p_begin + pix_per_block);
-  if (pl < ppb) {
-    float mean[8], rstd[8], ga[8], be[8], A[8], B[8];
+  long long ld;
+  const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
+  const __nv_bfloat16* dp = dy + static_cast<long long>(n) * hw * lddy + c;
+  float kr[8], km[8], ga[8], be[8], A[8], B[8];   // xhat = x*kr + km
+  {
+    int g_prev = -1;
+    float mean = 0.f, rstd = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      gn_mean_rstd(stats, n, (c + e) / cpg, groups, inv_m, eps, &mean[e], &rstd[e]);
+      const int g = (c + e) / cpg;
+      if (g != g_prev) {
+        gn_mean_rstd(stats, n, g, groups, inv_m, eps, &mean, &rstd);
+        g_prev = g;
+      }
+      kr[e] = rstd;
+      km[e] = -mean * rstd;
       ga[e] = gamma[c + e];
       be[e] = beta[c + e];
       A[e] = B[e] = 0.f;
     }
-    for (int p = p_begin + pl; p < p_end; p += ppb) {
-      const long long pix = static_cast<long long>(n) * hw + p;
-      float f[8], d[8];
-      unpack8(gn_load(s, pix, c), f);
-      unpack8(*reinterpret_cast<const bf16x8*>(dy + pix * lddy + c), d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float xh = (f[e] - mean[e]) * rstd[e];
-        float dz = d[e];
-        if (silu) dz *= silu_grad_f(xh * ga[e] + be[e]);
-        A[e] += dz;
-        B[e] += dz * xh;
-      }
-    }
+  }
+  int p = p_begin + pl;
+  for (; p + ppb < p_end; p += 2 * ppb) {
+    const bf16x8 rx0 = *reinterpret_cast<const bf16x8*>(xp + p * ld);
+    const bf16x8 rx1 = *reinterpret_cast<const bf16x8*>(xp + (p + ppb) * ld);
+    const bf16x8 rd0 = *reinterpret_cast<const bf16x8*>(dp + p * lddy);
+    const bf16x8 rd1 = *reinterpret_cast<const bf16x8*>(dp + (p + ppb) * lddy);
+    float f[8], d[8];
+    unpack8(rx0, f);
+    unpack8(rd0, d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&smc[(c + e) * 2], A[e]);
-      atomicAdd(&smc[(c + e) * 2 + 1], B[e]);
+      const float xh = fmaf(f[e], kr[e], km[e]);
+      const float dz = gn_dz<SILU>(d[e], fmaf(xh, ga[e], be[e]));
+      A[e] += dz;
+      B[e] = fmaf(dz, xh, B[e]);
     }
+    unpack8(rx1, f);
+    unpack8(rd1, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = fmaf(f[e], kr[e], km[e]);
+      const float dz = gn_dz<SILU>(d[e], fmaf(xh, ga[e], be[e]));
+      A[e] += dz;
+      B[e] = fmaf(dz, xh, B[e]);
+    }
+  }
+  for (; p < p_end; p += ppb) {
+    float f[8], d[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(xp + p * ld), f);
+    unpack8(*reinterpret_cast<const bf16x8*>(dp + p * lddy), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = fmaf(f[e], kr[e], km[e]);
+      const float dz = gn_dz<SILU>(d[e], fmaf(xh, ga[e], be[e]));
+      A[e] += dz;
+      B[e] = fmaf(dz, xh, B[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    atomicAdd(&smc[(c + e) * 2], A[e]);
+    atomicAdd(&smc[(c + e) * 2 + 1], B[e]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
@@ -194,7 +295,7 @@ gn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__
   }
 }
 
-// ---- backward pass 2: dx ------------------------------------------------------------------------------
+// ---- backward pass 2: dx = dz*k1 - k2 - xhat*k3 (+ addends), k1 = rstd*gamma, k2 = rstd*s1/m, k3 = rstd*s2/m
 struct GnDst {
   __nv_bfloat16* d0;
   __nv_bfloat16* d1;
@@ -204,21 +305,36 @@ struct GnDst {
   long long lda0, lda1;
 };
 
+template <bool SILU>
 __global__ void __launch_bounds__(kGnThreads)
-gn_bwd_apply_kernel(GnSrc s, int hw, long long total_vec, int cpg, int groups, const float* __restrict__ stats,
-                    float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
                     const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ coef, GnDst o,
-                    int V) {
+                    int pix_per_block, int V) {
   const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
-    const int v = static_cast<int>(i % V);
-    const long long pix = i / V;
-    const int n = static_cast<int>(pix / hw);
-    const int c = v * 8;
-    float f[8], d[8], r[8];
-    unpack8(gn_load(s, pix, c), f);
-    unpack8(*reinterpret_cast<const bf16x8*>(dy + pix * lddy + c), d);
+  const int n = blockIdx.y;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = v * 8;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(hw, p_begin + pix_per_block);
+  long long ld;
+  const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
+  const long long pix0 = static_cast<long long>(n) * hw;
+  const __nv_bfloat16* dp = dy + pix0 * lddy + c;
+  const __nv_bfloat16* a0p = o.add0 ? o.add0 + pix0 * o.lda0 + c : nullptr;
+  const __nv_bfloat16* a1p = o.add1 ? o.add1 + pix0 * o.lda1 + c : nullptr;
+  __nv_bfloat16* op;
+  long long ldo;
+  if (c < s.c0) {
+    op = o.d0 + pix0 * o.ld0 + c;
+    ldo = o.ld0;
+  } else {
+    op = o.d1 ? o.d1 + pix0 * o.ld1 + (c - s.c0) : nullptr;
+    ldo = o.ld1;
+  }
+  if (op == nullptr) return;   // gradient of this source not requested
+  float kr[8], km[8], ga[8], be[8], k1[8], k2[8], k3[8];
+  {
     int g_prev = -1;
     float mean = 0.f, rstd = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -231,28 +347,55 @@ gn_bwd_apply_kernel(GnSrc s, int hw, long long total_vec, int cpg, int groups, c
         s2 = cf.y * inv_m;
         g_prev = g;
       }
-      const float ga = gamma[c + e];
-      const float xh = (f[e] - mean) * rstd;
-      float dz = d[e];
-      if (silu) dz *= silu_grad_f(xh * ga + beta[c + e]);
-      r[e] = rstd * (dz * ga - s1 - xh * s2);
+      kr[e] = rstd;
+      km[e] = -mean * rstd;
+      ga[e] = gamma[c + e];
+      be[e] = beta[c + e];
+      k1[e] = rstd * ga[e];
+      k2[e] = rstd * s1;
+      k3[e] = rstd * s2;
     }
-    if (o.add0) {
-      float a[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(o.add0 + pix * o.lda0 + c), a);
+  }
+  for (int p = p_begin + pl; p < p_end; p += 2 * ppb) {
+    const bool two = p + ppb < p_end;
+    bf16x8 rx[2], rd[2], ra0[2], ra1[2];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) r[e] += a[e];
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 || two) {
+        const int q = p + u * ppb;
+        rx[u] = *reinterpret_cast<const bf16x8*>(xp + q * ld);
+        rd[u] = *reinterpret_cast<const bf16x8*>(dp + q * lddy);
+        if (a0p) ra0[u] = *reinterpret_cast<const bf16x8*>(a0p + q * o.lda0);
+        if (a1p) ra1[u] = *reinterpret_cast<const bf16x8*>(a1p + q * o.lda1);
+      }
     }
-    if (o.add1) {
-      float a[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(o.add1 + pix * o.lda1 + c), a);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) r[e] += a[e];
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 || two) {
+        float f[8], d[8], r[8];
+        unpack8(rx[u], f);
+        unpack8(rd[u], d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = fmaf(f[e], kr[e], km[e]);
+          const float dz = gn_dz<SILU>(d[e], fmaf(xh, ga[e], be[e]));
+          r[e] = fmaf(dz, k1[e], -fmaf(xh, k3[e], k2[e]));
+        }
+        if (a0p) {
+          float a[8];
+          unpack8(ra0[u], a);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += a[e];
+        }
+        if (a1p) {
+          float a[8];
+          unpack8(ra1[u], a);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += a[e];
+        }
+        *reinterpret_cast<bf16x8*>(op + (p + u * ppb) * ldo) = pack8(r);
+      }
     }
-    if (c < s.c0)
-      *reinterpret_cast<bf16x8*>(o.d0 + pix * o.ld0 + c) = pack8(r);
-    else if (o.d1)
-      *reinterpret_cast<bf16x8*>(o.d1 + pix * o.ld1 + (c - s.c0)) = pack8(r);
   }
 }
 
@@ -263,39 +406,31 @@ static int gn_check(const void* x0, int c0, long long ld0, const void* x1, int c
     return DDPM_ERR_INVALID;
   }
   const int C = c0 + c1;
-  if (c0 <= 0 || c0 % 8 || c1 < 0 || c1 % 8 || (c1 > 0 && !x1) || C % groups || C > kMaxC || ld0 % 8 || (c1 > 0 && ld1 % 8)) {
+  if (c0 <= 0 || c0 % 8 || c1 < 0 || c1 % 8 || (c1 > 0 && !x1) || C % groups || C > kMaxC || ld0 % 8 ||
+      (c1 > 0 && ld1 % 8) || C / 8 > kGnThreads) {
     set_last_error("%s: unsupported channel configuration c0=%d c1=%d groups=%d ld0=%lld ld1=%lld", who, c0, c1,
                    groups, ld0, ld1);
-    return DDPM_ERR_INVALID;
-  }
-  if ((C / groups) < 4 && (C / groups) != 1 && (C / groups) != 2) {
-    set_last_error("%s: channels per group %d unsupported", who, C / groups);
     return DDPM_ERR_INVALID;
   }
   return DDPM_OK;
 }
 
-static void gn_geometry(int C, int hw, int n, int* V, int* threads, int* pix_per_block, int* chunks) {
+// chunks of pixels per sample: ~`waves` waves of CTAs over the chip, at least `min_iters` loop trips per thread
+static void gn_geometry(int C, int hw, int n, int waves, int min_iters, int* V, int* threads, int* pix_per_block,
+                        int* chunks) {
   *V = C / 8;
   int ppb = kGnThreads / *V;
   if (ppb < 1) ppb = 1;
   *threads = *V * ppb;
-  // enough CTAs for ~4 waves, at least 8*ppb pixels per CTA
-  long long want = (4LL * kNumSMs + n - 1) / n;
+  long long want = (static_cast<long long>(waves) * kNumSMs * 2 + n - 1) / n;   // ~2 resident CTAs per SM
+  if (want < 1) want = 1;
   long long ppblk = (hw + want - 1) / want;
-  const long long min_ppblk = static_cast<long long>(ppb) * 8;
+  const long long min_ppblk = static_cast<long long>(ppb) * min_iters;
   if (ppblk < min_ppblk) ppblk = min_ppblk;
+  ppblk = (ppblk + ppb - 1) / ppb * ppb;
   if (ppblk > hw) ppblk = hw;
   *pix_per_block = static_cast<int>(ppblk);
   *chunks = static_cast<int>((hw + ppblk - 1) / ppblk);
-}
-
-static int stream_blocks(long long items) {
-  long long b = (items + kGnThreads - 1) / kGnThreads;
-  const long long cap = static_cast<long long>(kNumSMs) * 16;
-  if (b > cap) b = cap;
-  if (b < 1) b = 1;
-  return static_cast<int>(b);
 }
 
 }  // namespace ddpm
@@ -308,10 +443,9 @@ extern "C" int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* 
   if (int e = gn_check(x0, c0, ld0, x1, c1, ld1, n, hw, groups, "ddpm_gn_stats")) return e;
   DDPM_REQUIRE(stats, "ddpm_gn_stats: stats is null");
   const int C = c0 + c1;
-  DDPM_REQUIRE(C / 8 <= kGnThreads, "ddpm_gn_stats: C=%d too large", C);
   GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
   int V, threads, ppblk, chunks;
-  gn_geometry(C, hw, n, &V, &threads, &ppblk, &chunks);
+  gn_geometry(C, hw, n, 4, 4 * kUnroll, &V, &threads, &ppblk, &chunks);
   DDPM_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
   gn_stats_kernel<<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, ppblk, V);
   return check_launch("gn_stats_kernel");
@@ -325,11 +459,15 @@ extern "C" int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* 
   DDPM_REQUIRE(stats && gamma && beta && y && ldy % 8 == 0, "ddpm_gn_apply: bad argument");
   const int C = c0 + c1;
   GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
-  const int V = C / 8;
-  const long long total_vec = static_cast<long long>(n) * hw * V;
-  gn_apply_kernel<<<stream_blocks(total_vec), kGnThreads, 0, stream>>>(s, hw, total_vec, C / groups, groups, stats, eps,
-                                                                       gamma, beta, silu,
-                                                                       static_cast<__nv_bfloat16*>(y), ldy, V);
+  int V, threads, ppblk, chunks;
+  gn_geometry(C, hw, n, 4, 2 * kUnroll, &V, &threads, &ppblk, &chunks);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  if (silu)
+    gn_apply_kernel<true><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma, beta,
+                                                                   yp, ldy, ppblk, V);
+  else
+    gn_apply_kernel<false><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma, beta,
+                                                                    yp, ldy, ppblk, V);
   return check_launch("gn_apply_kernel");
 }
 
@@ -345,16 +483,19 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
                    (!add0 || ldadd0 % 8 == 0) && (!add1 || ldadd1 % 8 == 0),
                "ddpm_gn_bwd: strides must be multiples of 8");
   const int C = c0 + c1;
-  DDPM_REQUIRE(C / 8 <= kGnThreads, "ddpm_gn_bwd: C=%d too large", C);
   GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
+  const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
   int V, threads, ppblk, chunks;
-  gn_geometry(C, hw, n, &V, &threads, &ppblk, &chunks);
+  gn_geometry(C, hw, n, 4, 8, &V, &threads, &ppblk, &chunks);
   float* sums = ws;
   float* coef = ws + static_cast<long long>(n) * C * 2;
   DDPM_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C * n, stream));
-  gn_bwd_reduce_kernel<<<dim3(chunks, n), threads, C * 2 * sizeof(float), stream>>>(
-      s, hw, C / groups, groups, stats, eps, gamma, beta, silu, static_cast<const __nv_bfloat16*>(dy), lddy, sums,
-      ppblk, V);
+  if (silu)
+    gn_bwd_reduce_kernel<true><<<dim3(chunks, n), threads, C * 2 * sizeof(float), stream>>>(
+        s, hw, C / groups, groups, stats, eps, gamma, beta, dyp, lddy, sums, ppblk, V);
+  else
+    gn_bwd_reduce_kernel<false><<<dim3(chunks, n), threads, C * 2 * sizeof(float), stream>>>(
+        s, hw, C / groups, groups, stats, eps, gamma, beta, dyp, lddy, sums, ppblk, V);
   if (int e = check_launch("gn_bwd_reduce_kernel")) return e;
   gn_bwd_finalize_kernel<<<n + (C + kGnThreads - 1) / kGnThreads, kGnThreads, 0, stream>>>(sums, gamma, n, C,
                                                                                           C / groups, groups, coef,
@@ -362,9 +503,12 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
   if (int e = check_launch("gn_bwd_finalize_kernel")) return e;
   GnDst o{static_cast<__nv_bfloat16*>(dx0), static_cast<__nv_bfloat16*>(dx1), lddx0, lddx1,
           static_cast<const __nv_bfloat16*>(add0), static_cast<const __nv_bfloat16*>(add1), ldadd0, ldadd1};
-  const long long total_vec = static_cast<long long>(n) * hw * V;
-  gn_bwd_apply_kernel<<<stream_blocks(total_vec), kGnThreads, 0, stream>>>(
-      s, hw, total_vec, C / groups, groups, stats, eps, gamma, beta, silu, static_cast<const __nv_bfloat16*>(dy), lddy,
-      coef, o, V);
+  gn_geometry(C, hw, n, 4, 4, &V, &threads, &ppblk, &chunks);
+  if (silu)
+    gn_bwd_apply_kernel<true><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma,
+                                                                       beta, dyp, lddy, coef, o, ppblk, V);
+  else
+    gn_bwd_apply_kernel<false><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma,
+                                                                        beta, dyp, lddy, coef, o, ppblk, V);
   return check_launch("gn_bwd_apply_kernel");
 }

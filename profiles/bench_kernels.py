@@ -1,0 +1,159 @@
+"""Per-kernel microbenchmarks on the UNet's real shapes (run under gpurun; CUDA-event timing, L2 flushed between
+iterations by rotating through more input buffers than fit in the 126 MB L2).
+
+    python profiles/bench_kernels.py [conv|wgrad|gn|small|all] [--batch 64] [--iters 10]
+
+Prints one line per shape: achieved TFLOP/s (GEMM kernels) or GB/s (streaming kernels) and the fraction of the
+measured peak from MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+from polyp_image_generator_b200 import ops as ops_mod
+from polyp_image_generator_b200.ops import taps_1x1, taps_3x3
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        return {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
+
+
+def timeit(fn, iters, nbuf):
+    for i in range(3):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % nbuf)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bf(*shape):
+    return (torch.randn(*shape, device="cuda") * 0.5).to(torch.bfloat16)
+
+
+# (h, cin, cout, taps, count-per-forward) at S=128 -- SURVEY.md Appendix D
+CONV_SHAPES = [
+    (128, 128, 128, 9), (128, 256, 128, 9), (128, 256, 128, 1),
+    (64, 128, 128, 9), (64, 256, 256, 9), (64, 384, 128, 9), (64, 256, 128, 9),
+    (32, 256, 256, 9), (32, 512, 256, 9), (32, 128, 256, 9),
+    (16, 256, 256, 9), (16, 512, 512, 9), (16, 768, 256, 9), (16, 512, 256, 9),
+    (8, 512, 512, 9), (8, 1024, 512, 9), (8, 1024, 512, 1),
+    (4, 512, 512, 9), (4, 1024, 512, 9),
+]
+
+
+def bench_conv(ops, B, iters, pk):
+    print(f"# conv_gemm (fprop / dgrad), batch {B}; peak = {pk['bf16_tflops']} TFLOP/s (burst, kernel timed alone)")
+    for (h, cin, cout, taps) in CONV_SHAPES:
+        per = B * h * h * cin * 2
+        nbuf = max(2, min(8, int(300e6 // per) + 1))
+        xs = [bf(B, h, h, cin) for _ in range(nbuf)]
+        w = bf(cout, taps * cin) * 0.1
+        bias = torch.randn(cout, device="cuda")
+        out = torch.empty(B, h, h, cout, device="cuda", dtype=torch.bfloat16)
+        tp = taps_3x3(cin) if taps == 9 else taps_1x1()
+        ms = timeit(lambda i: ops.conv_gemm(xs[i], None, tp, w, cout, (B, h, h), bias=bias, out=out), iters, nbuf)
+        fl = 2.0 * B * h * h * cout * cin * taps
+        tf = fl / ms / 1e9
+        print(f"conv {h:3d}x{h:<3d} {cin:4d}->{cout:<4d} k{taps}  {ms:8.3f} ms  {tf:7.1f} TFLOP/s  "
+              f"{tf / pk['bf16_tflops']:.3f} of peak", flush=True)
+
+
+def bench_wgrad(ops, B, iters, pk):
+    print(f"# conv_wgrad, batch {B}")
+    for (h, cin, cout, taps) in CONV_SHAPES:
+        if cout % 64:
+            continue
+        x = bf(B, h, h, cin)
+        dy = bf(B, h, h, cout)
+        dw = torch.zeros(cout, taps * cin, device="cuda")
+        tp = taps_3x3(cin) if taps == 9 else taps_1x1()
+        ms = timeit(lambda i: ops.conv_wgrad(dy, x, None, tp, dw, (B, h, h)), iters, 1)
+        fl = 2.0 * B * h * h * cout * cin * taps
+        tf = fl / ms / 1e9
+        print(f"wgrad {h:3d}x{h:<3d} {cin:4d}->{cout:<4d} k{taps}  {ms:8.3f} ms  {tf:7.1f} TFLOP/s  "
+              f"{tf / pk['bf16_tflops']:.3f} of peak", flush=True)
+
+
+def bench_gn(ops, B, iters, pk):
+    print(f"# GroupNorm+SiLU, batch {B}; peak = {pk['hbm_gbs']} GB/s (measured copy)")
+    for (h, c0, c1) in [(128, 128, 0), (128, 128, 128), (64, 128, 0), (64, 256, 128), (32, 256, 0), (32, 256, 256),
+                        (16, 512, 256), (8, 512, 512), (4, 512, 0)]:
+        C = c0 + c1
+        xa = bf(B, h, h, c0)
+        xb = bf(B, h, h, c1) if c1 else None
+        gam, bet = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+        elems = B * h * h * C
+        ms_s = timeit(lambda i: ops.gn_stats(xa, xb, 32), iters, 1)
+        stats = ops.gn_stats(xa, xb, 32)
+        y = torch.empty(B, h, h, C, device="cuda", dtype=torch.bfloat16)
+        ms_a = timeit(lambda i: ops.gn_apply(xa, xb, 32, stats, 1e-5, gam, bet, True, out=y), iters, 1)
+        dy = bf(B, h, h, C)
+        ms_b = timeit(lambda i: ops.gn_bwd(xa, xb, 32, stats, 1e-5, gam, bet, True, dy), iters, 1)
+        print(f"gn {h:3d}x{h:<3d} c{c0}+{c1:<4d} stats {ms_s:7.3f} ms {2 * elems / ms_s / 1e6:6.0f} GB/s | "
+              f"apply {ms_a:7.3f} ms {4 * elems / ms_a / 1e6:6.0f} GB/s ({4 * elems / ms_a / 1e6 / pk['hbm_gbs']:.2f}) | "
+              f"bwd {ms_b:7.3f} ms {10 * elems / ms_b / 1e6:6.0f} GB/s (10 B/elem: 2 passes over x,dy + dx)",
+              flush=True)
+
+
+def bench_small(ops, B, iters, pk):
+    print(f"# 3-channel convs + elementwise, batch {B}, 128x128")
+    S, C = 128, 128
+    x = torch.randn(B, 3, S, S, device="cuda")
+    w_in = torch.randn(C, 9, 3, device="cuda") * 0.1
+    b_in = torch.randn(C, device="cuda")
+    ms = timeit(lambda i: ops.conv3_to_c(x, w_in, (27, 3, 1), False, b_in, C), iters, 1)
+    print(f"conv_in fwd      {ms:7.3f} ms  ({(x.numel() * 4 + B * S * S * C * 2) / ms / 1e6:6.0f} GB/s algorithmic)")
+    a = bf(B, S, S, C)
+    w_out = torch.randn(3, 9, C, device="cuda") * 0.1
+    b_out = torch.randn(3, device="cuda")
+    ms = timeit(lambda i: ops.conv_c_to_3(a, w_out, b_out, 3), iters, 1)
+    print(f"conv_out fwd     {ms:7.3f} ms  ({(x.numel() * 4 + B * S * S * C * 2) / ms / 1e6:6.0f} GB/s algorithmic)")
+    dw = torch.zeros(C, 9, 3, device="cuda")
+    ms = timeit(lambda i: ops.conv3_wgrad(a, x, dw, (27, 3, 1), False), iters, 1)
+    print(f"conv3 wgrad      {ms:7.3f} ms")
+    nz = torch.randn_like(x)
+    t = torch.randint(0, 1000, (B,), device="cuda")
+    tab = torch.rand(1000, device="cuda")
+    ms = timeit(lambda i: ops.add_noise(x, nz, t, tab, tab), iters, 1)
+    print(f"add_noise        {ms:7.4f} ms  {12 * x.numel() / ms / 1e6:6.0f} GB/s ({12 * x.numel() / ms / 1e6 / pk['hbm_gbs']:.2f})")
+    ms = timeit(lambda i: ops.mse_fwd_bwd(x, nz), iters, 1)
+    print(f"mse fwd+bwd      {ms:7.4f} ms  {12 * x.numel() / ms / 1e6:6.0f} GB/s ({12 * x.numel() / ms / 1e6 / pk['hbm_gbs']:.2f})")
+    ms = timeit(lambda i: ops.scheduler_step(x, nz, nz, 0.5, 0.5, 0.1, 0.9, 0.1, 1.0), iters, 1)
+    print(f"scheduler step   {ms:7.4f} ms  {16 * x.numel() / ms / 1e6:6.0f} GB/s ({16 * x.numel() / ms / 1e6 / pk['hbm_gbs']:.2f})")
+    ms = timeit(lambda i: ops.scheduler_step_philox(x, nz, 0.5, 0.5, 0.1, 0.9, 0.1, 1.0, 1, i), iters, 1)
+    print(f"step (philox)    {ms:7.4f} ms  {12 * x.numel() / ms / 1e6:6.0f} GB/s ({12 * x.numel() / ms / 1e6 / pk['hbm_gbs']:.2f})")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    ops = ops_mod.get()
+    pk = peaks()
+    torch.manual_seed(0)
+    if a.what in ("conv", "all"):
+        bench_conv(ops, a.batch, a.iters, pk)
+    if a.what in ("wgrad", "all"):
+        bench_wgrad(ops, a.batch, a.iters, pk)
+    if a.what in ("gn", "all"):
+        bench_gn(ops, a.batch, a.iters, pk)
+    if a.what in ("small", "all"):
+        bench_small(ops, a.batch, a.iters, pk)
