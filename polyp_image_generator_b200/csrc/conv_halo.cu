@@ -1,0 +1,297 @@
+// Halo-resident 3x3 stride-1 convolution (fprop and dgrad) on tcgen05 -- the high-resolution workhorse.
+//
+// Why: the generic tap-by-tap kernel (conv_igemm.cu) re-fetches every input pixel nine times from L2 and every
+// weight tile once per 128 output pixels; ncu shows it pinned on L2->SM bandwidth (lts throughput ~70 %, 8.7 TB/s)
+// at 34 % of tensor peak on the 128->128 @128^2 layers that carry 57 % of the UNet's FLOPs (profiles/).
+//
+// How: address each image in a *padded slot space* -- slot q = h * Wp + (w + 1), Wp = W + 1, where the one extra
+// slot per row is zero and serves as the right pad of row h and the left pad of row h + 1.  A 3x3 tap (dh, dw) then
+// is a pure shift by dh * Wp + dw slots.  A CTA owns 256 consecutive output slots (two M = 128 UMMA tiles, two TMEM
+// accumulators).  Per 64-channel chunk it loads the R padded rows that cover the tile plus its one-row halo ONCE
+// (one 4-D TMA box starting at w = -1: out-of-bounds rows/columns are zero-filled = the conv padding) and issues
+// all nine taps from that resident halo by shifting the start address of the SWIZZLE_128B operand descriptor by a
+// whole number of 128-byte rows (profiles/probe_shift: the hardware swizzles on absolute address bits, so any
+// 128-byte-aligned start is valid).  L2->SM traffic per FLOP drops ~2.6x.  Slots that fall on a pad position
+// produce garbage accumulator rows that are simply not stored (W / (W + 1) efficiency).
+//
+// Structure: persistent CTAs (one per SM), static round-robin tile schedule, warp-specialised:
+//   warps 0-7  epilogue (TMEM -> registers -> bias / time-embedding / residual -> bf16 NHWC), overlapped with the
+//              next tile's mainloop through double-buffered accumulators (2 x 256 TMEM columns)
+//   warp  8    halo producer (TMA, double-buffered halo)       warp 9   weight-tile producer (TMA, ring)
+//   warp 10    MMA issuer + TMEM owner
+#include "common.cuh"
+
+#include <cstring>
+
+#include "../../include/ddpm_b200.h"
+
+namespace ddpm {
+
+constexpr int kHaloThreads = 352;
+constexpr int kHaloBStages = 3;
+constexpr int kTileSlots = 256;
+constexpr int kHaloBBytes = 128 * 128;   // one weight tile: 128 cout rows x 64 ch
+
+struct HaloParams {
+  int N, H, W, Wp;
+  int kb0, kb1;
+  int Cout, Cin_total;
+  int R;                 // padded rows per halo box
+  int tiles_per_img, n_tiles, total_tiles;
+  uint32_t halo_bytes;   // R * Wp * 128
+  uint32_t halo_stride;  // halo_bytes rounded up to 1024
+  __nv_bfloat16* out;
+  long long ldo;
+  const float* bias;
+  const float* temb;
+  int ld_temb;
+  const __nv_bfloat16* res;
+  long long ldr;
+};
+
+__device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* halo = smem;                                   // 2 x halo_stride
+  uint8_t* bsm = smem + 2 * p.halo_stride;                // kHaloBStages x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + kHaloBStages * kHaloBBytes);
+  uint64_t* halo_full = bars;            // [2]
+  uint64_t* halo_empty = bars + 2;       // [2]
+  uint64_t* b_full = bars + 4;           // [kHaloBStages]
+  uint64_t* b_empty = b_full + kHaloBStages;
+  uint64_t* tmem_full = b_empty + kHaloBStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kbt = p.kb0 + p.kb1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.kb1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&halo_full[i], 1);
+      mbar_init(&halo_empty[i], 1);
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);     // one arrival per epilogue warp
+    }
+    for (int i = 0; i < kHaloBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 10) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ---------------- halo producer ----------------
+    if (lane == 0) {
+      uint32_t hidx = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles;
+        const int img = mt / p.tiles_per_img;
+        const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
+        const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
+        for (int c = 0; c < kbt; ++c, ++hidx) {
+          const uint32_t hb = hidx & 1, ph = (hidx >> 1) & 1;
+          mbar_wait(&halo_empty[hb], ph ^ 1);
+          mbar_expect_tx(&halo_full[hb], p.halo_bytes);
+          if (c < p.kb0)
+            tma_load_4d(halo + hb * p.halo_stride, &tmA0, &halo_full[hb], c * 64, -1, row_lo, img);
+          else
+            tma_load_4d(halo + hb * p.halo_stride, &tmA1, &halo_full[hb], (c - p.kb0) * 64, -1, row_lo, img);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- weight-tile producer ----------------
+    if (lane == 0) {
+      uint32_t bidx = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        for (int c = 0; c < kbt; ++c) {
+          for (int tap = 0; tap < 9; ++tap, ++bidx) {
+            const uint32_t s = bidx % kHaloBStages, ph = (bidx / kHaloBStages) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1);
+            mbar_expect_tx(&b_full[s], kHaloBBytes);
+            tma_load_2d(bsm + s * kHaloBBytes, &tmB, &b_full[s], tap * p.Cin_total + c * 64, nt * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+      uint32_t hidx = 0, bidx = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const int mt = tile / p.n_tiles;
+        const int img = mt / p.tiles_per_img;
+        const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
+        const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
+        const int rel0 = q0 - row_lo * p.Wp;            // slot of q0 inside the halo buffer
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * 256;
+        for (int c = 0; c < kbt; ++c, ++hidx) {
+          const uint32_t hb = hidx & 1, hph = (hidx >> 1) & 1;
+          mbar_wait(&halo_full[hb], hph);
+          const uint32_t h_addr = smem_u32(halo + hb * p.halo_stride);
+          for (int tap = 0; tap < 9; ++tap, ++bidx) {
+            const uint32_t s = bidx % kHaloBStages, ph = (bidx / kHaloBStages) & 1;
+            mbar_wait(&b_full[s], ph);
+            tc_fence_after();
+            const int r = tap / 3, sx = tap - r * 3;
+            const uint32_t a_addr = h_addr + static_cast<uint32_t>(rel0 + (r - 1) * p.Wp + (sx - 1)) * 128u;
+            const uint32_t b_addr = smem_u32(bsm + s * kHaloBBytes);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = make_smem_desc_sw128(a_addr + u * (128 * 128) + k * 32, 16, 1024);
+                const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                umma_bf16(d0 + u * 128, da, db, idesc, (c | tap | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&b_empty[s]);
+          }
+          umma_commit(&halo_empty[hb]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---------------- epilogue (8 warps) ----------------
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = warp >> 2;       // column half: chunks {0,1} or {2,3}
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int img = mt / p.tiles_per_img;
+      const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int u = 0; u < 2; ++u) {
+        const int slot = q0 + u * 128 + q * 32 + lane;
+        const int h = slot / p.Wp;
+        const int w = slot - h * p.Wp - 1;
+        const bool valid = (w >= 0) && (h < p.H);
+        const long long pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
+#pragma unroll 1
+        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + u * 128 + cc * 32, r);
+          tmem_ld_wait();
+          const int col = nt * 128 + cc * 32;
+          if (valid && col < p.Cout) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (p.temb) {
+              const float* t = p.temb + static_cast<long long>(img) * p.ld_temb + col;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(t + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (p.res) {
+              const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + pix * p.ldr + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float f[8];
+                unpack8(rp[j], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j * 8 + e] += f[e];
+              }
+            }
+            bf16x8* op = reinterpret_cast<bf16x8*>(p.out + pix * p.ldo + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc(tmem_base, 512);
+}
+
+// 4-D activation map with a caller-chosen box (not cached through make_act_map's (wb,hb,nb) key space clash:
+// the key includes the box, so the shared cache is safe to reuse)
+int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
+  if (env_int("DDPM_HALO", 1) == 0) return 1;
+  if (a->ntaps != 9 || a->out == nullptr || a->out_f32 != nullptr) return 1;
+  if (a->src_n != 0 && a->src_n != a->n) return 1;
+  const int cin_total = a->c0 + a->c1;
+  for (int t = 0; t < 9; ++t) {
+    if (a->tap_dn[t] != 0 || a->tap_dh[t] != t / 3 - 1 || a->tap_dw[t] != t % 3 - 1 || a->tap_wk[t] != t * cin_total)
+      return 1;
+  }
+  const int W = a->w, H = a->h, Wp = W + 1;
+  if (W < env_int("DDPM_HALO_MIN_W", 64) || Wp > 256) return 1;
+  HaloParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.N = a->n; p.H = H; p.W = W; p.Wp = Wp;
+  p.kb0 = a->c0 / 64; p.kb1 = a->c1 / 64;
+  p.Cout = a->cout; p.Cin_total = cin_total;
+  // rows covering [q0 - Wp - 1, q0 + 255 + Wp + 1] for any q0: floor((256 + 2*Wp + 1) / Wp) + 2, capped by the box limit
+  int R = (kTileSlots + 2 * Wp + 1) / Wp + 2;
+  if (R > 256) return 1;
+  p.R = R;
+  p.halo_bytes = static_cast<uint32_t>(R) * Wp * 128u;
+  p.halo_stride = (p.halo_bytes + 1023u) & ~1023u;
+  const size_t smem = 2ull * p.halo_stride + kHaloBStages * kHaloBBytes + 256 + 1024;
+  if (smem > 227 * 1024) return 1;
+  p.tiles_per_img = (H * Wp + kTileSlots - 1) / kTileSlots;
+  p.n_tiles = (a->cout + 127) / 128;
+  p.total_tiles = a->n * p.tiles_per_img * p.n_tiles;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.ldo = a->ldo;
+  p.bias = a->bias; p.temb = a->temb; p.ld_temb = a->ld_temb;
+  p.res = static_cast<const __nv_bfloat16*>(a->res); p.ldr = a->ldr;
+
+  CUtensorMap ma0, ma1, mb;
+  if (int e = make_act_map(&ma0, a->x0, a->c0, a->ld0, a->n, H, W, Wp, R, 1)) return e;
+  if (a->c1 > 0) {
+    if (int e = make_act_map(&ma1, a->x1, a->c1, a->ld1, a->n, H, W, Wp, R, 1)) return e;
+  } else {
+    ma1 = ma0;
+  }
+  const long long k_total = a->k_total > 0 ? a->k_total : a->ldw;
+  if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 128)) return e;
+  static size_t configured = 0;
+  if (smem > configured) {
+    DDPM_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  conv_halo_kernel<<<grid, kHaloThreads, smem, stream>>>(ma0, ma1, mb, p);
+  return check_launch("conv_halo_kernel");
+}
+
+}  // namespace ddpm

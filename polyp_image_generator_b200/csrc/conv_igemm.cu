@@ -424,7 +424,7 @@ static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // NHWC bf16 activation view [n][h][w][c] with pixel stride ld (elements); box = (64, wb, hb, nb)
-static int make_act_map(CUtensorMap* out, const void* ptr, int c, long long ld, int n, int h, int w, int wb, int hb,
+int make_act_map(CUtensorMap* out, const void* ptr, int c, long long ld, int n, int h, int w, int wb, int hb,
                         int nb) {
   MapKey k;
   std::memset(&k, 0, sizeof(k));
@@ -462,7 +462,7 @@ static int make_act_map(CUtensorMap* out, const void* ptr, int c, long long ld, 
 }
 
 // K-major weight matrix [rows][ld] bf16; box = (64, box_rows)
-static int make_wgt_map(CUtensorMap* out, const void* ptr, long long k_total, long long ld, int rows, int box_rows) {
+int make_wgt_map(CUtensorMap* out, const void* ptr, long long k_total, long long ld, int rows, int box_rows) {
   MapKey k;
   std::memset(&k, 0, sizeof(k));
   k.ptr = ptr;
@@ -545,7 +545,7 @@ static int launch_wgrad(const CUtensorMap& y, const CUtensorMap& x0, const CUten
   return check_launch("conv_wgrad_kernel");
 }
 
-static int env_int(const char* name, int dflt) {
+int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
 }
@@ -563,6 +563,10 @@ extern "C" int ddpm_conv_gemm(const ddpm_conv_args* a, void* stream_) {
   DDPM_REQUIRE(a->cout > 0 && a->cout % 32 == 0, "ddpm_conv_gemm: cout=%d must be a multiple of 32", a->cout);
   DDPM_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0, "ddpm_conv_gemm: empty pixel grid");
   DDPM_REQUIRE(a->ldo % 8 == 0 && (a->res == nullptr || a->ldr % 8 == 0), "ddpm_conv_gemm: ldo/ldr must be multiples of 8");
+  {
+    const int hr = launch_conv_halo(a, stream);   // 3x3 stride-1 convs at high resolution: halo-resident kernel
+    if (hr <= 0) return hr;
+  }
   GemmParams p;
   std::memset(&p, 0, sizeof(p));
   if (int e = fill_taps(&p.taps, a)) return e;

@@ -284,7 +284,9 @@ def g_gemm(ops):
     # --- 3x3 convs over the UNet's resolutions ---
     for (n, h, w_, cin, cout) in [(2, 16, 16, 128, 128), (1, 128, 128, 128, 128), (3, 32, 32, 256, 256),
                                   (4, 8, 8, 512, 512), (9, 4, 4, 512, 512), (2, 64, 64, 128, 256),
-                                  (2, 14, 14, 128, 128), (3, 7, 7, 64, 128), (1, 200, 136, 64, 128)]:
+                                  (2, 14, 14, 128, 128), (3, 7, 7, 64, 128), (1, 200, 136, 64, 128),
+                                  (3, 70, 96, 128, 256), (5, 64, 64, 256, 128), (2, 128, 128, 256, 128),
+                                  (1, 65, 64, 64, 64), (2, 3, 200, 64, 128)]:
         x = bf(torch.randn(n, h, w_, cin, device=dev))
         w4 = bf(torch.randn(cout, cin, 3, 3, device=dev) * 0.03)
         wk = w4.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
@@ -294,6 +296,13 @@ def g_gemm(ops):
         out = ops.conv_gemm(x, None, taps_3x3(cin), wk, cout, (n, h, w_), bias=b, temb=temb, res=res)
         want = conv_ref(x, w4, b) + temb[:, None, None, :] + res.float()
         ok &= report(f"conv3x3 n{n} {h}x{w_} {cin}->{cout} +bias+temb+res", out, want, 4e-3)
+    # --- halo kernel with two concatenated sources at high resolution ---
+    n, h, w_, c0, c1, cout = 2, 64, 64, 128, 64, 128
+    xa, xb = bf(torch.randn(n, h, w_, c0, device=dev)), bf(torch.randn(n, h, w_, c1, device=dev))
+    w4 = bf(torch.randn(cout, c0 + c1, 3, 3, device=dev) * 0.03)
+    wk = w4.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    out = ops.conv_gemm(xa, xb, taps_3x3(c0 + c1), wk, cout, (n, h, w_))
+    ok &= report("conv3x3 concat 128+64 -> 128 @64x64 (halo)", out, conv_ref(torch.cat([xa, xb], -1), w4, None), 4e-3)
     # --- concat of two sources + 1x1 ---
     n, h, w_, c0, c1, cout = 2, 16, 16, 256, 128, 256
     xa, xb = bf(torch.randn(n, h, w_, c0, device=dev)), bf(torch.randn(n, h, w_, c1, device=dev))
