@@ -2,6 +2,10 @@
 // /root/reference/generator_model/PolypGeneratorModel.py:25-48).  K = 27 resp. N = 3 is far below a UMMA tile,
 // and both layers are HBM-bound (SURVEY.md §7 "hard parts"), so they are plain SIMT kernels that also do the
 // NCHW-fp32 <-> NHWC-bf16 layout change at the model boundary for free.
+//
+// Mapping: the 128-channel side is spread over the 32 lanes of a warp (4 channels = one 8-byte access per lane), so
+// NHWC accesses are fully coalesced and the per-lane weights (27 x 4 resp. 9 x 3 x 4 floats) stay in registers; the
+// 3-channel side is warp-uniform (broadcast loads / shuffle reductions).
 #include "common.cuh"
 
 #include "../../include/ddpm_b200.h"
@@ -10,59 +14,36 @@ namespace ddpm {
 
 constexpr int kScThreads = 256;
 
-// out[n,h,w,co] = bias[co] + sum_{k<cin, tap} x[n,k,h+dh,w+dw] * w[co*s_co + tap'*s_tap + k*s_ci]
-// thread = (pixel, 8-channel group).  smem weights: [tap*cin + k][cout] fp32.
+struct __align__(8) bf16x4 {
+  __nv_bfloat162 v[2];
+};
+
+// out[n,h,w,co] = bias[co] + sum_{k<CIN, tap} x[n,k,h+dh,w+dw] * w[co*s_co + tap'*s_tap + k*s_ci]
+// warp = one pixel per iteration, lane = 4 output channels (chunk blockIdx.y of 128 channels)
+template <int CIN>
 __global__ void __launch_bounds__(kScThreads)
 conv3_to_c_kernel(const float* __restrict__ x, const float* __restrict__ w, long long s_co, long long s_tap,
                   long long s_ci, int flip, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                  long long ldo, int N, int H, int W, int cin, int cout, long long total) {
-  extern __shared__ float ws[];  // [9*cin][cout]
-  const int KK = 9 * cin;
-  for (int i = threadIdx.x; i < KK * cout; i += blockDim.x) {
-    const int co = i % cout, kk = i / cout;
-    const int tap = kk / cin, k = kk - tap * cin;
-    const int tp = flip ? 8 - tap : tap;
-    ws[i] = w[co * s_co + tp * s_tap + k * s_ci];
-  }
-  __syncthreads();
-  const int G = cout / 8;
-  const long long hw = static_cast<long long>(H) * W;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int g = static_cast<int>(i % G);
-    const long long pix = i / G;
-    const int n = static_cast<int>(pix / hw);
-    const int rem = static_cast<int>(pix - n * hw);
-    const int h = rem / W, wq = rem - h * W;
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[g * 8 + e] : 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int hh = h + tap / 3 - 1, ww = wq + tap % 3 - 1;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-      for (int k = 0; k < cin; ++k) {
-        const float xv = x[(static_cast<long long>(n) * cin + k) * hw + static_cast<long long>(hh) * W + ww];
-        const float4* wp = reinterpret_cast<const float4*>(ws + (tap * cin + k) * cout + g * 8);
-        const float4 w0 = wp[0], w1 = wp[1];
-        acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
-        acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
-      }
-    }
-    *reinterpret_cast<bf16x8*>(out + pix * ldo + g * 8) = pack8(acc);
-  }
-}
-
-// out[n,co,h,w] = bias[co] + sum_{tap, ci} a[n,h+dh,w+dw,ci] * w[co][tap][ci];  one warp per pixel.
-// COUT <= 4.  smem weights [cout][9][cin] fp32.
-template <int COUT>
-__global__ void __launch_bounds__(kScThreads)
-conv_c_to_3_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const float* __restrict__ w,
-                   const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W, int cin,
-                   long long npix) {
-  extern __shared__ float ws[];
-  for (int i = threadIdx.x; i < COUT * 9 * cin; i += blockDim.x) ws[i] = w[i];
-  __syncthreads();
+                  long long ldo, int N, int H, int W, int cout, long long npix) {
   const int lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * 128 + lane * 4;
+  const bool active = c0 < cout;
+  float wr[9][CIN][4];
+  float b4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int tp = flip ? 8 - tap : tap;
+#pragma unroll
+      for (int k = 0; k < CIN; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wr[tap][k][j] = w[(c0 + j) * s_co + tp * s_tap + k * s_ci];
+    }
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b4[j] = bias[c0 + j];
+    }
+  }
   const long long hw = static_cast<long long>(H) * W;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -70,29 +51,110 @@ conv_c_to_3_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const flo
     const int n = static_cast<int>(pix / hw);
     const int rem = static_cast<int>(pix - n * hw);
     const int h = rem / W, wq = rem - h * W;
-    float acc[COUT];
+    const float* xn = x + static_cast<long long>(n) * CIN * hw;
+    float xv[9][CIN];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
     for (int tap = 0; tap < 9; ++tap) {
       const int hh = h + tap / 3 - 1, ww = wq + tap % 3 - 1;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-      const __nv_bfloat16* ap = a + ((static_cast<long long>(n) * H + hh) * W + ww) * lda;
-      for (int c0 = lane * 8; c0 < cin; c0 += 256) {
-        float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(ap + c0), f);
+      const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-          const float* wp = ws + (c * 9 + tap) * cin + c0;
+      for (int k = 0; k < CIN; ++k) xv[tap][k] = in ? __ldg(xn + k * hw + static_cast<long long>(hh) * W + ww) : 0.f;
+    }
+    if (!active) continue;
+    float acc[4] = {b4[0], b4[1], b4[2], b4[3]};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[c] += f[e] * wp[e];
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int k = 0; k < CIN; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv[tap][k], wr[tap][k][j], acc[j]);
+    bf16x4 o;
+    o.v[0] = __floats2bfloat162_rn(acc[0], acc[1]);
+    o.v[1] = __floats2bfloat162_rn(acc[2], acc[3]);
+    *reinterpret_cast<bf16x4*>(out + pix * ldo + c0) = o;
+  }
+}
+
+// out[n,co,h,w] = bias[co] + sum_{tap, ci} a[n,h+dh,w+dw,ci] * w[co][tap][ci]
+// warp = 4 consecutive pixels of a row per iteration (shared 3x6 input window), lane = 4 input channels of a
+// 128-channel chunk; 4*COUT partial sums are reduced over the warp with shuffles.
+template <int COUT>
+__global__ void __launch_bounds__(kScThreads)
+conv_c_to_3_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const float* __restrict__ w,
+                   const float* __restrict__ bias, float* __restrict__ out, int N, int H, int W, int cin,
+                   long long ngroups, int groups_per_row) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = (cin + 127) / 128;
+  float wr[9][COUT][4];
+  auto load_w = [&](int chunk) {
+    const int c = chunk * 128 + lane * 4;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int co = 0; co < COUT; ++co)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wr[tap][co][j] = (c + j < cin) ? w[(co * 9 + tap) * cin + c + j] : 0.f;
+  };
+  if (nchunks == 1) load_w(0);
+  const long long hw = static_cast<long long>(H) * W;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long g = warp0; g < ngroups; g += nwarps) {
+    const long long rowid = g / groups_per_row;             // n * H + h
+    const int w0 = static_cast<int>(g - rowid * groups_per_row) * 4;
+    const int n = static_cast<int>(rowid / H);
+    const int h = static_cast<int>(rowid - static_cast<long long>(n) * H);
+    float acc[4][COUT];
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) acc[px][co] = 0.f;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      if (nchunks > 1) load_w(chunk);
+      const int c = chunk * 128 + lane * 4;
+      const bool cact = c < cin;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = h + r - 1;
+        if (hh < 0 || hh >= H) continue;
+        const __nv_bfloat16* rowp = a + (static_cast<long long>(n) * H + hh) * W * lda + c;
+        float f[6][4];
+#pragma unroll
+        for (int col = 0; col < 6; ++col) {
+          const int ww = w0 + col - 1;
+          if (cact && ww >= 0 && ww < W) {
+            const bf16x4 raw = *reinterpret_cast<const bf16x4*>(rowp + static_cast<long long>(ww) * lda);
+            const float2 lo = __bfloat1622float2(raw.v[0]), hi = __bfloat1622float2(raw.v[1]);
+            f[col][0] = lo.x; f[col][1] = lo.y; f[col][2] = hi.x; f[col][3] = hi.y;
+          } else {
+            f[col][0] = f[col][1] = f[col][2] = f[col][3] = 0.f;
+          }
         }
+#pragma unroll
+        for (int col = 0; col < 6; ++col)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int px = col - s;
+            if (px >= 0 && px < 4) {
+#pragma unroll
+              for (int co = 0; co < COUT; ++co) {
+                const float* wp = wr[r * 3 + s][co];
+                acc[px][co] = fmaf(f[col][0], wp[0], fmaf(f[col][1], wp[1], fmaf(f[col][2], wp[2],
+                              fmaf(f[col][3], wp[3], acc[px][co]))));
+              }
+            }
+          }
       }
     }
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) {
-      const float v = warp_sum(acc[c]);
-      if (lane == 0) out[(static_cast<long long>(n) * COUT + c) * hw + rem] = v + (bias ? bias[c] : 0.f);
-    }
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) {
+        const float v = warp_sum(acc[px][co]);
+        if (lane == 0 && w0 + px < W)
+          out[(static_cast<long long>(n) * COUT + co) * hw + static_cast<long long>(h) * W + w0 + px] =
+              v + (bias ? bias[co] : 0.f);
+      }
   }
 }
 
@@ -176,49 +238,41 @@ extern "C" int ddpm_conv3_to_c(const float* x, const float* w, long long w_sco, 
                                int flip, const float* bias, void* out, long long ldo, int n, int h, int wd, int cin,
                                int cout, void* stream) {
   DDPM_REQUIRE(x && w && out && n > 0 && h > 0 && wd > 0, "ddpm_conv3_to_c: bad argument");
-  DDPM_REQUIRE(cin >= 1 && cin <= 4 && cout % 8 == 0 && cout <= 512 && ldo % 8 == 0,
+  DDPM_REQUIRE(cin >= 1 && cin <= 4 && cout % 4 == 0 && cout <= 2048 && ldo % 4 == 0,
                "ddpm_conv3_to_c: unsupported channels cin=%d cout=%d", cin, cout);
-  const size_t smem = sizeof(float) * 9 * cin * cout;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    DDPM_CUDA(cudaFuncSetAttribute(conv3_to_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  const long long total = static_cast<long long>(n) * h * wd * (cout / 8);
-  long long blocks = (total + kScThreads - 1) / kScThreads;
+  const long long npix = static_cast<long long>(n) * h * wd;
+  long long blocks = (npix * 32 + kScThreads - 1) / kScThreads;
   if (blocks > kNumSMs * 8LL) blocks = kNumSMs * 8LL;
-  conv3_to_c_kernel<<<static_cast<int>(blocks), kScThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, w, w_sco, w_stap, w_sci, flip, bias, static_cast<__nv_bfloat16*>(out), ldo, n, h, wd, cin, cout, total);
+  dim3 grid(static_cast<unsigned>(blocks), (cout + 127) / 128);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
+  switch (cin) {
+    case 1: conv3_to_c_kernel<1><<<grid, kScThreads, 0, st>>>(x, w, w_sco, w_stap, w_sci, flip, bias, op, ldo, n, h, wd, cout, npix); break;
+    case 2: conv3_to_c_kernel<2><<<grid, kScThreads, 0, st>>>(x, w, w_sco, w_stap, w_sci, flip, bias, op, ldo, n, h, wd, cout, npix); break;
+    case 3: conv3_to_c_kernel<3><<<grid, kScThreads, 0, st>>>(x, w, w_sco, w_stap, w_sci, flip, bias, op, ldo, n, h, wd, cout, npix); break;
+    default: conv3_to_c_kernel<4><<<grid, kScThreads, 0, st>>>(x, w, w_sco, w_stap, w_sci, flip, bias, op, ldo, n, h, wd, cout, npix); break;
+  }
   return check_launch("conv3_to_c_kernel");
 }
 
 extern "C" int ddpm_conv_c_to_3(const void* a, long long lda, const float* w, const float* bias, float* out, int n,
                                 int h, int wd, int cin, int cout, void* stream) {
   DDPM_REQUIRE(a && w && out && n > 0 && h > 0 && wd > 0, "ddpm_conv_c_to_3: bad argument");
-  DDPM_REQUIRE(cout >= 1 && cout <= 4 && cin % 8 == 0 && cin <= 1024 && lda % 8 == 0,
+  DDPM_REQUIRE(cout >= 1 && cout <= 4 && cin % 4 == 0 && cin <= 2048 && lda % 4 == 0,
                "ddpm_conv_c_to_3: unsupported channels cin=%d cout=%d", cin, cout);
-  const size_t smem = sizeof(float) * cout * 9 * cin;
-  const long long npix = static_cast<long long>(n) * h * wd;
-  long long blocks = (npix * 32 + kScThreads - 1) / kScThreads;
+  const int gpr = (wd + 3) / 4;
+  const long long ngroups = static_cast<long long>(n) * h * gpr;
+  long long blocks = (ngroups * 32 + kScThreads - 1) / kScThreads;
   if (blocks > kNumSMs * 8LL) blocks = kNumSMs * 8LL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
-#define LAUNCH_C3(CO)                                                                                           \
-  {                                                                                                             \
-    static size_t configured = 0;                                                                               \
-    if (smem > 48 * 1024 && smem > configured) {                                                                \
-      DDPM_CUDA(cudaFuncSetAttribute(conv_c_to_3_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      configured = smem;                                                                                        \
-    }                                                                                                           \
-    conv_c_to_3_kernel<CO><<<static_cast<int>(blocks), kScThreads, smem, st>>>(ap, lda, w, bias, out, n, h, wd, cin, npix); \
-  }
+  const int g = static_cast<int>(blocks);
   switch (cout) {
-    case 1: LAUNCH_C3(1); break;
-    case 2: LAUNCH_C3(2); break;
-    case 3: LAUNCH_C3(3); break;
-    default: LAUNCH_C3(4); break;
+    case 1: conv_c_to_3_kernel<1><<<g, kScThreads, 0, st>>>(ap, lda, w, bias, out, n, h, wd, cin, ngroups, gpr); break;
+    case 2: conv_c_to_3_kernel<2><<<g, kScThreads, 0, st>>>(ap, lda, w, bias, out, n, h, wd, cin, ngroups, gpr); break;
+    case 3: conv_c_to_3_kernel<3><<<g, kScThreads, 0, st>>>(ap, lda, w, bias, out, n, h, wd, cin, ngroups, gpr); break;
+    default: conv_c_to_3_kernel<4><<<g, kScThreads, 0, st>>>(ap, lda, w, bias, out, n, h, wd, cin, ngroups, gpr); break;
   }
-#undef LAUNCH_C3
   return check_launch("conv_c_to_3_kernel");
 }
 

@@ -57,9 +57,9 @@ CONV_SHAPES = [
 ]
 
 
-def bench_conv(ops, B, iters, pk):
+def bench_conv(ops, B, iters, pk, first=None):
     print(f"# conv_gemm (fprop / dgrad), batch {B}; peak = {pk['bf16_tflops']} TFLOP/s (burst, kernel timed alone)")
-    for (h, cin, cout, taps) in CONV_SHAPES:
+    for (h, cin, cout, taps) in CONV_SHAPES[:first]:
         per = B * h * h * cin * 2
         nbuf = max(2, min(8, int(300e6 // per) + 1))
         xs = [bf(B, h, h, cin) for _ in range(nbuf)]
@@ -74,9 +74,9 @@ def bench_conv(ops, B, iters, pk):
               f"{tf / pk['bf16_tflops']:.3f} of peak", flush=True)
 
 
-def bench_wgrad(ops, B, iters, pk):
+def bench_wgrad(ops, B, iters, pk, first=None):
     print(f"# conv_wgrad, batch {B}")
-    for (h, cin, cout, taps) in CONV_SHAPES:
+    for (h, cin, cout, taps) in CONV_SHAPES[:first]:
         if cout % 64:
             continue
         x = bf(B, h, h, cin)
@@ -145,14 +145,15 @@ if __name__ == "__main__":
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--first", type=int, default=None, help="only the first N conv shapes (short ncu runs)")
     a = ap.parse_args()
     ops = ops_mod.get()
     pk = peaks()
     torch.manual_seed(0)
     if a.what in ("conv", "all"):
-        bench_conv(ops, a.batch, a.iters, pk)
+        bench_conv(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("wgrad", "all"):
-        bench_wgrad(ops, a.batch, a.iters, pk)
+        bench_wgrad(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("gn", "all"):
         bench_gn(ops, a.batch, a.iters, pk)
     if a.what in ("small", "all"):
