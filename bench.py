@@ -292,7 +292,9 @@ def run_b200(args, rank, world, local_rank):
     # ---- optional per-op breakdown (after the timed regions; CUDA events around every C-ABI op) ----
     if args.breakdown and rank == 0:
         ops.conv_gemm = orig_conv_gemm
-        pr = ops_mod.OpProfiler(ops).start()
+        pr = ops_mod.OpProfiler(ops)
+        pr.by_shape = args.breakdown_by_shape
+        pr.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(2):
@@ -311,7 +313,7 @@ def run_b200(args, rank, world, local_rank):
             gb = v["bytes"] / 2 / (ms * 1e-3) / 1e9 if v["bytes"] and ms > 0 else None
             out["ops"][name] = {"calls": v["calls"] // 2, "ms": round(ms, 3), "tflops": tf and round(tf, 1),
                                 "gbps": gb and round(gb, 1)}
-            print(f"[breakdown] {name:24s} calls {v['calls'] // 2:5d}  {ms:8.3f} ms  "
+            print(f"[breakdown] {name:36s} calls {v['calls'] // 2:5d}  {ms:8.3f} ms  "
                   f"{'%.1f TFLOP/s' % tf if tf else ''}{'%.0f GB/s' % gb if gb else ''}", file=sys.stderr)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as f:
@@ -385,6 +387,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="after timing, print a per-op CUDA-event breakdown")
+    ap.add_argument("--breakdown-by-shape", action="store_true", help="split conv / GroupNorm rows by layer shape")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

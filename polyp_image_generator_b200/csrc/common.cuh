@@ -66,28 +66,34 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
-};
+// Eight bf16 values moved as ONE 128-bit access.  (A struct of four __nv_bfloat162 is copied member-wise by nvcc --
+// four 32-bit LDG/STG per vector, 4x the L1/L2 wavefronts -- so the carrier type is the builtin uint4.)
+using bf16x8 = uint4;
+using bf16x4 = uint2;
 
-__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ bf16x8 pack8(const float* f) {
-  bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return p;
-}
-__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+__device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack2_bf16_(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+  f[0] = bf16lo_f(p.x); f[1] = bf16hi_f(p.x);
+  f[2] = bf16lo_f(p.y); f[3] = bf16hi_f(p.y);
+  f[4] = bf16lo_f(p.z); f[5] = bf16hi_f(p.z);
+  f[6] = bf16lo_f(p.w); f[7] = bf16hi_f(p.w);
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  return make_uint4(pack2_bf16_(f[0], f[1]), pack2_bf16_(f[2], f[3]), pack2_bf16_(f[4], f[5]), pack2_bf16_(f[6], f[7]));
+}
+__device__ __forceinline__ void unpack4(const bf16x4& p, float* f) {
+  f[0] = bf16lo_f(p.x); f[1] = bf16hi_f(p.x);
+  f[2] = bf16lo_f(p.y); f[3] = bf16hi_f(p.y);
+}
+__device__ __forceinline__ bf16x4 pack4(const float* f) {
+  return make_uint2(pack2_bf16_(f[0], f[1]), pack2_bf16_(f[2], f[3]));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) { return pack2_bf16_(a, b); }
 
 // ---------------------------------------------------------------------------------------------
 // PTX: shared-memory addresses, mbarrier

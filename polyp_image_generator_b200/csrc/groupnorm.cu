@@ -177,9 +177,10 @@ __device__ __forceinline__ float gn_dz(float dy, float z) {
 }
 
 // ---- backward pass 1: per-(n, c) sums of dz and dz*xhat ---------------------------------------------------
-// grid (chunks, N); dynamic smem: C*2 floats
+// grid (chunks, N); dynamic smem: C*2 floats.  The loop accumulates the raw moments S1 = sum dz, S2 = sum dz*x with
+// only the affine z = x*kz1 + kz0 in registers; sum dz*xhat = rstd*S2 - mean*rstd*S1 is formed once at the end.
 template <bool SILU>
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, 3)
 gn_bwd_reduce_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const __nv_bfloat16* __restrict__ dy, long long lddy, float* __restrict__ sums /*[N][C][2]*/,
@@ -197,7 +198,7 @@ gn_bwd_reduce_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restri
   long long ld;
   const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
   const __nv_bfloat16* dp = dy + static_cast<long long>(n) * hw * lddy + c;
-  float kr[8], km[8], ga[8], be[8], A[8], B[8];   // xhat = x*kr + km
+  float kz1[8], kz0[8], A[8], B[8];   // z = x*kz1 + kz0
   {
     int g_prev = -1;
     float mean = 0.f, rstd = 0.f;
@@ -208,37 +209,31 @@ gn_bwd_reduce_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restri
         gn_mean_rstd(stats, n, g, groups, inv_m, eps, &mean, &rstd);
         g_prev = g;
       }
-      kr[e] = rstd;
-      km[e] = -mean * rstd;
-      ga[e] = gamma[c + e];
-      be[e] = beta[c + e];
+      const float ga = gamma[c + e];
+      kz1[e] = rstd * ga;
+      kz0[e] = fmaf(-mean * rstd, ga, beta[c + e]);
       A[e] = B[e] = 0.f;
     }
   }
   int p = p_begin + pl;
-  for (; p + ppb < p_end; p += 2 * ppb) {
-    const bf16x8 rx0 = *reinterpret_cast<const bf16x8*>(xp + p * ld);
-    const bf16x8 rx1 = *reinterpret_cast<const bf16x8*>(xp + (p + ppb) * ld);
-    const bf16x8 rd0 = *reinterpret_cast<const bf16x8*>(dp + p * lddy);
-    const bf16x8 rd1 = *reinterpret_cast<const bf16x8*>(dp + (p + ppb) * lddy);
-    float f[8], d[8];
-    unpack8(rx0, f);
-    unpack8(rd0, d);
+  for (; p + (kUnroll - 1) * ppb < p_end; p += kUnroll * ppb) {
+    bf16x8 rx[kUnroll], rd[kUnroll];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xh = fmaf(f[e], kr[e], km[e]);
-      const float dz = gn_dz<SILU>(d[e], fmaf(xh, ga[e], be[e]));
-      A[e] += dz;
-      B[e] = fmaf(dz, xh, B[e]);
+    for (int u = 0; u < kUnroll; ++u) {
+      rx[u] = *reinterpret_cast<const bf16x8*>(xp + (p + u * ppb) * ld);
+      rd[u] = *reinterpret_cast<const bf16x8*>(dp + (p + u * ppb) * lddy);
     }
-    unpack8(rx1, f);
-    unpack8(rd1, d);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xh = fmaf(f[e], kr[e], km[e]);
-      const float dz = gn_dz<SILU>(d[e], fmaf(xh, ga[e], be[e]));
-      A[e] += dz;
-      B[e] = fmaf(dz, xh, B[e]);
+    for (int u = 0; u < kUnroll; ++u) {
+      float f[8], d[8];
+      unpack8(rx[u], f);
+      unpack8(rd[u], d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dz = gn_dz<SILU>(d[e], fmaf(f[e], kz1[e], kz0[e]));
+        A[e] += dz;
+        B[e] = fmaf(dz, f[e], B[e]);
+      }
     }
   }
   for (; p < p_end; p += ppb) {
@@ -247,16 +242,24 @@ gn_bwd_reduce_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restri
     unpack8(*reinterpret_cast<const bf16x8*>(dp + p * lddy), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float xh = fmaf(f[e], kr[e], km[e]);
-      const float dz = gn_dz<SILU>(d[e], fmaf(xh, ga[e], be[e]));
+      const float dz = gn_dz<SILU>(d[e], fmaf(f[e], kz1[e], kz0[e]));
       A[e] += dz;
-      B[e] = fmaf(dz, xh, B[e]);
+      B[e] = fmaf(dz, f[e], B[e]);
     }
   }
+  {
+    int g_prev = -1;
+    float mean = 0.f, rstd = 0.f;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    atomicAdd(&smc[(c + e) * 2], A[e]);
-    atomicAdd(&smc[(c + e) * 2 + 1], B[e]);
+    for (int e = 0; e < 8; ++e) {
+      const int g = (c + e) / cpg;
+      if (g != g_prev) {
+        gn_mean_rstd(stats, n, g, groups, inv_m, eps, &mean, &rstd);
+        g_prev = g;
+      }
+      atomicAdd(&smc[(c + e) * 2], A[e]);
+      atomicAdd(&smc[(c + e) * 2 + 1], rstd * (B[e] - mean * A[e]));
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
@@ -296,6 +299,7 @@ gn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__
 }
 
 // ---- backward pass 2: dx = dz*k1 - k2 - xhat*k3 (+ addends), k1 = rstd*gamma, k2 = rstd*s1/m, k3 = rstd*s2/m
+//      (xhat = x*rstd - mean*rstd is folded into the coefficients so only four 8-vectors stay in registers)
 struct GnDst {
   __nv_bfloat16* d0;
   __nv_bfloat16* d1;
@@ -305,8 +309,9 @@ struct GnDst {
   long long lda0, lda1;
 };
 
+// dx = dz*k1 - x*k4 - k5 with z = x*kz1 + kz0, k1 = rstd*gamma, k4 = rstd^2*s2/m, k5 = rstd*s1/m - mean*rstd^2*s2/m
 template <bool SILU>
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, 3)
 gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ coef, GnDst o,
@@ -333,7 +338,7 @@ gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restric
     ldo = o.ld1;
   }
   if (op == nullptr) return;   // gradient of this source not requested
-  float kr[8], km[8], ga[8], be[8], k1[8], k2[8], k3[8];
+  float kz1[8], kz0[8], k4[8], k5[8];
   {
     int g_prev = -1;
     float mean = 0.f, rstd = 0.f, s1 = 0.f, s2 = 0.f;
@@ -347,13 +352,11 @@ gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restric
         s2 = cf.y * inv_m;
         g_prev = g;
       }
-      kr[e] = rstd;
-      km[e] = -mean * rstd;
-      ga[e] = gamma[c + e];
-      be[e] = beta[c + e];
-      k1[e] = rstd * ga[e];
-      k2[e] = rstd * s1;
-      k3[e] = rstd * s2;
+      const float ga = gamma[c + e];
+      kz1[e] = rstd * ga;                                  // also k1
+      kz0[e] = fmaf(-mean * rstd, ga, beta[c + e]);
+      k4[e] = rstd * rstd * s2;
+      k5[e] = rstd * s1 - mean * k4[e];
     }
   }
   for (int p = p_begin + pl; p < p_end; p += 2 * ppb) {
@@ -377,9 +380,8 @@ gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restric
         unpack8(rd[u], d);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float xh = fmaf(f[e], kr[e], km[e]);
-          const float dz = gn_dz<SILU>(d[e], fmaf(xh, ga[e], be[e]));
-          r[e] = fmaf(dz, k1[e], -fmaf(xh, k3[e], k2[e]));
+          const float dz = gn_dz<SILU>(d[e], fmaf(f[e], kz1[e], kz0[e]));
+          r[e] = fmaf(dz, kz1[e], -fmaf(f[e], k4[e], k5[e]));
         }
         if (a0p) {
           float a[8];
@@ -415,19 +417,19 @@ static int gn_check(const void* x0, int c0, long long ld0, const void* x1, int c
   return DDPM_OK;
 }
 
-// chunks of pixels per sample: ~`waves` waves of CTAs over the chip, at least `min_iters` loop trips per thread
+// Pixel chunks per sample.  CTAs are kept SMALL (min_iters loop trips per thread) so that the grid is many waves
+// deep (<= kMaxCtas): with a handful of large CTAs per SM the last, partially filled wave cost up to 30 % of the
+// kernel (1216 CTAs over 888 resident slots = 1.37 waves).  `waves` is unused now and kept for call-site clarity.
+constexpr long long kMaxCtas = 148LL * 64;
 static void gn_geometry(int C, int hw, int n, int waves, int min_iters, int* V, int* threads, int* pix_per_block,
                         int* chunks) {
+  (void)waves;
   *V = C / 8;
   int ppb = kGnThreads / *V;
   if (ppb < 1) ppb = 1;
   *threads = *V * ppb;
-  long long want = (static_cast<long long>(waves) * kNumSMs * 2 + n - 1) / n;   // ~2 resident CTAs per SM
-  if (want < 1) want = 1;
-  long long ppblk = (hw + want - 1) / want;
-  const long long min_ppblk = static_cast<long long>(ppb) * min_iters;
-  if (ppblk < min_ppblk) ppblk = min_ppblk;
-  ppblk = (ppblk + ppb - 1) / ppb * ppb;
+  long long ppblk = static_cast<long long>(ppb) * min_iters;
+  while (static_cast<long long>(n) * ((hw + ppblk - 1) / ppblk) > kMaxCtas) ppblk += static_cast<long long>(ppb) * min_iters;
   if (ppblk > hw) ppblk = hw;
   *pix_per_block = static_cast<int>(ppblk);
   *chunks = static_cast<int>((hw + ppblk - 1) / ppblk);

@@ -14,10 +14,6 @@ namespace ddpm {
 
 constexpr int kScThreads = 256;
 
-struct __align__(8) bf16x4 {
-  __nv_bfloat162 v[2];
-};
-
 // out[n,h,w,co] = bias[co] + sum_{k<CIN, tap} x[n,k,h+dh,w+dw] * w[co*s_co + tap'*s_tap + k*s_ci]
 // warp = one pixel per iteration, lane = 4 output channels (chunk blockIdx.y of 128 channels)
 template <int CIN>
@@ -68,10 +64,7 @@ conv3_to_c_kernel(const float* __restrict__ x, const float* __restrict__ w, long
       for (int k = 0; k < CIN; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv[tap][k], wr[tap][k][j], acc[j]);
-    bf16x4 o;
-    o.v[0] = __floats2bfloat162_rn(acc[0], acc[1]);
-    o.v[1] = __floats2bfloat162_rn(acc[2], acc[3]);
-    *reinterpret_cast<bf16x4*>(out + pix * ldo + c0) = o;
+    *reinterpret_cast<bf16x4*>(out + pix * ldo + c0) = pack4(acc);
   }
 }
 
@@ -124,8 +117,7 @@ conv_c_to_3_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const flo
           const int ww = w0 + col - 1;
           if (cact && ww >= 0 && ww < W) {
             const bf16x4 raw = *reinterpret_cast<const bf16x4*>(rowp + static_cast<long long>(ww) * lda);
-            const float2 lo = __bfloat1622float2(raw.v[0]), hi = __bfloat1622float2(raw.v[1]);
-            f[col][0] = lo.x; f[col][1] = lo.y; f[col][2] = hi.x; f[col][3] = hi.y;
+            unpack4(raw, f[col]);
           } else {
             f[col][0] = f[col][1] = f[col][2] = f[col][3] = 0.f;
           }

@@ -421,6 +421,27 @@ class OpProfiler:
             pass
         return 0.0, 0.0
 
+    def _detail(self, name, args):
+        """Optional per-shape key ("conv_gemm|h128 c128->128 k9") when self.by_shape is set."""
+        if not getattr(self, "by_shape", False):
+            return ""
+        try:
+            if name == "conv_gemm":
+                x0, x1, taps, wgt, cout, grid = args[:6]
+                cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+                return f"|{grid[1]}x{grid[2]} c{cin}->{cout} k{len(taps)}"
+            if name == "conv_wgrad":
+                dy, x0, x1, taps, dw, grid = args[:6]
+                cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+                return f"|{grid[1]}x{grid[2]} c{cin}->{dy.shape[-1]} k{len(taps)}"
+            if name in ("gn_bwd", "gn_apply", "gn_stats"):
+                x0, x1 = args[0], args[1]
+                c = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+                return f"|{x0.shape[1]}x{x0.shape[2]} c{c}"
+        except Exception:  # noqa: BLE001
+            pass
+        return ""
+
     def start(self):
         for name in dir(self.b):
             fn = getattr(self.b, name)
@@ -434,7 +455,7 @@ class OpProfiler:
                 out = __fn(*a, **k)
                 e1.record()
                 fl, by = self._algorithmic(__name, a, k, out)
-                self.records.append((__name, e0, e1, fl, by))
+                self.records.append((__name + self._detail(__name, a), e0, e1, fl, by))
                 return out
 
             setattr(self.b, name, wrapped)

@@ -290,17 +290,27 @@ def test_lora_forward_backward_and_merge_vs_oracle(dev):
     og = dict(om.named_parameters())
     tot = sum(p.grad.norm() ** 2 for p in om.parameters() if p.grad is not None) ** 0.5
     num = den = 0.0
+    per_tensor = {}
     for n, p in m.named_parameters():
         if not p.requires_grad:
             assert p.grad is None
             continue
         g = og[n].grad
-        num += (p.grad.cpu() - g).norm().item() ** 2
+        e = (p.grad.cpu() - g).norm().item()
+        num += e ** 2
         den += g.norm().item() ** 2
-        # q/k adapters of the 4-token attentions have near-zero gradients: per-tensor check is loose, the
-        # whole-LoRA-gradient check below carries the 2e-2 north_star tolerance
-        assert ((p.grad.cpu() - g).norm() / (g.norm() + 5e-2 * tot)).item() < 0.15, n
-    assert (num / den) ** 0.5 < 2e-2
+        per_tensor[n] = (e / tot.item(), e / max(g.norm().item(), 1e-30),
+                         F.cosine_similarity(p.grad.cpu().reshape(1, -1), g.reshape(1, -1)).item())
+    worst = sorted(per_tensor.items(), key=lambda kv: -kv[1][0])[:6]
+    print("worst LoRA tensors (err/total, err/own, cos):", worst)
+    # the 2e-2 north_star bound is on the LoRA gradient as a whole; per tensor, the error must stay below 2 % of the
+    # whole-gradient norm (4-token attentions have tiny, cancellation-dominated dq/dk that bf16 cannot resolve
+    # relative to their own norm) and tensors carrying real signal must point the same way as the oracle's
+    assert (num / den) ** 0.5 < 2e-2, worst
+    for n, (e_tot, e_own, cos) in per_tensor.items():
+        assert e_tot < 2e-2, (n, e_tot, e_own, cos)
+        if og[n].grad.norm() > 0.05 * tot:
+            assert cos > 0.995 and e_own < 0.1, (n, e_tot, e_own, cos)
     assert len(lora_state_dict(m)) == 48
     merge_adapter(m)
     oracle.merge_adapter(om)
