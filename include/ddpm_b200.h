@@ -127,7 +127,12 @@ int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* x1, int c1,
 int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                   int groups, const float* stats, float eps, const float* gamma, const float* beta, int silu,
                   void* y, long long ldy, void* stream);
-/* GroupNorm(+SiLU) backward.  ws: fp32 workspace of n*(c0+c1)*2 + n*groups*2 floats.
+/* Fused GroupNorm forward: stats (as ddpm_gn_stats) AND y = act(GroupNorm(x)) in one persistent, cooperatively
+ * launched kernel whose second phase re-reads x from L2.  ws: n ints (team barrier counters). */
+int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
+                int groups, float eps, const float* gamma, const float* beta, int silu, float* stats, void* y,
+                long long ldy, int* ws, void* stream);
+/* GroupNorm(+SiLU) backward.  ws: workspace of n*(c0+c1)*2 floats followed by n ints (team barrier counters).
  *   dgamma/dbeta are accumulated (+=) when non-NULL.  dx = GN'(dy) + add0 + add1, written split over dx0|dx1. */
 int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                 int groups, const float* stats, float eps, const float* gamma, const float* beta, int silu,

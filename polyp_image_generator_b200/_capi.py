@@ -68,6 +68,7 @@ SIGNATURES = {
     "ddpm_conv3_wgrad": [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _ll, _i, _vp, _i, _i, _i, _vp],
     "ddpm_gn_stats": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _vp],
     "ddpm_gn_apply": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp],
+    "ddpm_gn_fwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp],
     "ddpm_gn_bwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp, _ll, _vp, _ll,
                     _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp],
     "ddpm_attn_fwd": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],

@@ -2,11 +2,15 @@
 // Replaces at::native::group_norm + a separate silu kernel per site (71 sites per UNet forward), and folds
 // torch.cat([h, skip], 1) into the load path: the input may be split over two tensors along channels.
 //
-// All kernels are HBM-bound streamers.  Thread mapping (all four kernels): a CTA owns a chunk of pixels of ONE
-// sample; thread (v, pl) owns the 8-channel vector v (one 16-byte access) and walks pixels pl, pl+ppb, ... of the
-// chunk.  Per-channel parameters (gamma, beta, mean, rstd, group coefficients) therefore live in registers for the
-// whole loop, the inner loop is 16-byte loads -> 8 FMAs (+ SiLU) -> 16-byte store with kUnroll pixels in flight,
-// and all index arithmetic is 32-bit.  Cross-CTA combines use fp32 atomics on tiny [N][groups] / [N][C] buffers.
+// Thread mapping (all kernels): a CTA owns a slice of pixels of ONE sample; thread (v, pl) owns the 8-channel vector
+// v (one 128-bit access) and walks pixels pl, pl+ppb, ... of the slice, so per-channel coefficients live in
+// registers for the whole loop.
+//
+// ncu (profiles/r1_groupnorm.md) showed these streamers are NOT bandwidth-bound but issue-bound: at bf16 the SiLU
+// derivative costs ~26 instructions and 4 MUFU ops per element against 6-10 bytes of traffic.  Hence
+//   * all arithmetic is packed fp32x2 (FFMA2/FADD2/FMUL2 on sm_100a: two lanes per issue slot),
+//   * sigmoid(z) = 0.5 + 0.5*tanh(z/2): ONE MUFU op (tanh.approx.f32) instead of ex2 + rcp,
+//   * the two-phase ops run as "team" kernels (below) whose second phase re-reads from L2 instead of HBM.
 #include "common.cuh"
 
 #include "../../include/ddpm_b200.h"
@@ -24,6 +28,15 @@ struct GnSrc {
   int c0, c1;
 };
 
+struct GnDst {
+  __nv_bfloat16* d0;
+  __nv_bfloat16* d1;
+  long long ld0, ld1;
+  const __nv_bfloat16* add0;
+  const __nv_bfloat16* add1;
+  long long lda0, lda1;
+};
+
 // pointer to this thread's 8-channel vector at pixel 0 of sample n, and its pixel stride (elements)
 __device__ __forceinline__ const __nv_bfloat16* gn_base(const GnSrc& s, int n, int hw, int c, long long* ld) {
   if (c < s.c0) {
@@ -34,18 +47,108 @@ __device__ __forceinline__ const __nv_bfloat16* gn_base(const GnSrc& s, int n, i
   return s.x1 + static_cast<long long>(n) * hw * s.ld1 + (c - s.c0);
 }
 
-__device__ __forceinline__ void gn_mean_rstd(const float* stats, int n, int g, int groups, float inv_m, float eps,
-                                             float* mean, float* rstd) {
-  const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<long long>(n) * groups + g) * 2);
+__device__ __forceinline__ void gn_mean_rstd_of(float2 st, float inv_m, float eps, float* mean, float* rstd) {
   const float mu = st.x * inv_m;
   const float var = fmaxf(st.y * inv_m - mu * mu, 0.f);
   *mean = mu;
   *rstd = rsqrtf(var + eps);
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// ---- packed fp32x2 helpers --------------------------------------------------------------------------------------
+struct f2x4 {
+  float2 p[4];   // 8 channels as 4 pairs
+};
+__device__ __forceinline__ f2x4 unpack8p(const bf16x8& r) {
+  f2x4 o;
+  o.p[0] = make_float2(bf16lo_f(r.x), bf16hi_f(r.x));
+  o.p[1] = make_float2(bf16lo_f(r.y), bf16hi_f(r.y));
+  o.p[2] = make_float2(bf16lo_f(r.z), bf16hi_f(r.z));
+  o.p[3] = make_float2(bf16lo_f(r.w), bf16hi_f(r.w));
+  return o;
+}
+__device__ __forceinline__ bf16x8 pack8p(const f2x4& v) {
+  return make_uint4(pack2_bf16_(v.p[0].x, v.p[0].y), pack2_bf16_(v.p[1].x, v.p[1].y),
+                    pack2_bf16_(v.p[2].x, v.p[2].y), pack2_bf16_(v.p[3].x, v.p[3].y));
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid of a pair: 0.5 + 0.5 * tanh(z / 2)
+__device__ __forceinline__ float2 sigmoid2(float2 z) {
+  const float2 h = __fmul2_rn(z, make_float2(0.5f, 0.5f));
+  const float2 t = make_float2(tanh_approx(h.x), tanh_approx(h.y));
+  return __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+}
+template <bool SILU>
+__device__ __forceinline__ float2 act2(float2 z) {
+  if (!SILU) return z;
+  return __fmul2_rn(z, sigmoid2(z));
+}
+// dz = dy * act'(z);  silu'(z) = s * (1 + z * (1 - s))
+template <bool SILU>
+__device__ __forceinline__ float2 dz2(float2 dy, float2 z) {
+  if (!SILU) return dy;
+  const float2 s = sigmoid2(z);
+  const float2 om = __ffma2_rn(s, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+  const float2 u = __ffma2_rn(z, om, make_float2(1.f, 1.f));
+  return __fmul2_rn(__fmul2_rn(dy, s), u);
+}
 
-// ---- statistics ------------------------------------------------------------------------------------
+// ---- statistics (standalone) ----------------------------------------------------------------------------------
+// accumulate (sum, sumsq) of this thread's 8 channels over pixels p_first, p_first + ppb, ... < p_end
+__device__ __forceinline__ void gn_accumulate_moments(const __nv_bfloat16* xp, long long ld, int p_first, int p_end,
+                                                      int ppb, f2x4* sum, f2x4* sq) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sum->p[j] = sq->p[j] = make_float2(0.f, 0.f);
+  int p = p_first;
+  for (; p + (kUnroll - 1) * ppb < p_end; p += kUnroll * ppb) {
+    bf16x8 raw[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) raw[u] = *reinterpret_cast<const bf16x8*>(xp + (p + u * ppb) * ld);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const f2x4 f = unpack8p(raw[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sum->p[j] = __fadd2_rn(sum->p[j], f.p[j]);
+        sq->p[j] = __ffma2_rn(f.p[j], f.p[j], sq->p[j]);
+      }
+    }
+  }
+  for (; p < p_end; p += ppb) {
+    const f2x4 f = unpack8p(*reinterpret_cast<const bf16x8*>(xp + p * ld));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sum->p[j] = __fadd2_rn(sum->p[j], f.p[j]);
+      sq->p[j] = __ffma2_rn(f.p[j], f.p[j], sq->p[j]);
+    }
+  }
+}
+
+// fold this thread's 8 channel moments into the per-group shared accumulators sm[g*2 + {0,1}]
+__device__ __forceinline__ void gn_fold_groups(const f2x4& sum, const f2x4& sq, int c, int cpg, float* sm) {
+  const float s8[8] = {sum.p[0].x, sum.p[0].y, sum.p[1].x, sum.p[1].y, sum.p[2].x, sum.p[2].y, sum.p[3].x, sum.p[3].y};
+  const float q8[8] = {sq.p[0].x, sq.p[0].y, sq.p[1].x, sq.p[1].y, sq.p[2].x, sq.p[2].y, sq.p[3].x, sq.p[3].y};
+  int g_prev = c / cpg;
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int g = (c + e) / cpg;
+    if (g != g_prev) {
+      atomicAdd(&sm[g_prev * 2], a);
+      atomicAdd(&sm[g_prev * 2 + 1], b);
+      a = b = 0.f;
+      g_prev = g;
+    }
+    a += s8[e];
+    b += q8[e];
+  }
+  atomicAdd(&sm[g_prev * 2], a);
+  atomicAdd(&sm[g_prev * 2 + 1], b);
+}
+
 // grid (chunks, N); block = V * ppb threads (V = C/8 vectors per pixel, ppb pixels in flight)
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(GnSrc s, int hw, int cpg, int groups, float* __restrict__ stats, int pix_per_block, int V) {
@@ -58,58 +161,64 @@ gn_stats_kernel(GnSrc s, int hw, int cpg, int groups, float* __restrict__ stats,
   const int p_end = min(hw, p_begin + pix_per_block);
   long long ld;
   const __nv_bfloat16* xp = gn_base(s, n, hw, v * 8, &ld);
-  float sum[8], sq[8];
+  f2x4 sum, sq;
+  gn_accumulate_moments(xp, ld, p_begin + pl, p_end, ppb, &sum, &sq);
+  gn_fold_groups(sum, sq, v * 8, cpg, sm);
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+    atomicAdd(&stats[static_cast<long long>(n) * groups * 2 + i], sm[i]);
+}
+
+// ---- forward apply (standalone) ---------------------------------------------------------------------------------
+// y = act(x * ka + kb) with ka = rstd*gamma, kb = beta - mean*rstd*gamma (per channel, in registers)
+__device__ __forceinline__ void gn_apply_coefs(const float* stats_n, int c, int cpg, float inv_m, float eps,
+                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                               bool bypass_l1, f2x4* ka, f2x4* kb) {
+  float a8[8], b8[8];
+  int g_prev = -1;
+  float mean = 0.f, rstd = 0.f;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) sum[e] = sq[e] = 0.f;
-  int p = p_begin + pl;
+  for (int e = 0; e < 8; ++e) {
+    const int g = (c + e) / cpg;
+    if (g != g_prev) {
+      const float2* sp = reinterpret_cast<const float2*>(stats_n + g * 2);
+      gn_mean_rstd_of(bypass_l1 ? __ldcg(sp) : *sp, inv_m, eps, &mean, &rstd);
+      g_prev = g;
+    }
+    a8[e] = rstd * gamma[c + e];
+    b8[e] = beta[c + e] - mean * a8[e];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    ka->p[j] = make_float2(a8[2 * j], a8[2 * j + 1]);
+    kb->p[j] = make_float2(b8[2 * j], b8[2 * j + 1]);
+  }
+}
+
+template <bool SILU>
+__device__ __forceinline__ void gn_apply_stream(const __nv_bfloat16* xp, long long ld, __nv_bfloat16* yp, long long ldy,
+                                                int p_first, int p_end, int ppb, const f2x4& ka, const f2x4& kb) {
+  int p = p_first;
   for (; p + (kUnroll - 1) * ppb < p_end; p += kUnroll * ppb) {
     bf16x8 raw[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) raw[u] = *reinterpret_cast<const bf16x8*>(xp + (p + u * ppb) * ld);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      float f[8];
-      unpack8(raw[u], f);
+      f2x4 f = unpack8p(raw[u]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        sum[e] += f[e];
-        sq[e] = fmaf(f[e], f[e], sq[e]);
-      }
+      for (int j = 0; j < 4; ++j) f.p[j] = act2<SILU>(__ffma2_rn(f.p[j], ka.p[j], kb.p[j]));
+      *reinterpret_cast<bf16x8*>(yp + (p + u * ppb) * ldy) = pack8p(f);
     }
   }
   for (; p < p_end; p += ppb) {
-    float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(xp + p * ld), f);
+    f2x4 f = unpack8p(*reinterpret_cast<const bf16x8*>(xp + p * ld));
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      sum[e] += f[e];
-      sq[e] = fmaf(f[e], f[e], sq[e]);
-    }
+    for (int j = 0; j < 4; ++j) f.p[j] = act2<SILU>(__ffma2_rn(f.p[j], ka.p[j], kb.p[j]));
+    *reinterpret_cast<bf16x8*>(yp + p * ldy) = pack8p(f);
   }
-  // fold the 8 channels into their groups
-  int g_prev = (v * 8) / cpg;
-  float a = 0.f, b = 0.f;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int g = (v * 8 + e) / cpg;
-    if (g != g_prev) {
-      atomicAdd(&sm[g_prev * 2], a);
-      atomicAdd(&sm[g_prev * 2 + 1], b);
-      a = b = 0.f;
-      g_prev = g;
-    }
-    a += sum[e];
-    b += sq[e];
-  }
-  atomicAdd(&sm[g_prev * 2], a);
-  atomicAdd(&sm[g_prev * 2 + 1], b);
-  __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-    atomicAdd(&stats[static_cast<long long>(n) * groups * 2 + i], sm[i]);
 }
 
-// ---- forward apply -----------------------------------------------------------------------------------
-// y = act(x * a + b) with a = rstd*gamma, b = beta - mean*rstd*gamma (per channel, in registers)
 template <bool SILU>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
@@ -124,281 +233,275 @@ gn_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ 
   long long ld;
   const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
   __nv_bfloat16* yp = y + static_cast<long long>(n) * hw * ldy + c;
-  float ka[8], kb[8];
-  {
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int g = (c + e) / cpg;
-      if (g != g_prev) {
-        gn_mean_rstd(stats, n, g, groups, inv_m, eps, &mean, &rstd);
-        g_prev = g;
-      }
-      ka[e] = rstd * gamma[c + e];
-      kb[e] = beta[c + e] - mean * ka[e];
-    }
-  }
-  int p = p_begin + pl;
-  for (; p + (kUnroll - 1) * ppb < p_end; p += kUnroll * ppb) {
-    bf16x8 raw[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) raw[u] = *reinterpret_cast<const bf16x8*>(xp + (p + u * ppb) * ld);
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      float f[8];
-      unpack8(raw[u], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float z = fmaf(f[e], ka[e], kb[e]);
-        f[e] = SILU ? z * fast_sigmoid(z) : z;
-      }
-      *reinterpret_cast<bf16x8*>(yp + (p + u * ppb) * ldy) = pack8(f);
-    }
-  }
-  for (; p < p_end; p += ppb) {
-    float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(xp + p * ld), f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float z = fmaf(f[e], ka[e], kb[e]);
-      f[e] = SILU ? z * fast_sigmoid(z) : z;
-    }
-    *reinterpret_cast<bf16x8*>(yp + p * ldy) = pack8(f);
-  }
+  f2x4 ka, kb;
+  gn_apply_coefs(stats + static_cast<long long>(n) * groups * 2, c, cpg, inv_m, eps, gamma, beta, false, &ka, &kb);
+  gn_apply_stream<SILU>(xp, ld, yp, ldy, p_begin + pl, p_end, ppb, ka, kb);
 }
 
-// dz = dy * act'(z) with z = xhat*gamma + beta
-template <bool SILU>
-__device__ __forceinline__ float gn_dz(float dy, float z) {
-  if (!SILU) return dy;
-  const float sg = fast_sigmoid(z);
-  return dy * sg * fmaf(z, 1.0f - sg, 1.0f);
+// =====================================================================================================
+// Fused two-phase kernels ("teams"): one persistent, cooperatively launched grid.  A team of `team_size` CTAs owns
+// one sample at a time: phase 1 reduces (statistics resp. backward sums) over the team's pixel slices, the team
+// meets at a global-memory barrier, phase 2 re-reads the SAME slices -- now L2 hits, because only
+// teams * sample_bytes (<= the L2 budget) are live between the phases -- and writes the result.  HBM traffic drops
+// from 6 to 4 B/elem (forward) and from 10 to 6 B/elem (backward).  CTAs of different teams share SMs, so one
+// team's barrier wait is covered by another team's streaming.
+// =====================================================================================================
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// ---- backward pass 1: per-(n, c) sums of dz and dz*xhat ---------------------------------------------------
-// grid (chunks, N); dynamic smem: C*2 floats.  The loop accumulates the raw moments S1 = sum dz, S2 = sum dz*x with
-// only the affine z = x*kz1 + kz0 in registers; sum dz*xhat = rstd*S2 - mean*rstd*S1 is formed once at the end.
-template <bool SILU>
-__global__ void __launch_bounds__(kGnThreads, 3)
-gn_bwd_reduce_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
-                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                     const __nv_bfloat16* __restrict__ dy, long long lddy, float* __restrict__ sums /*[N][C][2]*/,
-                     int pix_per_block, int V) {
-  extern __shared__ float smc[];
-  const int C = V * 8;
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) smc[i] = 0.f;
+// all threads of the CTA call this; `counter` is zero-initialised per (launch, sample)
+__device__ __forceinline__ void gn_team_barrier(int* counter, int expected) {
+  __threadfence();
   __syncthreads();
-  const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
-  const int n = blockIdx.y;
-  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
-  const int c = v * 8;
-  const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(hw, p_begin + pix_per_block);
-  long long ld;
-  const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
-  const __nv_bfloat16* dp = dy + static_cast<long long>(n) * hw * lddy + c;
-  float kz1[8], kz0[8], A[8], B[8];   // z = x*kz1 + kz0
-  {
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int g = (c + e) / cpg;
-      if (g != g_prev) {
-        gn_mean_rstd(stats, n, g, groups, inv_m, eps, &mean, &rstd);
-        g_prev = g;
-      }
-      const float ga = gamma[c + e];
-      kz1[e] = rstd * ga;
-      kz0[e] = fmaf(-mean * rstd, ga, beta[c + e]);
-      A[e] = B[e] = 0.f;
-    }
-  }
-  int p = p_begin + pl;
-  for (; p + (kUnroll - 1) * ppb < p_end; p += kUnroll * ppb) {
-    bf16x8 rx[kUnroll], rd[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      rx[u] = *reinterpret_cast<const bf16x8*>(xp + (p + u * ppb) * ld);
-      rd[u] = *reinterpret_cast<const bf16x8*>(dp + (p + u * ppb) * lddy);
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      float f[8], d[8];
-      unpack8(rx[u], f);
-      unpack8(rd[u], d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float dz = gn_dz<SILU>(d[e], fmaf(f[e], kz1[e], kz0[e]));
-        A[e] += dz;
-        B[e] = fmaf(dz, f[e], B[e]);
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1);
+    unsigned spins = 0;
+    while (ld_acquire_gpu(counter) < expected) {
+      __nanosleep(40);
+      if (++spins > (1u << 26)) {
+        printf("ddpm_b200: GroupNorm team barrier timed out (block %d)\n", blockIdx.x);
+        __trap();
       }
     }
-  }
-  for (; p < p_end; p += ppb) {
-    float f[8], d[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(xp + p * ld), f);
-    unpack8(*reinterpret_cast<const bf16x8*>(dp + p * lddy), d);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float dz = gn_dz<SILU>(d[e], fmaf(f[e], kz1[e], kz0[e]));
-      A[e] += dz;
-      B[e] = fmaf(dz, f[e], B[e]);
-    }
-  }
-  {
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int g = (c + e) / cpg;
-      if (g != g_prev) {
-        gn_mean_rstd(stats, n, g, groups, inv_m, eps, &mean, &rstd);
-        g_prev = g;
-      }
-      atomicAdd(&smc[(c + e) * 2], A[e]);
-      atomicAdd(&smc[(c + e) * 2 + 1], rstd * (B[e] - mean * A[e]));
-    }
+    __threadfence();
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
-    atomicAdd(&sums[static_cast<long long>(n) * C * 2 + i], smc[i]);
 }
 
-// ---- backward finalize: group coefficients + dgamma/dbeta ------------------------------------------------
-// blocks [0, N): coef[n][g] = (sum_c gamma*A, sum_c gamma*B);  blocks [N, N + ceil(C/256)): dgamma/dbeta
-__global__ void __launch_bounds__(kGnThreads)
-gn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma, int N, int C, int cpg,
-                       int groups, float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  if (static_cast<int>(blockIdx.x) < N) {
-    const int n = blockIdx.x;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-      float s1 = 0.f, s2 = 0.f;
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        const float2 ab = *reinterpret_cast<const float2*>(sums + (static_cast<long long>(n) * C + c) * 2);
-        s1 += gamma[c] * ab.x;
-        s2 += gamma[c] * ab.y;
-      }
-      coef[(static_cast<long long>(n) * groups + g) * 2] = s1;
-      coef[(static_cast<long long>(n) * groups + g) * 2 + 1] = s2;
-    }
-  } else {
-    const int c = (blockIdx.x - N) * blockDim.x + threadIdx.x;
-    if (c < C && (dgamma || dbeta)) {
-      float a = 0.f, b = 0.f;
-      for (int n = 0; n < N; ++n) {
-        const float2 ab = *reinterpret_cast<const float2*>(sums + (static_cast<long long>(n) * C + c) * 2);
-        a += ab.x;
-        b += ab.y;
-      }
-      if (dbeta) dbeta[c] += a;
-      if (dgamma) dgamma[c] += b;
-    }
-  }
-}
-
-// ---- backward pass 2: dx = dz*k1 - k2 - xhat*k3 (+ addends), k1 = rstd*gamma, k2 = rstd*s1/m, k3 = rstd*s2/m
-//      (xhat = x*rstd - mean*rstd is folded into the coefficients so only four 8-vectors stay in registers)
-struct GnDst {
-  __nv_bfloat16* d0;
-  __nv_bfloat16* d1;
-  long long ld0, ld1;
-  const __nv_bfloat16* add0;
-  const __nv_bfloat16* add1;
-  long long lda0, lda1;
+struct GnTeam {
+  int N, hw, cpg, groups, V, team_size, pix_per_cta;
+  float eps;
 };
 
-// dx = dz*k1 - x*k4 - k5 with z = x*kz1 + kz0, k1 = rstd*gamma, k4 = rstd^2*s2/m, k5 = rstd*s1/m - mean*rstd^2*s2/m
+// ---- forward: statistics + normalise/affine/SiLU --------------------------------------------------------------
 template <bool SILU>
-__global__ void __launch_bounds__(kGnThreads, 3)
-gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
-                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const __nv_bfloat16* __restrict__ dy, long long lddy, const float* __restrict__ coef, GnDst o,
-                    int pix_per_block, int V) {
-  const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
-  const int n = blockIdx.y;
+__global__ void __launch_bounds__(kGnThreads, 4)
+gn_fwd_fused_kernel(GnSrc s, GnTeam t, float* __restrict__ stats /*[N][groups][2], zeroed*/,
+                    int* __restrict__ counters /*[N], zeroed*/, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long ldy) {
+  __shared__ float sm[64 * 2];
+  const int team = blockIdx.x / t.team_size, rank = blockIdx.x - team * t.team_size;
+  const int nteams = gridDim.x / t.team_size;
+  const int V = t.V, hw = t.hw, cpg = t.cpg, groups = t.groups;
   const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int c = v * 8;
-  const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(hw, p_begin + pix_per_block);
-  long long ld;
-  const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
-  const long long pix0 = static_cast<long long>(n) * hw;
-  const __nv_bfloat16* dp = dy + pix0 * lddy + c;
-  const __nv_bfloat16* a0p = o.add0 ? o.add0 + pix0 * o.lda0 + c : nullptr;
-  const __nv_bfloat16* a1p = o.add1 ? o.add1 + pix0 * o.lda1 + c : nullptr;
-  __nv_bfloat16* op;
-  long long ldo;
-  if (c < s.c0) {
-    op = o.d0 + pix0 * o.ld0 + c;
-    ldo = o.ld0;
-  } else {
-    op = o.d1 ? o.d1 + pix0 * o.ld1 + (c - s.c0) : nullptr;
-    ldo = o.ld1;
-  }
-  if (op == nullptr) return;   // gradient of this source not requested
-  float kz1[8], kz0[8], k4[8], k5[8];
-  {
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int g = (c + e) / cpg;
-      if (g != g_prev) {
-        gn_mean_rstd(stats, n, g, groups, inv_m, eps, &mean, &rstd);
-        const float2 cf = *reinterpret_cast<const float2*>(coef + (static_cast<long long>(n) * groups + g) * 2);
-        s1 = cf.x * inv_m;
-        s2 = cf.y * inv_m;
-        g_prev = g;
-      }
-      const float ga = gamma[c + e];
-      kz1[e] = rstd * ga;                                  // also k1
-      kz0[e] = fmaf(-mean * rstd, ga, beta[c + e]);
-      k4[e] = rstd * rstd * s2;
-      k5[e] = rstd * s1 - mean * k4[e];
+  const int p_begin = rank * t.pix_per_cta;
+  const int p_end = min(hw, p_begin + t.pix_per_cta);
+  const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+  for (int n = team; n < t.N; n += nteams) {
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    long long ld;
+    const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
+    {
+      f2x4 sum, sq;
+      gn_accumulate_moments(xp, ld, p_begin + pl, p_end, ppb, &sum, &sq);
+      gn_fold_groups(sum, sq, c, cpg, sm);
     }
+    __syncthreads();
+    float* st = stats + static_cast<long long>(n) * groups * 2;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&st[i], sm[i]);
+    gn_team_barrier(&counters[n], t.team_size);
+    f2x4 ka, kb;
+    gn_apply_coefs(st, c, cpg, inv_m, t.eps, gamma, beta, true, &ka, &kb);
+    __nv_bfloat16* yp = y + static_cast<long long>(n) * hw * ldy + c;
+    gn_apply_stream<SILU>(xp, ld, yp, ldy, p_begin + pl, p_end, ppb, ka, kb);
+    __syncthreads();   // sm is reused by the next sample
   }
-  for (int p = p_begin + pl; p < p_end; p += 2 * ppb) {
-    const bool two = p + ppb < p_end;
-    bf16x8 rx[2], rd[2], ra0[2], ra1[2];
+}
+
+// ---- backward: per-channel sums -> group coefficients -> dx -------------------------------------------------------
+// dynamic smem: C*2 floats (per-channel sums of this CTA) + groups*2 floats (group coefficients)
+// z = x*kz1 + kz0;  dx = dz*kz1 + x*nk4 + nk5 (+ addends) with nk4 = -rstd^2*s2/m, nk5 = mean*rstd^2*s2/m - rstd*s1/m
+template <bool SILU>
+__global__ void __launch_bounds__(kGnThreads, 2)
+gn_bwd_fused_kernel(GnSrc s, GnTeam t, const float* __restrict__ stats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const __nv_bfloat16* __restrict__ dy, long long lddy,
+                    float* __restrict__ sums /*[N][C][2], zeroed*/, int* __restrict__ counters /*[N], zeroed*/,
+                    GnDst o) {
+  extern __shared__ float smc[];
+  const int team = blockIdx.x / t.team_size, rank = blockIdx.x - team * t.team_size;
+  const int nteams = gridDim.x / t.team_size;
+  const int V = t.V, hw = t.hw, cpg = t.cpg, groups = t.groups;
+  const int C = V * 8;
+  float* scoef = smc + C * 2;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = v * 8;
+  const int p_begin = rank * t.pix_per_cta;
+  const int p_end = min(hw, p_begin + t.pix_per_cta);
+  const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+  const bool writes = (c < s.c0) || (o.d1 != nullptr);
+  for (int n = team; n < t.N; n += nteams) {
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) smc[i] = 0.f;
+    __syncthreads();
+    long long ld;
+    const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
+    const long long pix0 = static_cast<long long>(n) * hw;
+    const __nv_bfloat16* dp = dy + pix0 * lddy + c;
+    const float* stats_n = stats + static_cast<long long>(n) * groups * 2;
+    f2x4 kz1, kz0;
+    gn_apply_coefs(stats_n, c, cpg, inv_m, t.eps, gamma, beta, false, &kz1, &kz0);
+    // ---- phase 1: S1 = sum dz, S2 = sum dz*x ----
+    {
+      f2x4 A, B;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 0 || two) {
-        const int q = p + u * ppb;
-        rx[u] = *reinterpret_cast<const bf16x8*>(xp + q * ld);
-        rd[u] = *reinterpret_cast<const bf16x8*>(dp + q * lddy);
-        if (a0p) ra0[u] = *reinterpret_cast<const bf16x8*>(a0p + q * o.lda0);
-        if (a1p) ra1[u] = *reinterpret_cast<const bf16x8*>(a1p + q * o.lda1);
+      for (int j = 0; j < 4; ++j) A.p[j] = B.p[j] = make_float2(0.f, 0.f);
+      int p = p_begin + pl;
+      for (; p + ppb < p_end; p += 2 * ppb) {
+        bf16x8 rx[2], rd[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          rx[u] = *reinterpret_cast<const bf16x8*>(xp + (p + u * ppb) * ld);
+          rd[u] = *reinterpret_cast<const bf16x8*>(dp + (p + u * ppb) * lddy);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const f2x4 f = unpack8p(rx[u]), d = unpack8p(rd[u]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 dz = dz2<SILU>(d.p[j], __ffma2_rn(f.p[j], kz1.p[j], kz0.p[j]));
+            A.p[j] = __fadd2_rn(A.p[j], dz);
+            B.p[j] = __ffma2_rn(dz, f.p[j], B.p[j]);
+          }
+        }
+      }
+      for (; p < p_end; p += ppb) {
+        const f2x4 f = unpack8p(*reinterpret_cast<const bf16x8*>(xp + p * ld));
+        const f2x4 d = unpack8p(*reinterpret_cast<const bf16x8*>(dp + p * lddy));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 dz = dz2<SILU>(d.p[j], __ffma2_rn(f.p[j], kz1.p[j], kz0.p[j]));
+          A.p[j] = __fadd2_rn(A.p[j], dz);
+          B.p[j] = __ffma2_rn(dz, f.p[j], B.p[j]);
+        }
+      }
+      const float a8[8] = {A.p[0].x, A.p[0].y, A.p[1].x, A.p[1].y, A.p[2].x, A.p[2].y, A.p[3].x, A.p[3].y};
+      const float b8[8] = {B.p[0].x, B.p[0].y, B.p[1].x, B.p[1].y, B.p[2].x, B.p[2].y, B.p[3].x, B.p[3].y};
+      int g_prev = -1;
+      float mean = 0.f, rstd = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int g = (c + e) / cpg;
+        if (g != g_prev) {
+          gn_mean_rstd_of(*reinterpret_cast<const float2*>(stats_n + g * 2), inv_m, t.eps, &mean, &rstd);
+          g_prev = g;
+        }
+        atomicAdd(&smc[(c + e) * 2], a8[e]);
+        atomicAdd(&smc[(c + e) * 2 + 1], rstd * (b8[e] - mean * a8[e]));   // sum dz*xhat
       }
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 0 || two) {
-        float f[8], d[8], r[8];
-        unpack8(rx[u], f);
-        unpack8(rd[u], d);
+    __syncthreads();
+    float* sn = sums + static_cast<long long>(n) * C * 2;
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(&sn[i], smc[i]);
+    gn_team_barrier(&counters[n], t.team_size);
+    // ---- group coefficients: (sum_c gamma*A, sum_c gamma*B) / m ----
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+        const float2 ab = __ldcg(reinterpret_cast<const float2*>(sn + cc * 2));
+        const float ga = gamma[cc];
+        s1 = fmaf(ga, ab.x, s1);
+        s2 = fmaf(ga, ab.y, s2);
+      }
+      scoef[g * 2] = s1 * inv_m;
+      scoef[g * 2 + 1] = s2 * inv_m;
+    }
+    __syncthreads();
+    // ---- phase 2 ----
+    if (writes) {
+      f2x4 nk4, nk5;
+      {
+        float k4[8], k5[8];
+        int g_prev = -1;
+        float mean = 0.f, rstd = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float dz = gn_dz<SILU>(d[e], fmaf(f[e], kz1[e], kz0[e]));
-          r[e] = fmaf(dz, kz1[e], -fmaf(f[e], k4[e], k5[e]));
+          const int g = (c + e) / cpg;
+          if (g != g_prev) {
+            gn_mean_rstd_of(*reinterpret_cast<const float2*>(stats_n + g * 2), inv_m, t.eps, &mean, &rstd);
+            s1 = scoef[g * 2];
+            s2 = scoef[g * 2 + 1];
+            g_prev = g;
+          }
+          k4[e] = -rstd * rstd * s2;
+          k5[e] = -rstd * s1 - mean * k4[e];
         }
-        if (a0p) {
-          float a[8];
-          unpack8(ra0[u], a);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] += a[e];
+        for (int j = 0; j < 4; ++j) {
+          nk4.p[j] = make_float2(k4[2 * j], k4[2 * j + 1]);
+          nk5.p[j] = make_float2(k5[2 * j], k5[2 * j + 1]);
         }
-        if (a1p) {
-          float a[8];
-          unpack8(ra1[u], a);
+      }
+      const __nv_bfloat16* a0p = o.add0 ? o.add0 + pix0 * o.lda0 + c : nullptr;
+      const __nv_bfloat16* a1p = o.add1 ? o.add1 + pix0 * o.lda1 + c : nullptr;
+      __nv_bfloat16* op;
+      long long ldo;
+      if (c < s.c0) {
+        op = o.d0 + pix0 * o.ld0 + c;
+        ldo = o.ld0;
+      } else {
+        op = o.d1 + pix0 * o.ld1 + (c - s.c0);
+        ldo = o.ld1;
+      }
+      for (int p = p_begin + pl; p < p_end; p += 2 * ppb) {
+        const bool two = p + ppb < p_end;
+        bf16x8 rx[2], rd[2], ra0[2], ra1[2];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] += a[e];
+        for (int u = 0; u < 2; ++u) {
+          if (u == 0 || two) {
+            const int q = p + u * ppb;
+            rx[u] = *reinterpret_cast<const bf16x8*>(xp + q * ld);
+            rd[u] = *reinterpret_cast<const bf16x8*>(dp + q * lddy);
+            if (a0p) ra0[u] = *reinterpret_cast<const bf16x8*>(a0p + q * o.lda0);
+            if (a1p) ra1[u] = *reinterpret_cast<const bf16x8*>(a1p + q * o.lda1);
+          }
         }
-        *reinterpret_cast<bf16x8*>(op + (p + u * ppb) * ldo) = pack8(r);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u == 0 || two) {
+            const f2x4 f = unpack8p(rx[u]), d = unpack8p(rd[u]);
+            f2x4 r;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 dz = dz2<SILU>(d.p[j], __ffma2_rn(f.p[j], kz1.p[j], kz0.p[j]));
+              r.p[j] = __ffma2_rn(dz, kz1.p[j], __ffma2_rn(f.p[j], nk4.p[j], nk5.p[j]));
+            }
+            if (a0p) {
+              const f2x4 a = unpack8p(ra0[u]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) r.p[j] = __fadd2_rn(r.p[j], a.p[j]);
+            }
+            if (a1p) {
+              const f2x4 a = unpack8p(ra1[u]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) r.p[j] = __fadd2_rn(r.p[j], a.p[j]);
+            }
+            *reinterpret_cast<bf16x8*>(op + (p + u * ppb) * ldo) = pack8p(r);
+          }
+        }
       }
     }
+    __syncthreads();   // smc / scoef are reused by the next sample
   }
+}
+
+// dgamma[c] += sum_n sums[n][c][1], dbeta[c] += sum_n sums[n][c][0]
+__global__ void __launch_bounds__(kGnThreads)
+gn_bwd_dparam_kernel(const float* __restrict__ sums, int N, int C, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float2 ab = *reinterpret_cast<const float2*>(sums + (static_cast<long long>(n) * C + c) * 2);
+    a += ab.x;
+    b += ab.y;
+  }
+  if (dbeta) dbeta[c] += a;
+  if (dgamma) dgamma[c] += b;
 }
 
 static int gn_check(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
@@ -417,13 +520,11 @@ static int gn_check(const void* x0, int c0, long long ld0, const void* x1, int c
   return DDPM_OK;
 }
 
-// Pixel chunks per sample.  CTAs are kept SMALL (min_iters loop trips per thread) so that the grid is many waves
-// deep (<= kMaxCtas): with a handful of large CTAs per SM the last, partially filled wave cost up to 30 % of the
-// kernel (1216 CTAs over 888 resident slots = 1.37 waves).  `waves` is unused now and kept for call-site clarity.
+// Pixel chunks per sample for the standalone kernels.  CTAs are kept SMALL (min_iters loop trips per thread) so the
+// grid is many waves deep (<= kMaxCtas): with a handful of large CTAs per SM the last, partially filled wave cost
+// up to 30 % of the kernel (1216 CTAs over 888 resident slots = 1.37 waves).
 constexpr long long kMaxCtas = 148LL * 64;
-static void gn_geometry(int C, int hw, int n, int waves, int min_iters, int* V, int* threads, int* pix_per_block,
-                        int* chunks) {
-  (void)waves;
+static void gn_geometry(int C, int hw, int n, int min_iters, int* V, int* threads, int* pix_per_block, int* chunks) {
   *V = C / 8;
   int ppb = kGnThreads / *V;
   if (ppb < 1) ppb = 1;
@@ -433,6 +534,43 @@ static void gn_geometry(int C, int hw, int n, int waves, int min_iters, int* V, 
   if (ppblk > hw) ppblk = hw;
   *pix_per_block = static_cast<int>(ppblk);
   *chunks = static_cast<int>((hw + ppblk - 1) / ppblk);
+}
+
+// Team geometry for the fused kernels.  `resident` = co-resident CTAs of the kernel (occupancy * SMs);
+// `sample_bytes` = bytes of one sample that phase 2 re-reads.  Teams are sized so that teams * sample_bytes stays
+// within the L2 budget and every CTA still has >= 2 loop trips.
+static void gn_team_geometry(int C, int hw, int n, int resident, double sample_bytes, GnTeam* t, int* threads,
+                             int* grid) {
+  const int V = C / 8;
+  int ppb = kGnThreads / V;
+  if (ppb < 1) ppb = 1;
+  *threads = V * ppb;
+  const double budget = static_cast<double>(env_int("DDPM_GN_L2_MB", 40)) * 1048576.0;
+  int max_teams = static_cast<int>(budget / sample_bytes);
+  if (max_teams < 1) max_teams = 1;
+  int teams = n < max_teams ? n : max_teams;
+  if (teams > resident) teams = resident;
+  int team_size = resident / teams;
+  const int max_ts = (hw + 2 * ppb - 1) / (2 * ppb);   // >= 2 pixels per thread row
+  if (team_size > max_ts) team_size = max_ts;
+  if (team_size < 1) team_size = 1;
+  teams = resident / team_size;
+  if (teams > n) teams = n;
+  int ppc = (hw + team_size - 1) / team_size;
+  ppc = (ppc + ppb - 1) / ppb * ppb;
+  t->V = V;
+  t->team_size = team_size;
+  t->pix_per_cta = ppc;
+  *grid = teams * team_size;
+}
+
+template <typename K>
+static int gn_resident_ctas(K kern, int threads, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  int dev = 0, sms = kNumSMs;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return occ * sms;
 }
 
 }  // namespace ddpm
@@ -447,7 +585,7 @@ extern "C" int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* 
   const int C = c0 + c1;
   GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
   int V, threads, ppblk, chunks;
-  gn_geometry(C, hw, n, 4, 4 * kUnroll, &V, &threads, &ppblk, &chunks);
+  gn_geometry(C, hw, n, 4 * kUnroll, &V, &threads, &ppblk, &chunks);
   DDPM_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
   gn_stats_kernel<<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, ppblk, V);
   return check_launch("gn_stats_kernel");
@@ -462,7 +600,7 @@ extern "C" int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* 
   const int C = c0 + c1;
   GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
   int V, threads, ppblk, chunks;
-  gn_geometry(C, hw, n, 4, 2 * kUnroll, &V, &threads, &ppblk, &chunks);
+  gn_geometry(C, hw, n, 2 * kUnroll, &V, &threads, &ppblk, &chunks);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   if (silu)
     gn_apply_kernel<true><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma, beta,
@@ -471,6 +609,33 @@ extern "C" int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* 
     gn_apply_kernel<false><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma, beta,
                                                                     yp, ldy, ppblk, V);
   return check_launch("gn_apply_kernel");
+}
+
+extern "C" int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,
+                           int hw, int groups, float eps, const float* gamma, const float* beta, int silu,
+                           float* stats, void* y, long long ldy, int* ws, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = gn_check(x0, c0, ld0, x1, c1, ld1, n, hw, groups, "ddpm_gn_fwd")) return e;
+  DDPM_REQUIRE(stats && gamma && beta && y && ws && ldy % 8 == 0, "ddpm_gn_fwd: bad argument");
+  const int C = c0 + c1;
+  GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
+  GnTeam t;
+  t.N = n; t.hw = hw; t.cpg = C / groups; t.groups = groups; t.eps = eps;
+  static int resident[2] = {0, 0};
+  const int ki = silu ? 1 : 0;
+  if (!resident[ki])
+    resident[ki] = silu ? gn_resident_ctas(gn_fwd_fused_kernel<true>, kGnThreads, 0)
+                        : gn_resident_ctas(gn_fwd_fused_kernel<false>, kGnThreads, 0);
+  int threads, grid;
+  gn_team_geometry(C, hw, n, resident[ki], 2.0 * hw * C, &t, &threads, &grid);
+  DDPM_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
+  DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * n, stream));
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  void* args[] = {&s, &t, &stats, &ws, &gamma, &beta, &yp, &ldy};
+  const void* fn = silu ? reinterpret_cast<const void*>(gn_fwd_fused_kernel<true>)
+                        : reinterpret_cast<const void*>(gn_fwd_fused_kernel<false>);
+  DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, stream));
+  return check_launch("gn_fwd_fused_kernel");
 }
 
 extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,
@@ -487,30 +652,30 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
   const int C = c0 + c1;
   GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
   const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
-  int V, threads, ppblk, chunks;
-  gn_geometry(C, hw, n, 4, 8, &V, &threads, &ppblk, &chunks);
-  float* sums = ws;
-  float* coef = ws + static_cast<long long>(n) * C * 2;
-  DDPM_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C * n, stream));
-  if (silu)
-    gn_bwd_reduce_kernel<true><<<dim3(chunks, n), threads, C * 2 * sizeof(float), stream>>>(
-        s, hw, C / groups, groups, stats, eps, gamma, beta, dyp, lddy, sums, ppblk, V);
-  else
-    gn_bwd_reduce_kernel<false><<<dim3(chunks, n), threads, C * 2 * sizeof(float), stream>>>(
-        s, hw, C / groups, groups, stats, eps, gamma, beta, dyp, lddy, sums, ppblk, V);
-  if (int e = check_launch("gn_bwd_reduce_kernel")) return e;
-  gn_bwd_finalize_kernel<<<n + (C + kGnThreads - 1) / kGnThreads, kGnThreads, 0, stream>>>(sums, gamma, n, C,
-                                                                                          C / groups, groups, coef,
-                                                                                          dgamma, dbeta);
-  if (int e = check_launch("gn_bwd_finalize_kernel")) return e;
   GnDst o{static_cast<__nv_bfloat16*>(dx0), static_cast<__nv_bfloat16*>(dx1), lddx0, lddx1,
           static_cast<const __nv_bfloat16*>(add0), static_cast<const __nv_bfloat16*>(add1), ldadd0, ldadd1};
-  gn_geometry(C, hw, n, 4, 4, &V, &threads, &ppblk, &chunks);
-  if (silu)
-    gn_bwd_apply_kernel<true><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma,
-                                                                       beta, dyp, lddy, coef, o, ppblk, V);
-  else
-    gn_bwd_apply_kernel<false><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma,
-                                                                        beta, dyp, lddy, coef, o, ppblk, V);
-  return check_launch("gn_bwd_apply_kernel");
+  float* sums = ws;
+  int* counters = reinterpret_cast<int*>(ws + static_cast<long long>(n) * C * 2);
+  GnTeam t;
+  t.N = n; t.hw = hw; t.cpg = C / groups; t.groups = groups; t.eps = eps;
+  const size_t smem = sizeof(float) * (C * 2 + groups * 2);
+  static int resident[2] = {0, 0};
+  const int ki = silu ? 1 : 0;
+  if (!resident[ki])
+    resident[ki] = silu ? gn_resident_ctas(gn_bwd_fused_kernel<true>, kGnThreads, sizeof(float) * (kMaxC * 2 + 128))
+                        : gn_resident_ctas(gn_bwd_fused_kernel<false>, kGnThreads, sizeof(float) * (kMaxC * 2 + 128));
+  int threads, grid;
+  const double sample_bytes = 2.0 * hw * C * (2 + (add0 ? 1 : 0) + (add1 ? 1 : 0));
+  gn_team_geometry(C, hw, n, resident[ki], sample_bytes, &t, &threads, &grid);
+  DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * static_cast<size_t>(n) * C * 2 + sizeof(int) * n, stream));
+  void* args[] = {&s, &t, &stats, &gamma, &beta, &dyp, &lddy, &sums, &counters, &o};
+  const void* fn = silu ? reinterpret_cast<const void*>(gn_bwd_fused_kernel<true>)
+                        : reinterpret_cast<const void*>(gn_bwd_fused_kernel<false>);
+  DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, stream));
+  if (int e = check_launch("gn_bwd_fused_kernel")) return e;
+  if (dgamma || dbeta) {
+    gn_bwd_dparam_kernel<<<(C + kGnThreads - 1) / kGnThreads, kGnThreads, 0, stream>>>(sums, n, C, dgamma, dbeta);
+    return check_launch("gn_bwd_dparam_kernel");
+  }
+  return DDPM_OK;
 }

@@ -248,6 +248,22 @@ class CudaOps:
         self.launches += 1
         return out
 
+    def gn_fwd(self, x0, x1, groups: int, eps: float, gamma, beta, silu: bool, out=None):
+        """Fused statistics + normalise/affine/(SiLU): -> (stats [n, groups, 2] fp32, y bf16 NHWC)."""
+        n, h, w, c0, ld0 = _nhwc(x0, "x0")
+        c1, ld1 = 0, 0
+        if x1 is not None:
+            _, _, _, c1, ld1 = _nhwc(x1, "x1")
+        stats = torch.empty((n, groups, 2), device=x0.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty((n, h, w, c0 + c1), device=x0.device, dtype=torch.bfloat16)
+        ws = torch.empty(n, device=x0.device, dtype=torch.int32)
+        _capi.check(self.lib.ddpm_gn_fwd(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, eps, _ptr(gamma),
+                                         _ptr(beta), int(silu), _ptr(stats), _ptr(out), _nhwc(out, "out")[4],
+                                         _ptr(ws), _stream()), "ddpm_gn_fwd")
+        self.launches += 1
+        return stats, out
+
     def gn_bwd(self, x0, x1, groups: int, stats, eps: float, gamma, beta, silu: bool, dy, add0=None, add1=None,
                dgamma=None, dbeta=None, need_dx1: bool = True):
         """-> (dx0, dx1).  dgamma / dbeta are accumulated in place."""
@@ -258,14 +274,14 @@ class CudaOps:
         C_ = c0 + c1
         dx0 = torch.empty((n, h, w, c0), device=x0.device, dtype=torch.bfloat16)
         dx1 = torch.empty((n, h, w, c1), device=x0.device, dtype=torch.bfloat16) if (c1 and need_dx1) else None
-        ws = torch.empty(n * C_ * 2 + n * groups * 2, device=x0.device, dtype=torch.float32)
+        ws = torch.empty(n * C_ * 2 + n, device=x0.device, dtype=torch.float32)
         _capi.check(self.lib.ddpm_gn_bwd(
             _ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats), eps, _ptr(gamma), _ptr(beta),
             int(silu), _ptr(dy), _nhwc(dy, "dy")[4],
             _ptr(add0), _nhwc(add0, "add0")[4] if add0 is not None else 0,
             _ptr(add1), _nhwc(add1, "add1")[4] if add1 is not None else 0,
             _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream()), "ddpm_gn_bwd")
-        self.launches += 4
+        self.launches += 2 if (dgamma is not None or dbeta is not None) else 1
         return dx0, dx1
 
     # ---- attention core ----------------------------------------------------------------------------------
@@ -405,6 +421,8 @@ class OpProfiler:
                 return 2.0 * n * h * w * dy.shape[-1] * cin * len(taps), 0.0
             if name == "gn_apply":
                 return 0.0, 4.0 * out.numel()                 # bf16 read + bf16 write
+            if name == "gn_fwd":
+                return 0.0, 4.0 * out[1].numel()              # bf16 read (second read is an L2 hit) + bf16 write
             if name == "gn_stats":
                 x0, x1 = args[0], args[1]
                 return 0.0, 2.0 * (x0.numel() + (x1.numel() if x1 is not None else 0))
@@ -434,7 +452,7 @@ class OpProfiler:
                 dy, x0, x1, taps, dw, grid = args[:6]
                 cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
                 return f"|{grid[1]}x{grid[2]} c{cin}->{dy.shape[-1]} k{len(taps)}"
-            if name in ("gn_bwd", "gn_apply", "gn_stats"):
+            if name in ("gn_bwd", "gn_apply", "gn_stats", "gn_fwd"):
                 x0, x1 = args[0], args[1]
                 c = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
                 return f"|{x0.shape[1]}x{x0.shape[2]} c{c}"

@@ -633,8 +633,7 @@ class UNet2DModel(nn.Module):
         # ---- out ----
         no = P.norm_out
         gam, bet = self._aview(no.g_off, (c0,)), self._aview(no.b_off, (c0,))
-        stats = ops.gn_stats(h, None, no.groups)
-        a = ops.gn_apply(h, None, no.groups, stats, no.eps, gam, bet, True)
+        stats, a = ops.gn_fwd(h, None, no.groups, no.eps, gam, bet, True)
         wco = self._aview(P.cout_w, (cfg.out_channels, 9, c0))
         out = ops.conv_c_to_3(a, wco, self._aview(P.cout_b, (cfg.out_channels,)), cfg.out_channels)
         if training:
@@ -653,12 +652,10 @@ class UNet2DModel(nn.Module):
         grid = (N, H, W)
         g1, be1 = self._norm_params(r.norm1)
         g2, be2 = self._norm_params(r.norm2)
-        stats1 = ops.gn_stats(x0, x1, r.norm1.groups)
-        a = ops.gn_apply(x0, x1, r.norm1.groups, stats1, r.norm1.eps, g1, be1, True)
+        stats1, a = ops.gn_fwd(x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True)
         temb = st.temb_all[:, r.temb_off:r.temb_off + r.cout]
         h1 = ops.conv_gemm(a, None, taps_3x3(r.cin), r.conv1.wf, r.cout, grid, bias=self._bias(r.conv1), temb=temb)
-        stats2 = ops.gn_stats(h1, None, r.norm2.groups)
-        b = ops.gn_apply(h1, None, r.norm2.groups, stats2, r.norm2.eps, g2, be2, True)
+        stats2, b = ops.gn_fwd(h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True)
         if r.short is not None:
             sc = ops.conv_gemm(x0, x1, taps_1x1(), r.short.wf, r.cout, grid, bias=self._bias(r.short))
         else:
@@ -674,8 +671,7 @@ class UNet2DModel(nn.Module):
         N, H, W, C = x.shape
         T = H * W
         gam, bet = self._norm_params(at.norm)
-        stats = ops.gn_stats(x, None, at.norm.groups)
-        xn = ops.gn_apply(x, None, at.norm.groups, stats, at.norm.eps, gam, bet, False)
+        stats, xn = ops.gn_fwd(x, None, at.norm.groups, at.norm.eps, gam, bet, False)
         xn2 = xn.view(1, 1, N * T, C)
         lora_qkv = at.qkv.lora.forward_extra(ops, xn2, self.training) if (at.qkv.lora and at.qkv.lora.active) else None
         qkv = ops.conv_gemm(xn2, lora_qkv.u if lora_qkv else None, self._lin_taps(at.qkv), at.qkv.wf, 3 * C,

@@ -90,10 +90,10 @@ def bench_wgrad(ops, B, iters, pk, first=None):
               f"{tf / pk['bf16_tflops']:.3f} of peak", flush=True)
 
 
-def bench_gn(ops, B, iters, pk):
+def bench_gn(ops, B, iters, pk, first=None):
     print(f"# GroupNorm+SiLU, batch {B}; peak = {pk['hbm_gbs']} GB/s (measured copy)")
     for (h, c0, c1) in [(128, 128, 0), (128, 128, 128), (64, 128, 0), (64, 256, 128), (32, 256, 0), (32, 256, 256),
-                        (16, 512, 256), (8, 512, 512), (4, 512, 0)]:
+                        (16, 512, 256), (8, 512, 512), (4, 512, 0)][:first]:
         C = c0 + c1
         xa = bf(B, h, h, c0)
         xb = bf(B, h, h, c1) if c1 else None
@@ -103,11 +103,13 @@ def bench_gn(ops, B, iters, pk):
         stats = ops.gn_stats(xa, xb, 32)
         y = torch.empty(B, h, h, C, device="cuda", dtype=torch.bfloat16)
         ms_a = timeit(lambda i: ops.gn_apply(xa, xb, 32, stats, 1e-5, gam, bet, True, out=y), iters, 1)
+        ms_f = timeit(lambda i: ops.gn_fwd(xa, xb, 32, 1e-5, gam, bet, True, out=y), iters, 1)
         dy = bf(B, h, h, C)
         ms_b = timeit(lambda i: ops.gn_bwd(xa, xb, 32, stats, 1e-5, gam, bet, True, dy), iters, 1)
         print(f"gn {h:3d}x{h:<3d} c{c0}+{c1:<4d} stats {ms_s:7.3f} ms {2 * elems / ms_s / 1e6:6.0f} GB/s | "
               f"apply {ms_a:7.3f} ms {4 * elems / ms_a / 1e6:6.0f} GB/s ({4 * elems / ms_a / 1e6 / pk['hbm_gbs']:.2f}) | "
-              f"bwd {ms_b:7.3f} ms {10 * elems / ms_b / 1e6:6.0f} GB/s (10 B/elem: 2 passes over x,dy + dx)",
+              f"fused fwd {ms_f:7.3f} ms {4 * elems / ms_f / 1e6:6.0f} GB/s ({4 * elems / ms_f / 1e6 / pk['hbm_gbs']:.2f}) | "
+              f"bwd {ms_b:7.3f} ms {6 * elems / ms_b / 1e6:6.0f} GB/s ({6 * elems / ms_b / 1e6 / pk['hbm_gbs']:.2f}; 6 B/elem: x, dy, dx)",
               flush=True)
 
 
@@ -155,6 +157,6 @@ if __name__ == "__main__":
     if a.what in ("wgrad", "all"):
         bench_wgrad(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("gn", "all"):
-        bench_gn(ops, a.batch, a.iters, pk)
+        bench_gn(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("small", "all"):
         bench_small(ops, a.batch, a.iters, pk)

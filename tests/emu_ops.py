@@ -180,6 +180,10 @@ class EmuOps:
             return out
         return r
 
+    def gn_fwd(self, x0, x1, groups, eps, gamma, beta, silu, out=None):
+        stats = self.gn_stats(x0, x1, groups)
+        return stats, self.gn_apply(x0, x1, groups, stats, eps, gamma, beta, silu, out=out)
+
     def gn_bwd(self, x0, x1, groups, stats, eps, gamma, beta, silu, dy, add0=None, add1=None, dgamma=None,
                dbeta=None, need_dx1=True):
         X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()

@@ -87,7 +87,8 @@ def g_gn(ops):
     dev = "cuda"
     torch.manual_seed(1)
     cases = [(2, 16, 16, 128, 0, True), (2, 8, 8, 512, 256, True), (3, 8, 8, 256, 128, True), (2, 4, 4, 512, 0, False),
-             (4, 32, 32, 256, 0, True), (2, 8, 8, 512, 512, True)]
+             (4, 32, 32, 256, 0, True), (2, 8, 8, 512, 512, True), (9, 64, 64, 128, 0, True), (5, 128, 128, 128, 128, True),
+             (70, 16, 16, 256, 0, False), (3, 5, 7, 64, 0, True)]
     for (n, h, w, c0, c1, silu) in cases:
         C = c0 + c1
         xa = bf(torch.randn(n, h, w, c0, device=dev) * 1.5 + 0.3)
@@ -105,6 +106,9 @@ def g_gn(ops):
         if silu:
             yr = F.silu(yr)
         ok &= report(f"gn fwd n{n} {h}x{w} c{c0}+{c1} silu={silu}", y, yr.permute(0, 2, 3, 1), 6e-3)
+        stats_f, y_f = ops.gn_fwd(xa, xb, 32, eps, gamma, beta, silu)
+        ok &= report("   gn fused fwd y", y_f, yr.permute(0, 2, 3, 1), 6e-3)
+        ok &= report("   gn fused fwd stats", stats_f, stats, 1e-5)
         dy = bf(torch.randn(n, h, w, C, device=dev))
         add0 = bf(torch.randn(n, h, w, C, device=dev))
         dgam = torch.zeros(C, device=dev)
