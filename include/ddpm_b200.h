@@ -82,6 +82,16 @@ typedef struct ddpm_conv_args {
   const float* bias;                         /* fp32 [cout] or NULL */
   const float* temb; int ld_temb;            /* fp32 [n][ld_temb] or NULL: ResnetBlock2D time-embedding add */
   const void* res; long long ldr;            /* bf16 NHWC residual or NULL */
+  /* Optional GroupNorm-backward fusion (gn_sums != NULL), for the dgrad GEMM whose result is the gradient w.r.t.
+   * y = act(GroupNorm(x)):  out = dz = result * act'(x*ka + kb) and gn_sums[n][co][0..1] += (sum dz, sum dz*x) over
+   * the sample's pixels.  x = (gn_x0 | gn_x1) bf16 NHWC with gn_c0 + (cout - gn_c0) channels; gn_coef is the
+   * per-(sample, channel) affine table written by ddpm_gn_fwd.  Requires h*w >= 128 or h*w % 32 == 0; gn_sums must
+   * be zero-filled. */
+  const void* gn_x0; long long gn_ld0; int gn_c0;
+  const void* gn_x1; long long gn_ld1;
+  const float* gn_coef;
+  int gn_silu;
+  float* gn_sums;
 } ddpm_conv_args;
 int ddpm_conv_gemm(const ddpm_conv_args* args, void* stream);
 
@@ -131,7 +141,9 @@ int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* x1, int c1,
  * launched kernel whose second phase re-reads x from L2.  ws: n ints (team barrier counters). */
 int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                 int groups, float eps, const float* gamma, const float* beta, int silu, float* stats, void* y,
-                long long ldy, int* ws, void* stream);
+                long long ldy, float* coef, int* ws, void* stream);
+/* coef (optional, fp32 [n][(c0+c1)/2][4]): (ka0, ka1, kb0, kb1) per channel pair with GN(x) = x*ka + kb; consumed by
+ * the GroupNorm-backward fusion of ddpm_conv_gemm. */
 /* GroupNorm(+SiLU) backward.  ws: workspace of n*(c0+c1)*2 floats followed by n ints (team barrier counters).
  *   dgamma/dbeta are accumulated (+=) when non-NULL.  dx = GN'(dy) + add0 + add1, written split over dx0|dx1. */
 int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
@@ -139,6 +151,16 @@ int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1, int c1, l
                 const void* dy, long long lddy, const void* add0, long long ldadd0, const void* add1,
                 long long ldadd1, void* dx0, long long lddx0, void* dx1, long long lddx1, float* dgamma,
                 float* dbeta, float* ws, void* stream);
+
+/* Second half of the GroupNorm backward when the first half ran in a conv epilogue (gn_sums of ddpm_conv_gemm):
+ *   dx = dz*rstd*gamma - xhat*rstd*mean_g(gamma*dz*xhat) - rstd*mean_g(gamma*dz) + add0 + add1,  split over dx0|dx1;
+ * dgamma[c] += sum_n (rstd*(S2 - mean*S1)), dbeta[c] += sum_n S1 when non-NULL.  One streaming pass, no
+ * transcendentals.  sums: [n][c0+c1][2] as accumulated by the conv epilogue. */
+int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
+                      int groups, const float* stats, float eps, const float* gamma, const void* dz, long long lddz,
+                      const float* sums, const void* add0, long long ldadd0, const void* add1, long long ldadd1,
+                      void* dx0, long long lddx0, void* dx1, long long lddx1, float* dgamma, float* dbeta,
+                      void* stream);
 
 /* Self-attention core on fused qkv [b*t][3*heads*d] bf16 (AttnProcessor2_0's scaled_dot_product_attention). */
 int ddpm_attn_fwd(const void* qkv, long long ldqkv, void* o, long long ldo, float* lse, int b, int t, int heads,

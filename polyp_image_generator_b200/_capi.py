@@ -34,6 +34,11 @@ class ConvArgs(C.Structure):
         ("bias", _vp),
         ("temb", _vp), ("ld_temb", _i),
         ("res", _vp), ("ldr", _ll),
+        ("gn_x0", _vp), ("gn_ld0", _ll), ("gn_c0", _i),
+        ("gn_x1", _vp), ("gn_ld1", _ll),
+        ("gn_coef", _vp),
+        ("gn_silu", _i),
+        ("gn_sums", _vp),
     ]
 
 
@@ -68,9 +73,11 @@ SIGNATURES = {
     "ddpm_conv3_wgrad": [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _ll, _i, _vp, _i, _i, _i, _vp],
     "ddpm_gn_stats": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _vp],
     "ddpm_gn_apply": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp],
-    "ddpm_gn_fwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp],
+    "ddpm_gn_fwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp, _vp],
     "ddpm_gn_bwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp, _ll, _vp, _ll,
                     _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp],
+    "ddpm_gn_bwd_apply": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll,
+                          _vp, _ll, _vp, _ll, _vp, _vp, _vp],
     "ddpm_attn_fwd": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
     "ddpm_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _f, _vp],
     "ddpm_timestep_embedding": [_vp, _vp, _vp, _i, _i, _i, _vp],

@@ -1,0 +1,176 @@
+// Shared epilogue of the tcgen05 conv kernels (conv_igemm.cu, conv_halo.cu): one thread owns one output pixel
+// (accumulator row) and walks 32-column chunks read from TMEM.
+//
+// Fused here, in the order diffusers applies them (ResnetBlock2D.forward, App. A.2 of SURVEY.md):
+//   + bias[co]  + temb[n, co] (time_emb_proj output)  + residual[pix, co]
+// and, for the dgrad GEMM that produces the gradient w.r.t. a GroupNorm(+SiLU) OUTPUT, the first half of the
+// GroupNorm backward:  dz = dy * act'(xhat*gamma + beta)  is written INSTEAD of dy, and the per-(sample, channel)
+// sums  S1 = sum dz,  S2 = sum dz * x  are reduced over the tile (butterfly over the 32 rows of a warp) and added to
+// gsums[n][c][2].  The epilogue warps are idle for most of a tile's mainloop, so the SiLU-derivative (1 MUFU + ~10
+// FP32 ops per element) costs nothing there, and the remaining GroupNorm backward is a single transcendental-free
+// streaming pass (gn_bwd_apply in groupnorm.cu): 6 B/elem instead of 10.
+#pragma once
+#include "common.cuh"
+
+namespace ddpm {
+
+struct EpiParams {
+  __nv_bfloat16* out;
+  long long ldo;
+  float* out_f32;          // optional fp32 output instead of bf16 (same indexing, ldo)
+  const float* bias;
+  const float* temb;
+  int ld_temb;
+  const __nv_bfloat16* res;
+  long long ldr;
+  int Cout;
+  // ---- GroupNorm-backward fusion (all NULL/0 when unused) ----
+  const __nv_bfloat16* gx0;   // GroupNorm INPUT x (channels [0, gc0)) ...
+  const __nv_bfloat16* gx1;   // ... and [gc0, Cout) when the input was a channel concat
+  long long gld0, gld1;
+  int gc0;
+  const float* gcoef;         // [N][Cout/2][4] = (ka0, ka1, kb0, kb1): z = x*ka + kb  (written by ddpm_gn_fwd)
+  float* gsums;               // [N][Cout][2] += (sum dz, sum dz*x)
+  int gsilu;
+};
+
+__device__ __forceinline__ float epi_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Column totals over the 32 lanes of a warp: a[j] (j = column) in, lane L returns the total of column L.
+__device__ __forceinline__ float warp_column_sums(float (&a)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? a[i] : a[i + s];
+      const float keep = up ? a[i + s] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return a[0];
+}
+
+struct EpiX {
+  bf16x8 r[4];   // 32 channels of the GroupNorm input at this thread's pixel
+};
+// Issue the loads of the GroupNorm input for (pix, col .. col+31) -- call this EARLY (before waiting on the
+// accumulator / while the previous chunk is processed) so the latency is off the critical path.
+__device__ __forceinline__ void epi_load_x(const EpiParams& e, bool valid, long long pix, int col, EpiX& x) {
+  if (e.gsums != nullptr && valid && col < e.Cout) {
+    const __nv_bfloat16* xp = (col < e.gc0) ? e.gx0 + pix * e.gld0 + col : e.gx1 + pix * e.gld1 + (col - e.gc0);
+    const bf16x8* xv = reinterpret_cast<const bf16x8*>(xp);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x.r[j] = xv[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x.r[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// v[32]: fp32 accumulators of (row = this thread's pixel, columns col .. col+31).  `n`, `pix` describe the pixel;
+// rows with valid == false are not stored and contribute zero to the sums.  All 32 lanes of the warp must call this
+// together when GN fusion is on (shuffles), and the warp's valid rows must belong to ONE sample (host-checked).
+// With GroupNorm fusion, this lane's column totals are ADDED to (t1, t2); the caller flushes them with
+// epi_flush_sums once all row blocks sharing these columns (and this sample) have been processed.
+template <bool GN = true>
+__device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bool valid, int n, long long pix, int col,
+                                          int lane, float& t1, float& t2, const EpiX& xin) {
+  const bool col_ok = col < e.Cout;
+  if (valid && col_ok) {
+    if (e.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(e.bias + col + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (e.temb) {
+      const float* t = e.temb + static_cast<long long>(n) * e.ld_temb + col;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(t + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (e.res) {
+      const bf16x8* rp = reinterpret_cast<const bf16x8*>(e.res + pix * e.ldr + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(rp[j], f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[j * 8 + q] += f[q];
+      }
+    }
+  }
+  if (GN && e.gsums != nullptr) {
+    // ---- GroupNorm backward, part 1 (warp-collective; packed fp32x2 math) ----
+    float s2[32];
+    if (valid && col_ok) {
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) unpack8(xin.r[j], x + 8 * j);
+      if (e.gsilu) {
+        const float4* cf = reinterpret_cast<const float4*>(e.gcoef) + (static_cast<long long>(n) * e.Cout + col) / 2;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float4 c4 = cf[j / 2];   // (ka_j, ka_j+1, kb_j, kb_j+1), warp-uniform address
+          const float2 z = __ffma2_rn(make_float2(x[j], x[j + 1]), make_float2(c4.x, c4.y), make_float2(c4.z, c4.w));
+          const float2 h = __fmul2_rn(z, make_float2(0.5f, 0.5f));
+          const float2 sg = __ffma2_rn(make_float2(epi_tanh(h.x), epi_tanh(h.y)), make_float2(0.5f, 0.5f),
+                                       make_float2(0.5f, 0.5f));
+          const float2 om = __ffma2_rn(sg, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+          const float2 u = __ffma2_rn(z, om, make_float2(1.f, 1.f));
+          const float2 dz = __fmul2_rn(__fmul2_rn(make_float2(v[j], v[j + 1]), sg), u);
+          v[j] = dz.x;
+          v[j + 1] = dz.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s2[j] = v[j] * x[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = 0.f;
+        s2[j] = 0.f;
+      }
+    }
+    float keep[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) keep[j] = v[j];
+    t1 += warp_column_sums(keep, lane);
+    t2 += warp_column_sums(s2, lane);
+  }
+  if (valid && col_ok) {
+    if (e.out_f32) {
+      float4* op = reinterpret_cast<float4*>(e.out_f32 + pix * e.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      bf16x8* op = reinterpret_cast<bf16x8*>(e.out + pix * e.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
+    }
+  }
+}
+
+// Adds this lane's column totals to gsums[n][col + lane][0..1].  `n_valid` < 0: the warp had no valid row.
+__device__ __forceinline__ void epi_flush_sums(const EpiParams& e, int n_valid, int col, int lane, float t1, float t2) {
+  if (e.gsums == nullptr || n_valid < 0 || col >= e.Cout) return;
+  float* dst = e.gsums + (static_cast<long long>(n_valid) * e.Cout + col + lane) * 2;
+  atomicAdd(dst, t1);
+  atomicAdd(dst + 1, t2);
+}
+// sample index of the warp's valid rows (host guarantees they agree), or -1
+__device__ __forceinline__ int epi_warp_sample(bool valid, int n) {
+  const unsigned vm = __ballot_sync(0xffffffffu, valid);
+  if (vm == 0u) return -1;
+  return __shfl_sync(0xffffffffu, n, __ffs(vm) - 1);
+}
+
+}  // namespace ddpm

@@ -20,6 +20,7 @@
 //   warp  8    halo producer (TMA, double-buffered halo)       warp 9   weight-tile producer (TMA, ring)
 //   warp 10    MMA issuer + TMEM owner
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 
 #include <cstring>
 
@@ -40,13 +41,7 @@ struct HaloParams {
   int tiles_per_img, n_tiles, total_tiles;
   uint32_t halo_bytes;   // R * Wp * 128
   uint32_t halo_stride;  // halo_bytes rounded up to 1024
-  __nv_bfloat16* out;
-  long long ldo;
-  const float* bias;
-  const float* temb;
-  int ld_temb;
-  const __nv_bfloat16* res;
-  long long ldr;
+  EpiParams epi;
 };
 
 __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -181,55 +176,46 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int img = mt / p.tiles_per_img;
       const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      mbar_wait(&tmem_full[acc], aph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int u = 0; u < 2; ++u) {
+      // step i = (cc, u): column chunk half*2 + i/2, row block i%2; the GroupNorm input of step i+1 is loaded while
+      // step i is processed, and that of step 0 while the tile's mainloop is still running
+      auto geom = [&](int i, int& col, bool& valid, long long& pix, int& u) {
+        u = i & 1;
+        col = nt * 128 + (half * 2 + (i >> 1)) * 32;
         const int slot = q0 + u * 128 + q * 32 + lane;
         const int h = slot / p.Wp;
         const int w = slot - h * p.Wp - 1;
-        const bool valid = (w >= 0) && (h < p.H);
-        const long long pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
+        valid = (w >= 0) && (h < p.H);
+        pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
+      };
+      EpiX xcur, xnext;
+      {
+        int col, u; bool valid; long long pix;
+        geom(0, col, valid, pix, u);
+        epi_load_x(p.epi, valid, pix, col, xcur);
+      }
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      float t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
-        for (int cc = half * 2; cc < half * 2 + 2; ++cc) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + u * 128 + cc * 32, r);
-          tmem_ld_wait();
-          const int col = nt * 128 + cc * 32;
-          if (valid && col < p.Cout) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-            if (p.temb) {
-              const float* t = p.temb + static_cast<long long>(img) * p.ld_temb + col;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(t + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-            if (p.res) {
-              const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + pix * p.ldr + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float f[8];
-                unpack8(rp[j], f);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[j * 8 + e] += f[e];
-              }
-            }
-            bf16x8* op = reinterpret_cast<bf16x8*>(p.out + pix * p.ldo + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
-          }
+      for (int i = 0; i < 4; ++i) {
+        int col, u; bool valid; long long pix;
+        if (i + 1 < 4) {
+          geom(i + 1, col, valid, pix, u);
+          epi_load_x(p.epi, valid, pix, col, xnext);
         }
+        geom(i, col, valid, pix, u);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + u * 128 + (half * 2 + (i >> 1)) * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        epi_chunk(p.epi, v, valid, img, pix, col, lane, t1, t2, xcur);
+        if (u == 1) {   // both row blocks of this column chunk done; a tile lies within one image
+          epi_flush_sums(p.epi, img, col, lane, t1, t2);
+          t1 = t2 = 0.f;
+        }
+        xcur = xnext;
       }
       tc_fence_before();
       __syncwarp();
@@ -270,10 +256,7 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
   p.tiles_per_img = (H * Wp + kTileSlots - 1) / kTileSlots;
   p.n_tiles = (a->cout + 127) / 128;
   p.total_tiles = a->n * p.tiles_per_img * p.n_tiles;
-  p.out = static_cast<__nv_bfloat16*>(a->out);
-  p.ldo = a->ldo;
-  p.bias = a->bias; p.temb = a->temb; p.ld_temb = a->ld_temb;
-  p.res = static_cast<const __nv_bfloat16*>(a->res); p.ldr = a->ldr;
+  if (int e = fill_epilogue(&p.epi, a)) return e;
 
   CUtensorMap ma0, ma1, mb;
   if (int e = make_act_map(&ma0, a->x0, a->c0, a->ld0, a->n, H, W, Wp, R, 1)) return e;

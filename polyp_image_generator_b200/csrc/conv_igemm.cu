@@ -18,6 +18,7 @@
 //      both operands are "MN-major" straight out of NHWC (pixels are the reduction index), split-K over
 //      pixel tiles with fp32 red.global.add into the gradient buffer.
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 
 #include <mutex>
 #include <unordered_map>
@@ -43,18 +44,10 @@ struct TapTable {
 struct GemmParams {
   int N, H, W;            // pixel grid
   int kb0, kb1;           // 64-channel blocks from source 0 / 1
-  int Cout;
   int wb, hb, nb;         // TMA box (pixels) = M tile shape
   int tiles_w, tiles_h, tiles_n;
   uint32_t a_bytes;       // bytes one A box delivers (wb*hb*nb*128)
-  __nv_bfloat16* out;
-  long long ldo;
-  float* out_f32;         // optional fp32 output instead of bf16 (same indexing, ldo)
-  const float* bias;
-  const float* temb;
-  int ld_temb;
-  const __nv_bfloat16* res;
-  long long ldr;
+  EpiParams epi;
   TapTable taps;
 };
 
@@ -70,8 +63,8 @@ struct GemmSmem {
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad / linear
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BLOCK_N, int STAGES, bool GN>
+__global__ void __launch_bounds__(kGemmThreads, (BLOCK_N == 128 ? 2 : 1))
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
   using L = GemmSmem<BLOCK_N, STAGES>;
@@ -168,52 +161,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
     const int col0 = nt * BLOCK_N;
 
+    EpiX xcur, xnext;
+    if (GN) epi_load_x(p.epi, valid, pix, col0, xcur);   // in flight while the mainloop runs
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    const int n_warp = (GN && p.epi.gsums) ? epi_warp_sample(valid, n) : -1;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
+      if (GN && c + 1 < BLOCK_N / 32) epi_load_x(p.epi, valid, pix, col0 + (c + 1) * 32, xnext);
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
       tmem_ld_wait();
-      const int col = col0 + c * 32;
-      if (valid && col < p.Cout) {
-        float v[32];
+      float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (p.temb) {
-          const float* t = p.temb + static_cast<long long>(n) * p.ld_temb + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(t + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (p.res) {
-          const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + pix * p.ldr + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f[8];
-            unpack8(rp[j], f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[j * 8 + e] += f[e];
-          }
-        }
-        if (p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldo + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          bf16x8* op = reinterpret_cast<bf16x8*>(p.out + pix * p.ldo + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
-        }
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      float t1 = 0.f, t2 = 0.f;
+      epi_chunk<GN>(p.epi, v, valid, n, pix, col0 + c * 32, lane, t1, t2, xcur);
+      if (GN) {
+        epi_flush_sums(p.epi, n_warp, col0 + c * 32, lane, t1, t2);
+        xcur = xnext;
       }
     }
   }
@@ -515,17 +481,40 @@ static int fill_taps(TapTable* t, const ddpm_conv_args* a) {
   return DDPM_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+int fill_epilogue(EpiParams* e, const ::ddpm_conv_args* a) {
+  std::memset(e, 0, sizeof(*e));
+  e->out = static_cast<__nv_bfloat16*>(a->out);
+  e->out_f32 = static_cast<float*>(a->out_f32);
+  e->ldo = a->ldo;
+  e->bias = a->bias; e->temb = a->temb; e->ld_temb = a->ld_temb;
+  e->res = static_cast<const __nv_bfloat16*>(a->res); e->ldr = a->ldr;
+  e->Cout = a->cout;
+  if (a->gn_sums != nullptr) {
+    DDPM_REQUIRE(a->gn_x0 && a->gn_coef, "ddpm_conv_gemm: incomplete GroupNorm-backward fusion arguments");
+    DDPM_REQUIRE(a->gn_c0 % 32 == 0 && a->gn_c0 > 0 && a->gn_c0 <= a->cout && (a->gn_c0 == a->cout || a->gn_x1) &&
+                     a->gn_ld0 % 8 == 0 && a->gn_ld1 % 8 == 0 && a->out_f32 == nullptr,
+                 "ddpm_conv_gemm: unsupported GroupNorm-backward fusion layout (gn_c0=%d cout=%d)", a->gn_c0, a->cout);
+    e->gx0 = static_cast<const __nv_bfloat16*>(a->gn_x0);
+    e->gx1 = static_cast<const __nv_bfloat16*>(a->gn_x1);
+    e->gld0 = a->gn_ld0; e->gld1 = a->gn_ld1; e->gc0 = a->gn_c0;
+    e->gcoef = a->gn_coef;
+    e->gsums = a->gn_sums;
+    e->gsilu = a->gn_silu;
+  }
+  return DDPM_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool GN>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
                        cudaStream_t stream) {
   using L = GemmSmem<BLOCK_N, STAGES>;
   static bool configured = false;
-  auto kern = conv_gemm_kernel<BLOCK_N, STAGES>;
+  auto kern = conv_gemm_kernel<BLOCK_N, STAGES, GN>;
   if (!configured) {
     DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  dim3 grid((p.Cout + BLOCK_N - 1) / BLOCK_N, p.tiles_w * p.tiles_h * p.tiles_n);
+  dim3 grid((p.epi.Cout + BLOCK_N - 1) / BLOCK_N, p.tiles_w * p.tiles_h * p.tiles_n);
   kern<<<grid, kGemmThreads, L::kTotal, stream>>>(a0, a1, b, p);
   return check_launch("conv_gemm_kernel");
 }
@@ -572,17 +561,17 @@ extern "C" int ddpm_conv_gemm(const ddpm_conv_args* a, void* stream_) {
   if (int e = fill_taps(&p.taps, a)) return e;
   p.N = a->n; p.H = a->h; p.W = a->w;
   p.kb0 = a->c0 / 64; p.kb1 = a->c1 / 64;
-  p.Cout = a->cout;
   choose_box(a->n, a->h, a->w, &p.wb, &p.hb, &p.nb);
   p.tiles_w = (a->w + p.wb - 1) / p.wb;
   p.tiles_h = (a->h + p.hb - 1) / p.hb;
   p.tiles_n = (a->n + p.nb - 1) / p.nb;
   p.a_bytes = static_cast<uint32_t>(p.wb * p.hb * p.nb) * 128u;
-  p.out = static_cast<__nv_bfloat16*>(a->out);
-  p.out_f32 = static_cast<float*>(a->out_f32);
-  p.ldo = a->ldo;
-  p.bias = a->bias; p.temb = a->temb; p.ld_temb = a->ld_temb;
-  p.res = static_cast<const __nv_bfloat16*>(a->res); p.ldr = a->ldr;
+  if (int e = fill_epilogue(&p.epi, a)) return e;
+  if (p.epi.gsums) {
+    // the fused GroupNorm sums are reduced per warp (32 consecutive tile rows): those must share one sample
+    DDPM_REQUIRE(p.nb == 1 || (p.wb * p.hb) % 32 == 0,
+                 "ddpm_conv_gemm: GroupNorm-backward fusion needs H*W >= 128 or H*W %% 32 == 0 (h=%d w=%d)", a->h, a->w);
+  }
   const int src_n = a->src_n > 0 ? a->src_n : a->n;
 
   CUtensorMap ma0, ma1, mb;
@@ -600,10 +589,12 @@ extern "C" int ddpm_conv_gemm(const ddpm_conv_args* a, void* stream_) {
   long long k_total = a->k_total > 0 ? a->k_total : a->ldw;
   if (block_n == 256) {
     if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 256)) return e;
-    return launch_gemm<256, 4>(ma0, ma1, mb, p, stream);
+    return p.epi.gsums ? launch_gemm<256, 4, true>(ma0, ma1, mb, p, stream)
+                       : launch_gemm<256, 4, false>(ma0, ma1, mb, p, stream);
   }
   if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 128)) return e;
-  return launch_gemm<128, 3>(ma0, ma1, mb, p, stream);
+  return p.epi.gsums ? launch_gemm<128, 3, true>(ma0, ma1, mb, p, stream)
+                     : launch_gemm<128, 3, false>(ma0, ma1, mb, p, stream);
 }
 
 extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream_) {

@@ -281,7 +281,8 @@ template <bool SILU>
 __global__ void __launch_bounds__(kGnThreads, 4)
 gn_fwd_fused_kernel(GnSrc s, GnTeam t, float* __restrict__ stats /*[N][groups][2], zeroed*/,
                     int* __restrict__ counters /*[N], zeroed*/, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long ldy) {
+                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long ldy,
+                    float* __restrict__ coef /*[N][C/2][4] or NULL*/) {
   __shared__ float sm[64 * 2];
   const int team = blockIdx.x / t.team_size, rank = blockIdx.x - team * t.team_size;
   const int nteams = gridDim.x / t.team_size;
@@ -307,6 +308,11 @@ gn_fwd_fused_kernel(GnSrc s, GnTeam t, float* __restrict__ stats /*[N][groups][2
     gn_team_barrier(&counters[n], t.team_size);
     f2x4 ka, kb;
     gn_apply_coefs(st, c, cpg, inv_m, t.eps, gamma, beta, true, &ka, &kb);
+    if (coef != nullptr && rank == 0 && pl == 0) {
+      float4* cp = reinterpret_cast<float4*>(coef) + (static_cast<long long>(n) * V * 8 + c) / 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cp[j] = make_float4(ka.p[j].x, ka.p[j].y, kb.p[j].x, kb.p[j].y);
+    }
     __nv_bfloat16* yp = y + static_cast<long long>(n) * hw * ldy + c;
     gn_apply_stream<SILU>(xp, ld, yp, ldy, p_begin + pl, p_end, ppb, ka, kb);
     __syncthreads();   // sm is reused by the next sample
@@ -504,6 +510,134 @@ gn_bwd_dparam_kernel(const float* __restrict__ sums, int N, int C, float* __rest
   if (dgamma) dgamma[c] += b;
 }
 
+// ---- backward, second half only (first half fused into the dgrad conv epilogue, conv_epilogue.cuh) ---------------
+// grid (chunks, N).  sums[n][c] = (S1 = sum dz, S2 = sum dz*x) raw moments.  dx = dz*k1 + x*nk4 + nk5 (+ addends).
+__global__ void __launch_bounds__(kGnThreads)
+gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
+                    const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dz, long long lddz,
+                    const float* __restrict__ sums, GnDst o, int pix_per_block, int V) {
+  __shared__ float scoef[64 * 2];
+  const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+  const int n = blockIdx.y;
+  const int C = V * 8;
+  const float* stats_n = stats + static_cast<long long>(n) * groups * 2;
+  const float* sn = sums + static_cast<long long>(n) * C * 2;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float mean, rstd;
+    gn_mean_rstd_of(*reinterpret_cast<const float2*>(stats_n + g * 2), inv_m, eps, &mean, &rstd);
+    float s1 = 0.f, s2 = 0.f;
+    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+      const float2 ab = *reinterpret_cast<const float2*>(sn + cc * 2);
+      const float ga = gamma[cc];
+      s1 = fmaf(ga, ab.x, s1);
+      s2 = fmaf(ga, rstd * (ab.y - mean * ab.x), s2);
+    }
+    scoef[g * 2] = s1 * inv_m;
+    scoef[g * 2 + 1] = s2 * inv_m;
+  }
+  __syncthreads();
+  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = v * 8;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(hw, p_begin + pix_per_block);
+  if (!((c < s.c0) || (o.d1 != nullptr))) return;   // gradient of this source not requested
+  long long ld;
+  const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
+  const long long pix0 = static_cast<long long>(n) * hw;
+  const __nv_bfloat16* dp = dz + pix0 * lddz + c;
+  f2x4 k1, nk4, nk5;
+  {
+    float a1[8], a4[8], a5[8];
+    int g_prev = -1;
+    float mean = 0.f, rstd = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (c + e) / cpg;
+      if (g != g_prev) {
+        gn_mean_rstd_of(*reinterpret_cast<const float2*>(stats_n + g * 2), inv_m, eps, &mean, &rstd);
+        s1 = scoef[g * 2];
+        s2 = scoef[g * 2 + 1];
+        g_prev = g;
+      }
+      a1[e] = rstd * gamma[c + e];
+      a4[e] = -rstd * rstd * s2;
+      a5[e] = -rstd * s1 - mean * a4[e];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      k1.p[j] = make_float2(a1[2 * j], a1[2 * j + 1]);
+      nk4.p[j] = make_float2(a4[2 * j], a4[2 * j + 1]);
+      nk5.p[j] = make_float2(a5[2 * j], a5[2 * j + 1]);
+    }
+  }
+  const __nv_bfloat16* a0p = o.add0 ? o.add0 + pix0 * o.lda0 + c : nullptr;
+  const __nv_bfloat16* a1p = o.add1 ? o.add1 + pix0 * o.lda1 + c : nullptr;
+  __nv_bfloat16* op;
+  long long ldo;
+  if (c < s.c0) {
+    op = o.d0 + pix0 * o.ld0 + c;
+    ldo = o.ld0;
+  } else {
+    op = o.d1 + pix0 * o.ld1 + (c - s.c0);
+    ldo = o.ld1;
+  }
+  for (int p = p_begin + pl; p < p_end; p += 2 * ppb) {
+    const bool two = p + ppb < p_end;
+    bf16x8 rx[2], rd[2], ra0[2], ra1[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 || two) {
+        const int q = p + u * ppb;
+        rx[u] = *reinterpret_cast<const bf16x8*>(xp + q * ld);
+        rd[u] = *reinterpret_cast<const bf16x8*>(dp + q * lddz);
+        if (a0p) ra0[u] = *reinterpret_cast<const bf16x8*>(a0p + q * o.lda0);
+        if (a1p) ra1[u] = *reinterpret_cast<const bf16x8*>(a1p + q * o.lda1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 || two) {
+        const f2x4 f = unpack8p(rx[u]), d = unpack8p(rd[u]);
+        f2x4 r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r.p[j] = __ffma2_rn(d.p[j], k1.p[j], __ffma2_rn(f.p[j], nk4.p[j], nk5.p[j]));
+        if (a0p) {
+          const f2x4 a = unpack8p(ra0[u]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r.p[j] = __fadd2_rn(r.p[j], a.p[j]);
+        }
+        if (a1p) {
+          const f2x4 a = unpack8p(ra1[u]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r.p[j] = __fadd2_rn(r.p[j], a.p[j]);
+        }
+        *reinterpret_cast<bf16x8*>(op + (p + u * ppb) * ldo) = pack8p(r);
+      }
+    }
+  }
+}
+
+// dgamma[c] += sum_n rstd*(S2 - mean*S1), dbeta[c] += sum_n S1   (raw moments from the conv epilogue)
+__global__ void __launch_bounds__(kGnThreads)
+gn_bwd_dparam_raw_kernel(const float* __restrict__ sums, const float* __restrict__ stats, int N, int C, int cpg,
+                         int groups, int hw, float eps, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+  const int g = c / cpg;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float mean, rstd;
+    gn_mean_rstd_of(*reinterpret_cast<const float2*>(stats + (static_cast<long long>(n) * groups + g) * 2), inv_m, eps,
+                    &mean, &rstd);
+    const float2 ab = *reinterpret_cast<const float2*>(sums + (static_cast<long long>(n) * C + c) * 2);
+    a += ab.x;
+    b += rstd * (ab.y - mean * ab.x);
+  }
+  if (dbeta) dbeta[c] += a;
+  if (dgamma) dgamma[c] += b;
+}
+
 static int gn_check(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                     int groups, const char* who) {
   if (!x0 || n <= 0 || hw <= 0 || groups <= 0 || groups > 64) {
@@ -613,7 +747,7 @@ extern "C" int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* 
 
 extern "C" int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,
                            int hw, int groups, float eps, const float* gamma, const float* beta, int silu,
-                           float* stats, void* y, long long ldy, int* ws, void* stream_) {
+                           float* stats, void* y, long long ldy, float* coef, int* ws, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int e = gn_check(x0, c0, ld0, x1, c1, ld1, n, hw, groups, "ddpm_gn_fwd")) return e;
   DDPM_REQUIRE(stats && gamma && beta && y && ws && ldy % 8 == 0, "ddpm_gn_fwd: bad argument");
@@ -631,7 +765,7 @@ extern "C" int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1
   DDPM_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
   DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * n, stream));
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
-  void* args[] = {&s, &t, &stats, &ws, &gamma, &beta, &yp, &ldy};
+  void* args[] = {&s, &t, &stats, &ws, &gamma, &beta, &yp, &ldy, &coef};
   const void* fn = silu ? reinterpret_cast<const void*>(gn_fwd_fused_kernel<true>)
                         : reinterpret_cast<const void*>(gn_fwd_fused_kernel<false>);
   DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, stream));
@@ -676,6 +810,35 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
   if (dgamma || dbeta) {
     gn_bwd_dparam_kernel<<<(C + kGnThreads - 1) / kGnThreads, kGnThreads, 0, stream>>>(sums, n, C, dgamma, dbeta);
     return check_launch("gn_bwd_dparam_kernel");
+  }
+  return DDPM_OK;
+}
+
+extern "C" int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,
+                                 int hw, int groups, const float* stats, float eps, const float* gamma, const void* dz,
+                                 long long lddz, const float* sums, const void* add0, long long ldadd0,
+                                 const void* add1, long long ldadd1, void* dx0, long long lddx0, void* dx1,
+                                 long long lddx1, float* dgamma, float* dbeta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = gn_check(x0, c0, ld0, x1, c1, ld1, n, hw, groups, "ddpm_gn_bwd_apply")) return e;
+  DDPM_REQUIRE(stats && gamma && dz && sums && dx0, "ddpm_gn_bwd_apply: null pointer argument");
+  DDPM_REQUIRE(lddz % 8 == 0 && lddx0 % 8 == 0 && (c1 == 0 || !dx1 || lddx1 % 8 == 0) &&
+                   (!add0 || ldadd0 % 8 == 0) && (!add1 || ldadd1 % 8 == 0),
+               "ddpm_gn_bwd_apply: strides must be multiples of 8");
+  const int C = c0 + c1;
+  GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
+  GnDst o{static_cast<__nv_bfloat16*>(dx0), static_cast<__nv_bfloat16*>(dx1), lddx0, lddx1,
+          static_cast<const __nv_bfloat16*>(add0), static_cast<const __nv_bfloat16*>(add1), ldadd0, ldadd1};
+  int V, threads, ppblk, chunks;
+  gn_geometry(C, hw, n, 8, &V, &threads, &ppblk, &chunks);
+  gn_bwd_apply_kernel<<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma,
+                                                               static_cast<const __nv_bfloat16*>(dz), lddz, sums, o,
+                                                               ppblk, V);
+  if (int e = check_launch("gn_bwd_apply_kernel")) return e;
+  if (dgamma || dbeta) {
+    gn_bwd_dparam_raw_kernel<<<(C + kGnThreads - 1) / kGnThreads, kGnThreads, 0, stream>>>(sums, stats, n, C, C / groups,
+                                                                                          groups, hw, eps, dgamma, dbeta);
+    return check_launch("gn_bwd_dparam_raw_kernel");
   }
   return DDPM_OK;
 }

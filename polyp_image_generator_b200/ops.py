@@ -131,9 +131,17 @@ class CudaOps:
         return out
 
     # ---- tcgen05 conv / linear -------------------------------------------------------------------------
+    @staticmethod
+    def gn_bwd_fusable(grid: Tuple[int, int, int]) -> bool:
+        """Can the GroupNorm-backward first half run in the dgrad epilogue of a conv over this pixel grid?"""
+        hw = grid[1] * grid[2]
+        return hw >= 128 or hw % 32 == 0
+
     def conv_gemm(self, x0, x1, taps: Sequence[Tap], wgt, cout: int, grid: Tuple[int, int, int], bias=None,
-                  temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0):
-        """out[n,h,w,co] = bias + temb[n] + res + sum_taps X[pix+tap] . wgt[co, wk:wk+cin]; see ddpm_conv_gemm."""
+                  temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0, gn=None):
+        """out[n,h,w,co] = bias + temb[n] + res + sum_taps X[pix+tap] . wgt[co, wk:wk+cin]; see ddpm_conv_gemm.
+        gn = (x0, x1, coef, silu, sums) with coef from gn_fwd(want_coef=True): fuse the first half of the backward of
+        y = act(GroupNorm(x0|x1)) into the epilogue (out becomes dz, sums[n, c] += (sum dz, sum dz*x))."""
         n, h, w = grid
         _, _, _, c0, ld0 = _nhwc(x0, "x0")
         a = _capi.ConvArgs()
@@ -159,6 +167,18 @@ class CudaOps:
             a.temb, a.ld_temb = _ptr(temb), temb.stride(0)
         if res is not None:
             a.res, a.ldr = _ptr(res), _nhwc(res, "res")[4]
+        if gn is not None:
+            gx0, gx1, gcoef, gsilu, gsums = gn
+            _, _, _, gc0, gld0 = _nhwc(gx0, "gn x0")
+            a.gn_x0, a.gn_ld0, a.gn_c0 = _ptr(gx0), gld0, gc0
+            if gx1 is not None:
+                a.gn_x1, a.gn_ld1 = _ptr(gx1), _nhwc(gx1, "gn x1")[4]
+            if gcoef.dtype != torch.float32 or not gcoef.is_contiguous() or gcoef.numel() != n * cout * 2:
+                raise ValueError("gn coef must be the contiguous fp32 [n, cout/2, 4] table written by gn_fwd")
+            a.gn_coef, a.gn_silu = _ptr(gcoef), int(gsilu)
+            if gsums.dtype != torch.float32 or not gsums.is_contiguous() or gsums.numel() != n * cout * 2:
+                raise ValueError("gn sums must be a contiguous fp32 [n, cout, 2] tensor")
+            a.gn_sums = _ptr(gsums)
         _capi.check(self.lib.ddpm_conv_gemm(C.byref(a), _stream()), "ddpm_conv_gemm")
         self.launches += 1
         return out
@@ -248,8 +268,9 @@ class CudaOps:
         self.launches += 1
         return out
 
-    def gn_fwd(self, x0, x1, groups: int, eps: float, gamma, beta, silu: bool, out=None):
-        """Fused statistics + normalise/affine/(SiLU): -> (stats [n, groups, 2] fp32, y bf16 NHWC)."""
+    def gn_fwd(self, x0, x1, groups: int, eps: float, gamma, beta, silu: bool, out=None, want_coef: bool = False):
+        """Fused statistics + normalise/affine/(SiLU): -> (stats [n, groups, 2] fp32, y bf16 NHWC[, coef]).
+        coef (want_coef): per-(sample, channel) affine table for the GroupNorm-backward fusion of conv_gemm."""
         n, h, w, c0, ld0 = _nhwc(x0, "x0")
         c1, ld1 = 0, 0
         if x1 is not None:
@@ -258,10 +279,13 @@ class CudaOps:
         if out is None:
             out = torch.empty((n, h, w, c0 + c1), device=x0.device, dtype=torch.bfloat16)
         ws = torch.empty(n, device=x0.device, dtype=torch.int32)
+        coef = torch.empty((n, (c0 + c1) // 2, 4), device=x0.device, dtype=torch.float32) if want_coef else None
         _capi.check(self.lib.ddpm_gn_fwd(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, eps, _ptr(gamma),
                                          _ptr(beta), int(silu), _ptr(stats), _ptr(out), _nhwc(out, "out")[4],
-                                         _ptr(ws), _stream()), "ddpm_gn_fwd")
+                                         _ptr(coef), _ptr(ws), _stream()), "ddpm_gn_fwd")
         self.launches += 1
+        if want_coef:
+            return stats, out, coef
         return stats, out
 
     def gn_bwd(self, x0, x1, groups: int, stats, eps: float, gamma, beta, silu: bool, dy, add0=None, add1=None,
@@ -281,6 +305,24 @@ class CudaOps:
             _ptr(add0), _nhwc(add0, "add0")[4] if add0 is not None else 0,
             _ptr(add1), _nhwc(add1, "add1")[4] if add1 is not None else 0,
             _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream()), "ddpm_gn_bwd")
+        self.launches += 2 if (dgamma is not None or dbeta is not None) else 1
+        return dx0, dx1
+
+    def gn_bwd_apply(self, x0, x1, groups: int, stats, eps: float, gamma, dz, sums, add0=None, add1=None,
+                     dgamma=None, dbeta=None, need_dx1: bool = True):
+        """Second half of the GroupNorm backward (first half fused into conv_gemm(gn=...)) -> (dx0, dx1)."""
+        n, h, w, c0, ld0 = _nhwc(x0, "x0")
+        c1, ld1 = 0, 0
+        if x1 is not None:
+            _, _, _, c1, ld1 = _nhwc(x1, "x1")
+        dx0 = torch.empty((n, h, w, c0), device=x0.device, dtype=torch.bfloat16)
+        dx1 = torch.empty((n, h, w, c1), device=x0.device, dtype=torch.bfloat16) if (c1 and need_dx1) else None
+        _capi.check(self.lib.ddpm_gn_bwd_apply(
+            _ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats), eps, _ptr(gamma),
+            _ptr(dz), _nhwc(dz, "dz")[4], _ptr(sums),
+            _ptr(add0), _nhwc(add0, "add0")[4] if add0 is not None else 0,
+            _ptr(add1), _nhwc(add1, "add1")[4] if add1 is not None else 0,
+            _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dgamma), _ptr(dbeta), _stream()), "ddpm_gn_bwd_apply")
         self.launches += 2 if (dgamma is not None or dbeta is not None) else 1
         return dx0, dx1
 
@@ -426,7 +468,7 @@ class OpProfiler:
             if name == "gn_stats":
                 x0, x1 = args[0], args[1]
                 return 0.0, 2.0 * (x0.numel() + (x1.numel() if x1 is not None else 0))
-            if name == "gn_bwd":
+            if name in ("gn_bwd", "gn_bwd_apply"):
                 x0, x1 = args[0], args[1]
                 return 0.0, 6.0 * (x0.numel() + (x1.numel() if x1 is not None else 0))   # x, dy read + dx write
             if name in ("add_noise", "mse_fwd_bwd"):
@@ -452,7 +494,7 @@ class OpProfiler:
                 dy, x0, x1, taps, dw, grid = args[:6]
                 cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
                 return f"|{grid[1]}x{grid[2]} c{cin}->{dy.shape[-1]} k{len(taps)}"
-            if name in ("gn_bwd", "gn_apply", "gn_stats", "gn_fwd"):
+            if name in ("gn_bwd", "gn_bwd_apply", "gn_apply", "gn_stats", "gn_fwd"):
                 x0, x1 = args[0], args[1]
                 c = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
                 return f"|{x0.shape[1]}x{x0.shape[2]} c{c}"

@@ -652,10 +652,18 @@ class UNet2DModel(nn.Module):
         grid = (N, H, W)
         g1, be1 = self._norm_params(r.norm1)
         g2, be2 = self._norm_params(r.norm2)
-        stats1, a = ops.gn_fwd(x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True)
+        fuse = st.tape is not None and ops.gn_bwd_fusable(grid)   # backward runs its first GN half in the dgrad epilogue
+        coef1 = coef2 = None
+        if fuse:
+            stats1, a, coef1 = ops.gn_fwd(x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True, want_coef=True)
+        else:
+            stats1, a = ops.gn_fwd(x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True)
         temb = st.temb_all[:, r.temb_off:r.temb_off + r.cout]
         h1 = ops.conv_gemm(a, None, taps_3x3(r.cin), r.conv1.wf, r.cout, grid, bias=self._bias(r.conv1), temb=temb)
-        stats2, b = ops.gn_fwd(h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True)
+        if fuse:
+            stats2, b, coef2 = ops.gn_fwd(h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True, want_coef=True)
+        else:
+            stats2, b = ops.gn_fwd(h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True)
         if r.short is not None:
             sc = ops.conv_gemm(x0, x1, taps_1x1(), r.short.wf, r.cout, grid, bias=self._bias(r.short))
         else:
@@ -663,7 +671,8 @@ class UNet2DModel(nn.Module):
         out = ops.conv_gemm(b, None, taps_3x3(r.cout), r.conv2.wf, r.cout, grid, bias=self._bias(r.conv2), res=sc)
         if st.tape is not None:
             st.tape.add(("resnet", r, SimpleNamespace(x0=x0, x1=x1, stats1=stats1, a=a, h1=h1, stats2=stats2, b=b,
-                                                       in_skip=in_skip, skip_idx=skip_idx, grid=grid)))
+                                                       in_skip=in_skip, skip_idx=skip_idx, grid=grid, coef1=coef1,
+                                                       coef2=coef2)))
         return out
 
     def _attn_fwd(self, st, at, x, in_skip=None):
@@ -831,16 +840,31 @@ class UNet2DModel(nn.Module):
             ops.reduce_hw(g, None, self._wgrad_views(G, r.short)[1])
         if r.conv2.trainable:
             ops.conv_wgrad(g, s.b, None, taps_3x3(r.cout), dW2, grid)
-        d_b = ops.conv_gemm(g, None, taps_3x3(r.cout), r.conv2.wd, r.cout, grid)
         g2, be2 = self._norm_params(r.norm2)
         dg, dbt = self._norm_grads(G, r.norm2)
-        d_h1, _ = ops.gn_bwd(s.h1, None, r.norm2.groups, s.stats2, r.norm2.eps, g2, be2, True, d_b, dgamma=dg, dbeta=dbt)
+        fuse = s.coef2 is not None
+        if fuse:   # SiLU/GroupNorm derivative + per-(n, c) sums in the dgrad epilogue, then one streaming pass
+            sums = torch.zeros((grid[0], r.cout, 2), device=g.device, dtype=torch.float32)
+            dz = ops.conv_gemm(g, None, taps_3x3(r.cout), r.conv2.wd, r.cout, grid,
+                               gn=(s.h1, None, s.coef2, True, sums))
+            d_h1, _ = ops.gn_bwd_apply(s.h1, None, r.norm2.groups, s.stats2, r.norm2.eps, g2, dz, sums,
+                                       dgamma=dg, dbeta=dbt)
+        else:
+            d_b = ops.conv_gemm(g, None, taps_3x3(r.cout), r.conv2.wd, r.cout, grid)
+            d_h1, _ = ops.gn_bwd(s.h1, None, r.norm2.groups, s.stats2, r.norm2.eps, g2, be2, True, d_b, dgamma=dg,
+                                 dbeta=dbt)
         # time embedding + conv1 bias share sum_hw(d_h1)
         dW1, db1 = self._wgrad_views(G, r.conv1)
         ops.reduce_hw(d_h1, st.d_temb_all[:, r.temb_off:r.temb_off + r.cout], db1 if r.conv1.bias_trainable else None)
         if r.conv1.trainable:
             ops.conv_wgrad(d_h1, s.a, None, taps_3x3(r.cin), dW1, grid)
-        d_a = ops.conv_gemm(d_h1, None, taps_3x3(r.cout), r.conv1.wd, r.cin, grid)
+        g1, be1 = self._norm_params(r.norm1)
+        if fuse:
+            sums1 = torch.zeros((grid[0], r.cin, 2), device=g.device, dtype=torch.float32)
+            d_a = ops.conv_gemm(d_h1, None, taps_3x3(r.cout), r.conv1.wd, r.cin, grid,
+                                gn=(s.x0, s.x1, s.coef1, True, sums1))
+        else:
+            d_a = ops.conv_gemm(d_h1, None, taps_3x3(r.cout), r.conv1.wd, r.cin, grid)
         if r.short is not None:
             if r.short.trainable:
                 ops.conv_wgrad(g, s.x0, s.x1, taps_1x1(), self._wgrad_views(G, r.short)[0], grid)
@@ -848,10 +872,13 @@ class UNet2DModel(nn.Module):
         else:
             d_sc = g
         extra = st.skip_grads.pop(s.in_skip, None) if s.in_skip is not None else None
-        g1, be1 = self._norm_params(r.norm1)
         dg, dbt = self._norm_grads(G, r.norm1)
-        dx0, dx1 = ops.gn_bwd(s.x0, s.x1, r.norm1.groups, s.stats1, r.norm1.eps, g1, be1, True, d_a, add0=d_sc,
-                              add1=extra, dgamma=dg, dbeta=dbt)
+        if fuse:
+            dx0, dx1 = ops.gn_bwd_apply(s.x0, s.x1, r.norm1.groups, s.stats1, r.norm1.eps, g1, d_a, sums1, add0=d_sc,
+                                        add1=extra, dgamma=dg, dbeta=dbt)
+        else:
+            dx0, dx1 = ops.gn_bwd(s.x0, s.x1, r.norm1.groups, s.stats1, r.norm1.eps, g1, be1, True, d_a, add0=d_sc,
+                                  add1=extra, dgamma=dg, dbeta=dbt)
         if s.x1 is not None:
             st.skip_grads[s.skip_idx] = dx1
         return dx0

@@ -67,8 +67,13 @@ class EmuOps:
             out[i0:i1, j0:j1, k0:k1] = X[i0 + dn:i1 + dn, j0 + dh:j1 + dh, k0 + dw:k1 + dw]
         return out
 
+    @staticmethod
+    def gn_bwd_fusable(grid):
+        hw = grid[1] * grid[2]
+        return hw >= 128 or hw % 32 == 0
+
     def conv_gemm(self, x0, x1, taps, wgt, cout, grid, bias=None, temb=None, res=None, out=None, out_f32=False,
-                  src_n=0):
+                  src_n=0, gn=None):
         n, h, w = grid
         X = x0 if x1 is None else torch.cat([x0, x1], -1)
         X = X.float()
@@ -83,6 +88,20 @@ class EmuOps:
             acc += temb[:, None, None, :cout]
         if res is not None:
             acc += res.float()
+        if gn is not None:
+            gx0, gx1, gcoef, gsilu, gsums = gn
+            Xg = (gx0 if gx1 is None else torch.cat([gx0, gx1], -1)).float()
+            if gsilu:
+                Cg = Xg.shape[-1]
+                ka = torch.stack([gcoef[..., 0], gcoef[..., 1]], -1).reshape(-1, Cg)
+                kb = torch.stack([gcoef[..., 2], gcoef[..., 3]], -1).reshape(-1, Cg)
+                with torch.enable_grad():
+                    z = (Xg * ka[:, None, None, :] + kb[:, None, None, :]).detach().requires_grad_(True)
+                    F.silu(z).backward(acc)
+                acc = z.grad
+            dzr = self._a(acc).float()
+            gsums[..., 0] += dzr.sum((1, 2))
+            gsums[..., 1] += (dzr * Xg).sum((1, 2))
         r = acc if out_f32 else self._a(acc)
         if out is not None:
             out.copy_(r)
@@ -180,9 +199,18 @@ class EmuOps:
             return out
         return r
 
-    def gn_fwd(self, x0, x1, groups, eps, gamma, beta, silu, out=None):
+    def gn_fwd(self, x0, x1, groups, eps, gamma, beta, silu, out=None, want_coef=False):
         stats = self.gn_stats(x0, x1, groups)
-        return stats, self.gn_apply(x0, x1, groups, stats, eps, gamma, beta, silu, out=out)
+        y = self.gn_apply(x0, x1, groups, stats, eps, gamma, beta, silu, out=out)
+        if not want_coef:
+            return stats, y
+        n, h, w, C = y.shape
+        cpg = C // groups
+        mean, rstd = self._mean_rstd(stats, cpg * h * w, eps)
+        ka = rstd.repeat_interleave(cpg, 1) * gamma                     # [n, C]
+        kb = beta - mean.repeat_interleave(cpg, 1) * ka
+        coef = torch.stack([ka[:, 0::2], ka[:, 1::2], kb[:, 0::2], kb[:, 1::2]], -1).contiguous()   # [n, C/2, 4]
+        return stats, y, coef
 
     def gn_bwd(self, x0, x1, groups, stats, eps, gamma, beta, silu, dy, add0=None, add1=None, dgamma=None,
                dbeta=None, need_dx1=True):
@@ -205,6 +233,35 @@ class EmuOps:
             dgamma += g.grad
         if dbeta is not None:
             dbeta += b.grad
+        dx = self._a(dx)
+        dx0 = dx[..., :c0].contiguous()
+        dx1 = dx[..., c0:].contiguous() if (x1 is not None and need_dx1) else None
+        return dx0, dx1
+
+    def gn_bwd_apply(self, x0, x1, groups, stats, eps, gamma, dz, sums, add0=None, add1=None, dgamma=None,
+                     dbeta=None, need_dx1=True):
+        X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
+        n, h, w, C = X.shape
+        c0 = x0.shape[-1]
+        cpg = C // groups
+        m = cpg * h * w
+        mean, rstd = self._mean_rstd(stats, m, eps)
+        mean_c = mean.repeat_interleave(cpg, 1)
+        rstd_c = rstd.repeat_interleave(cpg, 1)
+        S1 = sums[..., 0]
+        S2h = rstd_c * (sums[..., 1] - mean_c * S1)                       # sum dz * xhat
+        s1 = (gamma * S1).reshape(n, groups, cpg).sum(-1).repeat_interleave(cpg, 1) / m
+        s2 = (gamma * S2h).reshape(n, groups, cpg).sum(-1).repeat_interleave(cpg, 1) / m
+        xh = (X - mean_c[:, None, None, :]) * rstd_c[:, None, None, :]
+        dx = (dz.float() * gamma - s1[:, None, None, :] - xh * s2[:, None, None, :]) * rstd_c[:, None, None, :]
+        if add0 is not None:
+            dx = dx + add0.float()
+        if add1 is not None:
+            dx = dx + add1.float()
+        if dgamma is not None:
+            dgamma += S2h.sum(0)
+        if dbeta is not None:
+            dbeta += S1.sum(0)
         dx = self._a(dx)
         dx0 = dx[..., :c0].contiguous()
         dx1 = dx[..., c0:].contiguous() if (x1 is not None and need_dx1) else None

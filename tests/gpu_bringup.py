@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
 
-GROUPS = ["elementwise", "gn", "misc", "smallconv", "attention", "gemm", "wgrad"]
+GROUPS = ["elementwise", "gn", "misc", "smallconv", "attention", "gemm", "wgrad", "gnfuse"]
 
 
 def rel(a, b):
@@ -412,6 +412,53 @@ def g_wgrad(ops):
             xin = F.pad(xin, (0, 1, 0, 1))
         F.conv2d(xin, wr, None, stride=2, padding=pad).backward(dy.float().permute(0, 3, 1, 2))
         ok &= report(f"conv3x3 stride2 wgrad pad={pad}", dw, wr.grad.permute(0, 2, 3, 1).reshape(c, -1), 2e-3)
+    return ok
+
+
+def g_gnfuse(ops):
+    """GroupNorm backward split: first half in the dgrad conv epilogue (dz + per-(n,c) sums), second half streaming."""
+    from polyp_image_generator_b200.ops import taps_3x3
+    ok = True
+    dev = "cuda"
+    torch.manual_seed(11)
+    #        n, h,   w,   c0,  c1,  cin_of_dgrad
+    cases = [(2, 128, 128, 128, 0, 128), (3, 32, 32, 256, 0, 256), (4, 8, 8, 512, 0, 512), (2, 64, 64, 128, 128, 128),
+             (5, 16, 16, 256, 128, 256), (1, 64, 64, 128, 0, 256)]
+    for (n, h, w, c0, c1, cg) in cases:
+        C = c0 + c1
+        grid = (n, h, w)
+        assert ops.gn_bwd_fusable(grid)
+        xa = bf(torch.randn(n, h, w, c0, device=dev) * 1.3 + 0.2)
+        xb = bf(torch.randn(n, h, w, c1, device=dev) - 0.1) if c1 else None
+        gamma = torch.randn(C, device=dev) * 0.5 + 1
+        beta = torch.randn(C, device=dev) * 0.2
+        eps = 1e-5
+        stats, _, coef = ops.gn_fwd(xa, xb, 32, eps, gamma, beta, True, want_coef=True)
+        g = bf(torch.randn(n, h, w, cg, device=dev))
+        wd = bf(torch.randn(C, 9 * cg, device=dev) * 0.05)       # dgrad operand: [C (= conv input chans), 9*cg]
+        add0 = bf(torch.randn(n, h, w, C, device=dev))
+        # unfused reference path through the same kernels
+        d_y = ops.conv_gemm(g, None, taps_3x3(cg), wd, C, grid)
+        dg_r, db_r = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        r0, r1 = ops.gn_bwd(xa, xb, 32, stats, eps, gamma, beta, True, d_y, add0=add0, dgamma=dg_r, dbeta=db_r)
+        # fused path
+        sums = torch.zeros(n, C, 2, device=dev)
+        dz = ops.conv_gemm(g, None, taps_3x3(cg), wd, C, grid, gn=(xa, xb, coef, True, sums))
+        dg_f, db_f = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        f0, f1 = ops.gn_bwd_apply(xa, xb, 32, stats, eps, gamma, dz, sums, add0=add0, dgamma=dg_f, dbeta=db_f)
+        # fp32 autograd reference of the GroupNorm+SiLU backward on the bf16 dy the conv produced
+        xcat = torch.cat([xa, xb], -1) if c1 else xa
+        xr = xcat.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        F.silu(F.group_norm(xr, 32, gr, br, eps)).backward(d_y.float().permute(0, 3, 1, 2))
+        want = xr.grad.permute(0, 2, 3, 1) + add0.float()
+        got = torch.cat([f0, f1], -1) if c1 else f0
+        ref_k = torch.cat([r0, r1], -1) if c1 else r0
+        tag = f"gnfuse n{n} {h}x{w} c{c0}+{c1} <- {cg}"
+        ok &= report(tag + " dx vs autograd", got, want, 1e-2)
+        ok &= report("   dx vs unfused kernels", got, ref_k, 1e-2)
+        ok &= report("   dgamma", dg_f, gr.grad, 1e-2)
+        ok &= report("   dbeta", db_f, br.grad, 1e-2)
     return ok
 
 
