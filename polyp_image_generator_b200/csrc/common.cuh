@@ -49,6 +49,11 @@ int make_wgt_map(CUtensorMap* out, const void* ptr, long long k_total, long long
 int env_int(const char* name, int dflt);
 // halo-resident 3x3 conv: returns 1 when the problem is not eligible (caller falls back to the generic kernel)
 int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream);
+}
+struct ddpm_wgrad_args;
+namespace ddpm {
+// row-resident 3x3 wgrad: returns 1 when not eligible
+int launch_wgrad_row(const ::ddpm_wgrad_args* a, cudaStream_t stream);
 struct EpiParams;
 int fill_epilogue(EpiParams* e, const ::ddpm_conv_args* a);
 

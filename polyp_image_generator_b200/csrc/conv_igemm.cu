@@ -604,6 +604,10 @@ extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream_) {
                "ddpm_conv_wgrad: channel counts must be multiples of 64 (c0=%d c1=%d)", a->c0, a->c1);
   DDPM_REQUIRE(a->cout > 0 && a->cout % 64 == 0, "ddpm_conv_wgrad: cout=%d must be a multiple of 64", a->cout);
   DDPM_REQUIRE(a->ldw % 4 == 0, "ddpm_conv_wgrad: ldw must be a multiple of 4");
+  {
+    const int rr = launch_wgrad_row(a, stream);   // 3x3 stride-1 convs at high resolution: row-resident kernel
+    if (rr <= 0) return rr;
+  }
   WgradParams p;
   std::memset(&p, 0, sizeof(p));
   if (a->ntaps < 1 || a->ntaps > kMaxTaps) { set_last_error("ntaps=%d out of range", a->ntaps); return DDPM_ERR_INVALID; }

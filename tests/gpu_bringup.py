@@ -379,7 +379,10 @@ def g_wgrad(ops):
         want = dy.float().reshape(M, Co).t() @ x.float().reshape(M, Ci)
         ok &= report(f"linear wgrad M{M} Co{Co} Ci{Ci} splits={splits}", dw, want, 2e-3)
     for (n, h, w_, cin, cout) in [(2, 16, 16, 128, 128), (1, 64, 64, 128, 256), (4, 8, 8, 512, 512),
-                                  (9, 4, 4, 256, 512), (2, 14, 14, 128, 128), (3, 7, 7, 64, 128)]:
+                                  (9, 4, 4, 256, 512), (2, 14, 14, 128, 128), (3, 7, 7, 64, 128),
+                                  # row-resident kernel (W >= 64, W % 16 == 0, channels % 128 == 0)
+                                  (2, 128, 128, 128, 128), (1, 64, 64, 256, 128), (1, 256, 256, 128, 128),
+                                  (1, 80, 80, 128, 128), (3, 5, 64, 128, 256), (1, 64, 96, 384, 128)]:
         x = bf(torch.randn(n, h, w_, cin, device=dev))
         dy = bf(torch.randn(n, h, w_, cout, device=dev))
         dw = torch.zeros(cout, 9 * cin, device=dev)
@@ -398,6 +401,15 @@ def g_wgrad(ops):
     F.conv2d(torch.cat([xa, xb], -1).float().permute(0, 3, 1, 2), wr, None, padding=1).backward(
         dy.float().permute(0, 3, 1, 2))
     ok &= report("conv3x3 wgrad concat", dw, wr.grad.permute(0, 2, 3, 1).reshape(cout, -1), 2e-3)
+    n, h, w_, c0, c1, cout = 2, 64, 64, 128, 128, 128     # row-resident kernel, two sources
+    xa, xb = bf(torch.randn(n, h, w_, c0, device=dev)), bf(torch.randn(n, h, w_, c1, device=dev))
+    dy = bf(torch.randn(n, h, w_, cout, device=dev))
+    dw = torch.zeros(cout, 9 * (c0 + c1), device=dev)
+    ops.conv_wgrad(dy, xa, xb, taps_3x3(c0 + c1), dw, (n, h, w_))
+    wr = torch.zeros(cout, c0 + c1, 3, 3, device=dev, requires_grad=True)
+    F.conv2d(torch.cat([xa, xb], -1).float().permute(0, 3, 1, 2), wr, None, padding=1).backward(
+        dy.float().permute(0, 3, 1, 2))
+    ok &= report("conv3x3 wgrad concat 64x64 (row kernel)", dw, wr.grad.permute(0, 2, 3, 1).reshape(cout, -1), 2e-3)
     # stride 2
     for pad in (1, 0):
         n, h, w_, c = 2, 16, 16, 128
