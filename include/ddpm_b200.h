@@ -130,6 +130,14 @@ int ddpm_conv3_wgrad(const void* big, long long ldbig, int cbig, const float* sm
                      long long s_c, long long s_tap, long long s_k, int flip, float* dbias_small, int n, int h,
                      int wd, void* stream);
 
+/* The 3-channel boundary convs on tensor cores (conv_in forward / conv_out dgrad: K = 27 padded to one 64-wide
+ * k-block; conv_out forward: N = 3 padded to 32 output columns):
+ *   ddpm_im2col3: patches[pix][tap*cin + k] = src[n, k, h+tap/3-1, w+tap%3-1] (bf16 [n*h*w][64], zero padded);
+ *                 chan_sum[k] += sum of src[:, k] when non-NULL (conv_out bias gradient).
+ *   ddpm_nhwc_to_nchw_f32: out[n][k][h][w] = src[pix][k], k < cout <= 4 (src fp32 NHWC, pixel stride ld). */
+int ddpm_im2col3(const float* src, void* patches, int n, int h, int w, int cin, float* chan_sum, void* stream);
+int ddpm_nhwc_to_nchw_f32(const float* src, long long ld, float* out, int n, int h, int w, int cout, void* stream);
+
 /* GroupNorm statistics: stats[n][g] = (sum, sumsq) over the (possibly concatenated) channels of group g. */
 int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                   int groups, float* stats, void* stream);

@@ -71,6 +71,8 @@ SIGNATURES = {
     "ddpm_conv3_to_c": [_vp, _vp, _ll, _ll, _ll, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
     "ddpm_conv_c_to_3": [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ddpm_conv3_wgrad": [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _ll, _i, _vp, _i, _i, _i, _vp],
+    "ddpm_im2col3": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "ddpm_nhwc_to_nchw_f32": [_vp, _ll, _vp, _i, _i, _i, _i, _vp],
     "ddpm_gn_stats": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _vp],
     "ddpm_gn_apply": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp],
     "ddpm_gn_fwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp, _vp],

@@ -231,7 +231,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // the key includes the box, so the shared cache is safe to reuse)
 int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
   if (env_int("DDPM_HALO", 1) == 0) return 1;
-  if (a->ntaps != 9 || a->out == nullptr || a->out_f32 != nullptr) return 1;
+  if (a->ntaps != 9 || (a->out == nullptr && a->out_f32 == nullptr)) return 1;
   if (a->src_n != 0 && a->src_n != a->n) return 1;
   const int cin_total = a->c0 + a->c1;
   for (int t = 0; t < 9; ++t) {

@@ -245,6 +245,62 @@ __global__ void sumpool2x_kernel(const __nv_bfloat16* __restrict__ dy, long long
   }
 }
 
+// ---- 3-channel boundary convs as GEMMs --------------------------------------------------------------------------
+// im2col of a <=4-channel NCHW fp32 image for a 3x3 / pad-1 correlation: patches[pix][tap*cin + k] =
+// src[n, k, h + tap/3 - 1, w + tap%3 - 1] (bf16, zero outside the image), columns 9*cin .. 63 are zero.  One 128-byte
+// row per pixel = one SWIZZLE_128B k-block, so conv_in (and conv_out's dgrad) become ONE-k-block tcgen05 GEMMs.
+// Optionally accumulates the per-channel sums of src (conv_out's bias gradient).  One thread = one pixel x 8 columns.
+__global__ void __launch_bounds__(256)
+im2col3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ patches, int N, int H, int W, int cin,
+               float* __restrict__ chan_sum, long long npix) {
+  __shared__ float ssum[4];
+  if (threadIdx.x < 4) ssum[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long hw = static_cast<long long>(H) * W;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long pix = gid >> 3;
+  const int part = static_cast<int>(gid & 7);     // columns part*8 .. part*8+7
+  if (pix < npix) {
+    const int n = static_cast<int>(pix / hw);
+    const int rem = static_cast<int>(pix - n * hw);
+    const int h = rem / W, w = rem - h * W;
+    const float* sn = src + static_cast<long long>(n) * cin * hw;
+    float f[8];
+    const int kk = 9 * cin;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = part * 8 + e;
+      float v = 0.f;
+      if (col < kk) {
+        const int tap = col / cin, k = col - tap * cin;
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(sn + k * hw + static_cast<long long>(hh) * W + ww);
+      }
+      f[e] = v;
+    }
+    *reinterpret_cast<bf16x8*>(patches + pix * 64 + part * 8) = pack8(f);
+    if (chan_sum != nullptr && part == 0) {
+      for (int k = 0; k < cin; ++k) atomicAdd(&ssum[k], __ldg(sn + k * hw + rem));
+    }
+  }
+  if (chan_sum != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < cin) atomicAdd(&chan_sum[threadIdx.x], ssum[threadIdx.x]);
+  }
+}
+
+// out[n][k][h][w] (NCHW fp32) = src[pix][k] for k < cout, src NHWC fp32 with pixel stride ld (conv_out's GEMM result)
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_f32_kernel(const float* __restrict__ src, long long ld, float* __restrict__ out, int cout, long long hw,
+                        long long npix) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const long long n = pix / hw, rem = pix - n * hw;
+  const float4 v = *reinterpret_cast<const float4*>(src + pix * ld);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  for (int k = 0; k < cout; ++k) out[(n * cout + k) * hw + rem] = f[k];
+}
+
 }  // namespace ddpm
 
 using namespace ddpm;
@@ -362,4 +418,24 @@ extern "C" int ddpm_sumpool2x(const void* dy, long long ldy, const void* add, lo
       static_cast<const __nv_bfloat16*>(dy), ldy, static_cast<const __nv_bfloat16*>(add), ldadd,
       static_cast<__nv_bfloat16*>(out), n, h, w, c, total_vec);
   return check_launch("sumpool2x_kernel");
+}
+
+extern "C" int ddpm_im2col3(const float* src, void* patches, int n, int h, int w, int cin, float* chan_sum,
+                            void* stream) {
+  DDPM_REQUIRE(src && patches && n > 0 && h > 0 && w > 0 && cin >= 1 && cin <= 4, "ddpm_im2col3: bad argument");
+  const long long npix = static_cast<long long>(n) * h * w;
+  const long long blocks = (npix * 8 + 255) / 256;
+  im2col3_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(patches), n, h, w, cin, chan_sum, npix);
+  return check_launch("im2col3_kernel");
+}
+
+extern "C" int ddpm_nhwc_to_nchw_f32(const float* src, long long ld, float* out, int n, int h, int w, int cout,
+                                     void* stream) {
+  DDPM_REQUIRE(src && out && n > 0 && h > 0 && w > 0 && cout >= 1 && cout <= 4 && ld % 4 == 0 && ld >= 4,
+               "ddpm_nhwc_to_nchw_f32: bad argument");
+  const long long npix = static_cast<long long>(n) * h * w;
+  nhwc_to_nchw_f32_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld, out, cout, static_cast<long long>(h) * w, npix);
+  return check_launch("nhwc_to_nchw_f32_kernel");
 }

@@ -243,6 +243,23 @@ class CudaOps:
                                               _stream()), "ddpm_conv3_wgrad")
         self.launches += 1
 
+    def im2col3(self, x, chan_sum=None):
+        """x: NCHW fp32 [n, cin<=4, h, w] -> 3x3/pad-1 patches, NHWC bf16 [n, h, w, 64] (columns tap*cin + k)."""
+        n, cin, h, w = x.shape
+        out = torch.empty((n, h, w, 64), device=x.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_im2col3(_ptr(x), _ptr(out), n, h, w, cin, _ptr(chan_sum), _stream()), "ddpm_im2col3")
+        self.launches += 1
+        return out
+
+    def nhwc_to_nchw_f32(self, src, cout: int):
+        """src: fp32 [n, h, w, ld] -> NCHW fp32 [n, cout, h, w] of its first cout (<= 4) channels."""
+        n, h, w, ld = src.shape
+        out = torch.empty((n, cout, h, w), device=src.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_nhwc_to_nchw_f32(_ptr(src), ld, _ptr(out), n, h, w, cout, _stream()),
+                    "ddpm_nhwc_to_nchw_f32")
+        self.launches += 1
+        return out
+
     # ---- GroupNorm ---------------------------------------------------------------------------------------
     def gn_stats(self, x0, x1, groups: int):
         n, h, w, c0, ld0 = _nhwc(x0, "x0")

@@ -458,6 +458,12 @@ class UNet2DModel(nn.Module):
             boff = _align(boff + gobj.cout * (k + gobj.extra_k), 64)
             gobj.wd_off, gobj.wd_shape = boff, (gobj.cin, gobj.taps * gobj.cout)
             boff = _align(boff + gobj.cin * gobj.taps * gobj.cout, 64)
+        # boundary convs as one-k-block GEMMs: conv_in operand [c0, 64], conv_out fprop operand [32, 9*c0] (rows >=
+        # out_channels are zero) and conv_out dgrad operand [c0, 64]
+        c0 = self.conv_in.out_channels
+        P.cin_wf_off, boff = boff, _align(boff + c0 * 64, 64)
+        P.cout_wf_off, boff = boff, _align(boff + 32 * 9 * c0, 64)
+        P.cout_wd_off, boff = boff, _align(boff + c0 * 64, 64)
         P.bf16_total = boff
         return P
 
@@ -495,6 +501,11 @@ class UNet2DModel(nn.Module):
         for gobj in P.gemms:
             gobj.wf = self._bf16[gobj.wf_off:gobj.wf_off + gobj.wf_shape[0] * gobj.wf_shape[1]].view(gobj.wf_shape)
             gobj.wd = self._bf16[gobj.wd_off:gobj.wd_off + gobj.wd_shape[0] * gobj.wd_shape[1]].view(gobj.wd_shape)
+        c0 = self.conv_in.out_channels
+        self._cin_wf = self._bf16[P.cin_wf_off:P.cin_wf_off + c0 * 64].view(c0, 64)
+        self._cout_wf = self._bf16[P.cout_wf_off:P.cout_wf_off + 32 * 9 * c0].view(32, 9 * c0)
+        self._cout_wd = self._bf16[P.cout_wd_off:P.cout_wd_off + c0 * 64].view(c0, 64)
+        self._cout_b32 = torch.zeros(32, device=dev, dtype=torch.float32)
         self._wcache_key = None
 
     def _apply(self, fn, *a, **k):
@@ -514,7 +525,8 @@ class UNet2DModel(nn.Module):
         key = None
         if not training:
             key = tuple(w._version for gobj in P.gemms for w in gobj.weights) + \
-                tuple(p._version for _, p in P.extra_params)
+                tuple(p._version for _, p in P.extra_params) + \
+                (self.conv_in.weight._version, self.conv_out.weight._version, self.conv_out.bias._version)
             if key == self._wcache_key:
                 return
         ops = _ops.get()
@@ -534,6 +546,17 @@ class UNet2DModel(nn.Module):
                 o = _align(o + n)
             if gobj.lora is not None:
                 gobj.lora.write_operands(gobj)
+        # boundary convs (a few thousand elements: plain tensor copies)
+        cfg = self.config
+        c0, ci, co = cfg.block_out_channels[0], cfg.in_channels, cfg.out_channels
+        with torch.no_grad():
+            w_in = self._aview(P.cin_w, (c0, 9 * ci))                   # [c0][tap][ci]
+            self._cin_wf[:, :9 * ci].copy_(w_in)
+            w_out = self._aview(P.cout_w, (co, 9, c0))                  # [co][tap][ci]
+            self._cout_wf[:co].copy_(w_out.reshape(co, 9 * c0))
+            self._cout_b32[:co].copy_(self._aview(P.cout_b, (co,)))
+            if need_d:   # dgrad operand: Wd[ci][tap'*co_n + co] = w[co][8 - tap'][ci]
+                self._cout_wd[:, :9 * co].copy_(w_out.flip(1).permute(2, 1, 0).reshape(c0, 9 * co))
         self._wcache_key = key
 
     # ---------------------------------------------------------------------------------------------------------
@@ -602,8 +625,8 @@ class UNet2DModel(nn.Module):
                              d_temb_all=None)
 
         # ---- conv_in ----
-        wci = self._aview(P.cin_w, (c0, 9, cfg.in_channels))
-        h = ops.conv3_to_c(x, wci, (9 * cfg.in_channels, cfg.in_channels, 1), False, self._aview(P.cin_b, (c0,)), c0)
+        patches = ops.im2col3(x)                                   # [N, H, W, 64] bf16, one k-block
+        h = ops.conv_gemm(patches, None, taps_1x1(), self._cin_wf, c0, (N, H, W), bias=self._aview(P.cin_b, (c0,)))
         skips = [h]
 
         # ---- down ----
@@ -634,10 +657,10 @@ class UNet2DModel(nn.Module):
         no = P.norm_out
         gam, bet = self._aview(no.g_off, (c0,)), self._aview(no.b_off, (c0,))
         stats, a = ops.gn_fwd(h, None, no.groups, no.eps, gam, bet, True)
-        wco = self._aview(P.cout_w, (cfg.out_channels, 9, c0))
-        out = ops.conv_c_to_3(a, wco, self._aview(P.cout_b, (cfg.out_channels,)), cfg.out_channels)
+        o32 = ops.conv_gemm(a, None, taps_3x3(c0), self._cout_wf, 32, (N, H, W), bias=self._cout_b32, out_f32=True)
+        out = ops.nhwc_to_nchw_f32(o32, cfg.out_channels)
         if training:
-            tape.head = SimpleNamespace(x=x, t_emb=t_emb, e1=e1, emb=emb, h_last=h, stats=stats, a=a)
+            tape.head = SimpleNamespace(patches=patches, t_emb=t_emb, e1=e1, emb=emb, h_last=h, stats=stats, a=a)
         self.last_launches = ops.launches - l0
         return out
 
@@ -738,7 +761,7 @@ class UNet2DModel(nn.Module):
         P = self._plan
         cfg = self.config
         hd = tape.head
-        N = hd.x.shape[0]
+        N = hd.patches.shape[0]
         c0 = cfg.block_out_channels[0]
         ted = self._temb_dim
         G = torch.zeros(P.total, device=self._arena.device, dtype=torch.float32)
@@ -757,11 +780,15 @@ class UNet2DModel(nn.Module):
 
         # ---- conv_out / conv_norm_out ----
         no = P.norm_out
-        wco = self._aview(P.cout_w, (cfg.out_channels, 9, c0))
-        if self.conv_out.weight.requires_grad:
-            ops.conv3_wgrad(hd.a, d_out, self._gview(G, P.cout_w, (cfg.out_channels, 9, c0)), (1, c0, 9 * c0), True,
-                            self._gview(G, P.cout_b, (cfg.out_channels,)))
-        d_a = ops.conv3_to_c(d_out, wco, (1, c0, 9 * c0), True, None, c0)
+        co = cfg.out_channels
+        grid0 = tuple(hd.a.shape[:3])
+        train_out = self.conv_out.weight.requires_grad
+        pd = ops.im2col3(d_out, chan_sum=self._gview(G, P.cout_b, (co,)) if train_out else None)
+        if train_out:   # R[ci][tap'*co_n + co] = sum_pix a[pix, ci] * d_out[pix + off(tap'), co]
+            R = torch.zeros((c0, 64), device=G.device, dtype=torch.float32)
+            ops.conv_wgrad(hd.a, pd, None, taps_1x1(), R, grid0)
+            self._gview(G, P.cout_w, (co, 9, c0)).add_(R[:, :9 * co].view(c0, 9, co).flip(1).permute(2, 1, 0))
+        d_a = ops.conv_gemm(pd, None, taps_1x1(), self._cout_wd, c0, grid0)
         gam, bet = self._norm_params(no)
         tr = no.trainable
         g, _ = ops.gn_bwd(hd.h_last, None, no.groups, hd.stats, no.eps, gam, bet, True, d_a,
@@ -786,8 +813,9 @@ class UNet2DModel(nn.Module):
             # g is now the gradient of conv_in's output (skip 0 already folded in by the first resnet)
             if self.conv_in.weight.requires_grad:
                 ops.reduce_hw(g, None, self._gview(G, P.cin_b, (c0,)))
-                ops.conv3_wgrad(g, hd.x, self._gview(G, P.cin_w, (c0, 9, cfg.in_channels)),
-                                (9 * cfg.in_channels, cfg.in_channels, 1), False)
+                R = torch.zeros((c0, 64), device=G.device, dtype=torch.float32)
+                ops.conv_wgrad(g, hd.patches, None, taps_1x1(), R, tuple(g.shape[:3]))
+                self._gview(G, P.cin_w, (c0, 9 * cfg.in_channels)).add_(R[:, :9 * cfg.in_channels])
         # ---- time-embedding MLP ----
         if self._temb_trainable() or self.time_embedding.linear_1.weight.requires_grad:
             wt = self._aview(P.temb_w_off, (P.temb_total, ted))

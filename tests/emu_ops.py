@@ -170,6 +170,20 @@ class EmuOps:
             dbias_small += small.sum((0, 2, 3))
 
     # ---- GroupNorm -------------------------------------------------------------------------------------------
+    def im2col3(self, x, chan_sum=None):
+        n, cin, h, w = x.shape
+        xp = F.pad(x.float(), (1, 1, 1, 1))
+        cols = [xp[:, :, r:r + h, s:s + w] for r in range(3) for s in range(3)]        # tap-major
+        pat = torch.stack(cols, 1).permute(0, 3, 4, 1, 2).reshape(n, h, w, 9 * cin)  # [.., tap*cin + k]
+        out = torch.zeros((n, h, w, 64), dtype=torch.float32)
+        out[..., :9 * cin] = pat
+        if chan_sum is not None:
+            chan_sum += x.float().sum((0, 2, 3))
+        return self._a(out)
+
+    def nhwc_to_nchw_f32(self, src, cout):
+        return src[..., :cout].permute(0, 3, 1, 2).contiguous().float()
+
     def gn_stats(self, x0, x1, groups):
         X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
         n, h, w, C = X.shape
