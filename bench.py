@@ -203,7 +203,7 @@ def run_b200(args, rank, world, local_rank):
     model = UNet2DModel(**oracle.polyp_unet_config(S)).to(dev)
     model.train()
     sched = DDPMScheduler(num_train_timesteps=1000)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True, capturable=not args.no_graph)
     net = model
     if world > 1:
         from polyp_image_generator_b200.ddp import DistributedDataParallel
@@ -253,26 +253,33 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step(clean_dev, noise_dev, t_dev)
     barrier()
+    l_step0 = ops.launches
+    step(clean_dev, noise_dev, t_dev)
+    launches_per_step = ops.launches - l_step0
+    eager_step = step
+    if not args.no_graph:
+        # the timed steps replay the SAME launches from one CUDA graph (graphs.py): host issue time is ~44 ms per
+        # step in eager mode, as much as the GPU needs to execute it
+        from polyp_image_generator_b200.graphs import GraphedTrainStep
+        gstep = GraphedTrainStep(net, sched, opt, clean_dev.shape, max_grad_norm=1.0)
+        step = gstep
+    barrier()
 
     # ---- timed region 1: device-resident inputs ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = ops.launches
-    prof["on"] = True
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_begin.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         loss = step(clean_dev, noise_dev, t_dev)
+    host_issue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps   # CPU time to ENQUEUE one step (no sync)
     e_end.record()
     barrier()
-    prof["on"] = False
     clocks = sampler.stop()
-    launches = ops.launches - l0
+    launches = launches_per_step * args.steps
     ms_total = e_begin.elapsed_time(e_end)
-    gemm_ms = sum(a.elapsed_time(b) for a, b in prof["ev"])
-    gemm_launches = len(prof["ev"])
-    gemm_flops = prof["flops"]
     final_loss = float(loss.item())
 
     # ---- timed region 2: end to end (pinned host batch in, loss out, every step) ----
@@ -288,6 +295,63 @@ def run_b200(args, rank, world, local_rank):
     e2_end.record()
     barrier()
     ms_e2e = e2_begin.elapsed_time(e2_end)
+
+    # ---- roofline of the dominant kernel class: the same step, eager, with CUDA events around every conv GEMM launch
+    # (a graph replay cannot host per-kernel events; same kernels, same inputs, same stream)
+    barrier()
+    for _ in range(2):      # the graph capture emptied the eager allocator pool: refill it before timing launches
+        eager_step(clean_dev, noise_dev, t_dev)
+    barrier()
+    prof["on"] = True
+    e3_begin, e3_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e3_begin.record()
+    n_prof_steps = max(1, min(args.steps, 5))
+    for _ in range(n_prof_steps):
+        eager_step(clean_dev, noise_dev, t_dev)
+    e3_end.record()
+    barrier()
+    prof["on"] = False
+    ms_prof_total = e3_begin.elapsed_time(e3_end)
+    gemm_ms = sum(a.elapsed_time(b) for a, b in prof["ev"])
+    gemm_launches = len(prof["ev"])
+    gemm_flops = prof["flops"]
+    step = eager_step
+
+    # ---- secondary metric: reverse-diffusion sampling (BASELINE configs[2]: 256 images over 8 GPUs = 32 / GPU) ----
+    sampling = None
+    if not args.no_sampling:
+        from polyp_image_generator_b200 import DDPMPipeline
+        model.eval()
+        pipe = DDPMPipeline(unet=model, scheduler=DDPMScheduler(num_train_timesteps=1000))
+        sb, n_steps = args.sampling_batch, args.sampling_steps
+
+        def run_sampling(gen):
+            # num_inference_steps = n_steps: the same per-step work as the 1000-step loop (one UNet forward + one
+            # scheduler step + one noise draw per step), timed over n_steps steps and reported per step
+            pipe(batch_size=sb, generator=gen, num_inference_steps=3, output_type="uint8")        # warm-up
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pipe(batch_size=sb, generator=gen, num_inference_steps=n_steps, output_type="uint8")
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1) / n_steps
+
+        ms_dev = run_sampling(None)                                          # in-kernel Philox noise
+        ms_ref = run_sampling(torch.Generator("cpu").manual_seed(0 + rank))  # reference RNG contract (CPU draws)
+        ts = torch.tensor([ms_dev, ms_ref], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_dev, ms_ref = float(ts[0]), float(ts[1])
+        sampling = {
+            "per_gpu_batch": sb, "steps_timed": n_steps,
+            "ms_per_step_device_noise": round(ms_dev, 3), "ms_per_step_cpu_generator": round(ms_ref, 3),
+            "images_per_sec_1000_steps_device_noise": round(world * sb / (ms_dev * 1000 * 1e-3), 3),
+            "images_per_sec_1000_steps_cpu_generator": round(world * sb / (ms_ref * 1000 * 1e-3), 3),
+            "unit": "img/s (whole job, 1000 reverse steps per image)",
+            "fwd_tflops_device_noise": round(FWD_GFLOP_PER_IMG.get(S, 0.0) * sb / ms_dev, 1),
+        }
+        model.train()
 
     # ---- optional per-op breakdown (after the timed regions; CUDA events around every C-ABI op) ----
     if args.breakdown and rank == 0:
@@ -358,6 +422,8 @@ def run_b200(args, rank, world, local_rank):
             "params": 113673219, "optimizer": "torch AdamW(fused) + clip_grad_norm_(1.0)",
             "l2": "per-step working set (activations + 455 MB weights/grads) is far larger than the 126 MB L2",
             "algorithmic_gflop_per_step": round(step_gflop, 1), "final_loss": round(final_loss, 5),
+            "host_issue_ms_per_step": round(host_issue_ms, 2),
+            "cuda_graph": not args.no_graph,
         },
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": clean_host.numel() * 4,
@@ -367,11 +433,13 @@ def run_b200(args, rank, world, local_rank):
             "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv/linear fprop+dgrad)", "bound": "tensor",
             "achieved": round(achieved_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
             "frac": round(achieved_tf / peak_tf, 4), "traffic": None, "peak_source": peak_src,
-            "launches_timed": gemm_launches, "kernel_ms_per_step": round(gemm_ms / args.steps, 3),
-            "share_of_step": round(gemm_ms / ms_total, 4),
+            "launches_timed": gemm_launches, "kernel_ms_per_step": round(gemm_ms / n_prof_steps, 3),
+            "share_of_step": round(gemm_ms / ms_prof_total, 4),
+            "timed_in": "eager re-run of the same step with per-launch CUDA events (graph replays cannot host them)",
             "whole_step_tflops": round(step_gflop / ms_step, 2),
         },
         "cpu_baseline": cpu,
+        "sampling": sampling,
     }
     print(json.dumps(line), flush=True)
 
@@ -386,6 +454,10 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of a CUDA graph")
+    ap.add_argument("--no-sampling", action="store_true", help="skip the secondary sampling measurement")
+    ap.add_argument("--sampling-batch", type=int, default=32, help="images per GPU in the sampling measurement")
+    ap.add_argument("--sampling-steps", type=int, default=20, help="reverse steps timed (reported per step)")
     ap.add_argument("--breakdown", action="store_true", help="after timing, print a per-op CUDA-event breakdown")
     ap.add_argument("--breakdown-by-shape", action="store_true", help="split conv / GroupNorm rows by layer shape")
     args = ap.parse_args()

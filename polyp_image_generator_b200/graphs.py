@@ -1,0 +1,121 @@
+"""CUDA-graph replay of the two hot loops.
+
+One training step of the 113.7 M-parameter UNet is ~1000 kernel launches of 10-500 us; issuing them from Python takes
+~44 ms of host time per step (bench.py `host_issue_ms_per_step`), i.e. as much as the GPU needs to execute them, and a
+reverse-diffusion step at batch 32 (~330 launches, 7 ms of GPU work) is host-bound outright.  Both loops have static
+shapes, so they are captured ONCE into a CUDA graph and replayed:
+
+  * GraphedTrainStep -- add_noise -> UNet forward -> MSE -> backward (-> gradient all-reduce) -> clip -> AdamW,
+    the body of /root/reference/generator_model/train_from_scratch.py:83-113, replayed per step with the batch, the
+    noise and the timesteps copied into static device buffers;
+  * GraphedUNetForward -- eps = unet(x, t) for sampling (DDPMPipeline uses it automatically on CUDA).
+
+All kernels are the same C-ABI launches as in eager mode (they go to torch's current stream, which is the capturing
+stream); memory comes from the graph's private pool, so the TMA descriptors cached by (pointer, shape) stay valid.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+class GraphedUNetForward:
+    """eps = unet(x, t) with a scalar timestep, replayed from a CUDA graph (inference only)."""
+
+    def __init__(self, unet, batch: int, height: int, width: int):
+        dev = unet.device
+        if dev.type != "cuda":
+            raise RuntimeError("CUDA graphs need the model on a CUDA device")
+        self.unet = unet
+        self.x = torch.zeros((batch, unet.config.in_channels, height, width), device=dev, dtype=torch.float32)
+        self.t = torch.zeros((batch,), device=dev, dtype=torch.int64)
+        self._key = None
+        self.graph = None
+        self.out = None
+
+    def _weights_key(self):
+        return tuple(p._version for p in self.unet.parameters())
+
+    def _capture(self):
+        unet = self.unet
+        side = torch.cuda.Stream(device=self.x.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                      # warm-up: arena, operand cache, smem attributes, descriptors
+                unet(self.x, self.t)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = unet(self.x, self.t, return_dict=False)[0]
+        self._key = self._weights_key()
+
+    def __call__(self, x: torch.Tensor, t) -> torch.Tensor:
+        """Returns a STATIC output buffer that the next call overwrites."""
+        if self.graph is None:
+            self._capture()
+        elif self._key != self._weights_key():
+            # weights changed: one eager forward refreshes the bf16 operand copies IN PLACE (same addresses), so the
+            # captured graph, which only reads them, stays valid
+            with torch.no_grad():
+                self.unet(self.x, self.t)
+            self._key = self._weights_key()
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x)
+        self.t.fill_(int(t))
+        self.graph.replay()
+        return self.out
+
+
+class GraphedTrainStep:
+    """One optimisation step as a single CUDA-graph replay.
+
+        step = GraphedTrainStep(net, noise_scheduler, optimizer, batch_shape)   # net: UNet2DModel or its DDP wrapper
+        loss = step(clean, noise, timesteps)          # device scalar (static buffer); no host sync
+
+    The optimizer must be capturable (e.g. torch.optim.AdamW(..., fused=True, capturable=True)); pass lr as a device
+    tensor to drive a schedule from the host (lr.fill_(value) between replays).
+    """
+
+    def __init__(self, net, noise_scheduler, optimizer, batch_shape, max_grad_norm: Optional[float] = 1.0,
+                 warmup_iters: int = 3):
+        from .training import mse_loss
+        params = [p for p in net.parameters() if p.requires_grad]
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("CUDA graphs need the model on a CUDA device")
+        self.clean = torch.zeros(tuple(batch_shape), device=dev, dtype=torch.float32)
+        self.noise = torch.zeros(tuple(batch_shape), device=dev, dtype=torch.float32)
+        self.t = torch.zeros((batch_shape[0],), device=dev, dtype=torch.int64)
+
+        def body():
+            noisy = noise_scheduler.add_noise(self.clean, self.noise, self.t)
+            pred = net(noisy, self.t, return_dict=False)[0]
+            loss = mse_loss(pred, self.noise)
+            loss.backward()
+            if max_grad_norm is not None:
+                torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+            optimizer.step()
+            return loss.detach()
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup_iters):
+                optimizer.zero_grad(set_to_none=True)
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = body()
+        self.warmup_iters = warmup_iters
+
+    def __call__(self, clean: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        self.clean.copy_(clean, non_blocking=True)
+        self.noise.copy_(noise, non_blocking=True)
+        self.t.copy_(timesteps, non_blocking=True)
+        self.graph.replay()
+        return self.loss

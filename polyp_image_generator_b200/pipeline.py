@@ -39,9 +39,22 @@ class ImagePipelineOutput:
 
 
 class DDPMPipeline:
-    def __init__(self, unet, scheduler):
+    def __init__(self, unet, scheduler, use_cuda_graph: bool = True):
         self.unet = unet
         self.scheduler = scheduler
+        self.use_cuda_graph = use_cuda_graph      # replay the UNet forward from a CUDA graph (graphs.py) on CUDA
+        self._graphs = {}
+
+    def _graphed_forward(self, image):
+        if not image.is_cuda or not hasattr(self.unet, "_run_forward"):
+            return None
+        key = tuple(image.shape)
+        g = self._graphs.get(key)
+        if g is None:
+            from .graphs import GraphedUNetForward
+            g = GraphedUNetForward(self.unet, image.shape[0], image.shape[2], image.shape[3])
+            self._graphs = {key: g}       # keep one shape (the private pool of a graph holds all activations)
+        return g
 
     @property
     def device(self):
@@ -59,8 +72,9 @@ class DDPMPipeline:
         image_shape = (batch_size, self.unet.config.in_channels, *hw)
         image = randn_tensor(image_shape, generator=generator, device=self.device, dtype=torch.float32)
         self.scheduler.set_timesteps(num_inference_steps)
+        fwd = self._graphed_forward(image) if self.use_cuda_graph else None
         for t in self.scheduler._ts_list:
-            model_output = self.unet(image, t).sample
+            model_output = fwd(image, t) if fwd is not None else self.unet(image, t).sample
             image = self.scheduler.step(model_output, t, image, generator=generator,
                                         want_pred_original_sample=False).prev_sample
         if output_type == "pt_raw":           # extension: raw x_0 in [-1, 1] on the device
