@@ -115,6 +115,16 @@ int ddpm_conv_wgrad(const ddpm_wgrad_args* args, void* stream);
 int ddpm_prep_weight(const float* w, void* wf, long long ldwf, void* wd, long long ldwd, int cout, int taps, int cin,
                      void* stream);
 
+/* The same for ALL layers of the model in one launch: a device-resident table of descriptors (pointers into the
+ * fp32 parameter arena and the bf16 operand arena), tile_begin = running count of 32x32 tiles (ascending). */
+typedef struct ddpm_prep_desc {
+  const float* w; void* wf; long long ldwf; void* wd; long long ldwd;
+  int cout, taps, cin;
+  int tile_begin, tiles_x, tiles_y;   /* tiles_x = ceil(cin/32), tiles_y = ceil(cout/32); taps tiles in z */
+} ddpm_prep_desc;
+int ddpm_prep_weights_batched(const ddpm_prep_desc* table_dev, int n_entries, int total_tiles, int with_d,
+                              void* stream);
+
 /* conv_in (3 -> C, 3x3, pad 1): x NCHW fp32, w fp32 with element strides (w_sco, w_stap, w_sci), out NHWC bf16.
  * Also used as conv_out's dgrad (with transposed strides and flip=1). */
 int ddpm_conv3_to_c(const float* x, const float* w, long long w_sco, long long w_stap, long long w_sci, int flip,
@@ -168,7 +178,9 @@ int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const void* x1, int
                       int groups, const float* stats, float eps, const float* gamma, const void* dz, long long lddz,
                       const float* sums, const void* add0, long long ldadd0, const void* add1, long long ldadd1,
                       void* dx0, long long lddx0, void* dx1, long long lddx1, float* dgamma, float* dbeta,
-                      void* stream);
+                      float* out_nc, long long ld_nc, float* out_c, void* stream);
+/* out_nc[n][c] += sum_pix dx, out_c[c] += sum_{n,pix} dx when non-NULL (time-embedding / conv-bias gradients of the
+ * layer that produced x, fused here instead of a separate pass over dx). */
 
 /* Self-attention core on fused qkv [b*t][3*heads*d] bf16 (AttnProcessor2_0's scaled_dot_product_attention). */
 int ddpm_attn_fwd(const void* qkv, long long ldqkv, void* o, long long ldo, float* lse, int b, int t, int heads,

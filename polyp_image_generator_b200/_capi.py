@@ -56,6 +56,14 @@ class WgradArgs(C.Structure):
     ]
 
 
+class PrepDesc(C.Structure):
+    _fields_ = [
+        ("w", _vp), ("wf", _vp), ("ldwf", _ll), ("wd", _vp), ("ldwd", _ll),
+        ("cout", _i), ("taps", _i), ("cin", _i),
+        ("tile_begin", _i), ("tiles_x", _i), ("tiles_y", _i),
+    ]
+
+
 # name -> argtypes (every function returns int except ddpm_last_error)
 SIGNATURES = {
     "ddpm_abi_version": [],
@@ -68,6 +76,7 @@ SIGNATURES = {
     "ddpm_conv_gemm": [C.POINTER(ConvArgs), _vp],
     "ddpm_conv_wgrad": [C.POINTER(WgradArgs), _vp],
     "ddpm_prep_weight": [_vp, _vp, _ll, _vp, _ll, _i, _i, _i, _vp],
+    "ddpm_prep_weights_batched": [_vp, _i, _i, _i, _vp],
     "ddpm_conv3_to_c": [_vp, _vp, _ll, _ll, _ll, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
     "ddpm_conv_c_to_3": [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ddpm_conv3_wgrad": [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _ll, _i, _vp, _i, _i, _i, _vp],
@@ -79,7 +88,7 @@ SIGNATURES = {
     "ddpm_gn_bwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp, _ll, _vp, _ll,
                     _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp],
     "ddpm_gn_bwd_apply": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll,
-                          _vp, _ll, _vp, _ll, _vp, _vp, _vp],
+                          _vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp],
     "ddpm_attn_fwd": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
     "ddpm_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _f, _vp],
     "ddpm_timestep_embedding": [_vp, _vp, _vp, _i, _i, _i, _vp],

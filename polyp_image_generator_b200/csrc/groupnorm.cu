@@ -515,8 +515,14 @@ gn_bwd_dparam_kernel(const float* __restrict__ sums, int N, int C, float* __rest
 __global__ void __launch_bounds__(kGnThreads)
 gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
                     const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dz, long long lddz,
-                    const float* __restrict__ sums, GnDst o, int pix_per_block, int V) {
+                    const float* __restrict__ sums, GnDst o, int pix_per_block, int V,
+                    float* __restrict__ out_nc /*[N][ld_nc] += sum_pix dx, or NULL*/, long long ld_nc,
+                    float* __restrict__ out_c /*[C] += sum_{n,pix} dx, or NULL*/) {
   __shared__ float scoef[64 * 2];
+  extern __shared__ float scol[];   // [C] per-channel sums of this CTA's dx (only when out_nc / out_c)
+  const bool want_sums = (out_nc != nullptr) || (out_c != nullptr);
+  if (want_sums)
+    for (int i = threadIdx.x; i < V * 8; i += blockDim.x) scol[i] = 0.f;
   const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
   const int n = blockIdx.y;
   const int C = V * 8;
@@ -540,12 +546,15 @@ gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restric
   const int c = v * 8;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(hw, p_begin + pix_per_block);
-  if (!((c < s.c0) || (o.d1 != nullptr))) return;   // gradient of this source not requested
+  const bool writes = (c < s.c0) || (o.d1 != nullptr);   // else: gradient of this source not requested
+  if (!writes && !want_sums) return;
   long long ld;
   const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
   const long long pix0 = static_cast<long long>(n) * hw;
   const __nv_bfloat16* dp = dz + pix0 * lddz + c;
-  f2x4 k1, nk4, nk5;
+  f2x4 k1, nk4, nk5, csum;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) csum.p[j] = make_float2(0.f, 0.f);
   {
     float a1[8], a4[8], a5[8];
     int g_prev = -1;
@@ -572,12 +581,12 @@ gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restric
   }
   const __nv_bfloat16* a0p = o.add0 ? o.add0 + pix0 * o.lda0 + c : nullptr;
   const __nv_bfloat16* a1p = o.add1 ? o.add1 + pix0 * o.lda1 + c : nullptr;
-  __nv_bfloat16* op;
-  long long ldo;
+  __nv_bfloat16* op = nullptr;
+  long long ldo = 0;
   if (c < s.c0) {
     op = o.d0 + pix0 * o.ld0 + c;
     ldo = o.ld0;
-  } else {
+  } else if (o.d1 != nullptr) {
     op = o.d1 + pix0 * o.ld1 + (c - s.c0);
     ldo = o.ld1;
   }
@@ -611,8 +620,25 @@ gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restric
 #pragma unroll
           for (int j = 0; j < 4; ++j) r.p[j] = __fadd2_rn(r.p[j], a.p[j]);
         }
-        *reinterpret_cast<bf16x8*>(op + (p + u * ppb) * ldo) = pack8p(r);
+        if (op != nullptr) *reinterpret_cast<bf16x8*>(op + (p + u * ppb) * ldo) = pack8p(r);
+        if (want_sums) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) csum.p[j] = __fadd2_rn(csum.p[j], r.p[j]);
+        }
       }
+    }
+  }
+  if (want_sums) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&scol[c + 2 * j], csum.p[j].x);
+      atomicAdd(&scol[c + 2 * j + 1], csum.p[j].y);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < V * 8; i += blockDim.x) {
+      const float v = scol[i];
+      if (out_nc) atomicAdd(&out_nc[static_cast<long long>(n) * ld_nc + i], v);
+      if (out_c) atomicAdd(&out_c[i], v);
     }
   }
 }
@@ -818,7 +844,8 @@ extern "C" int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const vo
                                  int hw, int groups, const float* stats, float eps, const float* gamma, const void* dz,
                                  long long lddz, const float* sums, const void* add0, long long ldadd0,
                                  const void* add1, long long ldadd1, void* dx0, long long lddx0, void* dx1,
-                                 long long lddx1, float* dgamma, float* dbeta, void* stream_) {
+                                 long long lddx1, float* dgamma, float* dbeta, float* out_nc, long long ld_nc,
+                                 float* out_c, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int e = gn_check(x0, c0, ld0, x1, c1, ld1, n, hw, groups, "ddpm_gn_bwd_apply")) return e;
   DDPM_REQUIRE(stats && gamma && dz && sums && dx0, "ddpm_gn_bwd_apply: null pointer argument");
@@ -831,9 +858,12 @@ extern "C" int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const vo
           static_cast<const __nv_bfloat16*>(add0), static_cast<const __nv_bfloat16*>(add1), ldadd0, ldadd1};
   int V, threads, ppblk, chunks;
   gn_geometry(C, hw, n, 8, &V, &threads, &ppblk, &chunks);
-  gn_bwd_apply_kernel<<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma,
-                                                               static_cast<const __nv_bfloat16*>(dz), lddz, sums, o,
-                                                               ppblk, V);
+  const bool want_sums = out_nc || out_c;
+  // with the fused per-(n, c) output sums every CTA ends with C atomics: use larger CTAs there
+  gn_geometry(C, hw, n, want_sums ? 32 : 8, &V, &threads, &ppblk, &chunks);
+  gn_bwd_apply_kernel<<<dim3(chunks, n), threads, want_sums ? C * sizeof(float) : 0, stream>>>(
+      s, hw, C / groups, groups, stats, eps, gamma, static_cast<const __nv_bfloat16*>(dz), lddz, sums, o, ppblk, V,
+      out_nc, ld_nc, out_c);
   if (int e = check_launch("gn_bwd_apply_kernel")) return e;
   if (dgamma || dbeta) {
     gn_bwd_dparam_raw_kernel<<<(C + kGnThreads - 1) / kGnThreads, kGnThreads, 0, stream>>>(sums, stats, n, C, C / groups,

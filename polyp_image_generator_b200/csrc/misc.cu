@@ -60,40 +60,93 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
   if (lane == 0) y[static_cast<long long>(m) * N + n] = acc + (bias ? bias[n] : 0.f);
 }
 
-// dw[n][k] += sum_m dy[m][n] * act(x[m][k]);  db[n] += sum_m dy[m][n].  thread per (n, k), M small.
+// dw[n][k] += sum_m dy[m][n] * act(x[m][k]);  db[n] += sum_m dy[m][n].
+// CTA = (32 rows n) x (256 columns k); act(x) is evaluated once per (m, k) and dy is broadcast from smem.
+constexpr int kLwN = 32, kLwM = 64;
 __global__ void __launch_bounds__(kThreads)
 linear_f32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                         float* __restrict__ db, int M, int N, int K, int silu_in) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(N) * K) return;
-  const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
-  float acc = 0.f, accb = 0.f;
-  for (int m = 0; m < M; ++m) {
-    float xv = x[static_cast<long long>(m) * K + k];
-    if (silu_in) xv = silu_f(xv);
-    const float d = dy[static_cast<long long>(m) * N + n];
-    acc += d * xv;
-    accb += d;
+  __shared__ float dys[kLwM][kLwN];
+  const int k = blockIdx.x * kThreads + threadIdx.x;
+  const int n0 = blockIdx.y * kLwN;
+  float acc[kLwN];
+#pragma unroll
+  for (int j = 0; j < kLwN; ++j) acc[j] = 0.f;
+  float accb = 0.f;   // thread j < kLwN of the k-block 0 CTAs: bias gradient of row n0 + j
+  for (int m0 = 0; m0 < M; m0 += kLwM) {
+    const int mt = min(kLwM, M - m0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < mt * kLwN; i += kThreads) {
+      const int mm = i / kLwN, j = i - mm * kLwN;
+      dys[mm][j] = (n0 + j < N) ? dy[static_cast<long long>(m0 + mm) * N + n0 + j] : 0.f;
+    }
+    __syncthreads();
+    if (k < K) {
+      for (int mm = 0; mm < mt; ++mm) {
+        float xv = x[static_cast<long long>(m0 + mm) * K + k];
+        if (silu_in) xv = silu_f(xv);
+#pragma unroll
+        for (int j = 0; j < kLwN; ++j) acc[j] = fmaf(dys[mm][j], xv, acc[j]);
+      }
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x < kLwN)
+      for (int mm = 0; mm < mt; ++mm) accb += dys[mm][threadIdx.x];
   }
-  dw[i] += acc;
-  if (db && k == 0) db[n] += accb;
+  if (k < K) {
+#pragma unroll
+    for (int j = 0; j < kLwN; ++j)
+      if (n0 + j < N) dw[static_cast<long long>(n0 + j) * K + k] += acc[j];
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < kLwN && n0 + threadIdx.x < N) db[n0 + threadIdx.x] += accb;
 }
 
-// dx[m][k] (+)= act'(x[m][k]) * sum_n dy[m][n] * w[n][k];  grid (ceil(K/256), M)
+// dx[m][k] (+)= act'(x[m][k]) * sum_n dy[m][n] * w[n][k]
+// CTA = (256 columns k) x (a slice of n), ALL rows m: every w element is loaded once and used for up to 64 rows
+// (the old one-row-per-CTA kernel re-read the 20 MB time_emb_proj matrix 64 times); partial sums over the n slices
+// are combined with fp32 atomics (the derivative factor distributes over the sum).
+constexpr int kLdM = 64;
 __global__ void __launch_bounds__(kThreads)
 linear_f32_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ x,
-                        float* __restrict__ dx, int M, int N, int K, int silu_in, int accumulate) {
-  extern __shared__ float dys[];
-  const int m = blockIdx.y;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) dys[n] = dy[static_cast<long long>(m) * N + n];
-  __syncthreads();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  float acc = 0.f;
-  for (int n = 0; n < N; ++n) acc += dys[n] * w[static_cast<long long>(n) * K + k];
-  if (silu_in) acc *= silu_grad_f(x[static_cast<long long>(m) * K + k]);
-  float* o = dx + static_cast<long long>(m) * K + k;
-  *o = accumulate ? *o + acc : acc;
+                        float* __restrict__ dx, int M, int N, int K, int silu_in, int n_per_split) {
+  extern __shared__ float dyt[];   // [n_local][kLdM]
+  const int k = blockIdx.x * kThreads + threadIdx.x;
+  const int n_begin = blockIdx.y * n_per_split;
+  const int n_end = min(N, n_begin + n_per_split);
+  const int nl = n_end - n_begin;
+  for (int m0 = 0; m0 < M; m0 += kLdM) {
+    const int mt = min(kLdM, M - m0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nl * kLdM; i += kThreads) {
+      const int j = i / kLdM, mm = i - j * kLdM;
+      dyt[i] = (mm < mt) ? dy[static_cast<long long>(m0 + mm) * N + n_begin + j] : 0.f;
+    }
+    __syncthreads();
+    if (k < K) {
+      float acc[kLdM];
+#pragma unroll
+      for (int mm = 0; mm < kLdM; ++mm) acc[mm] = 0.f;
+      for (int j = 0; j < nl; ++j) {
+        const float wv = w[static_cast<long long>(n_begin + j) * K + k];
+        const float4* dr = reinterpret_cast<const float4*>(dyt + j * kLdM);
+#pragma unroll
+        for (int q = 0; q < kLdM / 4; ++q) {
+          const float4 d4 = dr[q];
+          acc[4 * q] = fmaf(d4.x, wv, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(d4.y, wv, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(d4.z, wv, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(d4.w, wv, acc[4 * q + 3]);
+        }
+      }
+#pragma unroll
+      for (int mm = 0; mm < kLdM; ++mm) {
+        if (mm < mt) {
+          float v = acc[mm];
+          if (silu_in) v *= silu_grad_f(x[static_cast<long long>(m0 + mm) * K + k]);
+          atomicAdd(dx + static_cast<long long>(m0 + mm) * K + k, v);
+        }
+      }
+    }
+  }
 }
 
 // ---- per-(n, c) sums over hw of a bf16 NHWC tensor -------------------------------------------------------
@@ -149,6 +202,46 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int ci = ci0 + r, co = co0 + threadIdx.x;
     if (ci < cin && co < cout)
       wd[static_cast<long long>(ci) * ldwd + static_cast<long long>(taps - 1 - tap) * cout + co] =
+          __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+// All layers in ONE launch: blockIdx.x walks the 32x32 tiles of every (layer, tap); the layer is found by binary
+// search in the device-resident descriptor table (tile_begin is ascending).
+__global__ void prep_weights_batched_kernel(const ddpm_prep_desc* __restrict__ table, int n_entries, int with_d) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n_entries - 1;
+  const int tid = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].tile_begin <= tid) lo = mid; else hi = mid - 1;
+  }
+  const ddpm_prep_desc d = table[lo];
+  int local = tid - d.tile_begin;
+  const int tx = local % d.tiles_x;
+  local /= d.tiles_x;
+  const int ty = local % d.tiles_y;
+  const int tap = local / d.tiles_y;
+  const float* w = d.w;
+  __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d.wf);
+  __nv_bfloat16* wd = with_d ? static_cast<__nv_bfloat16*>(d.wd) : nullptr;
+  const int cout = d.cout, taps = d.taps, cin = d.cin;
+  const int ci0 = tx * 32, co0 = ty * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    float v = 0.f;
+    if (co < cout && ci < cin) {
+      v = w[(static_cast<long long>(co) * taps + tap) * cin + ci];
+      if (wf) wf[static_cast<long long>(co) * d.ldwf + static_cast<long long>(tap) * cin + ci] = __float2bfloat16(v);
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  if (!wd) return;
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < cin && co < cout)
+      wd[static_cast<long long>(ci) * d.ldwd + static_cast<long long>(taps - 1 - tap) * cout + co] =
           __float2bfloat16(tile[threadIdx.x][r]);
   }
 }
@@ -325,23 +418,25 @@ extern "C" int ddpm_linear_f32(const float* x, const float* w, const float* bias
 extern "C" int ddpm_linear_f32_wgrad(const float* x, const float* dy, float* dw, float* db, int m, int n, int k,
                                      int silu_in, void* stream) {
   DDPM_REQUIRE(x && dy && dw && m > 0 && n > 0 && k > 0, "ddpm_linear_f32_wgrad: bad argument");
-  const long long items = static_cast<long long>(n) * k;
-  linear_f32_wgrad_kernel<<<static_cast<int>((items + kThreads - 1) / kThreads), kThreads, 0,
-                            static_cast<cudaStream_t>(stream)>>>(x, dy, dw, db, m, n, k, silu_in);
+  dim3 grid((k + kThreads - 1) / kThreads, (n + kLwN - 1) / kLwN);
+  linear_f32_wgrad_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dw, db, m, n, k, silu_in);
   return check_launch("linear_f32_wgrad_kernel");
 }
 
 extern "C" int ddpm_linear_f32_dgrad(const float* dy, const float* w, const float* x, float* dx, int m, int n, int k,
-                                     int silu_in, int accumulate, void* stream) {
-  DDPM_REQUIRE(dy && w && dx && m > 0 && n > 0 && k > 0 && n <= 12288, "ddpm_linear_f32_dgrad: bad argument");
+                                     int silu_in, int accumulate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPM_REQUIRE(dy && w && dx && m > 0 && n > 0 && k > 0, "ddpm_linear_f32_dgrad: bad argument");
   DDPM_REQUIRE(!silu_in || x, "ddpm_linear_f32_dgrad: silu_in needs x");
-  static bool configured = false;
-  if (!configured) {
-    DDPM_CUDA(cudaFuncSetAttribute(linear_f32_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4));
-    configured = true;
-  }
-  linear_f32_dgrad_kernel<<<dim3((k + kThreads - 1) / kThreads, m), kThreads, n * sizeof(float),
-                            static_cast<cudaStream_t>(stream)>>>(dy, w, x, dx, m, n, k, silu_in, accumulate);
+  const int ktiles = (k + kThreads - 1) / kThreads;
+  int splits = (2 * kNumSMs + ktiles - 1) / ktiles;         // ~2 CTAs per SM
+  if (splits > n) splits = n;
+  int nps = (n + splits - 1) / splits;
+  if (nps > 128) nps = 128;                                   // smem: nps * 64 floats <= 32 KB
+  splits = (n + nps - 1) / nps;
+  if (!accumulate) DDPM_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * static_cast<size_t>(m) * k, stream));
+  linear_f32_dgrad_kernel<<<dim3(ktiles, splits), kThreads, static_cast<size_t>(nps) * kLdM * sizeof(float), stream>>>(
+      dy, w, x, dx, m, n, k, silu_in, nps);
   return check_launch("linear_f32_dgrad_kernel");
 }
 
@@ -438,4 +533,12 @@ extern "C" int ddpm_nhwc_to_nchw_f32(const float* src, long long ld, float* out,
   nhwc_to_nchw_f32_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, ld, out, cout, static_cast<long long>(h) * w, npix);
   return check_launch("nhwc_to_nchw_f32_kernel");
+}
+
+extern "C" int ddpm_prep_weights_batched(const ddpm_prep_desc* table_dev, int n_entries, int total_tiles, int with_d,
+                                         void* stream) {
+  DDPM_REQUIRE(table_dev && n_entries > 0 && total_tiles > 0, "ddpm_prep_weights_batched: bad argument");
+  prep_weights_batched_kernel<<<total_tiles, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(table_dev, n_entries,
+                                                                                                  with_d);
+  return check_launch("prep_weights_batched_kernel");
 }

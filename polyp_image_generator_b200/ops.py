@@ -214,6 +214,27 @@ class CudaOps:
                     "ddpm_prep_weight")
         self.launches += 1
 
+    def build_prep_table(self, entries, device):
+        """entries: [(w fp32 [cout][taps][cin] view, wf bf16 view, wd bf16 view, cout, taps, cin)] -> (device table,
+        n, total_tiles).  The views must stay alive and in place (they are arena slices)."""
+        arr = (_capi.PrepDesc * len(entries))()
+        tiles = 0
+        for i, (w, wf, wd, cout, taps, cin) in enumerate(entries):
+            d = arr[i]
+            d.w, d.wf, d.ldwf = _ptr(w), _ptr(wf), wf.stride(0)
+            d.wd, d.ldwd = _ptr(wd), wd.stride(0)
+            d.cout, d.taps, d.cin = cout, taps, cin
+            d.tiles_x, d.tiles_y = (cin + 31) // 32, (cout + 31) // 32
+            d.tile_begin = tiles
+            tiles += d.tiles_x * d.tiles_y * taps
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        return raw, len(entries), tiles
+
+    def prep_weights_batched(self, table, n_entries: int, total_tiles: int, with_d: bool):
+        _capi.check(self.lib.ddpm_prep_weights_batched(_ptr(table), n_entries, total_tiles, int(with_d), _stream()),
+                    "ddpm_prep_weights_batched")
+        self.launches += 1
+
     # ---- 3-channel convs ---------------------------------------------------------------------------------
     def conv3_to_c(self, x, w, strides: Tuple[int, int, int], flip: bool, bias, cout: int, out=None):
         """x: NCHW fp32 [n, cin<=4, h, w] -> NHWC bf16 [n, h, w, cout]."""
@@ -326,8 +347,9 @@ class CudaOps:
         return dx0, dx1
 
     def gn_bwd_apply(self, x0, x1, groups: int, stats, eps: float, gamma, dz, sums, add0=None, add1=None,
-                     dgamma=None, dbeta=None, need_dx1: bool = True):
-        """Second half of the GroupNorm backward (first half fused into conv_gemm(gn=...)) -> (dx0, dx1)."""
+                     dgamma=None, dbeta=None, need_dx1: bool = True, out_nc=None, out_c=None):
+        """Second half of the GroupNorm backward (first half fused into conv_gemm(gn=...)) -> (dx0, dx1).
+        out_nc[n, c] / out_c[c] are INCREMENTED by the pixel sums of dx (the caller zero-fills out_nc)."""
         n, h, w, c0, ld0 = _nhwc(x0, "x0")
         c1, ld1 = 0, 0
         if x1 is not None:
@@ -339,7 +361,8 @@ class CudaOps:
             _ptr(dz), _nhwc(dz, "dz")[4], _ptr(sums),
             _ptr(add0), _nhwc(add0, "add0")[4] if add0 is not None else 0,
             _ptr(add1), _nhwc(add1, "add1")[4] if add1 is not None else 0,
-            _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dgamma), _ptr(dbeta), _stream()), "ddpm_gn_bwd_apply")
+            _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dgamma), _ptr(dbeta),
+            _ptr(out_nc), out_nc.stride(0) if out_nc is not None else 0, _ptr(out_c), _stream()), "ddpm_gn_bwd_apply")
         self.launches += 2 if (dgamma is not None or dbeta is not None) else 1
         return dx0, dx1
 

@@ -272,6 +272,7 @@ class UNet2DModel(nn.Module):
         self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
 
         self._arena: Optional[torch.Tensor] = None
+        self._prep_table = None
         self._plan = None
         self._wcache_key = None
         self._lora_layers: Dict[str, object] = {}
@@ -506,6 +507,7 @@ class UNet2DModel(nn.Module):
         self._cout_wf = self._bf16[P.cout_wf_off:P.cout_wf_off + 32 * 9 * c0].view(32, 9 * c0)
         self._cout_wd = self._bf16[P.cout_wd_off:P.cout_wd_off + c0 * 64].view(c0, 64)
         self._cout_b32 = torch.zeros(32, device=dev, dtype=torch.float32)
+        self._prep_table = None
         self._wcache_key = None
 
     def _apply(self, fn, *a, **k):
@@ -532,18 +534,37 @@ class UNet2DModel(nn.Module):
         ops = _ops.get()
         ar = self._arena
         need_d = training
+        if hasattr(ops, "prep_weights_batched"):
+            # every layer in ONE launch, driven by a device-resident descriptor table (built once per arena)
+            if self._prep_table is None:
+                entries = []
+                for gobj in P.gemms:
+                    k = gobj.taps * gobj.cin
+                    o = gobj.w_off
+                    for i, w in enumerate(gobj.weights):
+                        n = w.numel()
+                        rows = slice(i * gobj.cout_each, (i + 1) * gobj.cout_each)
+                        cols = slice(i * gobj.taps * gobj.cout_each, (i + 1) * gobj.taps * gobj.cout_each)
+                        entries.append((ar[o:o + n], gobj.wf[rows, :k], gobj.wd[:, cols], gobj.cout_each, gobj.taps,
+                                        gobj.cin))
+                        o = _align(o + n)
+                self._prep_table = ops.build_prep_table(entries, ar.device)
+            ops.prep_weights_batched(*self._prep_table, need_d)
+        else:
+            for gobj in P.gemms:
+                k = gobj.taps * gobj.cin
+                o = gobj.w_off
+                for i, w in enumerate(gobj.weights):
+                    n = w.numel()
+                    wseg = ar[o:o + n]
+                    rows = slice(i * gobj.cout_each, (i + 1) * gobj.cout_each)
+                    wf = gobj.wf[rows, :k]
+                    wd = gobj.wd[:, i * gobj.taps * gobj.cout_each:(i + 1) * gobj.taps * gobj.cout_each] \
+                        if need_d else None
+                    # wd for fused multi-weight gemms (qkv): [cin, cout_total], this weight's columns at an offset
+                    ops.prep_weight(wseg, wf, wd, gobj.cout_each, gobj.taps, gobj.cin)
+                    o = _align(o + n)
         for gobj in P.gemms:
-            k = gobj.taps * gobj.cin
-            o = gobj.w_off
-            for i, w in enumerate(gobj.weights):
-                n = w.numel()
-                wseg = ar[o:o + n]
-                rows = slice(i * gobj.cout_each, (i + 1) * gobj.cout_each)
-                wf = gobj.wf[rows, :k]
-                wd = gobj.wd[:, i * gobj.taps * gobj.cout_each:(i + 1) * gobj.taps * gobj.cout_each] if need_d else None
-                # wd for fused multi-weight gemms (qkv): [cin, cout_total] with this weight's columns at an offset
-                ops.prep_weight(wseg, wf, wd, gobj.cout_each, gobj.taps, gobj.cin)
-                o = _align(o + n)
             if gobj.lora is not None:
                 gobj.lora.write_operands(gobj)
         # boundary convs (a few thousand elements: plain tensor copies)
@@ -875,15 +896,20 @@ class UNet2DModel(nn.Module):
             sums = torch.zeros((grid[0], r.cout, 2), device=g.device, dtype=torch.float32)
             dz = ops.conv_gemm(g, None, taps_3x3(r.cout), r.conv2.wd, r.cout, grid,
                                gn=(s.h1, None, s.coef2, True, sums))
+            # the pixel sums of d_h1 (time-embedding gradient per sample, conv1 bias gradient) come out of the same pass
             d_h1, _ = ops.gn_bwd_apply(s.h1, None, r.norm2.groups, s.stats2, r.norm2.eps, g2, dz, sums,
-                                       dgamma=dg, dbeta=dbt)
+                                       dgamma=dg, dbeta=dbt,
+                                       out_nc=st.d_temb_all[:, r.temb_off:r.temb_off + r.cout],
+                                       out_c=self._wgrad_views(G, r.conv1)[1] if r.conv1.bias_trainable else None)
         else:
             d_b = ops.conv_gemm(g, None, taps_3x3(r.cout), r.conv2.wd, r.cout, grid)
             d_h1, _ = ops.gn_bwd(s.h1, None, r.norm2.groups, s.stats2, r.norm2.eps, g2, be2, True, d_b, dgamma=dg,
                                  dbeta=dbt)
         # time embedding + conv1 bias share sum_hw(d_h1)
         dW1, db1 = self._wgrad_views(G, r.conv1)
-        ops.reduce_hw(d_h1, st.d_temb_all[:, r.temb_off:r.temb_off + r.cout], db1 if r.conv1.bias_trainable else None)
+        if not fuse:
+            ops.reduce_hw(d_h1, st.d_temb_all[:, r.temb_off:r.temb_off + r.cout],
+                          db1 if r.conv1.bias_trainable else None)
         if r.conv1.trainable:
             ops.conv_wgrad(d_h1, s.a, None, taps_3x3(r.cin), dW1, grid)
         g1, be1 = self._norm_params(r.norm1)

@@ -253,7 +253,7 @@ class EmuOps:
         return dx0, dx1
 
     def gn_bwd_apply(self, x0, x1, groups, stats, eps, gamma, dz, sums, add0=None, add1=None, dgamma=None,
-                     dbeta=None, need_dx1=True):
+                     dbeta=None, need_dx1=True, out_nc=None, out_c=None):
         X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
         n, h, w, C = X.shape
         c0 = x0.shape[-1]
@@ -276,6 +276,10 @@ class EmuOps:
             dgamma += S2h.sum(0)
         if dbeta is not None:
             dbeta += S1.sum(0)
+        if out_nc is not None:
+            out_nc += dx.sum((1, 2))
+        if out_c is not None:
+            out_c += dx.sum((0, 1, 2))
         dx = self._a(dx)
         dx0 = dx[..., :c0].contiguous()
         dx1 = dx[..., c0:].contiguous() if (x1 is not None and need_dx1) else None

@@ -457,7 +457,9 @@ def g_gnfuse(ops):
         sums = torch.zeros(n, C, 2, device=dev)
         dz = ops.conv_gemm(g, None, taps_3x3(cg), wd, C, grid, gn=(xa, xb, coef, True, sums))
         dg_f, db_f = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
-        f0, f1 = ops.gn_bwd_apply(xa, xb, 32, stats, eps, gamma, dz, sums, add0=add0, dgamma=dg_f, dbeta=db_f)
+        o_nc, o_c = torch.zeros(n, C, device=dev), torch.zeros(C, device=dev)
+        f0, f1 = ops.gn_bwd_apply(xa, xb, 32, stats, eps, gamma, dz, sums, add0=add0, dgamma=dg_f, dbeta=db_f,
+                                  out_nc=o_nc, out_c=o_c)
         # fp32 autograd reference of the GroupNorm+SiLU backward on the bf16 dy the conv produced
         xcat = torch.cat([xa, xb], -1) if c1 else xa
         xr = xcat.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
@@ -471,6 +473,8 @@ def g_gnfuse(ops):
         ok &= report("   dx vs unfused kernels", got, ref_k, 1e-2)
         ok &= report("   dgamma", dg_f, gr.grad, 1e-2)
         ok &= report("   dbeta", db_f, br.grad, 1e-2)
+        ok &= report("   fused pixel sums [n, c]", o_nc, want.sum((1, 2)), 1e-2)
+        ok &= report("   fused pixel sums [c]", o_c, want.sum((0, 1, 2)), 1e-2)
     return ok
 
 
