@@ -32,7 +32,46 @@ struct EpiParams {
   const float* gcoef;         // [N][Cout/2][4] = (ka0, ka1, kb0, kb1): z = x*ka + kb  (written by ddpm_gn_fwd)
   float* gsums;               // [N][Cout][2] += (sum dz, sum dz*x)
   int gsilu;
+  int wide;                   // every pointer / stride above allows 32-byte (256-bit) row accesses
 };
+
+// 256-bit global accesses (sm_100: LDG/STG.E.256).  One thread owns one pixel row here, so a warp-wide access touches
+// 32 different 128-byte lines whatever its width; moving 32 instead of 16 bytes per lane halves the number of L1
+// wavefronts per tile, which is what bounded the fused epilogue (ncu: LSU data-pipe 65 %, profiles/r1_halo_fused.md).
+__device__ __forceinline__ void ld256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 64 bytes (32 bf16) from / to a 16-byte-aligned address; `wide` = the address is known to be 32-byte aligned
+__device__ __forceinline__ void ld64B(const void* p, uint32_t* w, bool wide) {
+  if (wide) {
+    ld256(p, w);
+    ld256(static_cast<const uint8_t*>(p) + 32, w + 8);
+  } else {
+    const uint4* q = static_cast<const uint4*>(p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = q[j];
+      w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+    }
+  }
+}
+__device__ __forceinline__ void st64B(void* p, const uint32_t* w, bool wide) {
+  if (wide) {
+    st256(p, w);
+    st256(static_cast<uint8_t*>(p) + 32, w + 8);
+  } else {
+    uint4* q = static_cast<uint4*>(p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  }
+}
 
 __device__ __forceinline__ float epi_tanh(float x) {
   float y;
@@ -56,19 +95,17 @@ __device__ __forceinline__ float warp_column_sums(float (&a)[32], int lane) {
 }
 
 struct EpiX {
-  bf16x8 r[4];   // 32 channels of the GroupNorm input at this thread's pixel
+  uint32_t w[16];   // 32 bf16 channels of the GroupNorm input at this thread's pixel
 };
 // Issue the loads of the GroupNorm input for (pix, col .. col+31) -- call this EARLY (before waiting on the
 // accumulator / while the previous chunk is processed) so the latency is off the critical path.
 __device__ __forceinline__ void epi_load_x(const EpiParams& e, bool valid, long long pix, int col, EpiX& x) {
   if (e.gsums != nullptr && valid && col < e.Cout) {
     const __nv_bfloat16* xp = (col < e.gc0) ? e.gx0 + pix * e.gld0 + col : e.gx1 + pix * e.gld1 + (col - e.gc0);
-    const bf16x8* xv = reinterpret_cast<const bf16x8*>(xp);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x.r[j] = xv[j];
+    ld64B(xp, x.w, e.wide != 0);
   } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x.r[j] = make_uint4(0u, 0u, 0u, 0u);
+    for (int j = 0; j < 16; ++j) x.w[j] = 0u;
   }
 }
 
@@ -98,13 +135,12 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
       }
     }
     if (e.res) {
-      const bf16x8* rp = reinterpret_cast<const bf16x8*>(e.res + pix * e.ldr + col);
+      uint32_t rw[16];
+      ld64B(e.res + pix * e.ldr + col, rw, e.wide != 0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float f[8];
-        unpack8(rp[j], f);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[j * 8 + q] += f[q];
+      for (int j = 0; j < 16; ++j) {
+        v[2 * j] += bf16lo_f(rw[j]);
+        v[2 * j + 1] += bf16hi_f(rw[j]);
       }
     }
   }
@@ -114,7 +150,10 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
     if (valid && col_ok) {
       float x[32];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) unpack8(xin.r[j], x + 8 * j);
+      for (int j = 0; j < 16; ++j) {
+        x[2 * j] = bf16lo_f(xin.w[j]);
+        x[2 * j + 1] = bf16hi_f(xin.w[j]);
+      }
       if (e.gsilu) {
         const float4* cf = reinterpret_cast<const float4*>(e.gcoef) + (static_cast<long long>(n) * e.Cout + col) / 2;
 #pragma unroll
@@ -152,9 +191,10 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
 #pragma unroll
       for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     } else {
-      bf16x8* op = reinterpret_cast<bf16x8*>(e.out + pix * e.ldo + col);
+      uint32_t ow[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) op[j] = pack8(v + 8 * j);
+      for (int j = 0; j < 16; ++j) ow[j] = pack2_bf16_(v[2 * j], v[2 * j + 1]);
+      st64B(e.out + pix * e.ldo + col, ow, e.wide != 0);
     }
   }
 }

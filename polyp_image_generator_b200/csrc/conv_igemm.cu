@@ -501,6 +501,11 @@ int fill_epilogue(EpiParams* e, const ::ddpm_conv_args* a) {
     e->gsums = a->gn_sums;
     e->gsilu = a->gn_silu;
   }
+  auto ok32 = [](const void* ptr, long long ld_elems) {
+    return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && (ld_elems * 2) % 32 == 0);
+  };
+  e->wide = (ok32(e->out, e->ldo) && ok32(e->res, e->ldr) && ok32(e->gx0, e->gld0) && ok32(e->gx1, e->gld1)) ? 1 : 0;
+  if (env_int("DDPM_EPI_WIDE", 1) == 0) e->wide = 0;
   return DDPM_OK;
 }
 

@@ -133,9 +133,12 @@ class CudaOps:
     # ---- tcgen05 conv / linear -------------------------------------------------------------------------
     @staticmethod
     def gn_bwd_fusable(grid: Tuple[int, int, int]) -> bool:
-        """Can the GroupNorm-backward first half run in the dgrad epilogue of a conv over this pixel grid?"""
+        """Should the GroupNorm-backward first half run in the dgrad epilogue of a conv over this pixel grid?
+        Possible when a warp's 32 tile rows share a sample (H*W >= 128 or H*W % 32 == 0); worth it from 64x64 up:
+        measured on B200 (profiles/bench_kernels.py convgn) the fused epilogue costs +0.058 ms at 128^2 against
+        0.19 ms saved in the GroupNorm pass, but +0.040 ms at 32^2 against 0.01 ms saved."""
         hw = grid[1] * grid[2]
-        return hw >= 128 or hw % 32 == 0
+        return hw >= 4096
 
     def conv_gemm(self, x0, x1, taps: Sequence[Tap], wgt, cout: int, grid: Tuple[int, int, int], bias=None,
                   temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0, gn=None):

@@ -74,6 +74,26 @@ def bench_conv(ops, B, iters, pk, first=None):
               f"{tf / pk['bf16_tflops']:.3f} of peak", flush=True)
 
 
+def bench_convgn(ops, B, iters, pk, first=None):
+    """dgrad conv with the GroupNorm-backward first half fused into the epilogue vs the plain conv."""
+    print(f"# conv_gemm dgrad: plain vs GroupNorm-backward epilogue fusion, batch {B}")
+    for (h, cin, cout) in [(128, 128, 128), (128, 128, 256), (64, 128, 128), (32, 256, 256), (16, 256, 256)][:first]:
+        g = bf(B, h, h, cin)
+        w = bf(cout, 9 * cin) * 0.1
+        x = bf(B, h, h, cout)
+        gam, bet = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+        _, _, coef = ops.gn_fwd(x, None, 32, 1e-5, gam, bet, True, want_coef=True)
+        out = torch.empty(B, h, h, cout, device="cuda", dtype=torch.bfloat16)
+        sums = torch.zeros(B, cout, 2, device="cuda")
+        tp = taps_3x3(cin)
+        ms_p = timeit(lambda i: ops.conv_gemm(g, None, tp, w, cout, (B, h, h), out=out), iters, 1)
+        ms_f = timeit(lambda i: ops.conv_gemm(g, None, tp, w, cout, (B, h, h), out=out,
+                                              gn=(x, None, coef, True, sums)), iters, 1)
+        fl = 2.0 * B * h * h * cout * cin * 9
+        print(f"convgn {h:3d}x{h:<3d} {cin:4d}->{cout:<4d} plain {ms_p:7.3f} ms {fl / ms_p / 1e9:7.1f} TFLOP/s | "
+              f"fused {ms_f:7.3f} ms {fl / ms_f / 1e9:7.1f} TFLOP/s  (+{ms_f - ms_p:.3f} ms)", flush=True)
+
+
 def bench_wgrad(ops, B, iters, pk, first=None):
     print(f"# conv_wgrad, batch {B}")
     for (h, cin, cout, taps) in CONV_SHAPES[:first]:
@@ -154,6 +174,8 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     if a.what in ("conv", "all"):
         bench_conv(ops, a.batch, a.iters, pk, a.first)
+    if a.what in ("convgn", "all"):
+        bench_convgn(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("wgrad", "all"):
         bench_wgrad(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("gn", "all"):

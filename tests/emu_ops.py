@@ -70,7 +70,7 @@ class EmuOps:
     @staticmethod
     def gn_bwd_fusable(grid):
         hw = grid[1] * grid[2]
-        return hw >= 128 or hw % 32 == 0
+        return hw >= 128 or hw % 32 == 0      # the CPU emulation exercises the fused path wherever it is POSSIBLE
 
     def conv_gemm(self, x0, x1, taps, wgt, cout, grid, bias=None, temb=None, res=None, out=None, out_f32=False,
                   src_n=0, gn=None):
