@@ -598,8 +598,14 @@ extern "C" int ddpm_conv_gemm(const ddpm_conv_args* a, void* stream_) {
                        : launch_gemm<256, 4, false>(ma0, ma1, mb, p, stream);
   }
   if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 128)) return e;
-  return p.epi.gsums ? launch_gemm<128, 3, true>(ma0, ma1, mb, p, stream)
-                     : launch_gemm<128, 3, false>(ma0, ma1, mb, p, stream);
+  if (p.epi.gsums) return launch_gemm<128, 3, true>(ma0, ma1, mb, p, stream);
+  // Few tiles (low-resolution layers): at most ~one CTA per SM is resident anyway, so a 3-stage ring keeps only two
+  // 32 KB loads in flight per SM and the CTA is latency-bound on L2 (8x8 512->512: 3.5x the MMA time).  Spend the
+  // whole shared memory on one CTA's ring instead.
+  const long long ctas = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_n * ((a->cout + 127) / 128);
+  if (ctas <= kNumSMs + kNumSMs / 2 && env_int("DDPM_DEEP_RING", 1))
+    return launch_gemm<128, 6, false>(ma0, ma1, mb, p, stream);
+  return launch_gemm<128, 3, false>(ma0, ma1, mb, p, stream);
 }
 
 extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream_) {
