@@ -107,6 +107,7 @@ typedef struct ddpm_wgrad_args {
   float* dw; long long ldw;                  /* fp32 [cout][ldw] */
   int accumulate;                            /* 1: add into dw, 0: dw must be zero-filled or splits==1 */
   int splits;                                /* 0 = auto */
+  float* dbias;                              /* optional fp32 [cout]: += sum_pix dY[pix, co] (bias gradient) */
 } ddpm_wgrad_args;
 int ddpm_conv_wgrad(const ddpm_wgrad_args* args, void* stream);
 
@@ -124,21 +125,6 @@ typedef struct ddpm_prep_desc {
 } ddpm_prep_desc;
 int ddpm_prep_weights_batched(const ddpm_prep_desc* table_dev, int n_entries, int total_tiles, int with_d,
                               void* stream);
-
-/* conv_in (3 -> C, 3x3, pad 1): x NCHW fp32, w fp32 with element strides (w_sco, w_stap, w_sci), out NHWC bf16.
- * Also used as conv_out's dgrad (with transposed strides and flip=1). */
-int ddpm_conv3_to_c(const float* x, const float* w, long long w_sco, long long w_stap, long long w_sci, int flip,
-                    const float* bias, void* out, long long ldo, int n, int h, int wd, int cin, int cout,
-                    void* stream);
-/* conv_out (C -> 3, 3x3, pad 1): a NHWC bf16, w fp32 [3][9][C], out NCHW fp32. */
-int ddpm_conv_c_to_3(const void* a, long long lda, const float* w, const float* bias, float* out, int n, int h,
-                     int wd, int cin, int cout, void* stream);
-/* weight grads of the two 3-channel convs:
- *   dw[c*s_c + tap'*s_tap + k*s_k] += sum_pix big[pix, c] * small[n, k, pix + tap]   (tap' = flip ? 8-tap : tap)
- *   big: NHWC bf16 [.., cbig]; small: NCHW fp32 [n][ksmall][h][w]; optional dbias_small[k] += sum small. */
-int ddpm_conv3_wgrad(const void* big, long long ldbig, int cbig, const float* small_, int ksmall, float* dw,
-                     long long s_c, long long s_tap, long long s_k, int flip, float* dbias_small, int n, int h,
-                     int wd, void* stream);
 
 /* The 3-channel boundary convs on tensor cores (conv_in forward / conv_out dgrad: K = 27 padded to one 64-wide
  * k-block; conv_out forward: N = 3 padded to 32 output columns):

@@ -53,6 +53,7 @@ class WgradArgs(C.Structure):
         ("dw", _vp), ("ldw", _ll),
         ("accumulate", _i),
         ("splits", _i),
+        ("dbias", _vp),
     ]
 
 
@@ -77,9 +78,6 @@ SIGNATURES = {
     "ddpm_conv_wgrad": [C.POINTER(WgradArgs), _vp],
     "ddpm_prep_weight": [_vp, _vp, _ll, _vp, _ll, _i, _i, _i, _vp],
     "ddpm_prep_weights_batched": [_vp, _i, _i, _i, _vp],
-    "ddpm_conv3_to_c": [_vp, _vp, _ll, _ll, _ll, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
-    "ddpm_conv_c_to_3": [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "ddpm_conv3_wgrad": [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _ll, _i, _vp, _i, _i, _i, _vp],
     "ddpm_im2col3": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "ddpm_nhwc_to_nchw_f32": [_vp, _ll, _vp, _i, _i, _i, _i, _vp],
     "ddpm_gn_stats": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _vp],

@@ -617,7 +617,9 @@ extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream_) {
   DDPM_REQUIRE(a->ldw % 4 == 0, "ddpm_conv_wgrad: ldw must be a multiple of 4");
   {
     const int rr = launch_wgrad_row(a, stream);   // 3x3 stride-1 convs at high resolution: row-resident kernel
-    if (rr <= 0) return rr;
+    if (rr < 0) return rr;
+    if (rr == 0)   // (a ones-column MMA for the bias was tried: it re-reads the dY tile and cost more than this pass)
+      return a->dbias ? ddpm_reduce_hw(a->dy, a->ldy, a->n, a->h * a->w, a->cout, nullptr, 0, a->dbias, stream_) : DDPM_OK;
   }
   WgradParams p;
   std::memset(&p, 0, sizeof(p));
@@ -669,8 +671,11 @@ extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream_) {
   } else {
     mx1 = mx0;
   }
-  if (block_n == 64) return launch_wgrad<64, 4>(my, mx0, mx1, p, splits, stream);
-  if (block_n == 128) return launch_wgrad<128, 3>(my, mx0, mx1, p, splits, stream);
-  set_last_error("ddpm_conv_wgrad: unsupported block_n=%d", block_n);
-  return DDPM_ERR_UNSUPPORTED;
+  int rc;
+  if (block_n == 64) rc = launch_wgrad<64, 4>(my, mx0, mx1, p, splits, stream);
+  else if (block_n == 128) rc = launch_wgrad<128, 3>(my, mx0, mx1, p, splits, stream);
+  else { set_last_error("ddpm_conv_wgrad: unsupported block_n=%d", block_n); return DDPM_ERR_UNSUPPORTED; }
+  if (rc != DDPM_OK || a->dbias == nullptr) return rc;
+  // bias gradient: a separate column reduction over dY
+  return ddpm_reduce_hw(a->dy, a->ldy, a->n, a->h * a->w, a->cout, nullptr, 0, a->dbias, stream_);
 }

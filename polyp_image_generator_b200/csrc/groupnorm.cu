@@ -708,6 +708,8 @@ static void gn_team_geometry(int C, int hw, int n, int resident, double sample_b
   const double budget = static_cast<double>(env_int("DDPM_GN_L2_MB", 40)) * 1048576.0;
   int max_teams = static_cast<int>(budget / sample_bytes);
   if (max_teams < 1) max_teams = 1;
+  // a tensor that fits L2 as a whole gets one team per sample: a single barrier per CTA instead of one per round
+  if (sample_bytes * n <= static_cast<double>(env_int("DDPM_GN_L2_WHOLE_MB", 100)) * 1048576.0) max_teams = n;
   int teams = n < max_teams ? n : max_teams;
   if (teams > resident) teams = resident;
   int team_size = resident / teams;

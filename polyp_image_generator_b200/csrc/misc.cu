@@ -346,37 +346,67 @@ __global__ void sumpool2x_kernel(const __nv_bfloat16* __restrict__ dy, long long
 __global__ void __launch_bounds__(256)
 im2col3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ patches, int N, int H, int W, int cin,
                float* __restrict__ chan_sum, long long npix) {
+  // one thread = one pixel: the 9*cin source reads are coalesced across the warp (adjacent pixels of a row) and hit
+  // L1 nine times over; the 128-byte patch row goes out as four 256-bit stores
   __shared__ float ssum[4];
   if (threadIdx.x < 4) ssum[threadIdx.x] = 0.f;
   __syncthreads();
   const long long hw = static_cast<long long>(H) * W;
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long pix = gid >> 3;
-  const int part = static_cast<int>(gid & 7);     // columns part*8 .. part*8+7
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
   if (pix < npix) {
     const int n = static_cast<int>(pix / hw);
     const int rem = static_cast<int>(pix - n * hw);
     const int h = rem / W, w = rem - h * W;
     const float* sn = src + static_cast<long long>(n) * cin * hw;
-    float f[8];
-    const int kk = 9 * cin;
+    float f[36];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int col = part * 8 + e;
-      float v = 0.f;
-      if (col < kk) {
-        const int tap = col / cin, k = col - tap * cin;
-        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(sn + k * hw + static_cast<long long>(hh) * W + ww);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        f[tap * 4 + k] = (in && k < cin) ? __ldg(sn + k * hw + static_cast<long long>(hh) * W + ww) : 0.f;
+    }
+    // pack to the dense [tap*cin + k] order
+    uint32_t wds[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) wds[j] = 0u;
+    float g[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) g[j] = 0.f;
+    if (cin == 3) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[tap * 3 + k] = f[tap * 4 + k];
+    } else if (cin == 4) {
+#pragma unroll
+      for (int j = 0; j < 36; ++j) g[j] = f[j];
+    } else if (cin == 1) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) g[tap] = f[tap * 4];
+    } else {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        g[tap * 2] = f[tap * 4];
+        g[tap * 2 + 1] = f[tap * 4 + 1];
       }
-      f[e] = v;
     }
-    *reinterpret_cast<bf16x8*>(patches + pix * 64 + part * 8) = pack8(f);
-    if (chan_sum != nullptr && part == 0) {
-      for (int k = 0; k < cin; ++k) atomicAdd(&ssum[k], __ldg(sn + k * hw + rem));
-    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) wds[j] = pack2_bf16(g[2 * j], g[2 * j + 1]);
+    uint4* dst = reinterpret_cast<uint4*>(patches + pix * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_uint4(wds[4 * j], wds[4 * j + 1], wds[4 * j + 2], wds[4 * j + 3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) csum[k] = f[4 * 4 + k];   // centre tap = the pixel itself
   }
   if (chan_sum != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = warp_sum(csum[k]);
+      if ((threadIdx.x & 31) == 0 && k < cin) atomicAdd(&ssum[k], v);
+    }
     __syncthreads();
     if (threadIdx.x < cin) atomicAdd(&chan_sum[threadIdx.x], ssum[threadIdx.x]);
   }
@@ -519,7 +549,7 @@ extern "C" int ddpm_im2col3(const float* src, void* patches, int n, int h, int w
                             void* stream) {
   DDPM_REQUIRE(src && patches && n > 0 && h > 0 && w > 0 && cin >= 1 && cin <= 4, "ddpm_im2col3: bad argument");
   const long long npix = static_cast<long long>(n) * h * w;
-  const long long blocks = (npix * 8 + 255) / 256;
+  const long long blocks = (npix + 255) / 256;
   im2col3_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(patches), n, h, w, cin, chan_sum, npix);
   return check_launch("im2col3_kernel");

@@ -187,8 +187,9 @@ class CudaOps:
         return out
 
     def conv_wgrad(self, dy, x0, x1, taps: Sequence[Tap], dw, grid: Tuple[int, int, int], accumulate: bool = True,
-                   src_n: int = 0, splits: int = 0):
-        """dw[co, wk+ci] (+)= sum_pix dy[pix, co] * X[pix+tap, ci]; dw: fp32 [cout, K] matrix view."""
+                   src_n: int = 0, splits: int = 0, dbias=None):
+        """dw[co, wk+ci] (+)= sum_pix dy[pix, co] * X[pix+tap, ci]; dw: fp32 [cout, K] matrix view.
+        dbias[co] += sum_pix dy[pix, co] when given (the launcher adds one column-reduction pass over dy)."""
         n, h, w = grid
         a = _capi.WgradArgs()
         _, _, _, cout, ldy = _nhwc(dy, "dy")
@@ -206,6 +207,7 @@ class CudaOps:
             raise ValueError("dw must be an fp32 [cout, K] matrix with unit inner stride")
         a.dw, a.ldw = _ptr(dw), dw.stride(0)
         a.accumulate, a.splits = int(accumulate), splits
+        a.dbias = _ptr(dbias)
         _capi.check(self.lib.ddpm_conv_wgrad(C.byref(a), _stream()), "ddpm_conv_wgrad")
         self.launches += 1
         return dw
@@ -238,35 +240,7 @@ class CudaOps:
                     "ddpm_prep_weights_batched")
         self.launches += 1
 
-    # ---- 3-channel convs ---------------------------------------------------------------------------------
-    def conv3_to_c(self, x, w, strides: Tuple[int, int, int], flip: bool, bias, cout: int, out=None):
-        """x: NCHW fp32 [n, cin<=4, h, w] -> NHWC bf16 [n, h, w, cout]."""
-        n, cin, h, wd = x.shape
-        if out is None:
-            out = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.bfloat16)
-        _capi.check(self.lib.ddpm_conv3_to_c(_ptr(x), _ptr(w), strides[0], strides[1], strides[2], int(flip),
-                                             _ptr(bias), _ptr(out), _nhwc(out, "out")[4], n, h, wd, cin, cout,
-                                             _stream()), "ddpm_conv3_to_c")
-        self.launches += 1
-        return out
-
-    def conv_c_to_3(self, a, w, bias, cout: int):
-        """a: NHWC bf16 -> NCHW fp32 [n, cout<=4, h, w]; w fp32 [cout][9][cin]."""
-        n, h, wd, cin, lda = _nhwc(a, "a")
-        out = torch.empty((n, cout, h, wd), device=a.device, dtype=torch.float32)
-        _capi.check(self.lib.ddpm_conv_c_to_3(_ptr(a), lda, _ptr(w), _ptr(bias), _ptr(out), n, h, wd, cin, cout,
-                                              _stream()), "ddpm_conv_c_to_3")
-        self.launches += 1
-        return out
-
-    def conv3_wgrad(self, big, small, dw, strides: Tuple[int, int, int], flip: bool, dbias_small=None):
-        n, h, wd, cbig, ldbig = _nhwc(big, "big")
-        ks = small.shape[1]
-        _capi.check(self.lib.ddpm_conv3_wgrad(_ptr(big), ldbig, cbig, _ptr(small), ks, _ptr(dw), strides[0],
-                                              strides[1], strides[2], int(flip), _ptr(dbias_small), n, h, wd,
-                                              _stream()), "ddpm_conv3_wgrad")
-        self.launches += 1
-
+    # ---- 3-channel boundary convs (as GEMMs) --------------------------------------------------------------
     def im2col3(self, x, chan_sum=None):
         """x: NCHW fp32 [n, cin<=4, h, w] -> 3x3/pad-1 patches, NHWC bf16 [n, h, w, 64] (columns tap*cin + k)."""
         n, cin, h, w = x.shape

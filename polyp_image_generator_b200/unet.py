@@ -881,14 +881,15 @@ class UNet2DModel(nn.Module):
         grid = s.grid
         # conv2 (+ shortcut bias shares the same column sums)
         dW2, db2 = self._wgrad_views(G, r.conv2)
-        if r.conv2.bias_trainable:
+        fold_bias = r.conv2.trainable and r.conv2.bias_trainable     # bias gradient rides on the wgrad GEMM
+        if r.conv2.bias_trainable and not fold_bias:
             ops.reduce_hw(g, None, db2)
-            if r.short is not None and r.short.bias_trainable:
-                self._wgrad_views(G, r.short)[1].copy_(db2)
-        elif r.short is not None and r.short.bias_trainable:
+        elif not r.conv2.bias_trainable and r.short is not None and r.short.bias_trainable:
             ops.reduce_hw(g, None, self._wgrad_views(G, r.short)[1])
         if r.conv2.trainable:
-            ops.conv_wgrad(g, s.b, None, taps_3x3(r.cout), dW2, grid)
+            ops.conv_wgrad(g, s.b, None, taps_3x3(r.cout), dW2, grid, dbias=db2 if fold_bias else None)
+        if r.conv2.bias_trainable and r.short is not None and r.short.bias_trainable:
+            self._wgrad_views(G, r.short)[1].copy_(db2)       # the shortcut bias sees the same column sums
         g2, be2 = self._norm_params(r.norm2)
         dg, dbt = self._norm_grads(G, r.norm2)
         fuse = s.coef2 is not None
@@ -974,10 +975,12 @@ class UNet2DModel(nn.Module):
         ops, G = st.ops, st.G
         N, H, W, C = s.shape
         dW, db = self._wgrad_views(G, d.conv)
-        if d.conv.bias_trainable:
+        fold_bias = d.conv.trainable and d.conv.bias_trainable
+        if d.conv.bias_trainable and not fold_bias:
             ops.reduce_hw(g, None, db)
         if d.conv.trainable:
-            ops.conv_wgrad(g, s.s2d, None, taps_s2d(C, N, d.pad), dW, s.grid, src_n=4 * N)
+            ops.conv_wgrad(g, s.s2d, None, taps_s2d(C, N, d.pad), dW, s.grid, src_n=4 * N,
+                           dbias=db if fold_bias else None)
         zi = ops.zero_insert2x(g, H, W)
         extra = st.skip_grads.pop(s.in_skip, None) if s.in_skip is not None else None
         # dgrad of the stride-2 conv = stride-1 correlation of the zero-inserted dY with the flipped taps
@@ -989,10 +992,11 @@ class UNet2DModel(nn.Module):
         ops, G = st.ops, st.G
         C = u.c
         dW, db = self._wgrad_views(G, u.conv)
-        if u.conv.bias_trainable:
+        fold_bias = u.conv.trainable and u.conv.bias_trainable
+        if u.conv.bias_trainable and not fold_bias:
             ops.reduce_hw(g, None, db)
         if u.conv.trainable:
-            ops.conv_wgrad(g, s.up, None, taps_3x3(C), dW, s.grid)
+            ops.conv_wgrad(g, s.up, None, taps_3x3(C), dW, s.grid, dbias=db if fold_bias else None)
         d_up = ops.conv_gemm(g, None, taps_3x3(C), u.conv.wd, C, s.grid)
         return ops.sumpool2x(d_up)
 

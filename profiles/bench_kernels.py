@@ -137,18 +137,17 @@ def bench_small(ops, B, iters, pk):
     print(f"# 3-channel convs + elementwise, batch {B}, 128x128")
     S, C = 128, 128
     x = torch.randn(B, 3, S, S, device="cuda")
-    w_in = torch.randn(C, 9, 3, device="cuda") * 0.1
+    ms = timeit(lambda i: ops.im2col3(x), iters, 1)
+    print(f"im2col3          {ms:7.3f} ms  ({(x.numel() * 4 + B * S * S * 64 * 2) / ms / 1e6:6.0f} GB/s algorithmic)")
+    pat = ops.im2col3(x)
+    wf = bf(C, 64) * 0.1
     b_in = torch.randn(C, device="cuda")
-    ms = timeit(lambda i: ops.conv3_to_c(x, w_in, (27, 3, 1), False, b_in, C), iters, 1)
-    print(f"conv_in fwd      {ms:7.3f} ms  ({(x.numel() * 4 + B * S * S * C * 2) / ms / 1e6:6.0f} GB/s algorithmic)")
+    ms = timeit(lambda i: ops.conv_gemm(pat, None, taps_1x1(), wf, C, (B, S, S), bias=b_in), iters, 1)
+    print(f"conv_in GEMM     {ms:7.3f} ms  ({(B * S * S * (64 + C) * 2) / ms / 1e6:6.0f} GB/s algorithmic)")
     a = bf(B, S, S, C)
-    w_out = torch.randn(3, 9, C, device="cuda") * 0.1
-    b_out = torch.randn(3, device="cuda")
-    ms = timeit(lambda i: ops.conv_c_to_3(a, w_out, b_out, 3), iters, 1)
-    print(f"conv_out fwd     {ms:7.3f} ms  ({(x.numel() * 4 + B * S * S * C * 2) / ms / 1e6:6.0f} GB/s algorithmic)")
-    dw = torch.zeros(C, 9, 3, device="cuda")
-    ms = timeit(lambda i: ops.conv3_wgrad(a, x, dw, (27, 3, 1), False), iters, 1)
-    print(f"conv3 wgrad      {ms:7.3f} ms")
+    wo = bf(32, 9 * C) * 0.1
+    ms = timeit(lambda i: ops.conv_gemm(a, None, taps_3x3(C), wo, 32, (B, S, S), out_f32=True), iters, 1)
+    print(f"conv_out GEMM    {ms:7.3f} ms")
     nz = torch.randn_like(x)
     t = torch.randint(0, 1000, (B,), device="cuda")
     tab = torch.rand(1000, device="cuda")

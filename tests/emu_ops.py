@@ -108,7 +108,9 @@ class EmuOps:
             return out
         return r
 
-    def conv_wgrad(self, dy, x0, x1, taps, dw, grid, accumulate=True, src_n=0, splits=0):
+    def conv_wgrad(self, dy, x0, x1, taps, dw, grid, accumulate=True, src_n=0, splits=0, dbias=None):
+        if dbias is not None:
+            dbias += dy.float().reshape(-1, dy.shape[-1]).sum(0)
         n, h, w = grid
         X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
         C = X.shape[-1]
@@ -138,38 +140,6 @@ class EmuOps:
         tp = 8 - tap if flip else tap
         return flat[co * strides[0] + tp * strides[1] + ci * strides[2]]
 
-    def conv3_to_c(self, x, w, strides, flip, bias, cout, out=None):
-        n, cin, h, wd = x.shape
-        w3 = self._w_from_strides(w, strides, flip, cout, cin)            # [cout][9][cin]
-        w4 = w3.reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
-        y = F.conv2d(x, w4, bias, padding=1).permute(0, 2, 3, 1)
-        r = self._a(y)
-        if out is not None:
-            out.copy_(r)
-            return out
-        return r.contiguous()
-
-    def conv_c_to_3(self, a, w, bias, cout):
-        cin = a.shape[-1]
-        w4 = w.reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
-        return F.conv2d(a.float().permute(0, 3, 1, 2), w4, bias, padding=1).contiguous()
-
-    def conv3_wgrad(self, big, small, dw, strides, flip, dbias_small=None):
-        n, h, wd, cbig = big.shape
-        ks = small.shape[1]
-        bigf = big.float().reshape(-1, cbig)
-        X = small.permute(0, 2, 3, 1)                                      # [n,h,w,ks]
-        flat = dw.reshape(-1)
-        for tap in range(9):
-            xs = self._shift(X, 0, tap // 3 - 1, tap % 3 - 1, n, h, wd).reshape(-1, ks)
-            contrib = bigf.t() @ xs                                        # [cbig, ks]
-            tp = 8 - tap if flip else tap
-            idx = (torch.arange(cbig).view(-1, 1) * strides[0] + tp * strides[1] + torch.arange(ks).view(1, -1) * strides[2])
-            flat.index_add_(0, idx.reshape(-1), contrib.reshape(-1))
-        if dbias_small is not None:
-            dbias_small += small.sum((0, 2, 3))
-
-    # ---- GroupNorm -------------------------------------------------------------------------------------------
     def im2col3(self, x, chan_sum=None):
         n, cin, h, w = x.shape
         xp = F.pad(x.float(), (1, 1, 1, 1))

@@ -182,44 +182,59 @@ def g_misc(ops):
 
 
 def g_smallconv(ops):
+    """The 3-channel boundary convs as one-k-block tcgen05 GEMMs (im2col3 + conv_gemm / conv_wgrad + nhwc_to_nchw)."""
+    from polyp_image_generator_b200.ops import taps_1x1, taps_3x3
     ok = True
     dev = "cuda"
     torch.manual_seed(3)
     torch.backends.cudnn.allow_tf32 = False
-    n, h, w, C = 2, 16, 24, 128
-    x = torch.randn(n, 3, h, w, device=dev)
-    wt = (torch.randn(C, 3, 3, 3, device=dev) * 0.2).contiguous(memory_format=torch.channels_last)
-    b = torch.randn(C, device=dev)
-    wphys = wt.permute(0, 2, 3, 1).reshape(C, 9, 3)  # [co][tap][ci] view of the physical layout
-    assert wphys.is_contiguous()
-    got = ops.conv3_to_c(x, wphys, (27, 3, 1), False, b, C)
-    want = F.conv2d(x, wt, b, padding=1).permute(0, 2, 3, 1)
-    ok &= report("conv_in fwd", got, want, 4e-3)
-    dy = bf(torch.randn(n, h, w, C, device=dev))
-    dw = torch.zeros(C, 9, 3, device=dev)
-    ops.conv3_wgrad(dy, x, dw, (27, 3, 1), False)
-    wr = wt.clone().requires_grad_(True)
-    F.conv2d(x, wr, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
-    ok &= report("conv_in wgrad", dw, wr.grad.permute(0, 2, 3, 1).reshape(C, 9, 3), 1e-4)
-    # conv_out
-    a = bf(torch.randn(n, h, w, C, device=dev))
-    wo = (torch.randn(3, C, 3, 3, device=dev) * 0.05).contiguous(memory_format=torch.channels_last)
-    bo = torch.randn(3, device=dev)
-    wophys = wo.permute(0, 2, 3, 1).reshape(3, 9, C)
-    got = ops.conv_c_to_3(a, wophys, bo, 3)
-    ar = a.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
-    wor = wo.clone().requires_grad_(True)
-    yr = F.conv2d(ar, wor, bo, padding=1)
-    ok &= report("conv_out fwd", got, yr, 1e-5)
-    dyo = torch.randn(n, 3, h, w, device=dev)
-    yr.backward(dyo)
-    da = ops.conv3_to_c(dyo, wophys, (1, C, 9 * C), True, None, C)
-    ok &= report("conv_out dgrad", da, ar.grad.permute(0, 2, 3, 1), 4e-3)
-    dwo = torch.zeros(3, 9, C, device=dev)
-    dbo = torch.zeros(3, device=dev)
-    ops.conv3_wgrad(a, dyo, dwo, (1, C, 9 * C), True, dbo)
-    ok &= report("conv_out wgrad", dwo, wor.grad.permute(0, 2, 3, 1).reshape(3, 9, C), 1e-4)
-    ok &= report("conv_out bgrad", dbo, dyo.sum((0, 2, 3)), 1e-5)
+    for (n, h, w, C) in [(2, 16, 24, 128), (3, 64, 64, 128), (1, 7, 5, 64)]:
+        grid = (n, h, w)
+        x = torch.randn(n, 3, h, w, device=dev)
+        wt = torch.randn(C, 3, 3, 3, device=dev) * 0.2
+        b = torch.randn(C, device=dev)
+        wf = torch.zeros(C, 64, device=dev, dtype=torch.bfloat16)
+        wf[:, :27] = wt.permute(0, 2, 3, 1).reshape(C, 27)                      # [co][tap][ci]
+        csum = torch.zeros(3, device=dev)
+        pat = ops.im2col3(x, chan_sum=csum)
+        xb = bf(x).float()
+        want_pat = F.unfold(xb, 3, padding=1).view(n, 3, 9, h, w).permute(0, 3, 4, 2, 1).reshape(n, h, w, 27)
+        ok &= report(f"im2col3 n{n} {h}x{w}", pat[..., :27], want_pat, 0.0)
+        ok &= report("   im2col3 zero padding", pat[..., 27:].float().abs().sum().reshape(1), torch.zeros(1, device=dev), 0.0)
+        ok &= report("   channel sums", csum, x.sum((0, 2, 3)), 1e-5)
+        got = ops.conv_gemm(pat, None, taps_1x1(), wf, C, grid, bias=b)
+        ok &= report("   conv_in fwd", got, F.conv2d(x, wt, b, padding=1).permute(0, 2, 3, 1), 4e-3)
+        dy = bf(torch.randn(n, h, w, C, device=dev))
+        R = torch.zeros(C, 64, device=dev)
+        ops.conv_wgrad(dy, pat, None, taps_1x1(), R, grid)
+        wr = wt.clone().requires_grad_(True)
+        F.conv2d(xb, wr, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+        ok &= report("   conv_in wgrad", R[:, :27], wr.grad.permute(0, 2, 3, 1).reshape(C, 27), 2e-3)
+        # conv_out: N = 3 padded to 32 output columns, fp32 NHWC result -> NCHW
+        a = bf(torch.randn(n, h, w, C, device=dev))
+        wo = torch.randn(3, C, 3, 3, device=dev) * 0.05
+        bo = torch.randn(3, device=dev)
+        wof = torch.zeros(32, 9 * C, device=dev, dtype=torch.bfloat16)
+        wof[:3] = wo.permute(0, 2, 3, 1).reshape(3, 9 * C)
+        b32 = torch.zeros(32, device=dev)
+        b32[:3] = bo
+        o32 = ops.conv_gemm(a, None, taps_3x3(C), wof, 32, grid, bias=b32, out_f32=True)
+        got = ops.nhwc_to_nchw_f32(o32, 3)
+        ar = a.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        wor = bf(wo).float().requires_grad_(True)
+        yr = F.conv2d(ar, wor, bo, padding=1)
+        ok &= report("   conv_out fwd", got, yr, 1e-4)
+        dyo = torch.randn(n, 3, h, w, device=dev)
+        yr.backward(bf(dyo).float())
+        pd = ops.im2col3(dyo)
+        wd = torch.zeros(C, 64, device=dev, dtype=torch.bfloat16)
+        wd[:, :27] = wo.permute(0, 2, 3, 1).reshape(3, 9, C).flip(1).permute(2, 1, 0).reshape(C, 27)
+        da = ops.conv_gemm(pd, None, taps_1x1(), wd, C, grid)
+        ok &= report("   conv_out dgrad", da, ar.grad.permute(0, 2, 3, 1), 4e-3)
+        R = torch.zeros(C, 64, device=dev)
+        ops.conv_wgrad(a, pd, None, taps_1x1(), R, grid)
+        dwo = R[:, :27].view(C, 9, 3).flip(1).permute(2, 1, 0)                  # [co][tap][ci]
+        ok &= report("   conv_out wgrad", dwo, wor.grad.permute(0, 2, 3, 1).reshape(3, 9, C), 2e-3)
     return ok
 
 
@@ -386,11 +401,13 @@ def g_wgrad(ops):
         x = bf(torch.randn(n, h, w_, cin, device=dev))
         dy = bf(torch.randn(n, h, w_, cout, device=dev))
         dw = torch.zeros(cout, 9 * cin, device=dev)
-        ops.conv_wgrad(dy, x, None, taps_3x3(cin), dw, (n, h, w_), accumulate=True)
+        db = torch.zeros(cout, device=dev)
+        ops.conv_wgrad(dy, x, None, taps_3x3(cin), dw, (n, h, w_), accumulate=True, dbias=db)
         wr = torch.zeros(cout, cin, 3, 3, device=dev, requires_grad=True)
         F.conv2d(x.float().permute(0, 3, 1, 2), wr, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
         ok &= report(f"conv3x3 wgrad n{n} {h}x{w_} {cin}->{cout}", dw, wr.grad.permute(0, 2, 3, 1).reshape(cout, -1),
                      2e-3)
+        ok &= report("   bias grad", db, dy.float().sum((0, 1, 2)), 2e-3)
     # concat
     n, h, w_, c0, c1, cout = 2, 16, 16, 256, 128, 128
     xa, xb = bf(torch.randn(n, h, w_, c0, device=dev)), bf(torch.randn(n, h, w_, c1, device=dev))

