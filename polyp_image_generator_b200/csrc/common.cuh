@@ -185,6 +185,20 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a CONVERGED warp.  The MMA / TMA issuing warps run their loops warp-uniformly and predicate only the
+// issuing instruction with this: inside an `if (lane == 0)` region the compiler cannot keep descriptors in uniform
+// registers and emits an ELECT / R2UR.BROADCAST retry loop (~17 SASS instructions) around every tcgen05.mma, which made
+// the single issuing thread -- not the tensor pipe -- the limiter of the conv kernels (~60 % of peak).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.  One thread issues.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -29,7 +29,7 @@
 namespace ddpm {
 
 constexpr int kHaloThreads = 352;
-constexpr int kHaloBStages = 3;
+constexpr int kHaloMaxBStages = 8;   // weight-tile ring depth is chosen at launch from the shared memory left over
 constexpr int kTileSlots = 256;
 constexpr int kHaloBBytes = 128 * 128;   // one weight tile: 128 cout rows x 64 ch
 
@@ -41,6 +41,7 @@ struct HaloParams {
   int tiles_per_img, n_tiles, total_tiles;
   uint32_t halo_bytes;   // R * Wp * 128
   uint32_t halo_stride;  // halo_bytes rounded up to 1024
+  int b_stages;          // weight-tile ring depth
   EpiParams epi;
 };
 
@@ -52,13 +53,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* halo = smem;                                   // 2 x halo_stride
-  uint8_t* bsm = smem + 2 * p.halo_stride;                // kHaloBStages x 16 KB
+  uint8_t* bsm = smem + 2 * p.halo_stride;                // b_stages x 16 KB
+  const int kHaloBStages = p.b_stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + kHaloBStages * kHaloBBytes);
   uint64_t* halo_full = bars;            // [2]
   uint64_t* halo_empty = bars + 2;       // [2]
   uint64_t* b_full = bars + 4;           // [kHaloBStages]
-  uint64_t* b_empty = b_full + kHaloBStages;
-  uint64_t* tmem_full = b_empty + kHaloBStages;   // [2]
+  uint64_t* b_empty = b_full + kHaloMaxBStages;
+  uint64_t* tmem_full = b_empty + kHaloMaxBStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -88,44 +90,46 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    // ---------------- halo producer ----------------
-    if (lane == 0) {
-      uint32_t hidx = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int img = mt / p.tiles_per_img;
-        const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
-        const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
-        for (int c = 0; c < kbt; ++c, ++hidx) {
-          const uint32_t hb = hidx & 1, ph = (hidx >> 1) & 1;
-          mbar_wait(&halo_empty[hb], ph ^ 1);
+    // ---------------- halo producer (warp-uniform loop, one elected lane issues) ----------------
+    uint32_t hidx = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles;
+      const int img = mt / p.tiles_per_img;
+      const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
+      const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
+      for (int c = 0; c < kbt; ++c, ++hidx) {
+        const uint32_t hb = hidx & 1, ph = (hidx >> 1) & 1;
+        mbar_wait(&halo_empty[hb], ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&halo_full[hb], p.halo_bytes);
           if (c < p.kb0)
             tma_load_4d(halo + hb * p.halo_stride, &tmA0, &halo_full[hb], c * 64, -1, row_lo, img);
           else
             tma_load_4d(halo + hb * p.halo_stride, &tmA1, &halo_full[hb], (c - p.kb0) * 64, -1, row_lo, img);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 9) {
     // ---------------- weight-tile producer ----------------
-    if (lane == 0) {
-      uint32_t bidx = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        for (int c = 0; c < kbt; ++c) {
-          for (int tap = 0; tap < 9; ++tap, ++bidx) {
-            const uint32_t s = bidx % kHaloBStages, ph = (bidx / kHaloBStages) & 1;
-            mbar_wait(&b_empty[s], ph ^ 1);
+    uint32_t bidx = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      for (int c = 0; c < kbt; ++c) {
+        for (int tap = 0; tap < 9; ++tap, ++bidx) {
+          const uint32_t s = bidx % kHaloBStages, ph = (bidx / kHaloBStages) & 1;
+          mbar_wait(&b_empty[s], ph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&b_full[s], kHaloBBytes);
             tma_load_2d(bsm + s * kHaloBBytes, &tmB, &b_full[s], tap * p.Cin_total + c * 64, nt * 128);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 10) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues) ----------------
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
       uint32_t hidx = 0, bidx = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -149,20 +153,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int r = tap / 3, sx = tap - r * 3;
             const uint32_t a_addr = h_addr + static_cast<uint32_t>(rel0 + (r - 1) * p.Wp + (sx - 1)) * 128u;
             const uint32_t b_addr = smem_u32(bsm + s * kHaloBBytes);
+            // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
+            const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
+            const uint64_t db0 = make_smem_desc_sw128(b_addr, 16, 1024);
+            const uint32_t first = (c | tap) != 0 ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+              for (int u = 0; u < 2; ++u) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = make_smem_desc_sw128(a_addr + u * (128 * 128) + k * 32, 16, 1024);
-                const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                umma_bf16(d0 + u * 128, da, db, idesc, (c | tap | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(d0 + u * 128, da0 + static_cast<uint64_t>((u * (128 * 128) + k * 32) >> 4),
+                            db0 + static_cast<uint64_t>((k * 32) >> 4), idesc, k == 0 ? first : 1u);
+                }
               }
+              umma_commit(&b_empty[s]);
             }
-            umma_commit(&b_empty[s]);
+            __syncwarp();
           }
-          umma_commit(&halo_empty[hb]);
+          if (elect_one()) umma_commit(&halo_empty[hb]);
+          __syncwarp();
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
       }
     }
   } else {
@@ -251,8 +263,14 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
   p.R = R;
   p.halo_bytes = static_cast<uint32_t>(R) * Wp * 128u;
   p.halo_stride = (p.halo_bytes + 1023u) & ~1023u;
-  const size_t smem = 2ull * p.halo_stride + kHaloBStages * kHaloBBytes + 256 + 1024;
-  if (smem > 227 * 1024) return 1;
+  const size_t fixed = 2ull * p.halo_stride + 512 + 1024;
+  if (fixed + 2 * kHaloBBytes > 227 * 1024) return 1;
+  int bst = static_cast<int>((227 * 1024 - fixed) / kHaloBBytes);
+  if (bst > kHaloMaxBStages) bst = kHaloMaxBStages;
+  bst = env_int("DDPM_HALO_BSTAGES", bst) < bst ? env_int("DDPM_HALO_BSTAGES", bst) : bst;
+  if (bst < 2) return 1;
+  p.b_stages = bst;
+  const size_t smem = fixed + static_cast<size_t>(bst) * kHaloBBytes;
   p.tiles_per_img = (H * Wp + kTileSlots - 1) / kTileSlots;
   p.n_tiles = (a->cout + 127) / 128;
   p.total_tiles = a->n * p.tiles_per_img * p.n_tiles;

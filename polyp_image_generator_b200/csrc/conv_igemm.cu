@@ -108,14 +108,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int total_iters = p.taps.ntaps * kbt;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int it = 0;
-      for (int t = 0; t < p.taps.ntaps; ++t) {
-        const int cw = w0 + p.taps.dw[t], ch = h0 + p.taps.dh[t], cn = n0 + p.taps.dn[t], wk = p.taps.wk[t];
-        for (int kb = 0; kb < kbt; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+    int it = 0;
+    for (int t = 0; t < p.taps.ntaps; ++t) {
+      const int cw = w0 + p.taps.dw[t], ch = h0 + p.taps.dh[t], cn = n0 + p.taps.dn[t], wk = p.taps.wk[t];
+      for (int kb = 0; kb < kbt; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + s * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_expect_tx(&full_bar[s], p.a_bytes + L::kBBytes);
@@ -125,28 +125,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_load_4d(sa, &tmA1, &full_bar[s], (kb - p.kb0) * kBlockK, cw, ch, cn);
           tma_load_2d(sb, &tmB, &full_bar[s], wk + kb * kBlockK, nt * BLOCK_N);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, false, false);
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes;
+    // whole warp runs the loop (warp-uniform descriptors stay in uniform registers); one elected lane issues
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, false, false);
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+      const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
+      const uint64_t db0 = make_smem_desc_sw128(a_addr + L::kABytes, 16, 1024);
+      const uint32_t first = it != 0 ? 1u : 0u;
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * kUmmaK * 2, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * kUmmaK * 2, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16(tmem_base, da0 + static_cast<uint64_t>((k * kUmmaK * 2) >> 4),
+                    db0 + static_cast<uint64_t>((k * kUmmaK * 2) >> 4), idesc, k == 0 ? first : 1u);
         umma_commit(&empty_bar[s]);
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; one thread per output pixel (tile row)
     const int q = warp & 3;
@@ -268,18 +272,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   const int nyb = ((cot * 2 + 1) * 64 < p.Cout) ? 2 : 1;  // 64-cout boxes actually present
 
   if (warp == 0) {
-    if (lane == 0) {
-      const int dn = p.taps.dn[tap], dh = p.taps.dh[tap], dw = p.taps.dw[tap];
-      for (int it = 0; it < n_iters; ++it) {
-        int mt = pt_begin + it;
-        const int tw = mt % p.tiles_w;
-        mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int tn = mt / p.tiles_h;
-        const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    const int dn = p.taps.dn[tap], dh = p.taps.dh[tap], dw = p.taps.dw[tap];
+    for (int it = 0; it < n_iters; ++it) {
+      int mt = pt_begin + it;
+      const int tw = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int tn = mt / p.tiles_h;
+      const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + s * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes;
         mbar_expect_tx(&full_bar[s], p.box_bytes * (nyb + ncb));
@@ -294,27 +298,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
                         n0 + dn);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, true, true);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes;
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, true, true);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+      const uint64_t da0 = make_smem_desc_sw128(a_addr, p.lbo, p.sbo);
+      const uint64_t db0 = make_smem_desc_sw128(a_addr + L::kABytes, p.lbo, p.sbo);
+      const uint32_t first = it != 0 ? 1u : 0u;
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBlockM / kUmmaK; ++k) {   // 128 pixel rows = 8 MMAs of K=16
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * kUmmaK * 128, p.lbo, p.sbo);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * kUmmaK * 128, p.lbo, p.sbo);
-          umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < kBlockM / kUmmaK; ++k)   // 128 pixel rows = 8 MMAs of K=16
+          umma_bf16(tmem_base, da0 + static_cast<uint64_t>((k * kUmmaK * 128) >> 4),
+                    db0 + static_cast<uint64_t>((k * kUmmaK * 128) >> 4), idesc, k == 0 ? first : 1u);
         umma_commit(&empty_bar[s]);
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;         // cout index within tile

@@ -82,21 +82,21 @@ conv_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
   const uint32_t a_bytes = 2u * p.a_box_bytes;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const int cb = cit * 2;                                  // first 64-channel block of the cin tile
-      const bool src0 = cb < p.kb0;
-      const CUtensorMap* mx = src0 ? &tmX0 : &tmX1;
-      const int cx = (src0 ? cb : cb - p.kb0) * 64;
-      for (int it = 0; it < n_iters; ++it) {
-        int seg = seg_begin + it;
-        const int sw = seg % p.segs_per_row;
-        seg /= p.segs_per_row;
-        const int h = seg % p.H;
-        const int n = seg / p.H;
-        const int w0 = sw * p.kw;
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    const int cb = cit * 2;                                  // first 64-channel block of the cin tile
+    const bool src0 = cb < p.kb0;
+    const CUtensorMap* mx = src0 ? &tmX0 : &tmX1;
+    const int cx = (src0 ? cb : cb - p.kb0) * 64;
+    for (int it = 0; it < n_iters; ++it) {
+      int seg = seg_begin + it;
+      const int sw = seg % p.segs_per_row;
+      seg /= p.segs_per_row;
+      const int h = seg % p.H;
+      const int n = seg / p.H;
+      const int w0 = sw * p.kw;
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + static_cast<size_t>(s) * p.stage_bytes;
         uint8_t* sb = sa + a_bytes;
         mbar_expect_tx(&full_bar[s], a_bytes + 2u * p.b_box_bytes);
@@ -105,30 +105,35 @@ conv_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
         tma_load_4d(sb, mx, &full_bar[s], cx, w0 - 1, h + r - 1, n);
         tma_load_4d(sb + p.b_box_stride, mx, &full_bar[s], cx + 64, w0 - 1, h + r - 1, n);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128, true, true);
-      const int ksteps = p.kw / 16;
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
+    // whole warp runs the loop (warp-uniform descriptors stay in uniform registers); one elected lane issues
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, true, true);
+    const int ksteps = p.kw / 16;
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+      const uint64_t da0 = make_smem_desc_sw128(a_addr, p.a_box_bytes, 1024);
+      const uint64_t db0 = make_smem_desc_sw128(a_addr + a_bytes, p.b_box_stride, 1024);
+      const uint32_t first = it != 0 ? 1u : 0u;
+      if (elect_one()) {
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 16 * 128, p.a_box_bytes, 1024);
-            const uint64_t db = make_smem_desc_sw128(b_addr + (k * 16 + t) * 128, p.b_box_stride, 1024);
-            umma_bf16(tmem_base + t * 128, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-          }
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + t * 128, da0 + static_cast<uint64_t>(k * 128),          // (k*16 rows * 128 B) >> 4
+                      db0 + static_cast<uint64_t>(k * 128 + t * 8), idesc, k == 0 ? first : 1u);
         }
         umma_commit(&empty_bar[s]);
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int co = cot * 128 + q * 32 + lane;
