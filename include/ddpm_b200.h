@@ -92,8 +92,13 @@ typedef struct ddpm_conv_args {
   const float* gn_coef;
   int gn_silu;
   float* gn_sums;
+  /* Optional split-K workspace (fp32, caller-owned): low-resolution layers whose tile grid covers less than half the
+   * SMs split the reduction over blockIdx.z, accumulate fp32 partial sums here and finish in a second pass.
+   * ddpm_conv_gemm_workspace_elems() says how many elements this problem would use (0 = it does not split). */
+  float* splitk_ws; long long splitk_ws_elems;
 } ddpm_conv_args;
 int ddpm_conv_gemm(const ddpm_conv_args* args, void* stream);
+long long ddpm_conv_gemm_workspace_elems(const ddpm_conv_args* args);
 
 /* Conv / linear weight gradient on tcgen05:
  *   dw[co][wk[tap] + ci] (+)= sum_pix dY[pix, co] * X[pix + (dn,dh,dw)[tap], ci]      (fp32, split-K) */

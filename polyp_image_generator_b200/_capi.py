@@ -39,6 +39,7 @@ class ConvArgs(C.Structure):
         ("gn_coef", _vp),
         ("gn_silu", _i),
         ("gn_sums", _vp),
+        ("splitk_ws", _vp), ("splitk_ws_elems", _ll),
     ]
 
 
@@ -75,6 +76,7 @@ SIGNATURES = {
     "ddpm_scheduler_step_philox": [_vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _ull, _ull, _vp],
     "ddpm_to_uint8_nhwc": [_vp, _vp, _i, _i, _i, _i, _vp],
     "ddpm_conv_gemm": [C.POINTER(ConvArgs), _vp],
+    "ddpm_conv_gemm_workspace_elems": [C.POINTER(ConvArgs)],
     "ddpm_conv_wgrad": [C.POINTER(WgradArgs), _vp],
     "ddpm_prep_weight": [_vp, _vp, _ll, _vp, _ll, _i, _i, _i, _vp],
     "ddpm_prep_weights_batched": [_vp, _i, _i, _i, _vp],
@@ -120,7 +122,7 @@ def load() -> C.CDLL:
     lib.ddpm_last_error.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
-        fn.restype = C.c_int
+        fn.restype = C.c_longlong if name.endswith("_workspace_elems") else C.c_int
         fn.argtypes = argtypes
     if lib.ddpm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libddpm_b200.so ABI {lib.ddpm_abi_version()} != binding ABI {ABI_VERSION}")

@@ -47,6 +47,8 @@ struct GemmParams {
   int wb, hb, nb;         // TMA box (pixels) = M tile shape
   int tiles_w, tiles_h, tiles_n;
   uint32_t a_bytes;       // bytes one A box delivers (wb*hb*nb*128)
+  int iters_per_split;    // split-K over blockIdx.z: (tap, k-block) iterations per CTA; 0 = whole reduction
+  float* splitk_ws;       // fp32 [pixels][Cout] partial-sum workspace (zero-filled) when splitting
   EpiParams epi;
   TapTable taps;
 };
@@ -105,28 +107,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t tmem_base = *tmem_base_slot;
 
   const int kbt = p.kb0 + p.kb1;
-  const int total_iters = p.taps.ntaps * kbt;
+  const int all_iters = p.taps.ntaps * kbt;
+  // split-K: this CTA reduces the (tap, k-block) iterations [g_begin, g_begin + total_iters)
+  const int g_begin = p.iters_per_split > 0 ? static_cast<int>(blockIdx.z) * p.iters_per_split : 0;
+  const int total_iters = p.iters_per_split > 0 ? max(0, min(all_iters - g_begin, p.iters_per_split)) : all_iters;
 
   if (warp == 0) {
-    int it = 0;
-    for (int t = 0; t < p.taps.ntaps; ++t) {
+    for (int it = 0; it < total_iters; ++it) {
+      const int g = g_begin + it;
+      const int t = g / kbt, kb = g - t * kbt;
       const int cw = w0 + p.taps.dw[t], ch = h0 + p.taps.dh[t], cn = n0 + p.taps.dn[t], wk = p.taps.wk[t];
-      for (int kb = 0; kb < kbt; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (elect_one()) {
-          uint8_t* sa = smem + s * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(&full_bar[s], p.a_bytes + L::kBBytes);
-          if (kb < p.kb0)
-            tma_load_4d(sa, &tmA0, &full_bar[s], kb * kBlockK, cw, ch, cn);
-          else
-            tma_load_4d(sa, &tmA1, &full_bar[s], (kb - p.kb0) * kBlockK, cw, ch, cn);
-          tma_load_2d(sb, &tmB, &full_bar[s], wk + kb * kBlockK, nt * BLOCK_N);
-        }
-        __syncwarp();
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        mbar_expect_tx(&full_bar[s], p.a_bytes + L::kBBytes);
+        if (kb < p.kb0)
+          tma_load_4d(sa, &tmA0, &full_bar[s], kb * kBlockK, cw, ch, cn);
+        else
+          tma_load_4d(sa, &tmA1, &full_bar[s], (kb - p.kb0) * kBlockK, cw, ch, cn);
+        tma_load_2d(sb, &tmB, &full_bar[s], wk + kb * kBlockK, nt * BLOCK_N);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // whole warp runs the loop (warp-uniform descriptors stay in uniform registers); one elected lane issues
@@ -176,6 +180,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
       tmem_ld_wait();
+      if (!GN && p.splitk_ws != nullptr) {
+        // split-K: add the raw partial sums to the fp32 workspace; bias / residual / bf16 happen in the finalize pass
+        if (valid && col0 + c * 32 < p.epi.Cout && total_iters > 0) {
+          float* dst = p.splitk_ws + pix * p.epi.Cout + col0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+        }
+        continue;
+      }
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -516,6 +532,45 @@ int fill_epilogue(EpiParams* e, const ::ddpm_conv_args* a) {
   return DDPM_OK;
 }
 
+// split-K finalize: out[pix][c] = bf16(ws[pix][c] + bias[c] + temb[n][c] + res[pix][c]); 8 channels per thread
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(const float* __restrict__ ws, EpiParams e, long long pixels, long long pix_per_img) {
+  const int V = e.Cout / 8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= pixels * V) return;
+  const long long pix = i / V;
+  const int col = static_cast<int>(i - pix * V) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(ws + pix * e.Cout + col);
+  const float4 b = *reinterpret_cast<const float4*>(ws + pix * e.Cout + col + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += e.bias[col + j];
+  }
+  if (e.temb) {
+    const float* t = e.temb + (pix / pix_per_img) * e.ld_temb + col;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+  if (e.res) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(e.res + pix * e.ldr + col), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += f[j];
+  }
+  *reinterpret_cast<bf16x8*>(e.out + pix * e.ldo + col) = pack8(v);
+}
+
+// Split-K plan for a problem with `ctas` output tiles and `iters` (tap, k-block) iterations: engage idle SMs when the
+// tile grid covers less than half the chip (low-resolution layers: 4x4 .. 16x16 maps at the bottom of the UNet).
+static int splitk_plan(long long ctas, int iters) {
+  if (env_int("DDPM_SPLITK", 1) == 0 || ctas > kNumSMs / 2 || iters < 16) return 1;
+  long long s = kNumSMs / ctas;
+  if (s > iters / 4) s = iters / 4;
+  if (s > 16) s = 16;
+  return s < 2 ? 1 : static_cast<int>(s);
+}
+
 template <int BLOCK_N, int STAGES, bool GN>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
                        cudaStream_t stream) {
@@ -526,7 +581,9 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  dim3 grid((p.epi.Cout + BLOCK_N - 1) / BLOCK_N, p.tiles_w * p.tiles_h * p.tiles_n);
+  const int all_iters = p.taps.ntaps * (p.kb0 + p.kb1);
+  const int splits = p.iters_per_split > 0 ? (all_iters + p.iters_per_split - 1) / p.iters_per_split : 1;
+  dim3 grid((p.epi.Cout + BLOCK_N - 1) / BLOCK_N, p.tiles_w * p.tiles_h * p.tiles_n, splits);
   kern<<<grid, kGemmThreads, L::kTotal, stream>>>(a0, a1, b, p);
   return check_launch("conv_gemm_kernel");
 }
@@ -606,6 +663,23 @@ extern "C" int ddpm_conv_gemm(const ddpm_conv_args* a, void* stream_) {
   }
   if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 128)) return e;
   if (p.epi.gsums) return launch_gemm<128, 3, true>(ma0, ma1, mb, p, stream);
+  {
+    const long long ctas0 = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_n * ((a->cout + 127) / 128);
+    const int iters = a->ntaps * (p.kb0 + p.kb1);
+    const int splits = (a->splitk_ws && !a->out_f32 && a->cout % 8 == 0) ? splitk_plan(ctas0, iters) : 1;
+    if (splits > 1) {
+      const long long pixels = static_cast<long long>(a->n) * a->h * a->w;
+      DDPM_REQUIRE(a->splitk_ws_elems >= pixels * a->cout, "ddpm_conv_gemm: split-K workspace too small");
+      DDPM_CUDA(cudaMemsetAsync(a->splitk_ws, 0, sizeof(float) * pixels * a->cout, stream));
+      p.iters_per_split = (iters + splits - 1) / splits;
+      p.splitk_ws = a->splitk_ws;
+      if (int e = launch_gemm<128, 6, false>(ma0, ma1, mb, p, stream)) return e;
+      const long long items = pixels * (a->cout / 8);
+      splitk_finalize_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(
+          a->splitk_ws, p.epi, pixels, static_cast<long long>(a->h) * a->w);
+      return check_launch("splitk_finalize_kernel");
+    }
+  }
   // Few tiles (low-resolution layers): at most ~one CTA per SM is resident anyway, so a 3-stage ring keeps only two
   // 32 KB loads in flight per SM and the CTA is latency-bound on L2 (8x8 512->512: 3.5x the MMA time).  Spend the
   // whole shared memory on one CTA's ring instead.
@@ -685,4 +759,16 @@ extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream_) {
   if (rc != DDPM_OK || a->dbias == nullptr) return rc;
   // bias gradient: a separate column reduction over dY
   return ddpm_reduce_hw(a->dy, a->ldy, a->n, a->h * a->w, a->cout, nullptr, 0, a->dbias, stream_);
+}
+
+extern "C" long long ddpm_conv_gemm_workspace_elems(const ddpm_conv_args* a) {
+  // fp32 elements of split-K workspace ddpm_conv_gemm would use for this problem (0: no split)
+  if (!a || a->out_f32 || a->gn_sums || a->cout % 8) return 0;
+  if (a->ntaps == 9 && a->w >= env_int("DDPM_HALO_MIN_W", 64)) return 0;      // halo-resident kernel
+  int wb, hb, nb;
+  choose_box(a->n, a->h, a->w, &wb, &hb, &nb);
+  const long long mt = static_cast<long long>((a->w + wb - 1) / wb) * ((a->h + hb - 1) / hb) * ((a->n + nb - 1) / nb);
+  if (a->cout % 256 == 0 && mt * (a->cout / 256) >= 2 * kNumSMs) return 0;    // BLOCK_N = 256 path
+  const int iters = a->ntaps * ((a->c0 + a->c1) / 64);
+  return splitk_plan(mt * ((a->cout + 127) / 128), iters) > 1 ? static_cast<long long>(a->n) * a->h * a->w * a->cout : 0;
 }

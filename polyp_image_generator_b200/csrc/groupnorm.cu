@@ -304,10 +304,16 @@ gn_fwd_fused_kernel(GnSrc s, GnTeam t, float* __restrict__ stats /*[N][groups][2
     }
     __syncthreads();
     float* st = stats + static_cast<long long>(n) * groups * 2;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&st[i], sm[i]);
-    gn_team_barrier(&counters[n], t.team_size);
     f2x4 ka, kb;
-    gn_apply_coefs(st, c, cpg, inv_m, t.eps, gamma, beta, true, &ka, &kb);
+    if (t.team_size == 1) {
+      // small maps: the CTA owns the whole sample -- statistics stay in shared memory, written out once
+      for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) st[i] = sm[i];
+      gn_apply_coefs(sm, c, cpg, inv_m, t.eps, gamma, beta, false, &ka, &kb);
+    } else {
+      for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&st[i], sm[i]);
+      gn_team_barrier(&counters[n], t.team_size);
+      gn_apply_coefs(st, c, cpg, inv_m, t.eps, gamma, beta, true, &ka, &kb);
+    }
     if (coef != nullptr && rank == 0 && pl == 0) {
       float4* cp = reinterpret_cast<float4*>(coef) + (static_cast<long long>(n) * V * 8 + c) / 2;
 #pragma unroll
@@ -401,13 +407,19 @@ gn_bwd_fused_kernel(GnSrc s, GnTeam t, const float* __restrict__ stats, const fl
     }
     __syncthreads();
     float* sn = sums + static_cast<long long>(n) * C * 2;
-    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(&sn[i], smc[i]);
-    gn_team_barrier(&counters[n], t.team_size);
+    const bool solo = t.team_size == 1;
+    if (solo) {
+      for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sn[i] = smc[i];   // kept for dgamma / dbeta
+    } else {
+      for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(&sn[i], smc[i]);
+      gn_team_barrier(&counters[n], t.team_size);
+    }
     // ---- group coefficients: (sum_c gamma*A, sum_c gamma*B) / m ----
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
       float s1 = 0.f, s2 = 0.f;
       for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-        const float2 ab = __ldcg(reinterpret_cast<const float2*>(sn + cc * 2));
+        const float2 ab = solo ? *reinterpret_cast<const float2*>(smc + cc * 2)
+                               : __ldcg(reinterpret_cast<const float2*>(sn + cc * 2));
         const float ga = gamma[cc];
         s1 = fmaf(ga, ab.x, s1);
         s2 = fmaf(ga, ab.y, s2);
@@ -718,6 +730,10 @@ static void gn_team_geometry(int C, int hw, int n, int resident, double sample_b
   if (team_size < 1) team_size = 1;
   teams = resident / team_size;
   if (teams > n) teams = n;
+  if (static_cast<long long>(hw) * C <= env_int("DDPM_GN_SOLO_ELEMS", 65536)) {
+    team_size = 1;                       // latency-sized sample: one CTA, no atomics / barrier / memsets
+    teams = resident < n ? resident : n;
+  }
   int ppc = (hw + team_size - 1) / team_size;
   ppc = (ppc + ppb - 1) / ppb * ppb;
   t->V = V;
@@ -790,8 +806,10 @@ extern "C" int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1
                         : gn_resident_ctas(gn_fwd_fused_kernel<false>, kGnThreads, 0);
   int threads, grid;
   gn_team_geometry(C, hw, n, resident[ki], 2.0 * hw * C, &t, &threads, &grid);
-  DDPM_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
-  DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * n, stream));
+  if (t.team_size > 1) {
+    DDPM_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
+    DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * n, stream));
+  }
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   void* args[] = {&s, &t, &stats, &ws, &gamma, &beta, &yp, &ldy, &coef};
   const void* fn = silu ? reinterpret_cast<const void*>(gn_fwd_fused_kernel<true>)
@@ -829,7 +847,8 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
   int threads, grid;
   const double sample_bytes = 2.0 * hw * C * (2 + (add0 ? 1 : 0) + (add1 ? 1 : 0));
   gn_team_geometry(C, hw, n, resident[ki], sample_bytes, &t, &threads, &grid);
-  DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * static_cast<size_t>(n) * C * 2 + sizeof(int) * n, stream));
+  if (t.team_size > 1)
+    DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * static_cast<size_t>(n) * C * 2 + sizeof(int) * n, stream));
   void* args[] = {&s, &t, &stats, &gamma, &beta, &dyp, &lddy, &sums, &counters, &o};
   const void* fn = silu ? reinterpret_cast<const void*>(gn_bwd_fused_kernel<true>)
                         : reinterpret_cast<const void*>(gn_bwd_fused_kernel<false>);

@@ -182,8 +182,12 @@ class CudaOps:
             if gsums.dtype != torch.float32 or not gsums.is_contiguous() or gsums.numel() != n * cout * 2:
                 raise ValueError("gn sums must be a contiguous fp32 [n, cout, 2] tensor")
             a.gn_sums = _ptr(gsums)
+        ws_elems = self.lib.ddpm_conv_gemm_workspace_elems(C.byref(a)) if gn is None and not out_f32 else 0
+        if ws_elems > 0:      # low-resolution layer: split-K over idle SMs, fp32 partial sums in a workspace
+            ws = torch.empty(ws_elems, device=x0.device, dtype=torch.float32)
+            a.splitk_ws, a.splitk_ws_elems = _ptr(ws), ws_elems
         _capi.check(self.lib.ddpm_conv_gemm(C.byref(a), _stream()), "ddpm_conv_gemm")
-        self.launches += 1
+        self.launches += 3 if ws_elems > 0 else 1
         return out
 
     def conv_wgrad(self, dy, x0, x1, taps: Sequence[Tap], dw, grid: Tuple[int, int, int], accumulate: bool = True,

@@ -305,7 +305,7 @@ def g_gemm(ops):
                                   (4, 8, 8, 512, 512), (9, 4, 4, 512, 512), (2, 64, 64, 128, 256),
                                   (2, 14, 14, 128, 128), (3, 7, 7, 64, 128), (1, 200, 136, 64, 128),
                                   (3, 70, 96, 128, 256), (5, 64, 64, 256, 128), (2, 128, 128, 256, 128),
-                                  (1, 65, 64, 64, 64), (2, 3, 200, 64, 128)]:
+                                  (1, 65, 64, 64, 64), (2, 3, 200, 64, 128), (32, 4, 4, 1024, 512), (16, 8, 8, 512, 1024)]:
         x = bf(torch.randn(n, h, w_, cin, device=dev))
         w4 = bf(torch.randn(cout, cin, 3, 3, device=dev) * 0.03)
         wk = w4.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
