@@ -1,11 +1,12 @@
-// Row-resident weight gradient of the 3x3 stride-1 convolutions at high resolution (W >= 64) on tcgen05.
+// Row-resident weight gradient of the 3x3 stride-1 convolutions (W >= 16, W % 16 == 0) on tcgen05.
 //
 // Why: the generic wgrad kernel (conv_igemm.cu) gives one CTA one (tap, 128 cout, 128 cin) tile, so every dY tile is
 // re-read once per tap and 64 KB of operands are fetched per 512 tensor-clocks (128 B/clk/SM) -- it is pinned on L2
 // bandwidth at ~690 TFLOP/s in the training step.
 //
 // How: a CTA owns one KERNEL ROW r (taps (r,0), (r,1), (r,2)), one 128-cout x 128-cin weight tile and a split-K range
-// of pixel segments.  A segment is `kw` consecutive pixels of one image row.  Per segment it loads
+// of pixel segments.  A segment is `kw` consecutive pixels of `hb` consecutive image rows (hb = 1 for W >= 128, else
+// hb * W ~ 128 so that narrow maps still feed K = 128 per stage).  Per segment it loads
 //     A = dY[n, h, w0 : w0+kw, cout tile]                      (two 64-channel TMA boxes, MN-major: pixels = K)
 //     B = X [n, h+r-1, w0-1 : w0+kw+1, cin tile]               (two boxes WITH a one-pixel halo on each side; TMA zero
 //                                                               fills w = -1, w = W and rows outside the image)
@@ -26,17 +27,19 @@ constexpr int kWrMaxStages = 8;
 
 struct WgradRowParams {
   int N, H, W;
-  int kw;                  // pixels per segment (K of one stage), multiple of 16
+  int kw;                  // pixels per segment row, multiple of 16
+  int hb;                  // image rows per segment (K of one stage = hb * kw)
   int segs_per_row;        // W / kw
-  int total_segs;          // N * H * segs_per_row
+  int hsegs;               // H / hb
+  int total_segs;          // N * hsegs * segs_per_row
   int segs_per_split;
   int cin_tiles, cout_tiles;
   int kb0;                 // 64-channel blocks in X source 0
   int Cin_total;
   int stages;
-  uint32_t a_box_bytes;    // kw * 128
-  uint32_t b_box_bytes;    // (kw + 2) * 128
-  uint32_t b_box_stride;   // (kw + 8) * 128  (1024-byte aligned)
+  uint32_t a_box_bytes;    // hb * kw * 128
+  uint32_t b_box_bytes;    // hb * (kw + 2) * 128
+  uint32_t b_box_stride;   // b_box_bytes rounded up to 1024
   uint32_t stage_bytes;
   float* dw;
   long long ldw;
@@ -90,8 +93,8 @@ conv_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
       int seg = seg_begin + it;
       const int sw = seg % p.segs_per_row;
       seg /= p.segs_per_row;
-      const int h = seg % p.H;
-      const int n = seg / p.H;
+      const int h = (seg % p.hsegs) * p.hb;
+      const int n = seg / p.hsegs;
       const int w0 = sw * p.kw;
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
@@ -123,10 +126,18 @@ conv_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
       if (elect_one()) {
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
+          uint32_t acc = first;
+          for (int hi = 0; hi < p.hb; ++hi) {
+            // descriptor start offsets in 16-byte units: (rows * 128 B) >> 4 = rows * 8
+            const uint64_t ao = static_cast<uint64_t>(hi * p.kw) * 8u;
+            const uint64_t bo = static_cast<uint64_t>(hi * (p.kw + 2) + t) * 8u;
 #pragma unroll 4
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tmem_base + t * 128, da0 + static_cast<uint64_t>(k * 128),          // (k*16 rows * 128 B) >> 4
-                      db0 + static_cast<uint64_t>(k * 128 + t * 8), idesc, k == 0 ? first : 1u);
+            for (int k = 0; k < ksteps; ++k) {
+              umma_bf16(tmem_base + t * 128, da0 + ao + static_cast<uint64_t>(k * 128),
+                        db0 + bo + static_cast<uint64_t>(k * 128), idesc, acc);
+              acc = 1u;
+            }
+          }
         }
         umma_commit(&empty_bar[s]);
       }
@@ -173,24 +184,33 @@ int launch_wgrad_row(const ::ddpm_wgrad_args* a, cudaStream_t stream) {
       return 1;
   }
   const int W = a->w;
-  if (W < env_int("DDPM_WGRAD_ROW_MIN_W", 64) || W % 16) return 1;
+  if (W < env_int("DDPM_WGRAD_ROW_MIN_W", 16) || W % 16) return 1;
   const int kw = W < 128 ? W : 128;
   if (W % kw) return 1;
+  int hb = 1;
+  if (W < 128) {
+    hb = 128 / W;
+    if (hb > a->h) hb = a->h;
+    while (hb > 1 && a->h % hb) --hb;
+  }
   if (a->cout % 128 || a->c0 % 128 || a->c1 % 128) return 1;
 
   WgradRowParams p;
   std::memset(&p, 0, sizeof(p));
   p.N = a->n; p.H = a->h; p.W = W;
   p.kw = kw;
+  p.hb = hb;
   p.segs_per_row = W / kw;
-  p.total_segs = a->n * a->h * p.segs_per_row;
+  p.hsegs = a->h / hb;
+  p.total_segs = a->n * p.hsegs * p.segs_per_row;
   p.cin_tiles = cin_total / 128;
   p.cout_tiles = a->cout / 128;
   p.kb0 = a->c0 / 64;
   p.Cin_total = cin_total;
-  p.a_box_bytes = static_cast<uint32_t>(kw) * 128u;
-  p.b_box_bytes = static_cast<uint32_t>(kw + 2) * 128u;
-  p.b_box_stride = static_cast<uint32_t>(kw + 8) * 128u;
+  p.a_box_bytes = static_cast<uint32_t>(hb * kw) * 128u;
+  p.b_box_bytes = static_cast<uint32_t>(hb * (kw + 2)) * 128u;
+  p.b_box_stride = (p.b_box_bytes + 1023u) & ~1023u;
+  if (p.a_box_bytes % 1024u) return 1;     // TMA destinations and descriptor bases stay 1024-byte aligned
   p.stage_bytes = 2u * p.a_box_bytes + 2u * p.b_box_stride;
   const size_t budget = 227 * 1024 - 1024 - 256;
   int stages = static_cast<int>(budget / p.stage_bytes);
@@ -213,11 +233,11 @@ int launch_wgrad_row(const ::ddpm_wgrad_args* a, cudaStream_t stream) {
   splits = (p.total_segs + p.segs_per_split - 1) / p.segs_per_split;
 
   CUtensorMap my, mx0, mx1;
-  if (int e = make_act_map(&my, a->dy, a->cout, a->ldy, a->n, a->h, W, kw, 1, 1)) return e;
-  if (int e = make_act_map(&mx0, a->x0, a->c0, a->ld0, a->n, a->h, W, kw + 2, 1, 1)) return e;
+  if (int e = make_act_map(&my, a->dy, a->cout, a->ldy, a->n, a->h, W, kw, hb, 1)) return e;
+  if (int e = make_act_map(&mx0, a->x0, a->c0, a->ld0, a->n, a->h, W, kw + 2, hb, 1)) return e;
   if (a->c1 > 0) {
     if (!a->x1) { set_last_error("ddpm_conv_wgrad: c1>0 but x1 is null"); return DDPM_ERR_INVALID; }
-    if (int e = make_act_map(&mx1, a->x1, a->c1, a->ld1, a->n, a->h, W, kw + 2, 1, 1)) return e;
+    if (int e = make_act_map(&mx1, a->x1, a->c1, a->ld1, a->n, a->h, W, kw + 2, hb, 1)) return e;
   } else {
     mx1 = mx0;
   }

@@ -397,7 +397,8 @@ def g_wgrad(ops):
                                   (9, 4, 4, 256, 512), (2, 14, 14, 128, 128), (3, 7, 7, 64, 128),
                                   # row-resident kernel (W >= 64, W % 16 == 0, channels % 128 == 0)
                                   (2, 128, 128, 128, 128), (1, 64, 64, 256, 128), (1, 256, 256, 128, 128),
-                                  (1, 80, 80, 128, 128), (3, 5, 64, 128, 256), (1, 64, 96, 384, 128)]:
+                                  (1, 80, 80, 128, 128), (3, 5, 64, 128, 256), (1, 64, 96, 384, 128), (3, 32, 32, 256, 256),
+                                  (2, 16, 16, 512, 256), (2, 48, 48, 128, 128), (2, 6, 32, 128, 128)]:
         x = bf(torch.randn(n, h, w_, cin, device=dev))
         dy = bf(torch.randn(n, h, w_, cout, device=dev))
         dw = torch.zeros(cout, 9 * cin, device=dev)
