@@ -11,50 +11,71 @@ namespace ddpm {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
-// qkv row layout: [q (heads*D) | k (heads*D) | v (heads*D)]
+// 8 bf16 (one 128-bit access) -> 8 floats at dst (16-byte aligned shared or local memory)
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* src, float* dst, float scale = 1.0f) {
+  float f[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(src), f);
+  *reinterpret_cast<float4*>(dst) = make_float4(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
+}
+
+// qkv row layout: [q (heads*D) | k (heads*D) | v (heads*D)];  D % 8 == 0, every row pointer 16-byte aligned
 template <int D>
 __global__ void attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldqkv, __nv_bfloat16* __restrict__ o,
                                 long long ldo, float* __restrict__ lse, int T, int heads, float scale_log2) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* ks = sm;            // [T][D]
   float* vs = sm + T * D;    // [T][D]
   const int b = blockIdx.x / heads, hd = blockIdx.x - b * heads;
   const int C = heads * D;
   const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * ldqkv + hd * D;
-  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
-    const int j = i / D, e = i - j * D;
-    ks[i] = __bfloat162float(base[j * ldqkv + C + e]);
-    vs[i] = __bfloat162float(base[j * ldqkv + 2 * C + e]);
+  for (int i = threadIdx.x; i < T * (D / 8); i += blockDim.x) {
+    const int j = i / (D / 8), e = (i - j * (D / 8)) * 8;
+    ld8_bf16(base + j * ldqkv + C + e, ks + j * D + e);
+    ld8_bf16(base + j * ldqkv + 2 * C + e, vs + j * D + e);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < T; i += blockDim.x) {
     float q[D], acc[D];
 #pragma unroll
-    for (int e = 0; e < D; ++e) {
-      q[e] = __bfloat162float(base[i * ldqkv + e]) * scale_log2;
-      acc[e] = 0.f;
-    }
+    for (int e = 0; e < D; e += 8) ld8_bf16(base + i * ldqkv + e, q + e, scale_log2);
+#pragma unroll
+    for (int e = 0; e < D; ++e) acc[e] = 0.f;
     float m = -INFINITY;
     for (int j = 0; j < T; ++j) {
       float s = 0.f;
 #pragma unroll
-      for (int e = 0; e < D; ++e) s += q[e] * ks[j * D + e];
+      for (int e = 0; e < D; e += 4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(ks + j * D + e);
+        s += q[e] * k4.x + q[e + 1] * k4.y + q[e + 2] * k4.z + q[e + 3] * k4.w;
+      }
       m = fmaxf(m, s);
     }
     float l = 0.f;
     for (int j = 0; j < T; ++j) {
       float s = 0.f;
 #pragma unroll
-      for (int e = 0; e < D; ++e) s += q[e] * ks[j * D + e];
+      for (int e = 0; e < D; e += 4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(ks + j * D + e);
+        s += q[e] * k4.x + q[e + 1] * k4.y + q[e + 2] * k4.z + q[e + 3] * k4.w;
+      }
       const float p = exp2f(s - m);
       l += p;
 #pragma unroll
-      for (int e = 0; e < D; ++e) acc[e] += p * vs[j * D + e];
+      for (int e = 0; e < D; e += 4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(vs + j * D + e);
+        acc[e] += p * v4.x; acc[e + 1] += p * v4.y; acc[e + 2] += p * v4.z; acc[e + 3] += p * v4.w;
+      }
     }
     const float inv = 1.0f / l;
     __nv_bfloat16* op = o + (static_cast<long long>(b) * T + i) * ldo + hd * D;
 #pragma unroll
-    for (int e = 0; e < D; ++e) op[e] = __float2bfloat16(acc[e] * inv);
+    for (int e = 0; e < D; e += 8) {
+      float f[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = acc[e + u] * inv;
+      *reinterpret_cast<bf16x8*>(op + e) = pack8(f);
+    }
     lse[(static_cast<long long>(b) * heads + hd) * T + i] = m + log2f(l);  // log2-domain logsumexp
   }
 }
@@ -65,7 +86,7 @@ __global__ void attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long
                                 const __nv_bfloat16* __restrict__ d_o, long long lddo, const float* __restrict__ lse,
                                 __nv_bfloat16* __restrict__ dqkv, long long lddqkv, int T, int heads, float scale,
                                 float scale_log2) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* qs = sm;                 // [T][D]  (pre-scaled by scale*log2e)
   float* ks = qs + T * D;
   float* vs = ks + T * D;
@@ -75,19 +96,24 @@ __global__ void attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long
   const int b = blockIdx.x / heads, hd = blockIdx.x - b * heads;
   const int C = heads * D;
   const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * ldqkv + hd * D;
-  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
-    const int j = i / D, e = i - j * D;
-    qs[i] = __bfloat162float(base[j * ldqkv + e]) * scale_log2;
-    ks[i] = __bfloat162float(base[j * ldqkv + C + e]);
-    vs[i] = __bfloat162float(base[j * ldqkv + 2 * C + e]);
-    dos[i] = __bfloat162float(d_o[(static_cast<long long>(b) * T + j) * lddo + hd * D + e]);
+  for (int i = threadIdx.x; i < T * (D / 8); i += blockDim.x) {
+    const int j = i / (D / 8), e = (i - j * (D / 8)) * 8;
+    ld8_bf16(base + j * ldqkv + e, qs + j * D + e, scale_log2);
+    ld8_bf16(base + j * ldqkv + C + e, ks + j * D + e);
+    ld8_bf16(base + j * ldqkv + 2 * C + e, vs + j * D + e);
+    ld8_bf16(d_o + (static_cast<long long>(b) * T + j) * lddo + hd * D + e, dos + j * D + e);
   }
   for (int i = threadIdx.x; i < T; i += blockDim.x) {
     Ls[i] = lse[(static_cast<long long>(b) * heads + hd) * T + i];
     float dsum = 0.f;
-    for (int e = 0; e < D; ++e)
-      dsum += __bfloat162float(d_o[(static_cast<long long>(b) * T + i) * lddo + hd * D + e]) *
-              __bfloat162float(o[(static_cast<long long>(b) * T + i) * ldo + hd * D + e]);
+#pragma unroll
+    for (int e = 0; e < D; e += 8) {
+      float a8[8], b8[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(d_o + (static_cast<long long>(b) * T + i) * lddo + hd * D + e), a8);
+      unpack8(*reinterpret_cast<const bf16x8*>(o + (static_cast<long long>(b) * T + i) * ldo + hd * D + e), b8);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dsum += a8[u] * b8[u];
+    }
     Ds[i] = dsum;
   }
   __syncthreads();
@@ -101,14 +127,26 @@ __global__ void attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long
       const float L = Ls[i], Di = Ds[i];
       for (int j = 0; j < T; ++j) {
         float s = 0.f, dp = 0.f;
+        float kk[D];
 #pragma unroll
-        for (int e = 0; e < D; ++e) { s += q[e] * ks[j * D + e]; dp += dov[e] * vs[j * D + e]; }
+        for (int e = 0; e < D; e += 4) {
+          const float4 k4 = *reinterpret_cast<const float4*>(ks + j * D + e);
+          const float4 v4 = *reinterpret_cast<const float4*>(vs + j * D + e);
+          kk[e] = k4.x; kk[e + 1] = k4.y; kk[e + 2] = k4.z; kk[e + 3] = k4.w;
+          s += q[e] * k4.x + q[e + 1] * k4.y + q[e + 2] * k4.z + q[e + 3] * k4.w;
+          dp += dov[e] * v4.x + dov[e + 1] * v4.y + dov[e + 2] * v4.z + dov[e + 3] * v4.w;
+        }
         const float ds = exp2f(s - L) * (dp - Di);
 #pragma unroll
-        for (int e = 0; e < D; ++e) dq[e] += ds * ks[j * D + e];
+        for (int e = 0; e < D; ++e) dq[e] += ds * kk[e];
       }
 #pragma unroll
-      for (int e = 0; e < D; ++e) dbase[i * lddqkv + e] = __float2bfloat16(dq[e] * scale);
+      for (int e = 0; e < D; e += 8) {
+        float f[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = dq[e + u] * scale;
+        *reinterpret_cast<bf16x8*>(dbase + i * lddqkv + e) = pack8(f);
+      }
     }
     // as key j = i: dv_j = sum_i p_ij dO_i ; dk_j = scale * sum_i dS_ij q_i
     {
@@ -118,18 +156,29 @@ __global__ void attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long
       for (int e = 0; e < D; ++e) { k[e] = ks[j * D + e]; v[e] = vs[j * D + e]; dk[e] = 0.f; dv[e] = 0.f; }
       for (int ii = 0; ii < T; ++ii) {
         float s = 0.f, dp = 0.f;
+        float qq[D], dd[D];
 #pragma unroll
-        for (int e = 0; e < D; ++e) { s += qs[ii * D + e] * k[e]; dp += dos[ii * D + e] * v[e]; }
+        for (int e = 0; e < D; e += 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(qs + ii * D + e);
+          const float4 d4 = *reinterpret_cast<const float4*>(dos + ii * D + e);
+          qq[e] = q4.x; qq[e + 1] = q4.y; qq[e + 2] = q4.z; qq[e + 3] = q4.w;
+          dd[e] = d4.x; dd[e + 1] = d4.y; dd[e + 2] = d4.z; dd[e + 3] = d4.w;
+          s += q4.x * k[e] + q4.y * k[e + 1] + q4.z * k[e + 2] + q4.w * k[e + 3];
+          dp += d4.x * v[e] + d4.y * v[e + 1] + d4.z * v[e + 2] + d4.w * v[e + 3];
+        }
         const float p = exp2f(s - Ls[ii]);
         const float ds = p * (dp - Ds[ii]);
 #pragma unroll
-        for (int e = 0; e < D; ++e) { dv[e] += p * dos[ii * D + e]; dk[e] += ds * qs[ii * D + e]; }
+        for (int e = 0; e < D; ++e) { dv[e] += p * dd[e]; dk[e] += ds * qq[e]; }
       }
       // qs is pre-scaled by scale*log2e: dk = scale * sum dS * q_raw = sum dS * qs / log2e
 #pragma unroll
-      for (int e = 0; e < D; ++e) {
-        dbase[j * lddqkv + C + e] = __float2bfloat16(dk[e] * (1.0f / kLog2e));
-        dbase[j * lddqkv + 2 * C + e] = __float2bfloat16(dv[e]);
+      for (int e = 0; e < D; e += 8) {
+        float fk[8], fv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { fk[u] = dk[e + u] * (1.0f / kLog2e); fv[u] = dv[e + u]; }
+        *reinterpret_cast<bf16x8*>(dbase + j * lddqkv + C + e) = pack8(fk);
+        *reinterpret_cast<bf16x8*>(dbase + j * lddqkv + 2 * C + e) = pack8(fv);
       }
     }
   }
@@ -160,6 +209,7 @@ using namespace ddpm;
 extern "C" int ddpm_attn_fwd(const void* qkv, long long ldqkv, void* o, long long ldo, float* lse, int b, int t,
                              int heads, int d, float scale, void* stream) {
   DDPM_REQUIRE(qkv && o && lse && b > 0 && t > 0 && heads > 0, "ddpm_attn_fwd: bad argument");
+  DDPM_REQUIRE(ldqkv % 8 == 0 && ldo % 8 == 0 && d % 8 == 0, "ddpm_attn_fwd: rows must be 16-byte aligned");
   const size_t smem = sizeof(float) * 2 * t * d;
   DDPM_REQUIRE(smem <= 200 * 1024, "ddpm_attn_fwd: t=%d d=%d does not fit shared memory", t, d);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -180,6 +230,8 @@ extern "C" int ddpm_attn_bwd(const void* qkv, long long ldqkv, const void* o, lo
                              long long lddo, const float* lse, void* dqkv, long long lddqkv, int b, int t, int heads,
                              int d, float scale, void* stream) {
   DDPM_REQUIRE(qkv && o && d_o && lse && dqkv && b > 0 && t > 0 && heads > 0, "ddpm_attn_bwd: bad argument");
+  DDPM_REQUIRE(ldqkv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddqkv % 8 == 0 && d % 8 == 0,
+               "ddpm_attn_bwd: rows must be 16-byte aligned");
   const size_t smem = sizeof(float) * (4 * t * d + 2 * t);
   DDPM_REQUIRE(smem <= 200 * 1024, "ddpm_attn_bwd: t=%d d=%d does not fit shared memory", t, d);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
