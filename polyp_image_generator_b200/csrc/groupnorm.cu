@@ -728,7 +728,7 @@ static void gn_team_geometry(int C, int hw, int n, int resident, double sample_b
   int ppb = kGnThreads / V;
   if (ppb < 1) ppb = 1;
   *threads = V * ppb;
-  const double budget = static_cast<double>(env_int("DDPM_GN_L2_MB", 40)) * 1048576.0;
+  const double budget = static_cast<double>(env_int("DDPM_GN_L2_MB", 64)) * 1048576.0;
   int max_teams = static_cast<int>(budget / sample_bytes);
   if (max_teams < 1) max_teams = 1;
   // a tensor that fits L2 as a whole gets one team per sample: a single barrier per CTA instead of one per round
