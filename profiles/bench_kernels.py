@@ -126,6 +126,11 @@ def bench_gn(ops, B, iters, pk, first=None):
         ms_f = timeit(lambda i: ops.gn_fwd(xa, xb, 32, 1e-5, gam, bet, True, out=y), iters, 1)
         dy = bf(B, h, h, C)
         ms_b = timeit(lambda i: ops.gn_bwd(xa, xb, 32, stats, 1e-5, gam, bet, True, dy), iters, 1)
+        sums = torch.zeros(B, C, 2, device="cuda")
+        ms_ba = timeit(lambda i: ops.gn_bwd_apply(xa, xb, 32, stats, 1e-5, gam, dy, sums), iters, 1)
+        ms_ba2 = timeit(lambda i: ops.gn_bwd_apply(xa, xb, 32, stats, 1e-5, gam, dy, sums, add0=dy), iters, 1)
+        print(f"   bwd_apply {ms_ba:7.3f} ms {6 * elems / ms_ba / 1e6:6.0f} GB/s | with add0 {ms_ba2:7.3f} ms "
+              f"{8 * elems / ms_ba2 / 1e6:6.0f} GB/s ({8 * elems / ms_ba2 / 1e6 / pk['hbm_gbs']:.2f})")
         print(f"gn {h:3d}x{h:<3d} c{c0}+{c1:<4d} stats {ms_s:7.3f} ms {2 * elems / ms_s / 1e6:6.0f} GB/s | "
               f"apply {ms_a:7.3f} ms {4 * elems / ms_a / 1e6:6.0f} GB/s ({4 * elems / ms_a / 1e6 / pk['hbm_gbs']:.2f}) | "
               f"fused fwd {ms_f:7.3f} ms {4 * elems / ms_f / 1e6:6.0f} GB/s ({4 * elems / ms_f / 1e6 / pk['hbm_gbs']:.2f}) | "
