@@ -889,9 +889,7 @@ extern "C" int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const vo
   GnDst o{static_cast<__nv_bfloat16*>(dx0), static_cast<__nv_bfloat16*>(dx1), lddx0, lddx1,
           static_cast<const __nv_bfloat16*>(add0), static_cast<const __nv_bfloat16*>(add1), ldadd0, ldadd1};
   int V, threads, ppblk, chunks;
-  gn_geometry(C, hw, n, 8, &V, &threads, &ppblk, &chunks);
   const bool want_sums = out_nc || out_c;
-  // with the fused per-(n, c) output sums every CTA ends with C atomics: use larger CTAs there
   // 32 loop trips per thread: measured sweep (4..64) -- below that the per-CTA prologue (group coefficients, 24
   // coefficient registers) dominates, 0.198 ms -> 0.165 ms at 128^2 x 128 channels
   gn_geometry(C, hw, n, env_int("DDPM_GN_BWD_APPLY_ITERS", 32), &V, &threads, &ppblk, &chunks);
