@@ -654,6 +654,9 @@ extern "C" int ddpm_conv_gemm(const ddpm_conv_args* a, void* stream_) {
   if (block_n == 0) {
     const long long mtiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_n;
     block_n = (a->cout % 256 == 0 && mtiles * (a->cout / 256) >= 2 * kNumSMs) ? 256 : 128;
+    // short reductions (1x1 shortcuts: 2-6 k-blocks) are memory- and epilogue-bound: the 256-wide tile runs one CTA
+    // per SM with its 8-chunk epilogue fully exposed; two co-resident 128-wide CTAs overlap each other instead
+    if (a->ntaps * (p.kb0 + p.kb1) <= 8) block_n = 128;
   }
   long long k_total = a->k_total > 0 ? a->k_total : a->ldw;
   if (block_n == 256) {
