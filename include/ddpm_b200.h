@@ -45,6 +45,18 @@ int ddpm_mse_fwd_bwd(const float* pred, const float* target, float* loss_sum, fl
 /* x *= *scale (device scalar): folds autograd's grad_output (e.g. GradScaler's scale) into dpred. */
 int ddpm_scale_by_device_scalar(float* x, const float* scale, long long n, void* stream);
 
+/* clip_grad_norm_(params, max_norm) + AdamW.step() over a FLAT fp32 parameter / gradient / moment arena --
+ * generator_model/train_from_scratch.py:106-108, :273.
+ *   ddpm_sumsq_f32: out += sum x^2 (caller zeroes out).
+ *   ddpm_adamw_flat: scal[0] (step) += 1; clip = min(1, max_norm / (sqrt(*gnorm_sq) + 1e-6)) when gnorm_sq != NULL;
+ *     g' = clip*g; p *= 1 - lr*wd; m += (g'-m)(1-b1); v = b2 v + (1-b2) g'^2;
+ *     p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)          (torch.optim.AdamW's op order)
+ *   scal: 4 device floats (step, clip, bias corrections), zero-initialised once; lr_dev (device scalar) overrides lr. */
+int ddpm_sumsq_f32(const float* x, long long n, float* out, void* stream);
+int ddpm_adamw_flat(float* p, const float* g, float* m, float* v, long long n, float* scal, const float* gnorm_sq,
+                    float max_norm, const float* lr_dev, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, void* stream);
+
 /* DDPMScheduler.step (fixed_small, epsilon, clip_sample) -- inside DDPMPipeline.__call__,
  * generator_model/train_from_scratch.py:51-54.
  *   x0 = clamp((x - sqrt_beta_prod*eps) / sqrt_alpha_prod, -clip, clip)   (clip<=0: no clamp)

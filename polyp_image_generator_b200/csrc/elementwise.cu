@@ -228,6 +228,91 @@ to_uint8_nhwc_kernel(const float* __restrict__ x, unsigned char* __restrict__ ou
   }
 }
 
+// ---- fused global-norm clip + AdamW over the flat parameter arena -----------------------
+// train_from_scratch.py:106-108: clip_grad_norm_(params, 1.0); optimizer.step().  With every parameter, gradient and
+// moment in ONE flat fp32 buffer the update is two streaming kernels (sum of squares; update) instead of ~30
+// multi-tensor launches; the clip coefficient is applied on the fly, so the gradients are read once.
+__global__ void __launch_bounds__(kEwThreads)
+sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = n >> 2;
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (long long i = (nvec << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc += x[i] * x[i];
+  __shared__ float red[kEwThreads / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kEwThreads / 32 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// scal[0] = step (incremented here), scal[1] = clip coefficient, scal[2] = 1 - beta1^step, scal[3] = 1 - beta2^step
+__global__ void adamw_tick_kernel(float* __restrict__ scal, const float* __restrict__ gnorm_sq, float max_norm,
+                                  float beta1, float beta2) {
+  const float step = scal[0] + 1.0f;
+  scal[0] = step;
+  float coef = 1.0f;
+  if (gnorm_sq != nullptr && max_norm > 0.f) coef = fminf(1.0f, max_norm / (sqrtf(*gnorm_sq) + 1e-6f));
+  scal[1] = coef;
+  scal[2] = 1.0f - powf(beta1, step);
+  scal[3] = 1.0f - powf(beta2, step);
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  long long n, const float* __restrict__ scal, const float* __restrict__ lr_dev, float lr_host,
+                  float beta1, float beta2, float eps, float wd) {
+  const float lr = lr_dev ? *lr_dev : lr_host;
+  const float coef = scal[1];
+  const float step_size = lr / scal[2];
+  const float inv_sqrt_bc2 = rsqrtf(scal[3]);
+  const float decay = 1.0f - lr * wd;
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = n >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = reinterpret_cast<float*>(&pp);
+    const float* ga = reinterpret_cast<const float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm);
+    float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = ga[j] * coef;
+      const float pj = pa[j] * decay;
+      const float mj = ma[j] + (gr - ma[j]) * omb1;
+      const float vj = va[j] * beta2 + gr * gr * omb2;
+      const float denom = sqrtf(vj) * inv_sqrt_bc2 + eps;
+      pa[j] = pj - step_size * (mj / denom);
+      ma[j] = mj;
+      va[j] = vj;
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (long long i = (nvec << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gr = g[i] * coef;
+    const float pj = p[i] * decay;
+    const float mj = m[i] + (gr - m[i]) * omb1;
+    const float vj = v[i] * beta2 + gr * gr * omb2;
+    p[i] = pj - step_size * (mj / (sqrtf(vj) * inv_sqrt_bc2 + eps));
+    m[i] = mj;
+    v[i] = vj;
+  }
+}
+
 }  // namespace ddpm
 
 using namespace ddpm;
@@ -356,4 +441,26 @@ extern "C" int ddpm_dropout(const void* x, const void* add, void* out, long long
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(out),
       n / 8, thresh, 1.0f / (1.0f - p), seed, offset);
   return check_launch("dropout_kernel");
+}
+
+extern "C" int ddpm_sumsq_f32(const float* x, long long n, float* out, void* stream) {
+  DDPM_REQUIRE(x && out && n >= 0, "ddpm_sumsq_f32: bad argument");
+  DDPM_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0, "ddpm_sumsq_f32: x must be 16-byte aligned");
+  if (n == 0) return DDPM_OK;
+  sumsq_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  return check_launch("sumsq_kernel");
+}
+
+extern "C" int ddpm_adamw_flat(float* p, const float* g, float* m, float* v, long long n, float* scal,
+                               const float* gnorm_sq, float max_norm, const float* lr_dev, float lr, float beta1,
+                               float beta2, float eps, float weight_decay, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPM_REQUIRE(p && g && m && v && scal && n > 0, "ddpm_adamw_flat: bad argument");
+  DDPM_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                reinterpret_cast<uintptr_t>(v)) % 16 == 0, "ddpm_adamw_flat: buffers must be 16-byte aligned");
+  adamw_tick_kernel<<<1, 1, 0, stream>>>(scal, gnorm_sq, max_norm, beta1, beta2);
+  if (int e = check_launch("adamw_tick_kernel")) return e;
+  adamw_flat_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, stream>>>(p, g, m, v, n, scal, lr_dev, lr, beta1, beta2, eps,
+                                                                     weight_decay);
+  return check_launch("adamw_flat_kernel");
 }

@@ -35,7 +35,7 @@ class GraphedUNetForward:
         self.out = None
 
     def _weights_key(self):
-        return tuple(p._version for p in self.unet.parameters())
+        return (getattr(self.unet, "_weights_epoch", 0),) + tuple(p._version for p in self.unet.parameters())
 
     def _capture(self):
         unet = self.unet
@@ -74,8 +74,8 @@ class GraphedTrainStep:
         step = GraphedTrainStep(net, noise_scheduler, optimizer, batch_shape)   # net: UNet2DModel or its DDP wrapper
         loss = step(clean, noise, timesteps)          # device scalar (static buffer); no host sync
 
-    The optimizer must be capturable (e.g. torch.optim.AdamW(..., fused=True, capturable=True)); pass lr as a device
-    tensor to drive a schedule from the host (lr.fill_(value) between replays).
+    The optimizer must be capturable: optim.FusedAdamW (set its lr_tensor to a device scalar to drive a schedule from
+    the host: lr_tensor.fill_(value) between replays) or torch.optim.AdamW(..., fused=True, capturable=True).
     """
 
     def __init__(self, net, noise_scheduler, optimizer, batch_shape, max_grad_norm: Optional[float] = 1.0,
@@ -94,8 +94,8 @@ class GraphedTrainStep:
             pred = net(noisy, self.t, return_dict=False)[0]
             loss = mse_loss(pred, self.noise)
             loss.backward()
-            if max_grad_norm is not None:
-                torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+            if max_grad_norm is not None and getattr(optimizer, "max_grad_norm", None) is None:
+                torch.nn.utils.clip_grad_norm_(params, max_grad_norm)   # optim.FusedAdamW clips inside its update
             optimizer.step()
             return loss.detach()
 
@@ -112,10 +112,14 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = body()
         self.warmup_iters = warmup_iters
+        unet = getattr(net, "module", net)
+        self._invalidate = getattr(unet, "invalidate_weight_cache", None)
 
     def __call__(self, clean: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
         self.clean.copy_(clean, non_blocking=True)
         self.noise.copy_(noise, non_blocking=True)
         self.t.copy_(timesteps, non_blocking=True)
         self.graph.replay()
+        if self._invalidate is not None:        # replays update the weights without bumping autograd versions
+            self._invalidate()
         return self.loss

@@ -107,6 +107,18 @@ class CudaOps:
         self.launches += 1
         return x
 
+    def sumsq(self, x, out):
+        """out += sum(x^2) over a flat fp32 tensor."""
+        _capi.check(self.lib.ddpm_sumsq_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "ddpm_sumsq_f32")
+        self.launches += 1
+
+    def adamw_flat(self, p, g, m, v, scal, gnorm_sq, max_norm, lr_dev, lr, beta1, beta2, eps, weight_decay):
+        _capi.check(self.lib.ddpm_adamw_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(scal),
+                                             _ptr(gnorm_sq), float(max_norm or 0.0), _ptr(lr_dev), float(lr),
+                                             float(beta1), float(beta2), float(eps), float(weight_decay), _stream()),
+                    "ddpm_adamw_flat")
+        self.launches += 2
+
     def scheduler_step(self, eps, x, z, sa, sb, c0, ct, sigma, clip, want_x0=False):
         prev = torch.empty_like(x)
         x0 = torch.empty_like(x) if want_x0 else None

@@ -73,8 +73,8 @@ def train_step(model, noise_scheduler, optimizer, clean_images: torch.Tensor, no
     else:
         loss.backward()
     params = [p for p in model.parameters() if p.requires_grad]
-    if max_grad_norm is not None:
-        torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+    if max_grad_norm is not None and getattr(optimizer, "max_grad_norm", None) is None:
+        torch.nn.utils.clip_grad_norm_(params, max_grad_norm)       # optim.FusedAdamW clips inside its update
     if scaler is not None:
         scaler.step(optimizer)
         scaler.update()

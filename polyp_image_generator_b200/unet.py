@@ -21,6 +21,7 @@ from __future__ import annotations
 import json
 import math
 import os
+import weakref
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Sequence, Tuple, Union
@@ -172,6 +173,18 @@ class _Tape:
 
     def add(self, fn):
         self.steps.append(fn)
+
+
+# arena data_ptr -> owning model: writers that bypass autograd's version counters (optim.FusedAdamW, graph replays)
+# call arena_written() so the eval-mode bf16 operand cache is refreshed
+_ARENA_OWNERS: Dict[int, "weakref.ref"] = {}
+
+
+def arena_written(data_ptr: int) -> None:
+    ref = _ARENA_OWNERS.get(data_ptr)
+    m = ref() if ref is not None else None
+    if m is not None:
+        m.invalidate_weight_cache()
 
 
 def _align(n, a=4):
@@ -498,6 +511,7 @@ class UNet2DModel(nn.Module):
                 view.copy_(p.detach().to(device=dev, dtype=torch.float32))
                 p.data = view
         self._arena = new
+        _ARENA_OWNERS[new.data_ptr()] = weakref.ref(self)
         self._bf16 = torch.zeros(P.bf16_total, device=dev, dtype=getattr(_ops.get(), 'operand_dtype', torch.bfloat16))
         for gobj in P.gemms:
             gobj.wf = self._bf16[gobj.wf_off:gobj.wf_off + gobj.wf_shape[0] * gobj.wf_shape[1]].view(gobj.wf_shape)
@@ -516,7 +530,9 @@ class UNet2DModel(nn.Module):
         return out
 
     def invalidate_weight_cache(self):
+        """The fp32 arena was written behind autograd's version counters (fused optimizer, CUDA-graph replay)."""
         self._wcache_key = None
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
 
     def _seg(self, buf, off, n):
         return buf[off:off + n]

@@ -140,6 +140,23 @@ class EmuOps:
         tp = 8 - tap if flip else tap
         return flat[co * strides[0] + tp * strides[1] + ci * strides[2]]
 
+    def sumsq(self, x, out):
+        out += (x.float() ** 2).sum()
+
+    def adamw_flat(self, p, g, m, v, scal, gnorm_sq, max_norm, lr_dev, lr, beta1, beta2, eps, weight_decay):
+        scal[0] += 1
+        step = float(scal[0])
+        coef = 1.0
+        if gnorm_sq is not None and max_norm and max_norm > 0:
+            coef = min(1.0, max_norm / (float(gnorm_sq.sqrt()) + 1e-6))
+        lr_ = float(lr_dev) if lr_dev is not None else lr
+        gr = g * coef
+        p.mul_(1 - lr_ * weight_decay)
+        m.lerp_(gr, 1 - beta1)
+        v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        p.addcdiv_(m, (v.sqrt() / (bc2 ** 0.5)).add_(eps), value=-lr_ / bc1)
+
     def im2col3(self, x, chan_sum=None):
         n, cin, h, w = x.shape
         xp = F.pad(x.float(), (1, 1, 1, 1))

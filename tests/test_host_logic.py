@@ -34,8 +34,8 @@ def test_capi_argument_validation_without_gpu(built_lib):
     assert "null pointer" in _capi.last_error()
     a = _capi.ConvArgs()
     assert lib.ddpm_conv_gemm(ctypes.byref(a), None) < 0
-    assert lib.ddpm_attn_fwd(1, 8, 1, 8, 1, 1, 4, 1, 7, 1.0, None) < 0
-    assert "head_dim=7" in _capi.last_error()
+    assert lib.ddpm_attn_fwd(1, 8, 1, 8, 1, 1, 4, 1, 24, 1.0, None) < 0
+    assert "head_dim=24" in _capi.last_error()
 
 
 def test_product_refuses_cpu_tensors(built_lib):
@@ -245,3 +245,42 @@ def test_pipeline_matches_oracle_pipeline(emu_backend):
     assert len(pil) == 1 and pil[0].size == (32, 32)
     with pytest.raises(ValueError):
         pa(batch_size=1, num_inference_steps=1001)
+
+
+def test_fused_adamw_matches_clip_plus_torch_adamw(emu_backend):
+    """optim.FusedAdamW (flat-arena clip + AdamW, train_from_scratch.py:106-108,273) vs clip_grad_norm_ + torch AdamW."""
+    from polyp_image_generator_b200 import FusedAdamW, UNet2DModel
+    cfg = _small_cfg(32)
+    torch.manual_seed(0)
+    a, b = UNet2DModel(**cfg), UNet2DModel(**cfg)
+    b.load_state_dict(a.state_dict())
+    oa = FusedAdamW(a.parameters(), lr=3e-4, weight_decay=0.01, max_grad_norm=1.0)
+    ob = torch.optim.AdamW(b.parameters(), lr=3e-4, weight_decay=0.01)
+    x, t, tgt = torch.randn(2, 3, 32, 32), torch.tensor([3, 600]), torch.randn(2, 3, 32, 32)
+    for it in range(3):
+        for m in (a, b):
+            (torch.nn.functional.mse_loss(m(x, t).sample, tgt) * (40.0 if it == 0 else 1.0)).backward()
+        oa.step()
+        torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
+        ob.step()
+        oa.zero_grad()
+        ob.zero_grad()
+        sa, sb = a.state_dict(), b.state_dict()
+        for k in sa:
+            assert torch.allclose(sa[k], sb[k], rtol=1e-5, atol=1e-6), (it, k)   # lr = 3e-4: <= 0.4 % of one update
+    assert float(oa._scal[0]) == 3.0
+    a.eval()
+    with torch.no_grad():
+        a(x, 5)
+    key = a._wcache_key
+    assert key is not None
+    (torch.nn.functional.mse_loss(a.train()(x, t).sample, tgt)).backward()
+    a.eval()
+    with torch.no_grad():
+        a(x, 5)
+    oa.step()                                   # writes the arena behind the version counters ...
+    assert a._wcache_key is None                # ... and tells the model to refresh its bf16 operands
+    # foreign / frozen parameters are refused instead of silently skipped
+    a.conv_in.weight.requires_grad_(False)
+    with pytest.raises(NotImplementedError):
+        FusedAdamW([p for p in a.parameters() if p.requires_grad], lr=1e-4).step()

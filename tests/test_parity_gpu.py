@@ -243,6 +243,42 @@ def test_training_reduces_loss(dev):
     assert losses[-1] < 0.7 * losses[0], losses
 
 
+def test_fused_adamw_vs_torch_adamw(dev):
+    """clip_grad_norm_(1.0) + AdamW.step() (train_from_scratch.py:106-108) as two streaming kernels over the flat
+    arena, against torch's own clip + AdamW on identical gradients: fp32, <= 1e-6 relative to the update size."""
+    from polyp_image_generator_b200 import FusedAdamW, UNet2DModel
+    from polyp_image_generator_b200.training import mse_loss
+    cfg = _small_cfg(32)
+    torch.manual_seed(3)
+    m = UNet2DModel(**cfg).to(dev).train()
+    x, t = torch.randn(4, 3, 32, 32, device=dev), torch.randint(0, 1000, (4,), device=dev)
+    tgt = torch.randn(4, 3, 32, 32, device=dev)
+    opt = FusedAdamW(m.parameters(), lr=2e-4, weight_decay=0.01, max_grad_norm=1.0)
+    shadow = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+    ref = torch.optim.AdamW(shadow, lr=2e-4, weight_decay=0.01)
+    for it in range(4):
+        (mse_loss(m(x, t, return_dict=False)[0], tgt) * (30.0 if it == 0 else 1.0)).backward()
+        for q, p in zip(shadow, m.parameters()):
+            q.grad = p.grad.detach().clone()
+        gn = torch.nn.utils.clip_grad_norm_(shadow, 1.0)
+        if it == 0:
+            assert gn.item() > 1.0                      # step 0 exercises the clip branch
+        ref.step()
+        opt.step()
+        opt.zero_grad()
+        worst = max((p.detach() - q.detach()).abs().max().item() for q, p in zip(shadow, m.parameters()))
+        assert worst <= 2e-4 * 5e-3, (it, worst)        # 0.5 % of one lr-sized update (fp32 op-order noise)
+        with torch.no_grad():                           # keep both on the same trajectory
+            for q, p in zip(shadow, m.parameters()):
+                q.copy_(p)
+    # the sum-of-squares kernel against torch
+    from polyp_image_generator_b200 import ops as ops_mod
+    v = torch.randn(1_000_003, device=dev)
+    out = torch.zeros(1, device=dev)
+    ops_mod.get().sumsq(v, out)
+    assert abs(out.item() - (v.double() ** 2).sum().item()) / out.item() < 1e-5
+
+
 def test_pipeline_sampling_vs_oracle(dev):
     """DDPMPipeline: same CPU generator -> same images as the oracle pipeline (8 strided steps, small UNet)."""
     from polyp_image_generator_b200 import DDPMPipeline, DDPMScheduler, UNet2DModel
