@@ -192,6 +192,22 @@ int ddpm_attn_bwd(const void* qkv, long long ldqkv, const void* o, long long ldo
                   const float* lse, void* dqkv, long long lddqkv, int b, int t, int heads, int d, float scale,
                   void* stream);
 
+/* Wide-head attention (head_dim > 64, e.g. the single 512-wide head of the google/ddpm-celebahq-256 architecture that
+ * train_with_lora_all_classes.py:316-330 fine-tunes): the core is composed from a batched tcgen05 GEMM and row softmax
+ * kernels (bgemm.cu) over the same fused qkv buffer.
+ *   ddpm_bgemm: C[z] = alpha * A[z] (m x k) * B[z] (k x n) for z = (batch, head); bf16 operands, fp32 accumulation,
+ *     C bf16 or fp32 (c_f32).  x_mn = 0: reduction index contiguous (A(i,kk) = a[i*lda+kk], B(kk,j) = b[j*ldb+kk]);
+ *     x_mn = 1: output index contiguous (A(i,kk) = a[kk*lda+i], B(kk,j) = b[kk*ldb+j]).  Strides in elements,
+ *     multiples of 8; *_head / *_batch are the element offsets between heads / samples.
+ *   ddpm_softmax_rows: P = softmax(S) per row (S fp32 with the d^-1/2 scale already applied, P bf16).
+ *   ddpm_softmax_rows_bwd: dS = scale * P o (dP - rowsum(P o dP)) (dS bf16, leading dimension ldp). */
+int ddpm_bgemm(const void* a, long long lda, long long a_head, long long a_batch, int a_mn, const void* b,
+               long long ldb, long long b_head, long long b_batch, int b_mn, void* c, long long ldc, long long c_head,
+               long long c_batch, int c_f32, int m, int n, int k, int heads, int batch, float alpha, void* stream);
+int ddpm_softmax_rows(const float* s, long long lds, void* p, long long ldp, long long rows, int t, void* stream);
+int ddpm_softmax_rows_bwd(const void* p, long long ldp, const float* dp, long long lddp, void* ds, long long rows,
+                          int t, float scale, void* stream);
+
 /* Timesteps(128) sinusoid -> fp32 [b][dim]; t int64[b] (device); freqs fp32[dim/2] (device) =
  * exp(-ln(10000) * j / (dim/2 - freq_shift)) tabulated by the host. */
 int ddpm_timestep_embedding(const long long* t, const float* freqs, float* out, int b, int dim,

@@ -72,6 +72,9 @@ SIGNATURES = {
     "ddpm_add_noise": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp],
     "ddpm_mse_fwd_bwd": [_vp, _vp, _vp, _vp, _ll, _vp],
     "ddpm_scale_by_device_scalar": [_vp, _vp, _ll, _vp],
+    "ddpm_bgemm": [_vp, _ll, _ll, _ll, _i, _vp, _ll, _ll, _ll, _i, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "ddpm_softmax_rows": [_vp, _ll, _vp, _ll, _ll, _i, _vp],
+    "ddpm_softmax_rows_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _f, _vp],
     "ddpm_sumsq_f32": [_vp, _ll, _vp, _vp],
     "ddpm_adamw_flat": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _vp, _f, _f, _f, _f, _f, _vp],
     "ddpm_scheduler_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _vp],

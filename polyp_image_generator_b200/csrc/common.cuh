@@ -46,6 +46,7 @@ constexpr int kNumSMs = 148;
 // host-side helpers shared by the tcgen05 kernels (defined in conv_igemm.cu / conv_halo.cu)
 int make_act_map(CUtensorMap* out, const void* ptr, int c, long long ld, int n, int h, int w, int wb, int hb, int nb);
 int make_wgt_map(CUtensorMap* out, const void* ptr, long long k_total, long long ld, int rows, int box_rows);
+int make_map4(CUtensorMap* out, const void* ptr, const long long dims[4], const long long strides[3], const int box[4]);
 int env_int(const char* name, int dflt);
 // halo-resident 3x3 conv: returns 1 when the problem is not eligible (caller falls back to the generic kernel)
 int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream);

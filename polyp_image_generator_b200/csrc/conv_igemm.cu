@@ -398,6 +398,7 @@ struct MapKey {
   const void* ptr;
   uint64_t d[4];
   uint64_t ld;
+  uint64_t st[3];
   uint32_t box[4];
   bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
@@ -481,6 +482,44 @@ int make_wgt_map(CUtensorMap* out, const void* ptr, long long k_total, long long
     return DDPM_ERR_CUDA;
   }
   std::lock_guard<std::mutex> g(g_map_mu);
+  g_maps.emplace(k, *out);
+  return DDPM_OK;
+}
+
+// generic 4-D bf16 view: dims[0] contiguous, dims[1..3] with element strides st[0..2]; SWIZZLE_128B, box[0] = 64
+int make_map4(CUtensorMap* out, const void* ptr, const long long dims_[4], const long long st_[3], const int box_[4]) {
+  MapKey k;
+  std::memset(&k, 0, sizeof(k));
+  k.ptr = ptr;
+  k.ld = 0x4D41503400000000ull;   // tag: generic map
+  for (int i = 0; i < 4; ++i) { k.d[i] = dims_[i]; k.box[i] = box_[i]; }
+  for (int i = 0; i < 3; ++i) k.st[i] = st_[i];
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_maps.find(k);
+    if (it != g_maps.end()) { *out = it->second; return DDPM_OK; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point unavailable"); return DDPM_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (st_[0] % 8) || (st_[1] % 8) || (st_[2] % 8)) {
+    set_last_error("matrix view not 16-byte aligned (ptr=%p strides=%lld,%lld,%lld)", ptr, st_[0], st_[1], st_[2]);
+    return DDPM_ERR_INVALID;
+  }
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) { dims[i] = (cuuint64_t)dims_[i]; box[i] = (cuuint32_t)box_[i]; }
+  for (int i = 0; i < 3; ++i) strides[i] = (cuuint64_t)st_[i] * 2;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(dims=%lld,%lld,%lld,%lld strides=%lld,%lld,%lld box=%d,%d,%d,%d) failed: %d",
+                   dims_[0], dims_[1], dims_[2], dims_[3], st_[0], st_[1], st_[2], box_[0], box_[1], box_[2], box_[3],
+                   (int)r);
+    return DDPM_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(g_map_mu);
+  if (g_maps.size() > 65536) g_maps.clear();
   g_maps.emplace(k, *out);
   return DDPM_OK;
 }

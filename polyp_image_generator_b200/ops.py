@@ -360,8 +360,58 @@ class CudaOps:
         return dx0, dx1
 
     # ---- attention core ----------------------------------------------------------------------------------
+    NARROW_HEAD_DIMS = (8, 16, 32, 64)      # attention.cu (SIMT, one CTA per head); wider heads: bgemm.cu (tcgen05)
+
+    def bgemm(self, a, lda, a_head, a_batch, a_mn, b, ldb, b_head, b_batch, b_mn, c, ldc, c_head, c_batch, m, n, k,
+              heads, batch, alpha=1.0):
+        """c[z] = alpha * a[z] (m x k) @ b[z] (k x n), z = (batch, head); a, b bf16 views, c bf16 or fp32."""
+        _capi.check(self.lib.ddpm_bgemm(_ptr(a), lda, a_head, a_batch, int(a_mn), _ptr(b), ldb, b_head, b_batch,
+                                        int(b_mn), _ptr(c), ldc, c_head, c_batch, int(c.dtype == torch.float32),
+                                        m, n, k, heads, batch, float(alpha), _stream()), "ddpm_bgemm")
+        self.launches += 1
+
+    def _attn_wide_fwd(self, qkv, b, t, heads, d, scale):
+        C, ld, tp = heads * d, qkv.stride(0), (t + 7) // 8 * 8
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:3 * C]
+        s = torch.empty((b, heads, t, tp), device=qkv.device, dtype=torch.float32)
+        p = torch.empty((b, heads, t, tp), device=qkv.device, dtype=torch.bfloat16)
+        o = torch.empty((b * t, C), device=qkv.device, dtype=torch.bfloat16)
+        # S = scale * Q K^T
+        self.bgemm(q, ld, d, t * ld, 0, k, ld, d, t * ld, 0, s, tp, t * tp, heads * t * tp, t, t, d, heads, b, scale)
+        _capi.check(self.lib.ddpm_softmax_rows(_ptr(s), tp, _ptr(p), tp, b * heads * t, t, _stream()),
+                    "ddpm_softmax_rows")
+        # O = P V
+        self.bgemm(p, tp, t * tp, heads * t * tp, 0, v, ld, d, t * ld, 1, o, C, d, t * C, t, d, t, heads, b)
+        self.launches += 1
+        return o, p
+
+    def _attn_wide_bwd(self, qkv, d_o, p, b, t, heads, d, scale):
+        C, ld, tp, ldg = heads * d, qkv.stride(0), p.shape[-1], d_o.stride(0)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:3 * C]
+        dqkv = torch.empty_like(qkv)
+        ldd = dqkv.stride(0)
+        dq, dk, dv = dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:3 * C]
+        dp = torch.empty((b, heads, t, tp), device=qkv.device, dtype=torch.float32)
+        ds = torch.empty_like(p)
+        ps, pb = t * tp, heads * t * tp
+        # dP = dO V^T
+        self.bgemm(d_o, ldg, d, t * ldg, 0, v, ld, d, t * ld, 0, dp, tp, ps, pb, t, t, d, heads, b)
+        _capi.check(self.lib.ddpm_softmax_rows_bwd(_ptr(p), tp, _ptr(dp), tp, _ptr(ds), b * heads * t, t, float(scale),
+                                                   _stream()), "ddpm_softmax_rows_bwd")
+        self.launches += 1
+        # dV = P^T dO,  dQ = dS K,  dK = dS^T Q   (dS carries the scale)
+        self.bgemm(p, tp, ps, pb, 1, d_o, ldg, d, t * ldg, 1, dv, ldd, d, t * ldd, t, d, t, heads, b)
+        self.bgemm(ds, tp, ps, pb, 0, k, ld, d, t * ld, 1, dq, ldd, d, t * ldd, t, d, t, heads, b)
+        self.bgemm(ds, tp, ps, pb, 1, q, ld, d, t * ld, 1, dk, ldd, d, t * ldd, t, d, t, heads, b)
+        return dqkv
+
     def attn_fwd(self, qkv, b: int, t: int, heads: int, d: int, scale: float):
-        """qkv: bf16 [b*t, 3*heads*d] -> (o bf16 [b*t, heads*d], lse fp32 [b, heads, t])."""
+        """qkv: bf16 [b*t, 3*heads*d] -> (o bf16 [b*t, heads*d], aux).  aux (kept for backward) is the fp32 log-sum-exp
+        [b, heads, t] for narrow heads and the bf16 probabilities [b, heads, t, t8] for wide ones."""
+        if d not in self.NARROW_HEAD_DIMS:
+            if d % 8 or d < 64:
+                raise NotImplementedError(f"attention head_dim={d}: supported are 8/16/32/64 and multiples of 8 above")
+            return self._attn_wide_fwd(qkv, b, t, heads, d, scale)
         o = torch.empty((b * t, heads * d), device=qkv.device, dtype=torch.bfloat16)
         lse = torch.empty((b, heads, t), device=qkv.device, dtype=torch.float32)
         _capi.check(self.lib.ddpm_attn_fwd(_ptr(qkv), qkv.stride(0), _ptr(o), o.stride(0), _ptr(lse), b, t, heads, d,
@@ -370,6 +420,8 @@ class CudaOps:
         return o, lse
 
     def attn_bwd(self, qkv, o, d_o, lse, b: int, t: int, heads: int, d: int, scale: float):
+        if d not in self.NARROW_HEAD_DIMS:
+            return self._attn_wide_bwd(qkv, d_o, lse, b, t, heads, d, scale)
         dqkv = torch.empty_like(qkv)
         _capi.check(self.lib.ddpm_attn_bwd(_ptr(qkv), qkv.stride(0), _ptr(o), o.stride(0), _ptr(d_o), d_o.stride(0),
                                            _ptr(lse), _ptr(dqkv), dqkv.stride(0), b, t, heads, d, scale, _stream()),

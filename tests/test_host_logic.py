@@ -140,7 +140,7 @@ def test_unet_state_dict_and_arena(emu_backend):
     assert torch.equal(m2.conv_out.weight, m.conv_out.weight)
 
 
-@pytest.mark.parametrize("variant", ["polyp", "celebahq"])
+@pytest.mark.parametrize("variant", ["polyp", "celebahq", "celebahq_1head"])
 def test_unet_forward_backward_programs_match_oracle(emu_backend, variant):
     from polyp_image_generator_b200 import UNet2DModel
     if variant == "polyp":
@@ -148,7 +148,8 @@ def test_unet_forward_backward_programs_match_oracle(emu_backend, variant):
     else:
         cfg = oracle.celebahq_unet_config(64)
         cfg["block_out_channels"] = (64, 64, 128, 128, 128, 128)
-        cfg["attention_head_dim"] = 16
+        if variant == "celebahq":
+            cfg["attention_head_dim"] = 16
         S = 64
     torch.manual_seed(0)
     om = oracle.UNet2DModel(**cfg)

@@ -167,7 +167,8 @@ def test_unet_golden_small_case(dev):
         assert d / (g.norm().item() + 5e-2 * tot) < 5e-2, k
 
 
-@pytest.mark.parametrize("variant,S,B", [("polyp_small", 32, 3), ("celebahq_small", 64, 2), ("polyp_full", 64, 4)])
+@pytest.mark.parametrize("variant,S,B", [("polyp_small", 32, 3), ("celebahq_small", 64, 2), ("celebahq_1head", 64, 3),
+                                         ("polyp_full", 64, 4), ("celebahq_full", 64, 2)])
 def test_unet_forward_backward_vs_oracle(dev, variant, S, B):
     from polyp_image_generator_b200 import UNet2DModel
     from polyp_image_generator_b200.training import mse_loss
@@ -177,6 +178,11 @@ def test_unet_forward_backward_vs_oracle(dev, variant, S, B):
         cfg = oracle.celebahq_unet_config(S)
         cfg["block_out_channels"] = (64, 64, 128, 128, 128, 128)
         cfg["attention_head_dim"] = 16
+    elif variant == "celebahq_1head":          # attention_head_dim=None: ONE head as wide as the block (bgemm.cu path)
+        cfg = oracle.celebahq_unet_config(S)
+        cfg["block_out_channels"] = (64, 64, 128, 128, 128, 128)
+    elif variant == "celebahq_full":           # BASELINE configs[3]/[4] architecture (1 head x 512), reduced resolution
+        cfg = oracle.celebahq_unet_config(S)
     else:
         cfg = oracle.polyp_unet_config(S)      # BASELINE configs[0]: the real 113.7 M-parameter model at 64x64, batch 4
     torch.manual_seed(0)
@@ -241,6 +247,62 @@ def test_training_reduces_loss(dev):
     t = torch.randint(0, 1000, (8,), device=dev)
     losses = [train_step(m, s, opt, x0, nz, t).item() for _ in range(12)]
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+@pytest.mark.parametrize("m,n,k,heads,batch", [(256, 256, 512, 1, 3), (64, 64, 512, 1, 2), (16, 16, 128, 2, 2),
+                                               (49, 49, 72, 3, 2), (196, 200, 136, 1, 2), (300, 520, 264, 2, 1)])
+def test_bgemm_all_layouts(dev, m, n, k, heads, batch):
+    """ddpm_bgemm (batched tcgen05 GEMM of the wide-head attention): the four operand layouts, ragged edges
+    (TMA zero fill), head / batch strides, bf16 and fp32 outputs, against a float64 matmul of the same bf16 inputs."""
+    from polyp_image_generator_b200 import ops as ops_mod
+    o = ops_mod.get()
+    g = torch.Generator(device=dev).manual_seed(m * 131 + n * 7 + k)
+    r8 = lambda x: (x + 7) // 8 * 8
+    for a_mn in (0, 1):
+        for b_mn in (0, 1):
+            # storage: K-major A is [batch][heads][m][k8], MN-major A is [batch][heads][k][m8] (likewise B)
+            ash = (batch, heads, k, r8(m)) if a_mn else (batch, heads, m, r8(k))
+            bsh = (batch, heads, k, r8(n)) if b_mn else (batch, heads, n, r8(k))
+            A = torch.randn(ash, device=dev, generator=g).to(torch.bfloat16)
+            Bm = torch.randn(bsh, device=dev, generator=g).to(torch.bfloat16)
+            Al = (A[..., :m].transpose(-1, -2) if a_mn else A[..., :k]).double()      # logical m x k
+            Bl = (Bm[..., :n] if b_mn else Bm[..., :k].transpose(-1, -2)).double()    # logical k x n
+            want = 0.5 * (Al @ Bl)
+            for dt in (torch.float32, torch.bfloat16):
+                C = torch.full((batch, heads, m, r8(n)), float("nan"), device=dev, dtype=dt)
+                o.bgemm(A, ash[3], ash[2] * ash[3], heads * ash[2] * ash[3], a_mn,
+                        Bm, bsh[3], bsh[2] * bsh[3], heads * bsh[2] * bsh[3], b_mn,
+                        C, r8(n), m * r8(n), heads * m * r8(n), m, n, k, heads, batch, alpha=0.5)
+                got = C[..., :n].double()
+                tol = 1e-5 if dt == torch.float32 else 6e-3
+                assert torch.isfinite(got).all(), (a_mn, b_mn, dt)
+                assert ((got - want).norm() / want.norm()).item() < tol, (a_mn, b_mn, dt)
+                if r8(n) > n:      # columns past n are never written
+                    assert torch.isnan(C[..., n:].float()).all()
+
+
+@pytest.mark.parametrize("b,t,heads,d", [(3, 256, 1, 512), (2, 64, 1, 512), (2, 16, 1, 512), (2, 49, 2, 128),
+                                         (1, 196, 1, 256)])
+def test_wide_head_attention_vs_sdpa(dev, b, t, heads, d):
+    """AttnProcessor2_0's scaled_dot_product_attention for wide heads (celebahq: 1 x 512), forward and backward, against
+    torch SDPA in fp32 on the CPU (same bf16 qkv)."""
+    from polyp_image_generator_b200 import ops as ops_mod
+    o = ops_mod.get()
+    torch.manual_seed(t + d)
+    C = heads * d
+    qkv = (torch.randn(b * t, 3 * C) * 0.7).to(torch.bfloat16)
+    d_o = torch.randn(b * t, C).to(torch.bfloat16)
+    scale = d ** -0.5
+    out, aux = o.attn_fwd(qkv.to(dev), b, t, heads, d, scale)
+    dqkv = o.attn_bwd(qkv.to(dev), out, d_o.to(dev), aux, b, t, heads, d, scale)
+    ref = qkv.float().clone().requires_grad_(True)
+    q, k, v = [x.reshape(b, t, heads, d).transpose(1, 2) for x in ref.split(C, dim=1)]
+    want = F.scaled_dot_product_attention(q, k, v, scale=scale)
+    want = want.transpose(1, 2).reshape(b * t, C)
+    want.backward(d_o.float())
+    assert rel(out, want) < 1e-2
+    for i, name in enumerate("qkv"):
+        assert rel(dqkv[:, i * C:(i + 1) * C], ref.grad[:, i * C:(i + 1) * C]) < 1.5e-2, name
 
 
 def test_fused_adamw_vs_torch_adamw(dev):
