@@ -187,6 +187,61 @@ def conv_gemm_flops(args_tuple):
     return 2.0 * n * h * w * cout * cin * taps
 
 
+LORA_BWD_FRACTION = 0.741      # dgrad only downstream of down_blocks.4.attentions.0, wgrad only LoRA
+
+
+def run_lora_finetune(args, dev, world, rank, barrier):
+    """train_with_lora_all_classes.py:120-180 over the drop-in objects: celebahq-architecture UNet (1 head x 512,
+    downsample_padding 0), r=8 / alpha=8 / dropout 0.3 adapters on to_q, to_k, to_v, to_out.0, everything else frozen;
+    add_noise -> forward -> MSE -> backward (LoRA gradients only) -> all-reduce -> clip 1.0 -> AdamW, graph-replayed."""
+    import torch.distributed as dist
+    import oracle
+    from polyp_image_generator_b200 import DDPMScheduler, LoraConfig, UNet2DModel
+    from polyp_image_generator_b200.graphs import GraphedTrainStep
+    S, B = args.lora_size, args.lora_batch
+    torch.manual_seed(1)
+    model = UNet2DModel(**oracle.celebahq_unet_config(S)).to(dev)
+    model.add_adapter(LoraConfig(r=8, lora_alpha=8, target_modules=["to_q", "to_k", "to_v", "to_out.0"],
+                                 lora_dropout=0.3, init_lora_weights="gaussian"))
+    model.to(dev).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    n_train = sum(p.numel() for p in params)
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=True)
+    net = model
+    if world > 1:
+        from polyp_image_generator_b200.ddp import DistributedDataParallel
+        net = DistributedDataParallel(model)
+    sched = DDPMScheduler(num_train_timesteps=1000)
+    clean = synthetic_polyp_batch(B, S, 777 + rank).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(888 + rank)
+    noise = torch.randn(clean.shape, device=dev, generator=gen)
+    t = torch.randint(0, 1000, (B,), device=dev, dtype=torch.int64, generator=gen)
+    step = GraphedTrainStep(net, sched, opt, clean.shape, max_grad_norm=1.0)
+    for _ in range(3):
+        step(clean, noise, t)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_steps = max(args.steps, 10)
+    e0.record()
+    for _ in range(n_steps):
+        loss = step(clean, noise, t)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / n_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    gflop = FWD_GFLOP_PER_IMG.get(S, 0.0) * (1.0 + LORA_BWD_FRACTION) * B
+    out = {"workload": f"celebahq-architecture UNet2DModel LoRA fine-tune step, {S}x{S}, batch {B}/GPU, bf16, r=8 "
+                       "alpha=8 dropout=0.3 on to_q/to_k/to_v/to_out.0",
+           "trainable_params": n_train, "ms_per_step": round(ms, 3), "images_per_sec": round(world * B / (ms * 1e-3), 2),
+           "algorithmic_gflop_per_step": round(gflop, 1), "tflops": round(gflop / ms, 1), "steps_timed": n_steps,
+           "final_loss": round(float(loss.item()), 5), "cuda_graph": True}
+    del step, model, net, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from polyp_image_generator_b200 import DDPMScheduler, UNet2DModel
@@ -384,6 +439,11 @@ def run_b200(args, rank, world, local_rank):
         }
         model.train()
 
+    # ---- secondary metric: LoRA fine-tune step at 256x256 on the celebahq-architecture UNet (BASELINE configs[3]) ----
+    lora = None
+    if not args.no_lora:
+        lora = run_lora_finetune(args, dev, world, rank, barrier)
+
     # ---- optional per-op breakdown (after the timed regions; CUDA events around every C-ABI op) ----
     if args.breakdown and rank == 0:
         ops.conv_gemm = orig_conv_gemm
@@ -482,6 +542,7 @@ def run_b200(args, rank, world, local_rank):
         },
         "cpu_baseline": cpu,
         "sampling": sampling,
+        "lora_finetune": lora,
     }
     print(json.dumps(line), flush=True)
 
@@ -499,6 +560,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of a CUDA graph")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch clip_grad_norm_ + AdamW(fused) instead of "
                     "optim.FusedAdamW")
+    ap.add_argument("--no-lora", action="store_true", help="skip the secondary LoRA fine-tune measurement")
+    ap.add_argument("--lora-batch", type=int, default=8, help="per-GPU batch of the LoRA measurement "
+                    "(config_diffusion.py:7 train_batch_size = 8)")
+    ap.add_argument("--lora-size", type=int, default=256)
     ap.add_argument("--no-sampling", action="store_true", help="skip the secondary sampling measurement")
     ap.add_argument("--sampling-batch", type=int, default=32, help="images per GPU in the sampling measurement")
     ap.add_argument("--sampling-steps", type=int, default=20, help="reverse steps timed (reported per step)")

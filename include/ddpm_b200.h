@@ -228,9 +228,11 @@ int ddpm_reduce_hw(const void* x, long long ld, int n, int hw, int c, float* out
 
 /* LoRA adapter-branch dropout (peft lora_dropout; generator_model/train_with_lora_all_classes.py:316-322):
  * out = (add ? add : 0) + x * keep / (1-p), keep regenerated from (seed, offset) by Philox -- no mask is stored.
- * Forward: add = NULL.  Backward: x = grad of the dropped tensor, add = the other gradient contribution. bf16. */
+ * Forward: add = NULL.  Backward: x = grad of the dropped tensor, add = the other gradient contribution. bf16.
+ * tick (may be NULL): device-resident step counter added to the upper counter word, so CUDA-graph replays of a
+ * training step draw fresh masks. */
 int ddpm_dropout(const void* x, const void* add, void* out, long long n, float p, unsigned long long seed,
-                 unsigned long long offset, void* stream);
+                 unsigned long long offset, const unsigned long long* tick, void* stream);
 
 /* Layout helpers (bf16 NHWC, contiguous outputs). */
 int ddpm_space_to_depth(const void* x, long long ldx, void* out, int n, int h, int w, int c, int pad_lo,

@@ -411,7 +411,10 @@ __device__ __forceinline__ void dropout_mask8(long long vec_idx, unsigned long l
 __global__ void __launch_bounds__(kEwThreads)
 dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ add,
                __nv_bfloat16* __restrict__ out, long long nvec, uint32_t thresh, float keep_scale,
-               unsigned long long seed, unsigned long long offset) {
+               unsigned long long seed, unsigned long long offset, const unsigned long long* __restrict__ tick) {
+  // tick: device-resident step counter (upper Philox counter word), so a CUDA-graph replay of the step draws a
+  // fresh mask although seed / offset are baked into the captured launch
+  if (tick != nullptr) offset += *tick << 32;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     float f[8], m[8];
@@ -431,7 +434,7 @@ dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 }  // namespace ddpm
 
 extern "C" int ddpm_dropout(const void* x, const void* add, void* out, long long n, float p, unsigned long long seed,
-                            unsigned long long offset, void* stream) {
+                            unsigned long long offset, const unsigned long long* tick, void* stream) {
   DDPM_REQUIRE(x && out && n >= 0 && n % 8 == 0 && p >= 0.f && p < 1.f, "ddpm_dropout: bad argument (n %% 8, 0<=p<1)");
   DDPM_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
                "ddpm_dropout: pointers must be 16-byte aligned");
@@ -439,7 +442,7 @@ extern "C" int ddpm_dropout(const void* x, const void* add, void* out, long long
   const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
   dropout_kernel<<<ew_blocks(n / 8), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(out),
-      n / 8, thresh, 1.0f / (1.0f - p), seed, offset);
+      n / 8, thresh, 1.0f / (1.0f - p), seed, offset, tick);
   return check_launch("dropout_kernel");
 }
 

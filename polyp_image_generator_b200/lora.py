@@ -211,7 +211,7 @@ class GemmLora:
                 self.a_ext[off:off + m.r] = m.A.detach().to(dt)
             self.at_ext.copy_(self.a_ext.t())
 
-    def forward_extra(self, ops, x2: torch.Tensor, training: bool):
+    def forward_extra(self, ops, x2: torch.Tensor, training: bool, tick: Optional[torch.Tensor] = None):
         """U = dropout(x) A_ext^T as a [1, 1, M, 64] bf16 tensor (the extra k-block of the projection's A operand)."""
         M = x2.shape[2]
         p = self.p if training else 0.0
@@ -220,9 +220,9 @@ class GemmLora:
         if p > 0.0:
             GemmLora._seed_counter += 1
             seed, offset = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, GemmLora._seed_counter
-            xd = ops.dropout(x2.contiguous(), p, seed, offset)
+            xd = ops.dropout(x2.contiguous(), p, seed, offset, tick=tick)
         u = ops.conv_gemm(xd, None, taps_1x1(), self.a_ext, LORA_K, (1, 1, M))
-        return SimpleNamespace(u=u, xd=xd, p=p, seed=seed, offset=offset)
+        return SimpleNamespace(u=u, xd=xd, p=p, seed=seed, offset=offset, tick=tick)
 
     def backward(self, ops, s, x2, dy2, d_x):
         """Adds the adapter's contribution to d_x and stores dA / dB in self.grads (keyed by id(param))."""
@@ -240,5 +240,5 @@ class GemmLora:
             self.grads[id(m.B)] = dB_ext[i * self.ce:(i + 1) * self.ce, off:off + m.r] * m.scaling
         if s.p > 0.0:
             dxl = ops.conv_gemm(dU, None, taps_1x1(), self.at_ext, self.cin, (1, 1, M))
-            return ops.dropout(dxl, s.p, s.seed, s.offset, add=d_x.contiguous())
+            return ops.dropout(dxl, s.p, s.seed, s.offset, add=d_x.contiguous(), tick=s.tick)
         return ops.conv_gemm(dU, None, taps_1x1(), self.at_ext, self.cin, (1, 1, M), res=d_x)

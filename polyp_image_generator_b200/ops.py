@@ -477,12 +477,14 @@ class CudaOps:
                     "ddpm_reduce_hw")
         self.launches += 1
 
-    def dropout(self, x, p: float, seed: int, offset: int, add=None):
-        """out = (add or 0) + x * keep/(1-p); keep is a pure function of (seed, offset, index).  bf16, contiguous."""
+    def dropout(self, x, p: float, seed: int, offset: int, add=None, tick=None):
+        """out = (add or 0) + x * keep/(1-p); keep is a pure function of (seed, offset, tick, index).  bf16, contiguous.
+        tick: optional int64 device scalar (step counter) so CUDA-graph replays draw fresh masks."""
         if not x.is_contiguous() or (add is not None and not add.is_contiguous()):
             raise ValueError("dropout needs contiguous tensors")
         out = torch.empty_like(x)
-        _capi.check(self.lib.ddpm_dropout(_ptr(x), _ptr(add), _ptr(out), x.numel(), float(p), seed, offset, _stream()),
+        _capi.check(self.lib.ddpm_dropout(_ptr(x), _ptr(add), _ptr(out), x.numel(), float(p), seed, offset, _ptr(tick),
+                                          _stream()),
                     "ddpm_dropout")
         self.launches += 1
         return out

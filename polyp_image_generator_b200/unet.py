@@ -659,7 +659,14 @@ class UNet2DModel(nn.Module):
         emb = ops.linear_f32(e1, w2, b2, True)
         temb_all = ops.linear_f32(emb, wt, bt, True)           # [N, sum C] fp32
         st = SimpleNamespace(temb_all=temb_all, N=N, tape=tape, ops=ops,
-                             d_temb_all=None)
+                             d_temb_all=None, rng_tick=None)
+        if training and any(g.lora is not None and g.lora.active and g.lora.p > 0.0 for g in P.gemms):
+            # device-resident step counter for the adapter dropout: a CUDA-graph replay of the step draws new masks
+            tick = getattr(self, "_rng_tick", None)
+            if tick is None or tick.device != x.device:
+                tick = self._rng_tick = torch.zeros(1, device=x.device, dtype=torch.int64)
+            tick.add_(1)
+            st.rng_tick = tick
 
         # ---- conv_in ----
         patches = ops.im2col3(x)                                   # [N, H, W, 64] bf16, one k-block
@@ -742,12 +749,14 @@ class UNet2DModel(nn.Module):
         gam, bet = self._norm_params(at.norm)
         stats, xn = ops.gn_fwd(x, None, at.norm.groups, at.norm.eps, gam, bet, False)
         xn2 = xn.view(1, 1, N * T, C)
-        lora_qkv = at.qkv.lora.forward_extra(ops, xn2, self.training) if (at.qkv.lora and at.qkv.lora.active) else None
+        lora_qkv = at.qkv.lora.forward_extra(ops, xn2, self.training, st.rng_tick) \
+            if (at.qkv.lora and at.qkv.lora.active) else None
         qkv = ops.conv_gemm(xn2, lora_qkv.u if lora_qkv else None, self._lin_taps(at.qkv), at.qkv.wf, 3 * C,
                             (1, 1, N * T), bias=self._bias(at.qkv))
         o, lse = ops.attn_fwd(qkv.view(N * T, 3 * C), N, T, at.heads, at.d, at.d ** -0.5)
         o2 = o.view(1, 1, N * T, C)
-        lora_o = at.out.lora.forward_extra(ops, o2, self.training) if (at.out.lora and at.out.lora.active) else None
+        lora_o = at.out.lora.forward_extra(ops, o2, self.training, st.rng_tick) \
+            if (at.out.lora and at.out.lora.active) else None
         out = ops.conv_gemm(o2, lora_o.u if lora_o else None, self._lin_taps(at.out), at.out.wf, C, (1, 1, N * T),
                             bias=self._bias(at.out), res=x.view(1, 1, N * T, C)).view(N, H, W, C)
         if st.tape is not None:

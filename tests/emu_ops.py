@@ -325,7 +325,9 @@ class EmuOps:
         if out_c is not None:
             out_c += s.sum(0)
 
-    def dropout(self, x, p, seed, offset, add=None):
+    def dropout(self, x, p, seed, offset, add=None, tick=None):
+        if tick is not None:
+            offset += int(tick) << 32
         g = torch.Generator().manual_seed((seed * 1000003 + offset) & 0x7FFFFFFFFFFF)
         keep = (torch.rand(x.shape, generator=g) >= p).float() / (1.0 - p)
         r = x.float() * keep

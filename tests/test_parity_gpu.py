@@ -466,6 +466,12 @@ def test_lora_dropout_kernel(dev):
     want = add.float() + g.float() * (y != 0).float() / 0.7
     assert rel(back, want) < 5e-3
     assert torch.equal(o.dropout(x, 0.0, 1, 1), x)
+    # device-resident step counter (CUDA-graph replays): tick 0 == no tick, tick 1 draws another mask
+    tick = torch.zeros(1, device=dev, dtype=torch.int64)
+    assert torch.equal(o.dropout(x, 0.3, 11, 5, tick=tick), y)
+    tick.add_(1)
+    y4 = o.dropout(x, 0.3, 11, 5, tick=tick)
+    assert not torch.equal(y4, y) and abs((y4 == 0).float().mean().item() - 0.3) < 5e-3
 
 
 def test_full_size_properties_128(dev):
