@@ -23,6 +23,9 @@ def __getattr__(name):
     if name in ("FusedAdamW",):
         from . import optim
         return getattr(optim, name)
+    if name in ("evaluate", "top_up", "generate_images"):
+        from . import sampling
+        return getattr(sampling, name)
     if name in ("DistributedDataParallel",):
         from . import ddp
         return getattr(ddp, name)

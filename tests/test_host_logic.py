@@ -285,3 +285,42 @@ def test_fused_adamw_matches_clip_plus_torch_adamw(emu_backend):
     a.conv_in.weight.requires_grad_(False)
     with pytest.raises(NotImplementedError):
         FusedAdamW([p for p in a.parameters() if p.requires_grad], lr=1e-4).step()
+
+
+def test_sampling_bookkeeping_file_names_seeds_and_shards(emu_backend, tmp_path):
+    """train_from_scratch.py:39-66 / train_with_lora_per_class.py:59-88,262-290: ragged last batch, seed + batch_id,
+    1-based <n>.png names, rank shards reproduce the single-process image set, top-up counts existing files."""
+    from types import SimpleNamespace
+    import numpy as np
+    from PIL import Image
+    from polyp_image_generator_b200 import DDPMPipeline, DDPMScheduler, UNet2DModel
+    from polyp_image_generator_b200.sampling import count_samples, evaluate, top_up
+    cfg = _small_cfg(32)
+    cfg["block_out_channels"] = (64, 64, 64, 64, 64, 64)
+    torch.manual_seed(0)
+    pipe = DDPMPipeline(unet=UNet2DModel(**cfg), scheduler=DDPMScheduler())
+    single = SimpleNamespace(output_dir=str(tmp_path / "one"), eval_batch_size=3, seed=11)
+    paths = evaluate(single, 0, pipe, "AD", 7, num_inference_steps=2, verbose=False)
+    assert [os.path.basename(p) for p in paths] == [f"{i}.png" for i in range(1, 8)]
+    # batch 2 (the ragged one: image 7) was drawn from seed 11 + 2
+    want = pipe(batch_size=1, generator=torch.Generator("cpu").manual_seed(13), num_inference_steps=2,
+                output_type="uint8").images[0].numpy()
+    assert np.array_equal(np.asarray(Image.open(paths[6])), want)
+    # two ranks, no communication: same files, same pixels
+    shard = SimpleNamespace(output_dir=str(tmp_path / "two"), eval_batch_size=3, seed=11)
+    p0 = evaluate(shard, 0, pipe, "AD", 7, rank=0, world=2, num_inference_steps=2, verbose=False)
+    p1 = evaluate(shard, 0, pipe, "AD", 7, rank=1, world=2, num_inference_steps=2, verbose=False)
+    assert sorted(os.path.basename(p) for p in p0 + p1) == sorted(os.path.basename(p) for p in paths)
+    assert [os.path.basename(p) for p in p1] == ["4.png", "5.png", "6.png"]
+    for p in paths:
+        q = os.path.join(shard.output_dir, "samples", "AD", os.path.basename(p))
+        assert np.array_equal(np.asarray(Image.open(p)), np.asarray(Image.open(q)))
+    # top-up: 7 files present, 9 wanted -> the reference regenerates 1.png, 2.png; continue_numbering appends 8, 9
+    d = os.path.join(single.output_dir, "samples", "AD")
+    assert count_samples(d) == 7 and top_up(single, pipe, "AD", 7, num_inference_steps=2, verbose=False) == []
+    again = top_up(single, pipe, "AD", 9, num_inference_steps=2, verbose=False)
+    assert [os.path.basename(p) for p in again] == ["1.png", "2.png"] and count_samples(d) == 7
+    more = top_up(single, pipe, "AD", 9, continue_numbering=True, num_inference_steps=2, verbose=False)
+    assert [os.path.basename(p) for p in more] == ["8.png", "9.png"] and count_samples(d) == 9
+    fresh = top_up(single, pipe, "HP", 2, num_inference_steps=2, verbose=False)
+    assert [os.path.basename(p) for p in fresh] == ["1.png", "2.png"]
