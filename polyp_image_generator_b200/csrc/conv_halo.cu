@@ -89,17 +89,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The three single-warp roles below are ISSUE-bound if written naively (ncu source view, profiles/r1_halo_issue.md:
+  // the MMA warp never waits on a barrier, it spends ~1000 clk per tap executing ~170 SASS instructions -- a runtime
+  // modulo for the ring slot, tap / 3, descriptor construction, R2UR moves -- against 512 clk of tensor work).  So:
+  // ring slots and phases advance incrementally, taps are fully unrolled, and descriptors are one 64-bit add away from
+  // a per-chunk base.
   if (warp == 8) {
     // ---------------- halo producer (warp-uniform loop, one elected lane issues) ----------------
-    uint32_t hidx = 0;
+    uint32_t hb = 0, hph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles;
       const int img = mt / p.tiles_per_img;
       const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
       const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
-      for (int c = 0; c < kbt; ++c, ++hidx) {
-        const uint32_t hb = hidx & 1, ph = (hidx >> 1) & 1;
-        mbar_wait(&halo_empty[hb], ph ^ 1);
+      for (int c = 0; c < kbt; ++c) {
+        mbar_wait(&halo_empty[hb], hph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&halo_full[hb], p.halo_bytes);
           if (c < p.kb0)
@@ -108,74 +112,79 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_load_4d(halo + hb * p.halo_stride, &tmA1, &halo_full[hb], (c - p.kb0) * 64, -1, row_lo, img);
         }
         __syncwarp();
+        hb ^= 1;
+        hph ^= (hb == 0);
       }
     }
   } else if (warp == 9) {
     // ---------------- weight-tile producer ----------------
-    uint32_t bidx = 0;
+    uint32_t bs = 0, bph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       for (int c = 0; c < kbt; ++c) {
-        for (int tap = 0; tap < 9; ++tap, ++bidx) {
-          const uint32_t s = bidx % kHaloBStages, ph = (bidx / kHaloBStages) & 1;
-          mbar_wait(&b_empty[s], ph ^ 1);
+        int kcol = c * 64;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, kcol += p.Cin_total) {
+          mbar_wait(&b_empty[bs], bph ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&b_full[s], kHaloBBytes);
-            tma_load_2d(bsm + s * kHaloBBytes, &tmB, &b_full[s], tap * p.Cin_total + c * 64, nt * 128);
+            mbar_expect_tx(&b_full[bs], kHaloBBytes);
+            tma_load_2d(bsm + bs * kHaloBBytes, &tmB, &b_full[bs], kcol, nt * 128);
           }
           __syncwarp();
+          if (++bs == static_cast<uint32_t>(kHaloBStages)) { bs = 0; bph ^= 1; }
         }
       }
     }
   } else if (warp == 10) {
     // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues) ----------------
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
-      uint32_t hidx = 0, bidx = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-        const int mt = tile / p.n_tiles;
-        const int img = mt / p.tiles_per_img;
-        const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
-        const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
-        const int rel0 = q0 - row_lo * p.Wp;            // slot of q0 inside the halo buffer
-        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], aph ^ 1);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * 256;
-        for (int c = 0; c < kbt; ++c, ++hidx) {
-          const uint32_t hb = hidx & 1, hph = (hidx >> 1) & 1;
-          mbar_wait(&halo_full[hb], hph);
-          const uint32_t h_addr = smem_u32(halo + hb * p.halo_stride);
-          for (int tap = 0; tap < 9; ++tap, ++bidx) {
-            const uint32_t s = bidx % kHaloBStages, ph = (bidx / kHaloBStages) & 1;
-            mbar_wait(&b_full[s], ph);
-            tc_fence_after();
-            const int r = tap / 3, sx = tap - r * 3;
-            const uint32_t a_addr = h_addr + static_cast<uint32_t>(rel0 + (r - 1) * p.Wp + (sx - 1)) * 128u;
-            const uint32_t b_addr = smem_u32(bsm + s * kHaloBBytes);
-            // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
-            const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
-            const uint64_t db0 = make_smem_desc_sw128(b_addr, 16, 1024);
-            const uint32_t first = (c | tap) != 0 ? 1u : 0u;
-            if (elect_one()) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+    const uint64_t db_base = make_smem_desc_sw128(smem_u32(bsm), 16, 1024);
+    const uint32_t row_step = static_cast<uint32_t>(p.Wp) * 8u;     // one padded image row, in 16-byte descriptor units
+    uint32_t bs = 0, bph = 0, hb = 0, hph = 0, acc = 0, aph = 0;
+    uint64_t db = db_base;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles;
+      const int img = mt / p.tiles_per_img;
+      const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
+      const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
+      const int rel00 = q0 - row_lo * p.Wp - p.Wp - 1;   // slot of tap (-1, -1) of output slot q0 inside the halo buffer
+      mbar_wait(&tmem_empty[acc], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * 256;
+      for (int c = 0; c < kbt; ++c) {
+        mbar_wait(&halo_full[hb], hph);
+        const uint32_t h_addr = smem_u32(halo + hb * p.halo_stride);
+        // descriptors differ only in the 14-bit start-address field: build one per chunk, then add (bytes >> 4)
+        const uint64_t da_c = make_smem_desc_sw128(h_addr + static_cast<uint32_t>(rel00) * 128u, 16, 1024);
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          const uint64_t da = da_c + static_cast<uint64_t>((tap / 3) * row_step + (tap % 3) * 8u);
+          const uint32_t first = (tap != 0 || c != 0) ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_bf16(d0 + u * 128, da0 + static_cast<uint64_t>((u * (128 * 128) + k * 32) >> 4),
-                            db0 + static_cast<uint64_t>((k * 32) >> 4), idesc, k == 0 ? first : 1u);
-                }
-              }
-              umma_commit(&b_empty[s]);
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d0 + u * 128, da + static_cast<uint64_t>(u * 1024 + k * 2), db + static_cast<uint64_t>(k * 2),
+                          idesc, k == 0 ? first : 1u);
             }
-            __syncwarp();
+            umma_commit(&b_empty[bs]);
           }
-          if (elect_one()) umma_commit(&halo_empty[hb]);
           __syncwarp();
+          db += kHaloBBytes >> 4;
+          if (++bs == static_cast<uint32_t>(kHaloBStages)) { bs = 0; bph ^= 1; db = db_base; }
         }
-        if (elect_one()) umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&halo_empty[hb]);
         __syncwarp();
+        hb ^= 1;
+        hph ^= (hb == 0);
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      aph ^= (acc == 0);
     }
   } else {
     // ---------------- epilogue (8 warps) ----------------

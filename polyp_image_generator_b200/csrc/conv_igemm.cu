@@ -112,14 +112,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int g_begin = p.iters_per_split > 0 ? static_cast<int>(blockIdx.z) * p.iters_per_split : 0;
   const int total_iters = p.iters_per_split > 0 ? max(0, min(all_iters - g_begin, p.iters_per_split)) : all_iters;
 
+  // Single-warp roles are issue-bound unless their loops are lean (profiles/r1_halo_issue.md): ring slot / phase and
+  // the (tap, k-block) pair advance incrementally -- no per-iteration division or modulo.
   if (warp == 0) {
+    int t = g_begin / kbt, kb = g_begin - t * kbt;
+    uint32_t s = 0, ph = 1;     // ph: parity to wait for on empty_bar (starts "free")
     for (int it = 0; it < total_iters; ++it) {
-      const int g = g_begin + it;
-      const int t = g / kbt, kb = g - t * kbt;
       const int cw = w0 + p.taps.dw[t], ch = h0 + p.taps.dh[t], cn = n0 + p.taps.dn[t], wk = p.taps.wk[t];
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
+      mbar_wait(&empty_bar[s], ph);
       if (elect_one()) {
         uint8_t* sa = smem + s * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes;
@@ -131,18 +131,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tma_load_2d(sb, &tmB, &full_bar[s], wk + kb * kBlockK, nt * BLOCK_N);
       }
       __syncwarp();
+      if (++kb == kbt) { kb = 0; ++t; }
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // whole warp runs the loop (warp-uniform descriptors stay in uniform registers); one elected lane issues
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, false, false);
+    const uint64_t da_base = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    uint64_t da0 = da_base;
+    uint32_t s = 0, ph = 0;
     for (int it = 0; it < total_iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-      const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
-      const uint64_t db0 = make_smem_desc_sw128(a_addr + L::kABytes, 16, 1024);
+      const uint64_t db0 = da0 + (L::kABytes >> 4);
       const uint32_t first = it != 0 ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
@@ -152,6 +153,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         umma_commit(&empty_bar[s]);
       }
       __syncwarp();
+      da0 += L::kStageBytes >> 4;
+      if (++s == STAGES) { s = 0; ph ^= 1; da0 = da_base; }
     }
     if (elect_one()) umma_commit(tmem_full_bar);
     __syncwarp();
@@ -289,16 +292,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
 
   if (warp == 0) {
     const int dn = p.taps.dn[tap], dh = p.taps.dh[tap], dw = p.taps.dw[tap];
+    // pixel-tile coordinates advance incrementally (no per-iteration division: the producer warp is issue-bound)
+    int tw = pt_begin % p.tiles_w;
+    int th = (pt_begin / p.tiles_w) % p.tiles_h;
+    int tn = pt_begin / (p.tiles_w * p.tiles_h);
+    uint32_t s = 0, ph = 1;
     for (int it = 0; it < n_iters; ++it) {
-      int mt = pt_begin + it;
-      const int tw = mt % p.tiles_w;
-      mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int tn = mt / p.tiles_h;
       const int w0 = tw * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
+      mbar_wait(&empty_bar[s], ph);
       if (elect_one()) {
         uint8_t* sa = smem + s * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes;
@@ -315,17 +316,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         }
       }
       __syncwarp();
+      if (++tw == p.tiles_w) {
+        tw = 0;
+        if (++th == p.tiles_h) { th = 0; ++tn; }
+      }
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, true, true);
+    const uint64_t da_base = make_smem_desc_sw128(smem_u32(smem), p.lbo, p.sbo);
+    uint64_t da0 = da_base;
+    uint32_t s = 0, ph = 0;
     for (int it = 0; it < n_iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-      const uint64_t da0 = make_smem_desc_sw128(a_addr, p.lbo, p.sbo);
-      const uint64_t db0 = make_smem_desc_sw128(a_addr + L::kABytes, p.lbo, p.sbo);
+      const uint64_t db0 = da0 + (L::kABytes >> 4);
       const uint32_t first = it != 0 ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
@@ -335,6 +340,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         umma_commit(&empty_bar[s]);
       }
       __syncwarp();
+      da0 += L::kStageBytes >> 4;
+      if (++s == STAGES) { s = 0; ph ^= 1; da0 = da_base; }
     }
     if (elect_one()) umma_commit(tmem_full_bar);
     __syncwarp();

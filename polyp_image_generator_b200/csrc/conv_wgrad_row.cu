@@ -89,16 +89,16 @@ conv_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
     const bool src0 = cb < p.kb0;
     const CUtensorMap* mx = src0 ? &tmX0 : &tmX1;
     const int cx = (src0 ? cb : cb - p.kb0) * 64;
+    // segment coordinates, ring slot and phase advance incrementally: no per-iteration division in the issuing warps
+    int sw = seg_begin % p.segs_per_row;
+    int hs = (seg_begin / p.segs_per_row) % p.hsegs;
+    int n = seg_begin / (p.segs_per_row * p.hsegs);
+    int s = 0;
+    uint32_t ph = 1;
     for (int it = 0; it < n_iters; ++it) {
-      int seg = seg_begin + it;
-      const int sw = seg % p.segs_per_row;
-      seg /= p.segs_per_row;
-      const int h = (seg % p.hsegs) * p.hb;
-      const int n = seg / p.hsegs;
+      const int h = hs * p.hb;
       const int w0 = sw * p.kw;
-      const int s = it % S;
-      const uint32_t ph = (it / S) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
+      mbar_wait(&empty_bar[s], ph);
       if (elect_one()) {
         uint8_t* sa = smem + static_cast<size_t>(s) * p.stage_bytes;
         uint8_t* sb = sa + a_bytes;
@@ -109,19 +109,25 @@ conv_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
         tma_load_4d(sb + p.b_box_stride, mx, &full_bar[s], cx + 64, w0 - 1, h + r - 1, n);
       }
       __syncwarp();
+      if (++sw == p.segs_per_row) {
+        sw = 0;
+        if (++hs == p.hsegs) { hs = 0; ++n; }
+      }
+      if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // whole warp runs the loop (warp-uniform descriptors stay in uniform registers); one elected lane issues
     constexpr uint32_t idesc = make_idesc_bf16(128, 128, true, true);
     const int ksteps = p.kw / 16;
+    const uint64_t da_base = make_smem_desc_sw128(smem_u32(smem), p.a_box_bytes, 1024);
+    const uint64_t db_base = make_smem_desc_sw128(smem_u32(smem) + a_bytes, p.b_box_stride, 1024);
+    const uint64_t stage_step = p.stage_bytes >> 4;
+    uint64_t da0 = da_base, db0 = db_base;
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < n_iters; ++it) {
-      const int s = it % S;
-      const uint32_t ph = (it / S) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
-      const uint64_t da0 = make_smem_desc_sw128(a_addr, p.a_box_bytes, 1024);
-      const uint64_t db0 = make_smem_desc_sw128(a_addr + a_bytes, p.b_box_stride, 1024);
       const uint32_t first = it != 0 ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
@@ -142,6 +148,9 @@ conv_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
         umma_commit(&empty_bar[s]);
       }
       __syncwarp();
+      da0 += stage_step;
+      db0 += stage_step;
+      if (++s == S) { s = 0; ph ^= 1; da0 = da_base; db0 = db_base; }
     }
     if (elect_one()) umma_commit(tmem_full_bar);
     __syncwarp();
