@@ -70,6 +70,12 @@ int ddpm_scheduler_step(const float* eps, const float* x, const float* z, float*
 int ddpm_scheduler_step_philox(const float* eps, const float* x, float* prev, long long n, float sqrt_alpha_prod,
                                float sqrt_beta_prod, float c0, float ct, float sigma, float clip,
                                unsigned long long seed, unsigned long long offset, void* stream);
+/* DDIMScheduler.step (epsilon prediction) -- strided sampler on the same UNet:
+ *   x0 = clamp((x - sqrt_beta_prod*eps)/sqrt_alpha_prod);  eps' = use_clipped ? (x - sqrt_alpha_prod*x0)/sqrt_beta_prod : eps
+ *   prev = sqrt_alpha_prod_prev*x0 + dir_coef*eps' (+ sigma*z when z != NULL);  pred_x0 optional. */
+int ddpm_ddim_step(const float* eps, const float* x, const float* z, float* prev, float* pred_x0, long long n,
+                   float sqrt_alpha_prod, float sqrt_beta_prod, float sqrt_alpha_prod_prev, float dir_coef, float sigma,
+                   float clip, int use_clipped_model_output, void* stream);
 
 /* DDPMPipeline post-processing: (x/2+0.5).clamp(0,1) -> NHWC uint8 via round(x*255). x: NCHW fp32. */
 int ddpm_to_uint8_nhwc(const float* x, unsigned char* out, int n, int c, int h, int w, void* stream);

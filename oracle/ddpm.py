@@ -12,6 +12,8 @@ from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Optional
 
+import math
+
 import numpy as np
 import torch
 
@@ -35,6 +37,25 @@ class DDPMSchedulerOutput:
     pred_original_sample: Optional[torch.Tensor] = None
 
 
+def make_betas(beta_schedule: str, beta_start: float, beta_end: float, num_train_timesteps: int) -> torch.Tensor:
+    """diffusers' beta tables (scheduling_ddpm.py / scheduling_ddim.py __init__): "linear" is what
+    train_from_scratch.py:270 uses; "scaled_linear" is the Stable-Diffusion table behind the noise_scheduler of
+    train_with_lora_all_classes.py:314; "squaredcos_cap_v2" is betas_for_alpha_bar(cosine)."""
+    if beta_schedule == "linear":
+        return torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+    if beta_schedule == "scaled_linear":
+        return torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    if beta_schedule == "squaredcos_cap_v2":
+        def alpha_bar(t):
+            return math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+        betas = []
+        for i in range(num_train_timesteps):
+            t1, t2 = i / num_train_timesteps, (i + 1) / num_train_timesteps
+            betas.append(min(1 - alpha_bar(t2) / alpha_bar(t1), 0.999))
+        return torch.tensor(betas, dtype=torch.float32)
+    raise NotImplementedError(f"{beta_schedule} is not implemented")
+
+
 class DDPMScheduler:
     """Appendix B.1-B.3 for the configuration the reference uses (all other knobs rejected)."""
 
@@ -42,15 +63,14 @@ class DDPMScheduler:
                  beta_schedule: str = "linear", variance_type: str = "fixed_small", clip_sample: bool = True,
                  prediction_type: str = "epsilon", clip_sample_range: float = 1.0,
                  timestep_spacing: str = "leading", steps_offset: int = 0):
-        if beta_schedule != "linear" or variance_type != "fixed_small" or prediction_type != "epsilon" \
-                or timestep_spacing != "leading":
-            raise NotImplementedError("oracle covers linear / fixed_small / epsilon / leading only")
+        if variance_type != "fixed_small" or prediction_type != "epsilon" or timestep_spacing != "leading":
+            raise NotImplementedError("oracle covers fixed_small / epsilon / leading only")
         self.config = SimpleNamespace(
             num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
             beta_schedule=beta_schedule, variance_type=variance_type, clip_sample=clip_sample,
             prediction_type=prediction_type, clip_sample_range=clip_sample_range,
             timestep_spacing=timestep_spacing, steps_offset=steps_offset)
-        self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        self.betas = make_betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
         self.alphas = 1.0 - self.betas
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
         self.one = torch.tensor(1.0)
@@ -139,6 +159,98 @@ class DDPMScheduler:
         while len(sqrt_one_minus_alpha_prod.shape) < len(original_samples.shape):
             sqrt_one_minus_alpha_prod = sqrt_one_minus_alpha_prod.unsqueeze(-1)
         return sqrt_alpha_prod * original_samples + sqrt_one_minus_alpha_prod * noise
+
+    def __len__(self):
+        return self.config.num_train_timesteps
+
+
+@dataclass
+class DDIMSchedulerOutput:
+    prev_sample: torch.Tensor
+    pred_original_sample: Optional[torch.Tensor] = None
+
+
+class DDIMScheduler:
+    """diffusers 0.33.1 DDIMScheduler (epsilon prediction, leading spacing) -- the strided sampler of SURVEY.md §8(f)
+    rank 4 on the same UNet.  eta = 0 is deterministic DDIM; eta = 1 has DDPM's posterior variance."""
+
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", clip_sample: bool = True, set_alpha_to_one: bool = True,
+                 steps_offset: int = 0, prediction_type: str = "epsilon", clip_sample_range: float = 1.0,
+                 timestep_spacing: str = "leading"):
+        if prediction_type != "epsilon" or timestep_spacing != "leading":
+            raise NotImplementedError("oracle covers epsilon / leading only")
+        self.config = SimpleNamespace(
+            num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+            beta_schedule=beta_schedule, clip_sample=clip_sample, set_alpha_to_one=set_alpha_to_one,
+            steps_offset=steps_offset, prediction_type=prediction_type, clip_sample_range=clip_sample_range,
+            timestep_spacing=timestep_spacing)
+        self.betas = make_betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        T = self.config.num_train_timesteps
+        if num_inference_steps > T:
+            raise ValueError(
+                f"`num_inference_steps`: {num_inference_steps} cannot be larger than `self.config.train_timesteps`:"
+                f" {T} as the unet model trained with this scheduler can only handle"
+                f" maximal {T} timesteps.")
+        self.num_inference_steps = num_inference_steps
+        step_ratio = T // num_inference_steps
+        timesteps = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
+        timesteps += self.config.steps_offset
+        self.timesteps = torch.from_numpy(timesteps).to(device)
+
+    def _get_variance(self, timestep, prev_timestep):
+        alpha_prod_t = self.alphas_cumprod[timestep]
+        alpha_prod_t_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        beta_prod_t = 1 - alpha_prod_t
+        beta_prod_t_prev = 1 - alpha_prod_t_prev
+        return (beta_prod_t_prev / beta_prod_t) * (1 - alpha_prod_t / alpha_prod_t_prev)
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
+             generator=None, variance_noise: Optional[torch.Tensor] = None, return_dict: bool = True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating "
+                             "the scheduler")
+        prev_timestep = timestep - self.config.num_train_timesteps // self.num_inference_steps
+        alpha_prod_t = self.alphas_cumprod[timestep]
+        alpha_prod_t_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        beta_prod_t = 1 - alpha_prod_t
+        pred_original_sample = (sample - beta_prod_t ** 0.5 * model_output) / alpha_prod_t ** 0.5
+        pred_epsilon = model_output
+        if self.config.clip_sample:
+            pred_original_sample = pred_original_sample.clamp(-self.config.clip_sample_range,
+                                                              self.config.clip_sample_range)
+        variance = self._get_variance(timestep, prev_timestep)
+        std_dev_t = eta * variance ** 0.5
+        if use_clipped_model_output:
+            pred_epsilon = (sample - alpha_prod_t ** 0.5 * pred_original_sample) / beta_prod_t ** 0.5
+        pred_sample_direction = (1 - alpha_prod_t_prev - std_dev_t ** 2) ** 0.5 * pred_epsilon
+        prev_sample = alpha_prod_t_prev ** 0.5 * pred_original_sample + pred_sample_direction
+        if eta > 0:
+            if variance_noise is not None and generator is not None:
+                raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either "
+                                 "`generator` or `variance_noise` stays `None`.")
+            if variance_noise is None:
+                variance_noise = randn_tensor(model_output.shape, generator=generator, device=model_output.device,
+                                              dtype=model_output.dtype)
+            prev_sample = prev_sample + std_dev_t * variance_noise
+        if not return_dict:
+            return (prev_sample, pred_original_sample)
+        return DDIMSchedulerOutput(prev_sample=prev_sample, pred_original_sample=pred_original_sample)
+
+    add_noise = DDPMScheduler.add_noise
 
     def __len__(self):
         return self.config.num_train_timesteps

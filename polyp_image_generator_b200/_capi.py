@@ -78,6 +78,7 @@ SIGNATURES = {
     "ddpm_sumsq_f32": [_vp, _ll, _vp, _vp],
     "ddpm_adamw_flat": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _vp, _f, _f, _f, _f, _f, _vp],
     "ddpm_scheduler_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _vp],
+    "ddpm_ddim_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _i, _vp],
     "ddpm_scheduler_step_philox": [_vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _ull, _ull, _vp],
     "ddpm_to_uint8_nhwc": [_vp, _vp, _i, _i, _i, _i, _vp],
     "ddpm_conv_gemm": [C.POINTER(ConvArgs), _vp],

@@ -154,6 +154,49 @@ scheduler_step_kernel(const float* __restrict__ eps, const float* __restrict__ x
   }
 }
 
+// ---- DDIM step (strided sampler on the same UNet) --------------------------------------
+//   x0 = clamp((x - sb*eps)/sa);  eps' = use_clipped ? (x - sa*x0)/sb : eps;  prev = sap*x0 + dir*eps' (+ sigma*z)
+// same op order (and no FMA contraction) as the torch expressions of diffusers' DDIMScheduler.step, so bit-identical
+struct DdimCoef {
+  float sa, sb, sap, dir, sigma, clip;
+  int use_clipped;
+};
+__device__ __forceinline__ float ddim_one(float e, float x, float z, bool has_z, const DdimCoef& k, float* x0_out) {
+  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sb, e)), k.sa);
+  if (k.clip > 0.f) x0 = fminf(fmaxf(x0, -k.clip), k.clip);
+  *x0_out = x0;
+  float pe = e;
+  if (k.use_clipped) pe = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sa, x0)), k.sb);
+  float prev = __fadd_rn(__fmul_rn(k.sap, x0), __fmul_rn(k.dir, pe));
+  if (has_z) prev = __fadd_rn(prev, __fmul_rn(k.sigma, z));
+  return prev;
+}
+__global__ void __launch_bounds__(kEwThreads)
+ddim_step_kernel(const float* __restrict__ eps, const float* __restrict__ x, const float* __restrict__ z,
+                 float* __restrict__ prev, float* __restrict__ pred_x0, long long n, DdimCoef k) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = n >> 2;
+  const bool has_z = z != nullptr;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 e = reinterpret_cast<const float4*>(eps)[i];
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_z) zv = reinterpret_cast<const float4*>(z)[i];
+    float4 o, p0;
+    o.x = ddim_one(e.x, xv.x, zv.x, has_z, k, &p0.x);
+    o.y = ddim_one(e.y, xv.y, zv.y, has_z, k, &p0.y);
+    o.z = ddim_one(e.z, xv.z, zv.z, has_z, k, &p0.z);
+    o.w = ddim_one(e.w, xv.w, zv.w, has_z, k, &p0.w);
+    reinterpret_cast<float4*>(prev)[i] = o;
+    if (pred_x0) reinterpret_cast<float4*>(pred_x0)[i] = p0;
+  }
+  for (long long i = (nvec << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float p0;
+    prev[i] = ddim_one(eps[i], x[i], has_z ? z[i] : 0.f, has_z, k, &p0);
+    if (pred_x0) pred_x0[i] = p0;
+  }
+}
+
 // Philox4x32-10, counter = (element-quad index, offset), key = seed
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -366,6 +409,20 @@ extern "C" int ddpm_scheduler_step(const float* eps, const float* x, const float
   scheduler_step_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(eps, x, z, prev,
                                                                                                   pred_x0, n, k);
   return check_launch("scheduler_step_kernel");
+}
+
+extern "C" int ddpm_ddim_step(const float* eps, const float* x, const float* z, float* prev, float* pred_x0, long long n,
+                              float sqrt_alpha_prod, float sqrt_beta_prod, float sqrt_alpha_prod_prev, float dir_coef,
+                              float sigma, float clip, int use_clipped_model_output, void* stream) {
+  DDPM_REQUIRE(eps && x && prev && n >= 0, "ddpm_ddim_step: bad argument");
+  DDPM_REQUIRE((reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z) |
+                reinterpret_cast<uintptr_t>(prev) | reinterpret_cast<uintptr_t>(pred_x0)) % 16 == 0,
+               "ddpm_ddim_step: pointers must be 16-byte aligned");
+  if (n == 0) return DDPM_OK;
+  DdimCoef k{sqrt_alpha_prod, sqrt_beta_prod, sqrt_alpha_prod_prev, dir_coef, sigma, clip, use_clipped_model_output};
+  ddim_step_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(eps, x, z, prev, pred_x0,
+                                                                                               n, k);
+  return check_launch("ddim_step_kernel");
 }
 
 extern "C" int ddpm_scheduler_step_philox(const float* eps, const float* x, float* prev, long long n,

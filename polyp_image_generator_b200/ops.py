@@ -119,6 +119,14 @@ class CudaOps:
                     "ddpm_adamw_flat")
         self.launches += 2
 
+    def ddim_step(self, eps, x, z, sa, sb, sap, dirc, sigma, clip, use_clipped, want_x0=False):
+        prev = torch.empty_like(x)
+        x0 = torch.empty_like(x) if want_x0 else None
+        _capi.check(self.lib.ddpm_ddim_step(_ptr(eps), _ptr(x), _ptr(z), _ptr(prev), _ptr(x0), x.numel(), sa, sb, sap,
+                                            dirc, sigma, clip, int(bool(use_clipped)), _stream()), "ddpm_ddim_step")
+        self.launches += 1
+        return prev, x0
+
     def scheduler_step(self, eps, x, z, sa, sb, c0, ct, sigma, clip, want_x0=False):
         prev = torch.empty_like(x)
         x0 = torch.empty_like(x) if want_x0 else None

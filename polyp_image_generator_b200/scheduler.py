@@ -45,10 +45,25 @@ def step_coefficients(alphas_cumprod: torch.Tensor, t: int, prev_t: int) -> Dict
     }
 
 
+def make_betas(beta_schedule: str, beta_start: float, beta_end: float, num_train_timesteps: int) -> torch.Tensor:
+    """diffusers' beta tables: "linear" (train_from_scratch.py:270), "scaled_linear" (the Stable-Diffusion table of the
+    noise_scheduler in train_with_lora_all_classes.py:314), "squaredcos_cap_v2" (cosine)."""
+    if beta_schedule == "linear":
+        return torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+    if beta_schedule == "scaled_linear":
+        return torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    if beta_schedule == "squaredcos_cap_v2":
+        import math
+        bar = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+        T = num_train_timesteps
+        return torch.tensor([min(1 - bar((i + 1) / T) / bar(i / T), 0.999) for i in range(T)], dtype=torch.float32)
+    raise NotImplementedError(f"{beta_schedule} is not implemented")
+
+
 class DDPMScheduler:
     """Same constructor signature and attributes as diffusers.DDPMScheduler for the configuration the reference uses
-    (linear betas, fixed_small variance, epsilon prediction, leading spacing); other modes raise NotImplementedError
-    rather than silently computing something else."""
+    (fixed_small variance, epsilon prediction, leading spacing; linear / scaled_linear / cosine betas); other modes
+    raise NotImplementedError rather than silently computing something else."""
 
     order = 1
 
@@ -60,7 +75,7 @@ class DDPMScheduler:
                  rescale_betas_zero_snr: bool = False):
         if trained_betas is not None or thresholding or rescale_betas_zero_snr:
             raise NotImplementedError("trained_betas / thresholding / rescale_betas_zero_snr are not on the hot path")
-        if beta_schedule != "linear":
+        if beta_schedule not in ("linear", "scaled_linear", "squaredcos_cap_v2"):
             raise NotImplementedError(f"{beta_schedule} is not implemented for {self.__class__}")
         if variance_type != "fixed_small" or prediction_type != "epsilon" or timestep_spacing != "leading":
             raise NotImplementedError("only variance_type='fixed_small', prediction_type='epsilon', "
@@ -71,7 +86,7 @@ class DDPMScheduler:
             prediction_type=prediction_type, thresholding=False, dynamic_thresholding_ratio=dynamic_thresholding_ratio,
             clip_sample_range=clip_sample_range, sample_max_value=sample_max_value,
             timestep_spacing=timestep_spacing, steps_offset=steps_offset, rescale_betas_zero_snr=False)
-        self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        self.betas = make_betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
         self.alphas = 1.0 - self.betas
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
         self.one = torch.tensor(1.0)
@@ -178,3 +193,85 @@ class DDPMScheduler:
         if not return_dict:
             return (prev, x0)
         return DDPMSchedulerOutput(prev_sample=prev, pred_original_sample=x0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DDIM: the strided sampler on the same UNet
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class DDIMSchedulerOutput:
+    prev_sample: torch.Tensor
+    pred_original_sample: Optional[torch.Tensor] = None
+
+
+def ddim_coefficients(alphas_cumprod: torch.Tensor, final_alpha_cumprod: torch.Tensor, t: int, prev_t: int,
+                      eta: float) -> Dict[str, float]:
+    """fp32 scalars of DDIMScheduler.step, same op order as diffusers (0-dim fp32 tensor arithmetic)."""
+    ac = alphas_cumprod.detach().to("cpu", torch.float32)
+    alpha_prod_t = ac[t]
+    alpha_prod_t_prev = ac[prev_t] if prev_t >= 0 else final_alpha_cumprod.detach().to("cpu", torch.float32)
+    beta_prod_t = 1 - alpha_prod_t
+    beta_prod_t_prev = 1 - alpha_prod_t_prev
+    variance = (beta_prod_t_prev / beta_prod_t) * (1 - alpha_prod_t / alpha_prod_t_prev)
+    std_dev_t = eta * variance ** 0.5
+    return {"sa": float(alpha_prod_t ** 0.5), "sb": float(beta_prod_t ** 0.5), "sap": float(alpha_prod_t_prev ** 0.5),
+            "dir": float((1 - alpha_prod_t_prev - std_dev_t ** 2) ** 0.5), "sigma": float(std_dev_t)}
+
+
+class DDIMScheduler(DDPMScheduler):
+    """diffusers.DDIMScheduler for epsilon prediction / leading spacing; `step` is one single-pass kernel
+    (ddpm_ddim_step).  With num_inference_steps = 50 the 1024-image-per-class sampling of BASELINE configs[4] needs 20x
+    fewer UNet forwards than the 1000-step DDPM loop."""
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", trained_betas=None, clip_sample: bool = True,
+                 set_alpha_to_one: bool = True, steps_offset: int = 0, prediction_type: str = "epsilon",
+                 thresholding: bool = False, dynamic_thresholding_ratio: float = 0.995, clip_sample_range: float = 1.0,
+                 sample_max_value: float = 1.0, timestep_spacing: str = "leading",
+                 rescale_betas_zero_snr: bool = False):
+        super().__init__(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                         beta_schedule=beta_schedule, trained_betas=trained_betas, clip_sample=clip_sample,
+                         prediction_type=prediction_type, thresholding=thresholding,
+                         dynamic_thresholding_ratio=dynamic_thresholding_ratio, clip_sample_range=clip_sample_range,
+                         sample_max_value=sample_max_value, timestep_spacing=timestep_spacing,
+                         steps_offset=steps_offset, rescale_betas_zero_snr=rescale_betas_zero_snr)
+        del self.config.variance_type
+        self.config.set_alpha_to_one = set_alpha_to_one
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.num_inference_steps = None
+
+    def previous_timestep(self, timestep):
+        return int(timestep) - self.config.num_train_timesteps // self.num_inference_steps
+
+    def step(self, model_output: torch.Tensor, timestep: Union[int, torch.Tensor], sample: torch.Tensor,
+             eta: float = 0.0, use_clipped_model_output: bool = False, generator=None,
+             variance_noise: Optional[torch.Tensor] = None, return_dict: bool = True,
+             want_pred_original_sample: bool = True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating "
+                             "the scheduler")
+        if model_output.dtype != torch.float32 or sample.dtype != torch.float32:
+            raise TypeError("scheduler step kernel computes in fp32 (the pipeline runs the scheduler in fp32)")
+        t = int(timestep)
+        key = (t, float(eta))
+        c = self._coef_cache.get(key)
+        if c is None:
+            c = ddim_coefficients(self.alphas_cumprod, self.final_alpha_cumprod, t, self.previous_timestep(t), eta)
+            self._coef_cache[key] = c
+        clip = float(self.config.clip_sample_range) if self.config.clip_sample else 0.0
+        z = None
+        if eta > 0:
+            if variance_noise is not None and generator is not None:
+                raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either "
+                                 "`generator` or `variance_noise` stays `None`.")
+            if variance_noise is None:
+                from .pipeline import randn_tensor
+                variance_noise = randn_tensor(model_output.shape, generator=generator, device=model_output.device,
+                                              dtype=model_output.dtype)
+            z = variance_noise.contiguous()
+        prev, x0 = _ops.get().ddim_step(model_output.contiguous(), sample.contiguous(), z, c["sa"], c["sb"], c["sap"],
+                                        c["dir"], c["sigma"], clip, use_clipped_model_output,
+                                        want_x0=want_pred_original_sample)
+        if not return_dict:
+            return (prev, x0)
+        return DDIMSchedulerOutput(prev_sample=prev, pred_original_sample=x0)

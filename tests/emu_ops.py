@@ -36,6 +36,17 @@ class EmuOps:
         x.mul_(scale.reshape(()))
         return x
 
+    def ddim_step(self, eps, x, z, sa, sb, sap, dirc, sigma, clip, use_clipped, want_x0=False):
+        f = lambda v: torch.tensor(v, dtype=torch.float32)
+        x0 = (x - f(sb) * eps) / f(sa)
+        if clip > 0:
+            x0 = x0.clamp(-clip, clip)
+        pe = (x - f(sa) * x0) / f(sb) if use_clipped else eps
+        prev = f(sap) * x0 + f(dirc) * pe
+        if z is not None:
+            prev = prev + f(sigma) * z
+        return prev, (x0 if want_x0 else None)
+
     def scheduler_step(self, eps, x, z, sa, sb, c0, ct, sigma, clip, want_x0=False):
         f = lambda v: torch.tensor(v, dtype=torch.float32)
         x0 = (x - f(sb) * eps) / f(sa)

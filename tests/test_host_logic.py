@@ -69,7 +69,7 @@ def test_scheduler_tables_and_timesteps_match_oracle():
     with pytest.raises(ValueError, match="cannot be larger"):
         a.set_timesteps(1001)
     with pytest.raises(NotImplementedError):
-        DDPMScheduler(beta_schedule="squaredcos_cap_v2")
+        DDPMScheduler(beta_schedule="sigmoid")
 
 
 def test_scheduler_step_and_add_noise_through_emulation(emu_backend):
@@ -324,3 +324,66 @@ def test_sampling_bookkeeping_file_names_seeds_and_shards(emu_backend, tmp_path)
     assert [os.path.basename(p) for p in more] == ["8.png", "9.png"] and count_samples(d) == 9
     fresh = top_up(single, pipe, "HP", 2, num_inference_steps=2, verbose=False)
     assert [os.path.basename(p) for p in fresh] == ["1.png", "2.png"]
+
+
+def test_beta_schedules_and_ddim_scheduler_match_oracle(emu_backend):
+    """scaled_linear / cosine tables and the DDIM strided sampler, against the oracle restatement."""
+    from polyp_image_generator_b200 import DDIMScheduler, DDPMScheduler
+    for sched, (b0, b1) in (("linear", (1e-4, 0.02)), ("scaled_linear", (0.00085, 0.012)), ("squaredcos_cap_v2", (1e-4, 0.02))):
+        a = DDPMScheduler(beta_schedule=sched, beta_start=b0, beta_end=b1)
+        b = oracle.DDPMScheduler(beta_schedule=sched, beta_start=b0, beta_end=b1)
+        assert torch.equal(a.betas, b.betas) and torch.equal(a.alphas_cumprod, b.alphas_cumprod)
+    # SD-style forward noising (the noise_scheduler of train_with_lora_all_classes.py:314 uses this table)
+    a, b = DDPMScheduler(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012), \
+        oracle.DDPMScheduler(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012)
+    torch.manual_seed(1)
+    x, e, z = torch.randn(2, 3, 8, 8), torch.randn(2, 3, 8, 8), torch.randn(2, 3, 8, 8)
+    t = torch.tensor([0, 999])
+    assert torch.allclose(a.add_noise(x, e, t), b.add_noise(x, e, t), rtol=1e-6, atol=1e-7)
+    a, b = DDIMScheduler(), oracle.DDIMScheduler()
+    with pytest.raises(ValueError, match="set_timesteps"):
+        a.step(e, 10, x)
+    for n in (50, 7, 1000):
+        a.set_timesteps(n)
+        b.set_timesteps(n)
+        assert torch.equal(a.timesteps, b.timesteps)
+        for tt in (a.timesteps.tolist()[0], a.timesteps.tolist()[len(a.timesteps) // 2], a.timesteps.tolist()[-1]):
+            for eta, clipped in ((0.0, False), (0.0, True), (0.5, False), (1.0, True)):
+                ra = a.step(e, tt, x, eta=eta, use_clipped_model_output=clipped, variance_noise=z if eta > 0 else None)
+                rb = b.step(e, torch.tensor(tt), x, eta=eta, use_clipped_model_output=clipped,
+                            variance_noise=z if eta > 0 else None)
+                assert torch.allclose(ra.prev_sample, rb.prev_sample, rtol=1e-6, atol=1e-6), (n, tt, eta, clipped)
+                assert torch.allclose(ra.pred_original_sample, rb.pred_original_sample, rtol=1e-6, atol=1e-6)
+    ga, gb = torch.Generator().manual_seed(9), torch.Generator().manual_seed(9)
+    assert torch.allclose(a.step(e, 500, x, eta=1.0, generator=ga).prev_sample,
+                          b.step(e, torch.tensor(500), x, eta=1.0, generator=gb).prev_sample, rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError, match="Cannot pass both"):
+        a.step(e, 500, x, eta=1.0, generator=ga, variance_noise=z)
+    with pytest.raises(ValueError, match="cannot be larger"):
+        a.set_timesteps(1001)
+
+
+def test_ddim_pipeline_matches_oracle_loop_and_round_trips(emu_backend, tmp_path):
+    from polyp_image_generator_b200 import DDIMPipeline, DDIMScheduler, UNet2DModel
+    cfg = _small_cfg(32)
+    cfg["block_out_channels"] = (64, 64, 64, 64, 64, 64)
+    torch.manual_seed(0)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    pipe = DDIMPipeline(unet=m, scheduler=DDIMScheduler())
+    got = pipe(batch_size=2, generator=torch.Generator("cpu").manual_seed(4), num_inference_steps=5, eta=0.3,
+               output_type="np").images
+    # the oracle loop (diffusers DDIMPipeline.__call__): x_T from the generator, then step(..., eta, generator)
+    osch = oracle.DDIMScheduler()
+    g = torch.Generator("cpu").manual_seed(4)
+    img = oracle.randn_tensor((2, 3, 32, 32), generator=g)
+    osch.set_timesteps(5)
+    with torch.no_grad():
+        for t in osch.timesteps:
+            img = osch.step(om(img, t).sample, t, img, eta=0.3, use_clipped_model_output=False, generator=g).prev_sample
+    want = (img / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).numpy()
+    assert abs(got - want).max() <= 1.0 / 255 + 1e-6
+    pipe.save_pretrained(str(tmp_path / "p"))
+    back = DDIMPipeline.from_pretrained(str(tmp_path / "p"))
+    assert type(back.scheduler).__name__ == "DDIMScheduler" and back.scheduler.config.set_alpha_to_one is True

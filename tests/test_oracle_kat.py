@@ -137,3 +137,41 @@ def test_golden_vectors_reproduce():
     assert case["loss"] == pytest.approx(g["loss"], rel=1e-5)
     for k, v in g["grad_norms"].items():
         assert case["grad_norms"][k] == pytest.approx(v, rel=1e-3, abs=1e-9)
+
+
+def test_beta_schedule_tables_kat():
+    """make_betas against an independent float64 derivation and the well-known Stable-Diffusion end points."""
+    import numpy as np
+    sl = oracle.make_betas("scaled_linear", 0.00085, 0.012, 1000)
+    ref = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000) ** 2
+    assert np.allclose(sl.double().numpy(), ref, rtol=3e-6)
+    ac = torch.cumprod(1 - sl, 0)
+    assert ac[0].item() == pytest.approx(0.99915, abs=1e-6) and ac[999].item() == pytest.approx(0.0046601, rel=2e-3)
+    cos = oracle.make_betas("squaredcos_cap_v2", 0, 0, 1000)
+    bar = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+    assert cos[0].item() == pytest.approx(1 - bar(1e-3) / bar(0.0), rel=1e-5)
+    assert cos[999].item() == pytest.approx(0.999) and (cos[1:] >= cos[:-1] - 1e-7).all()
+    with pytest.raises(NotImplementedError):
+        oracle.make_betas("sigmoid", 1e-4, 0.02, 10)
+
+
+def test_oracle_ddim_closed_form_properties():
+    """eta = 0 DDIM with the TRUE noise walks x_t = sa x0 + sb eps back along the same (x0, eps) line; eta = 1 has the
+    DDPM posterior standard deviation (step_coefficients KAT above: 1.002560183e-01 at t = 500 -> 499)."""
+    s = oracle.DDIMScheduler(clip_sample=False)
+    s.set_timesteps(1000)
+    torch.manual_seed(0)
+    x0, eps = torch.randn(2, 3, 8, 8).clamp(-1, 1), torch.randn(2, 3, 8, 8)
+    ac = s.alphas_cumprod
+    xt = ac[500] ** 0.5 * x0 + (1 - ac[500]) ** 0.5 * eps
+    out = s.step(eps, torch.tensor(500), xt, eta=0.0)
+    assert torch.allclose(out.pred_original_sample, x0, atol=2e-5)
+    assert torch.allclose(out.prev_sample, ac[499] ** 0.5 * x0 + (1 - ac[499]) ** 0.5 * eps, atol=2e-5)
+    z = torch.randn_like(x0)
+    d = s.step(eps, torch.tensor(500), xt, eta=1.0, variance_noise=z).prev_sample - \
+        s.step(eps, torch.tensor(500), xt, eta=1.0, variance_noise=torch.zeros_like(z)).prev_sample
+    assert torch.allclose(d, 1.002560183e-01 * z, rtol=1e-5, atol=1e-7)
+    s.set_timesteps(50)                      # strided: t = 980 -> 960, last step t = 0 -> final_alpha_cumprod = 1
+    assert s.timesteps[0].item() == 980 and s.timesteps[-1].item() == 0
+    x1 = ac[0] ** 0.5 * x0 + (1 - ac[0]) ** 0.5 * eps
+    assert torch.allclose(s.step(eps, torch.tensor(0), x1).prev_sample, x0, atol=2e-5)

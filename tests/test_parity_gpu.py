@@ -66,6 +66,34 @@ def test_scheduler_step_bit_exact(dev, n_steps):
         assert torch.equal(got.pred_original_sample.cpu(), want.pred_original_sample), t
 
 
+@pytest.mark.parametrize("n_steps", [50, 1000])
+def test_ddim_step_bit_exact(dev, n_steps):
+    """DDIMScheduler.step in one kernel, bit-identical to the oracle's torch expressions."""
+    from polyp_image_generator_b200 import DDIMScheduler
+    a, b = DDIMScheduler(), oracle.DDIMScheduler()
+    a.set_timesteps(n_steps)
+    b.set_timesteps(n_steps)
+    torch.manual_seed(2)
+    x, e, z = torch.randn(4, 3, 32, 32), torch.randn(4, 3, 32, 32), torch.randn(4, 3, 32, 32)
+    ts = a.timesteps.tolist()
+    for t in [ts[0], ts[len(ts) // 2], ts[-1]]:
+        for eta, clipped in ((0.0, False), (0.0, True), (0.7, False), (1.0, True)):
+            zz = z if eta > 0 else None
+            want = b.step(e, torch.tensor(t), x, eta=eta, use_clipped_model_output=clipped, variance_noise=zz)
+            got = a.step(e.to(dev), t, x.to(dev), eta=eta, use_clipped_model_output=clipped,
+                         variance_noise=zz.to(dev) if zz is not None else None)
+            assert torch.equal(got.prev_sample.cpu(), want.prev_sample), (t, eta, clipped)
+            assert torch.equal(got.pred_original_sample.cpu(), want.pred_original_sample), (t, eta, clipped)
+    # ragged size (scalar tail) and the scaled_linear table
+    a2 = DDIMScheduler(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, clip_sample=False)
+    b2 = oracle.DDIMScheduler(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, clip_sample=False)
+    a2.set_timesteps(25)
+    b2.set_timesteps(25)
+    x, e = torch.randn(1, 3, 7, 5), torch.randn(1, 3, 7, 5)
+    want = b2.step(e, torch.tensor(480), x).prev_sample
+    assert torch.equal(a2.step(e.to(dev), 480, x.to(dev)).prev_sample.cpu(), want)
+
+
 def test_scheduler_golden_trajectory(dev):
     """50-step trajectory with a deterministic stand-in for the UNet; CPU generator consumed in diffusers' order."""
     import json
