@@ -240,6 +240,18 @@ int ddpm_reduce_hw(const void* x, long long ld, int n, int hw, int c, float* out
 int ddpm_dropout(const void* x, const void* add, void* out, long long n, float p, unsigned long long seed,
                  unsigned long long offset, const unsigned long long* tick, void* stream);
 
+/* Input transform of generator_model/PolypDiffusionDataset.py:52-59 on the device:
+ * Resize((S,S)) [Pillow's two-pass antialiased bilinear resampler, 8-bit fixed point] -> hflip -> ToTensor ->
+ * Normalize([0.5],[0.5]).  bounds int32 [out][2] = (first source index, tap count), coeffs int32 [out][ksize] =
+ * Pillow's normalize_coeffs_8bpc tables (22 fractional bits), built by the host.  c = 1 or 3 interleaved channels.
+ *   ddpm_resize_h_u8:        dst u8 [rows][out_w][c] from src u8 [rows][w][c]                (horizontal pass)
+ *   ddpm_resize_v_normalize: out f32 [b][c][out_h][w] from src u8 [b][h][w][c]; flip u8 [b] or NULL (vertical pass,
+ *                            flip, /255, (x-0.5)/0.5).  Pass identity tables to skip a resampling pass. */
+int ddpm_resize_h_u8(const unsigned char* src, unsigned char* dst, long long rows, int w, int c, int out_w,
+                     const int* bounds, const int* coeffs, int ksize, void* stream);
+int ddpm_resize_v_normalize(const unsigned char* src, float* out, int b, int h, int w, int c, int out_h,
+                            const int* bounds, const int* coeffs, int ksize, const unsigned char* flip, void* stream);
+
 /* Layout helpers (bf16 NHWC, contiguous outputs). */
 int ddpm_space_to_depth(const void* x, long long ldx, void* out, int n, int h, int w, int c, int pad_lo,
                         void* stream);                      /* out[(ph*2+pw)*n + b][h/2][w/2][c] */

@@ -497,6 +497,24 @@ class CudaOps:
         self.launches += 1
         return out
 
+    # ---- input transform (csrc/preprocess.cu) ------------------------------------------------------------------
+    def preprocess_u8(self, frames, out_h: int, out_w: int, htab, vtab, flips):
+        """uint8 [B, H, W, C] -> fp32 [B, C, out_h, out_w] in [-1, 1]: Pillow bilinear resize (two 8-bit passes), flip,
+        /255, (x - 0.5)/0.5.  htab / vtab = (bounds, coeffs, ksize) device tables for the two passes."""
+        b, h, w, c = frames.shape
+        mid = frames
+        if w != out_w:
+            mid = torch.empty((b, h, out_w, c), device=frames.device, dtype=torch.uint8)
+            _capi.check(self.lib.ddpm_resize_h_u8(_ptr(frames), _ptr(mid), b * h, w, c, out_w, _ptr(htab[0]),
+                                                  _ptr(htab[1]), htab[2], _stream()), "ddpm_resize_h_u8")
+            self.launches += 1
+        out = torch.empty((b, c, out_h, out_w), device=frames.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_resize_v_normalize(_ptr(mid), _ptr(out), b, h, out_w, c, out_h, _ptr(vtab[0]),
+                                                     _ptr(vtab[1]), vtab[2], _ptr(flips), _stream()),
+                    "ddpm_resize_v_normalize")
+        self.launches += 1
+        return out
+
     # ---- layout helpers ----------------------------------------------------------------------------------------
     def space_to_depth(self, x):
         n, h, w, c, ld = _nhwc(x, "x")

@@ -62,6 +62,26 @@ class EmuOps:
         z = torch.randn(x.shape, generator=g) if sigma != 0 else None
         return self.scheduler_step(eps, x, z, sa, sb, c0, ct, sigma, clip)[0]
 
+    def preprocess_u8(self, frames, out_h, out_w, htab, vtab, flips):
+        def one_pass(x, tab, axis):            # x int64 [..]; gather-accumulate along `axis` with the integer tables
+            bounds, coeffs, ksize = tab
+            outs = []
+            for o in range(bounds.shape[0]):
+                lo, n = int(bounds[o, 0]), int(bounds[o, 1])
+                acc = torch.full_like(x.select(axis, 0), 1 << 21)
+                for i in range(n):
+                    acc = acc + x.select(axis, lo + i) * int(coeffs[o, i])
+                outs.append((acc >> 22).clamp(0, 255))
+            return torch.stack(outs, axis)
+        x = frames.to(torch.int64)
+        if frames.shape[2] != out_w:
+            x = one_pass(x, htab, 2)
+        x = one_pass(x, vtab, 1)
+        if flips is not None:
+            x = torch.where(flips.bool().view(-1, 1, 1, 1), x.flip(2), x)
+        t = x.permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+        return (t - 0.5) / 0.5
+
     def to_uint8_nhwc(self, x):
         return ((x / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8)
 
