@@ -78,6 +78,9 @@ class DistributedDataParallel(nn.Module):
         seg = G[final_from:hi]
         if side is not None:
             side.wait_stream(torch.cuda.current_stream())
+            wg = getattr(self.module, "_wgrad_stream", None)
+            if wg is not None:            # the weight gradients themselves are produced on the model's wgrad stream
+                side.wait_stream(wg)
             with torch.cuda.stream(side):
                 self._allreduce_mean(seg)
             seg.record_stream(side)

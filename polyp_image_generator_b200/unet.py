@@ -285,6 +285,7 @@ class UNet2DModel(nn.Module):
         self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
 
         self._arena: Optional[torch.Tensor] = None
+        self._wgrad_stream = None
         self._prep_table = None
         self._plan = None
         self._wcache_key = None
@@ -812,7 +813,14 @@ class UNet2DModel(nn.Module):
         ted = self._temb_dim
         G = torch.zeros(P.total, device=self._arena.device, dtype=torch.float32)
         d_temb_all = torch.zeros((N, P.temb_total), device=G.device, dtype=torch.float32)
-        st = SimpleNamespace(ops=ops, G=G, d_temb_all=d_temb_all, skip_grads={}, N=N)
+        st = SimpleNamespace(ops=ops, G=G, d_temb_all=d_temb_all, skip_grads={}, N=N, wg_stream=None, keep=[])
+        if G.is_cuda and os.environ.get("DDPM_WGRAD_STREAM", "1") != "0":
+            # Weight gradients feed nothing downstream in backward, so they run on a second stream: the tensor-bound
+            # wgrad GEMMs overlap the HBM-bound GroupNorm-backward kernels and the latency-bound low-resolution layers
+            # (in a captured step these become parallel graph branches).  Joined before the arena is handed back.
+            if self._wgrad_stream is None or self._wgrad_stream.device != G.device:
+                self._wgrad_stream = torch.cuda.Stream(device=G.device)
+            st.wg_stream = self._wgrad_stream
         d_out = d_out.to(torch.float32).contiguous()
 
         # earliest tape step that still has trainable parameters at or before it (LoRA: stop early)
@@ -876,8 +884,23 @@ class UNet2DModel(nn.Module):
                 d_e1 = ops.linear_f32_dgrad(d_emb, w2, hd.e1, True)
                 ops.linear_f32_wgrad(hd.t_emb, d_e1, self._gview(G, P.te.w1, (ted, c0)),
                                      self._gview(G, P.te.b1, (ted,)), False)
+        if st.wg_stream is not None:
+            torch.cuda.current_stream().wait_stream(st.wg_stream)
         self.last_launches_bwd = ops.launches - l0
         return G, st
+
+    @staticmethod
+    def _async_wgrad(st, fn):
+        """Run fn() -- weight-gradient kernels whose results backward itself never reads -- on the wgrad stream.  The
+        closure keeps its operand tensors alive until backward has joined the stream (st.keep)."""
+        side = st.wg_stream
+        if side is None:
+            fn()
+            return
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        st.keep.append(fn)
 
     def _head_trainable(self):
         return self.conv_in.weight.requires_grad or self.time_embedding.linear_1.weight.requires_grad or \
@@ -911,10 +934,17 @@ class UNet2DModel(nn.Module):
             ops.reduce_hw(g, None, db2)
         elif not r.conv2.bias_trainable and r.short is not None and r.short.bias_trainable:
             ops.reduce_hw(g, None, self._wgrad_views(G, r.short)[1])
-        if r.conv2.trainable:
-            ops.conv_wgrad(g, s.b, None, taps_3x3(r.cout), dW2, grid, dbias=db2 if fold_bias else None)
-        if r.conv2.bias_trainable and r.short is not None and r.short.bias_trainable:
-            self._wgrad_views(G, r.short)[1].copy_(db2)       # the shortcut bias sees the same column sums
+        share_bias = r.conv2.bias_trainable and r.short is not None and r.short.bias_trainable
+
+        def wgrad2(g=g):
+            if r.conv2.trainable:
+                ops.conv_wgrad(g, s.b, None, taps_3x3(r.cout), dW2, grid, dbias=db2 if fold_bias else None)
+            if share_bias:
+                self._wgrad_views(G, r.short)[1].copy_(db2)       # the shortcut bias sees the same column sums
+        if fold_bias or not r.conv2.bias_trainable:
+            self._async_wgrad(st, wgrad2)
+        else:
+            wgrad2()        # db2 came from reduce_hw on the main stream: keep the copy ordered behind it
         g2, be2 = self._norm_params(r.norm2)
         dg, dbt = self._norm_grads(G, r.norm2)
         fuse = s.coef2 is not None
@@ -937,7 +967,7 @@ class UNet2DModel(nn.Module):
             ops.reduce_hw(d_h1, st.d_temb_all[:, r.temb_off:r.temb_off + r.cout],
                           db1 if r.conv1.bias_trainable else None)
         if r.conv1.trainable:
-            ops.conv_wgrad(d_h1, s.a, None, taps_3x3(r.cin), dW1, grid)
+            self._async_wgrad(st, lambda d_h1=d_h1: ops.conv_wgrad(d_h1, s.a, None, taps_3x3(r.cin), dW1, grid))
         g1, be1 = self._norm_params(r.norm1)
         if fuse:
             sums1 = torch.zeros((grid[0], r.cin, 2), device=g.device, dtype=torch.float32)
@@ -947,7 +977,8 @@ class UNet2DModel(nn.Module):
             d_a = ops.conv_gemm(d_h1, None, taps_3x3(r.cout), r.conv1.wd, r.cin, grid)
         if r.short is not None:
             if r.short.trainable:
-                ops.conv_wgrad(g, s.x0, s.x1, taps_1x1(), self._wgrad_views(G, r.short)[0], grid)
+                self._async_wgrad(st, lambda g=g: ops.conv_wgrad(g, s.x0, s.x1, taps_1x1(),
+                                                                 self._wgrad_views(G, r.short)[0], grid))
             d_sc = ops.conv_gemm(g, None, taps_1x1(), r.short.wd, r.cin, grid)
         else:
             d_sc = g
@@ -974,7 +1005,7 @@ class UNet2DModel(nn.Module):
             ops.reduce_hw(g2, None, dbo)
         o2 = s.o.view(1, 1, M, C)
         if at.out.trainable:
-            ops.conv_wgrad(g2, o2, None, taps_1x1(), dWo, (1, 1, M))
+            self._async_wgrad(st, lambda: ops.conv_wgrad(g2, o2, None, taps_1x1(), dWo, (1, 1, M)))
         d_o = ops.conv_gemm(g2, None, taps_1x1(), at.out.wd, C, (1, 1, M))
         if s.lora_o is not None:
             d_o = at.out.lora.backward(ops, s.lora_o, o2, g2, d_o)
@@ -985,7 +1016,7 @@ class UNet2DModel(nn.Module):
             ops.reduce_hw(dq2, None, dbq)
         xn2 = s.xn.view(1, 1, M, C)
         if at.qkv.trainable:
-            ops.conv_wgrad(dq2, xn2, None, taps_1x1(), dWq, (1, 1, M))
+            self._async_wgrad(st, lambda: ops.conv_wgrad(dq2, xn2, None, taps_1x1(), dWq, (1, 1, M)))
         d_xn = ops.conv_gemm(dq2, None, taps_1x1(), at.qkv.wd, C, (1, 1, M))
         if s.lora_qkv is not None:
             d_xn = at.qkv.lora.backward(ops, s.lora_qkv, xn2, dq2, d_xn)
@@ -1004,8 +1035,8 @@ class UNet2DModel(nn.Module):
         if d.conv.bias_trainable and not fold_bias:
             ops.reduce_hw(g, None, db)
         if d.conv.trainable:
-            ops.conv_wgrad(g, s.s2d, None, taps_s2d(C, N, d.pad), dW, s.grid, src_n=4 * N,
-                           dbias=db if fold_bias else None)
+            self._async_wgrad(st, lambda g=g: ops.conv_wgrad(g, s.s2d, None, taps_s2d(C, N, d.pad), dW, s.grid,
+                                                             src_n=4 * N, dbias=db if fold_bias else None))
         zi = ops.zero_insert2x(g, H, W)
         extra = st.skip_grads.pop(s.in_skip, None) if s.in_skip is not None else None
         # dgrad of the stride-2 conv = stride-1 correlation of the zero-inserted dY with the flipped taps
@@ -1021,7 +1052,8 @@ class UNet2DModel(nn.Module):
         if u.conv.bias_trainable and not fold_bias:
             ops.reduce_hw(g, None, db)
         if u.conv.trainable:
-            ops.conv_wgrad(g, s.up, None, taps_3x3(C), dW, s.grid, dbias=db if fold_bias else None)
+            self._async_wgrad(st, lambda g=g: ops.conv_wgrad(g, s.up, None, taps_3x3(C), dW, s.grid,
+                                                             dbias=db if fold_bias else None))
         d_up = ops.conv_gemm(g, None, taps_3x3(C), u.conv.wd, C, s.grid)
         return ops.sumpool2x(d_up)
 
