@@ -380,6 +380,9 @@ def run_b200(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel class: the same step, eager, with CUDA events around every conv GEMM launch
     # (a graph replay cannot host per-kernel events; same kernels, same inputs, same stream)
     barrier()
+    # per-launch events need every kernel serialised on ONE stream: the timed steps run weight gradients on a second
+    # stream (parallel graph branches), which would smear concurrent kernels into each other's event brackets
+    os.environ["DDPM_WGRAD_STREAM"] = "0"
     for _ in range(2):      # the graph capture emptied the eager allocator pool: refill it before timing launches
         eager_step(clean_dev, noise_dev, t_dev)
     barrier()
@@ -402,6 +405,8 @@ def run_b200(args, rank, world, local_rank):
     all_tf = sum(prof["flops"].values()) / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0
     ops.conv_wgrad = orig_conv_wgrad
     step = eager_step
+    if not args.breakdown:
+        os.environ.pop("DDPM_WGRAD_STREAM", None)
 
     # ---- secondary metric: reverse-diffusion sampling (BASELINE configs[2]: 256 images over 8 GPUs = 32 / GPU) ----
     sampling = None
@@ -475,6 +480,7 @@ def run_b200(args, rank, world, local_rank):
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as f:
             json.dump(out, f, indent=1)
+    os.environ.pop("DDPM_WGRAD_STREAM", None)
 
     tt = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -530,7 +536,8 @@ def run_b200(args, rank, world, local_rank):
             "frac": round(achieved_tf / peak_tf, 4), "traffic": None, "peak_source": peak_src,
             "launches_timed": gemm_launches, "kernel_ms_per_step": round(gemm_ms / n_prof_steps, 3),
             "share_of_step": round(gemm_ms / ms_prof_total, 4),
-            "timed_in": "eager re-run of the same step with per-launch CUDA events (graph replays cannot host them)",
+            "timed_in": "eager single-stream re-run of the same step with per-launch CUDA events (graph replays cannot "
+                        "host them; the timed steps additionally overlap weight gradients on a second stream)",
             "whole_step_tflops": round(step_gflop / ms_step, 2),
             "other_conv_kernels": {
                 "generic_gemm_tflops (low-res 3x3, 1x1, linears, boundary convs)": round(cls_tf["gemm"], 1),

@@ -188,6 +188,11 @@ int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const void* x1, int
                       const float* sums, const void* add0, long long ldadd0, const void* add1, long long ldadd1,
                       void* dx0, long long lddx0, void* dx1, long long lddx1, float* dgamma, float* dbeta,
                       float* out_nc, long long ld_nc, float* out_c, void* stream);
+/* dgamma / dbeta reductions alone (call the two functions above with dgamma = dbeta = NULL first): lets the caller
+ * issue them on another stream.  stats == NULL: sums = the centred sums ddpm_gn_bwd left at the start of its ws;
+ * otherwise sums = raw moments from the conv-epilogue fusion (as passed to ddpm_gn_bwd_apply). */
+int ddpm_gn_bwd_dparams(const float* sums, const float* stats, int n, int c, int groups, int hw, float eps,
+                        float* dgamma, float* dbeta, void* stream);
 /* out_nc[n][c] += sum_pix dx, out_c[c] += sum_{n,pix} dx when non-NULL (time-embedding / conv-bias gradients of the
  * layer that produced x, fused here instead of a separate pass over dx). */
 

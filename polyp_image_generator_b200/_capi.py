@@ -77,6 +77,7 @@ SIGNATURES = {
     "ddpm_softmax_rows_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _f, _vp],
     "ddpm_resize_h_u8": [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _i, _vp],
     "ddpm_resize_v_normalize": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp],
+    "ddpm_gn_bwd_dparams": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "ddpm_sumsq_f32": [_vp, _ll, _vp, _vp],
     "ddpm_adamw_flat": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _vp, _f, _f, _f, _f, _f, _vp],
     "ddpm_scheduler_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _vp],

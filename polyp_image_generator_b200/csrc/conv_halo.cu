@@ -42,6 +42,7 @@ struct HaloParams {
   uint32_t halo_bytes;   // R * Wp * 128
   uint32_t halo_stride;  // halo_bytes rounded up to 1024
   int b_stages;          // weight-tile ring depth
+  int mma_n;             // UMMA N: 128, or Cout rounded up to 16 for narrow outputs (conv_out: 3 -> 32 columns)
   EpiParams epi;
 };
 
@@ -137,7 +138,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 10) {
     // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues) ----------------
-    constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+    const uint32_t idesc = make_idesc_bf16(128, p.mma_n, false, false);
     const uint64_t db_base = make_smem_desc_sw128(smem_u32(bsm), 16, 1024);
     const uint32_t row_step = static_cast<uint32_t>(p.Wp) * 8u;     // one padded image row, in 16-byte descriptor units
     uint32_t bs = 0, bph = 0, hb = 0, hph = 0, acc = 0, aph = 0;
@@ -279,6 +280,7 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
   bst = env_int("DDPM_HALO_BSTAGES", bst) < bst ? env_int("DDPM_HALO_BSTAGES", bst) : bst;
   if (bst < 2) return 1;
   p.b_stages = bst;
+  p.mma_n = a->cout >= 128 ? 128 : ((a->cout + 15) / 16) * 16;   // narrow outputs: do not multiply the zero rows
   const size_t smem = fixed + static_cast<size_t>(bst) * kHaloBBytes;
   p.tiles_per_img = (H * Wp + kTileSlots - 1) / kTileSlots;
   p.n_tiles = (a->cout + 127) / 128;

@@ -872,6 +872,23 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
   return DDPM_OK;
 }
 
+// The dgamma / dbeta reductions on their own, so a caller can issue them off the critical path (another stream): call
+// ddpm_gn_bwd / ddpm_gn_bwd_apply with dgamma = dbeta = NULL, then this.  stats == NULL: `sums` are the centred sums
+// ddpm_gn_bwd leaves in its workspace; otherwise the raw moments of the conv-epilogue fusion.
+extern "C" int ddpm_gn_bwd_dparams(const float* sums, const float* stats, int n, int c, int groups, int hw, float eps,
+                                   float* dgamma, float* dbeta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DDPM_REQUIRE(sums && n > 0 && c > 0 && groups > 0 && c % groups == 0 && hw > 0, "ddpm_gn_bwd_dparams: bad argument");
+  if (!dgamma && !dbeta) return DDPM_OK;
+  if (stats == nullptr) {
+    gn_bwd_dparam_kernel<<<(c + 7) / 8, kGnThreads, 0, stream>>>(sums, n, c, dgamma, dbeta);
+    return check_launch("gn_bwd_dparam_kernel");
+  }
+  gn_bwd_dparam_raw_kernel<<<(c + 7) / 8, kGnThreads, 0, stream>>>(sums, stats, n, c, c / groups, groups, hw, eps,
+                                                                   dgamma, dbeta);
+  return check_launch("gn_bwd_dparam_raw_kernel");
+}
+
 extern "C" int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,
                                  int hw, int groups, const float* stats, float eps, const float* gamma, const void* dz,
                                  long long lddz, const float* sums, const void* add0, long long ldadd0,

@@ -328,8 +328,9 @@ class CudaOps:
         return stats, out
 
     def gn_bwd(self, x0, x1, groups: int, stats, eps: float, gamma, beta, silu: bool, dy, add0=None, add1=None,
-               dgamma=None, dbeta=None, need_dx1: bool = True):
-        """-> (dx0, dx1).  dgamma / dbeta are accumulated in place."""
+               dgamma=None, dbeta=None, need_dx1: bool = True, defer=None):
+        """-> (dx0, dx1).  dgamma / dbeta are accumulated in place.  defer(fn): run the parameter-gradient reduction
+        through fn on the caller's side stream instead of behind the main kernel."""
         n, h, w, c0, ld0 = _nhwc(x0, "x0")
         c1, ld1 = 0, 0
         if x1 is not None:
@@ -338,33 +339,46 @@ class CudaOps:
         dx0 = torch.empty((n, h, w, c0), device=x0.device, dtype=torch.bfloat16)
         dx1 = torch.empty((n, h, w, c1), device=x0.device, dtype=torch.bfloat16) if (c1 and need_dx1) else None
         ws = torch.empty(n * C_ * 2 + n, device=x0.device, dtype=torch.float32)
+        want_dp = dgamma is not None or dbeta is not None
+        dg_in, db_in = (None, None) if (defer is not None and want_dp) else (dgamma, dbeta)
         _capi.check(self.lib.ddpm_gn_bwd(
             _ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats), eps, _ptr(gamma), _ptr(beta),
             int(silu), _ptr(dy), _nhwc(dy, "dy")[4],
             _ptr(add0), _nhwc(add0, "add0")[4] if add0 is not None else 0,
             _ptr(add1), _nhwc(add1, "add1")[4] if add1 is not None else 0,
-            _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream()), "ddpm_gn_bwd")
-        self.launches += 2 if (dgamma is not None or dbeta is not None) else 1
+            _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dg_in), _ptr(db_in), _ptr(ws), _stream()), "ddpm_gn_bwd")
+        if defer is not None and want_dp:
+            defer(lambda: _capi.check(self.lib.ddpm_gn_bwd_dparams(_ptr(ws), None, n, C_, groups, h * w, eps,
+                                                                   _ptr(dgamma), _ptr(dbeta), _stream()),
+                                      "ddpm_gn_bwd_dparams"))
+        self.launches += 2 if want_dp else 1
         return dx0, dx1
 
     def gn_bwd_apply(self, x0, x1, groups: int, stats, eps: float, gamma, dz, sums, add0=None, add1=None,
-                     dgamma=None, dbeta=None, need_dx1: bool = True, out_nc=None, out_c=None):
+                     dgamma=None, dbeta=None, need_dx1: bool = True, out_nc=None, out_c=None, defer=None):
         """Second half of the GroupNorm backward (first half fused into conv_gemm(gn=...)) -> (dx0, dx1).
-        out_nc[n, c] / out_c[c] are INCREMENTED by the pixel sums of dx (the caller zero-fills out_nc)."""
+        out_nc[n, c] / out_c[c] are INCREMENTED by the pixel sums of dx (the caller zero-fills out_nc).
+        defer(fn): as in gn_bwd."""
         n, h, w, c0, ld0 = _nhwc(x0, "x0")
         c1, ld1 = 0, 0
         if x1 is not None:
             _, _, _, c1, ld1 = _nhwc(x1, "x1")
         dx0 = torch.empty((n, h, w, c0), device=x0.device, dtype=torch.bfloat16)
         dx1 = torch.empty((n, h, w, c1), device=x0.device, dtype=torch.bfloat16) if (c1 and need_dx1) else None
+        want_dp = dgamma is not None or dbeta is not None
+        dg_in, db_in = (None, None) if (defer is not None and want_dp) else (dgamma, dbeta)
         _capi.check(self.lib.ddpm_gn_bwd_apply(
             _ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats), eps, _ptr(gamma),
             _ptr(dz), _nhwc(dz, "dz")[4], _ptr(sums),
             _ptr(add0), _nhwc(add0, "add0")[4] if add0 is not None else 0,
             _ptr(add1), _nhwc(add1, "add1")[4] if add1 is not None else 0,
-            _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dgamma), _ptr(dbeta),
+            _ptr(dx0), c0, _ptr(dx1), c1, _ptr(dg_in), _ptr(db_in),
             _ptr(out_nc), out_nc.stride(0) if out_nc is not None else 0, _ptr(out_c), _stream()), "ddpm_gn_bwd_apply")
-        self.launches += 2 if (dgamma is not None or dbeta is not None) else 1
+        if defer is not None and want_dp:
+            defer(lambda: _capi.check(self.lib.ddpm_gn_bwd_dparams(_ptr(sums), _ptr(stats), n, c0 + c1, groups, h * w, eps,
+                                                                   _ptr(dgamma), _ptr(dbeta), _stream()),
+                                      "ddpm_gn_bwd_dparams"))
+        self.launches += 2 if want_dp else 1
         return dx0, dx1
 
     # ---- attention core ----------------------------------------------------------------------------------

@@ -813,7 +813,8 @@ class UNet2DModel(nn.Module):
         ted = self._temb_dim
         G = torch.zeros(P.total, device=self._arena.device, dtype=torch.float32)
         d_temb_all = torch.zeros((N, P.temb_total), device=G.device, dtype=torch.float32)
-        st = SimpleNamespace(ops=ops, G=G, d_temb_all=d_temb_all, skip_grads={}, N=N, wg_stream=None, keep=[])
+        st = SimpleNamespace(ops=ops, G=G, d_temb_all=d_temb_all, skip_grads={}, N=N, wg_stream=None, keep=[],
+                             defer_kw={})
         if G.is_cuda and os.environ.get("DDPM_WGRAD_STREAM", "1") != "0":
             # Weight gradients feed nothing downstream in backward, so they run on a second stream: the tensor-bound
             # wgrad GEMMs overlap the HBM-bound GroupNorm-backward kernels and the latency-bound low-resolution layers
@@ -821,6 +822,7 @@ class UNet2DModel(nn.Module):
             if self._wgrad_stream is None or self._wgrad_stream.device != G.device:
                 self._wgrad_stream = torch.cuda.Stream(device=G.device)
             st.wg_stream = self._wgrad_stream
+            st.defer_kw = {"defer": lambda fn: self._async_wgrad(st, fn)}     # GroupNorm dgamma / dbeta reductions too
         d_out = d_out.to(torch.float32).contiguous()
 
         # earliest tape step that still has trainable parameters at or before it (LoRA: stop early)
@@ -847,7 +849,7 @@ class UNet2DModel(nn.Module):
         tr = no.trainable
         g, _ = ops.gn_bwd(hd.h_last, None, no.groups, hd.stats, no.eps, gam, bet, True, d_a,
                           dgamma=self._gview(G, no.g_off, (c0,)) if tr else None,
-                          dbeta=self._gview(G, no.b_off, (c0,)) if tr else None)
+                          dbeta=self._gview(G, no.b_off, (c0,)) if tr else None, **st.defer_kw)
 
         prog = getattr(self, "_grad_progress_hook", None)
         for i in range(len(tape.steps) - 1, first_needed - 1, -1):
@@ -956,11 +958,12 @@ class UNet2DModel(nn.Module):
             d_h1, _ = ops.gn_bwd_apply(s.h1, None, r.norm2.groups, s.stats2, r.norm2.eps, g2, dz, sums,
                                        dgamma=dg, dbeta=dbt,
                                        out_nc=st.d_temb_all[:, r.temb_off:r.temb_off + r.cout],
-                                       out_c=self._wgrad_views(G, r.conv1)[1] if r.conv1.bias_trainable else None)
+                                       out_c=self._wgrad_views(G, r.conv1)[1] if r.conv1.bias_trainable else None,
+                                       **st.defer_kw)
         else:
             d_b = ops.conv_gemm(g, None, taps_3x3(r.cout), r.conv2.wd, r.cout, grid)
             d_h1, _ = ops.gn_bwd(s.h1, None, r.norm2.groups, s.stats2, r.norm2.eps, g2, be2, True, d_b, dgamma=dg,
-                                 dbeta=dbt)
+                                 dbeta=dbt, **st.defer_kw)
         # time embedding + conv1 bias share sum_hw(d_h1)
         dW1, db1 = self._wgrad_views(G, r.conv1)
         if not fuse:
@@ -986,10 +989,10 @@ class UNet2DModel(nn.Module):
         dg, dbt = self._norm_grads(G, r.norm1)
         if fuse:
             dx0, dx1 = ops.gn_bwd_apply(s.x0, s.x1, r.norm1.groups, s.stats1, r.norm1.eps, g1, d_a, sums1, add0=d_sc,
-                                        add1=extra, dgamma=dg, dbeta=dbt)
+                                        add1=extra, dgamma=dg, dbeta=dbt, **st.defer_kw)
         else:
             dx0, dx1 = ops.gn_bwd(s.x0, s.x1, r.norm1.groups, s.stats1, r.norm1.eps, g1, be1, True, d_a, add0=d_sc,
-                                  add1=extra, dgamma=dg, dbeta=dbt)
+                                  add1=extra, dgamma=dg, dbeta=dbt, **st.defer_kw)
         if s.x1 is not None:
             st.skip_grads[s.skip_idx] = dx1
         return dx0
@@ -1024,7 +1027,7 @@ class UNet2DModel(nn.Module):
         gam, bet = self._norm_params(at.norm)
         dg, dbt = self._norm_grads(G, at.norm)
         dx, _ = ops.gn_bwd(s.x, None, at.norm.groups, s.stats, at.norm.eps, gam, bet, False, d_xn.view(N, H, W, C),
-                           add0=g, add1=extra, dgamma=dg, dbeta=dbt)
+                           add0=g, add1=extra, dgamma=dg, dbeta=dbt, **st.defer_kw)
         return dx
 
     def _down_bwd(self, st, d, s, g):
