@@ -405,8 +405,7 @@ def run_b200(args, rank, world, local_rank):
     all_tf = sum(prof["flops"].values()) / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0
     ops.conv_wgrad = orig_conv_wgrad
     step = eager_step
-    if not args.breakdown:
-        os.environ.pop("DDPM_WGRAD_STREAM", None)
+    os.environ.pop("DDPM_WGRAD_STREAM", None)
 
     # ---- secondary metric: reverse-diffusion sampling (BASELINE configs[2]: 256 images over 8 GPUs = 32 / GPU) ----
     sampling = None
@@ -451,6 +450,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- optional per-op breakdown (after the timed regions; CUDA events around every C-ABI op) ----
     if args.breakdown and rank == 0:
+        os.environ["DDPM_WGRAD_STREAM"] = "0"       # per-op events: one stream
         ops.conv_gemm = orig_conv_gemm
         for _ in range(2):
             step(clean_dev, noise_dev, t_dev)
