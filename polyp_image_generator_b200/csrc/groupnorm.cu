@@ -825,7 +825,12 @@ extern "C" int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1
   void* args[] = {&s, &t, &stats, &ws, &gamma, &beta, &yp, &ldy, &coef};
   const void* fn = silu ? reinterpret_cast<const void*>(gn_fwd_fused_kernel<true>)
                         : reinterpret_cast<const void*>(gn_fwd_fused_kernel<false>);
-  DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, stream));
+  // co-residency (cooperative launch) is only needed when CTAs of a team wait for each other; a solo-CTA launch is an
+  // ordinary kernel node, which a captured step can overlap with its neighbours
+  if (t.team_size > 1)
+    DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, stream));
+  else
+    DDPM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, 0, stream));
   return check_launch("gn_fwd_fused_kernel");
 }
 
@@ -863,7 +868,10 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
   void* args[] = {&s, &t, &stats, &gamma, &beta, &dyp, &lddy, &sums, &counters, &o};
   const void* fn = silu ? reinterpret_cast<const void*>(gn_bwd_fused_kernel<true>)
                         : reinterpret_cast<const void*>(gn_bwd_fused_kernel<false>);
-  DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, stream));
+  if (t.team_size > 1)
+    DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, stream));
+  else
+    DDPM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, stream));
   if (int e = check_launch("gn_bwd_fused_kernel")) return e;
   if (dgamma || dbeta) {
     gn_bwd_dparam_kernel<<<(C + 7) / 8, kGnThreads, 0, stream>>>(sums, n, C, dgamma, dbeta);
