@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 #define DDPM_MAX_TAPS 9
-#define DDPM_ABI_VERSION 1
+#define DDPM_ABI_VERSION 2
 
 const char* ddpm_last_error(void);
 int ddpm_abi_version(void);
@@ -110,6 +110,10 @@ typedef struct ddpm_conv_args {
   const float* gn_coef;
   int gn_silu;
   float* gn_sums;
+  /* Optional statistics of the GroupNorm that CONSUMES this output: out_csum[n][co][0..1] += (sum out, sum out^2) over
+   * the sample's pixels, of the bf16 values actually stored (zero-filled by the caller; same h*w rule as gn_sums;
+   * excludes gn_sums / out_f32).  ddpm_gn_stats_from_csum + ddpm_gn_apply then replace the two-phase ddpm_gn_fwd. */
+  float* out_csum;
   /* Optional split-K workspace (fp32, caller-owned): low-resolution layers whose tile grid covers less than half the
    * SMs split the reduction over blockIdx.z, accumulate fp32 partial sums here and finish in a second pass.
    * ddpm_conv_gemm_workspace_elems() says how many elements this problem would use (0 = it does not split). */
@@ -160,10 +164,16 @@ int ddpm_nhwc_to_nchw_f32(const float* src, long long ld, float* out, int n, int
 /* GroupNorm statistics: stats[n][g] = (sum, sumsq) over the (possibly concatenated) channels of group g. */
 int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                   int groups, float* stats, void* stream);
-/* y = act(GroupNorm(x)) with act = SiLU (silu=1) or identity; y bf16 NHWC contiguous over c0+c1 channels. */
+/* y = act(GroupNorm(x)) with act = SiLU (silu=1) or identity; y bf16 NHWC contiguous over c0+c1 channels.
+ * coef (may be NULL): per-(sample, channel) affine table [n][(c0+c1)/2][4] for the gn_sums fusion of ddpm_conv_gemm. */
 int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                   int groups, const float* stats, float eps, const float* gamma, const float* beta, int silu,
-                  void* y, long long ldy, void* stream);
+                  void* y, long long ldy, float* coef, void* stream);
+/* stats (as ddpm_gn_stats) from the per-(sample, channel) moments accumulated by the producing conv epilogues
+ * (ddpm_conv_args.out_csum), for an input that may be the concat of two tensors: with it the GroupNorm forward is ONE
+ * streaming pass (ddpm_gn_apply, 4 B/elem) instead of the two-phase ddpm_gn_fwd. */
+int ddpm_gn_stats_from_csum(const float* csum0, int c0, const float* csum1, int c1, int n, int groups, float* stats,
+                            void* stream);
 /* Fused GroupNorm forward: stats (as ddpm_gn_stats) AND y = act(GroupNorm(x)) in one persistent, cooperatively
  * launched kernel whose second phase re-reads x from L2.  ws: n ints (team barrier counters). */
 int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,

@@ -12,7 +12,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libddpm_b200.so"
 
 MAX_TAPS = 9
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _ll = C.c_longlong
 _vp = C.c_void_p
@@ -39,6 +39,7 @@ class ConvArgs(C.Structure):
         ("gn_coef", _vp),
         ("gn_silu", _i),
         ("gn_sums", _vp),
+        ("out_csum", _vp),
         ("splitk_ws", _vp), ("splitk_ws_elems", _ll),
     ]
 
@@ -92,7 +93,8 @@ SIGNATURES = {
     "ddpm_im2col3": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "ddpm_nhwc_to_nchw_f32": [_vp, _ll, _vp, _i, _i, _i, _i, _vp],
     "ddpm_gn_stats": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _vp],
-    "ddpm_gn_apply": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp],
+    "ddpm_gn_apply": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp, _vp],
+    "ddpm_gn_stats_from_csum": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
     "ddpm_gn_fwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp, _vp],
     "ddpm_gn_bwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp, _ll, _vp, _ll,
                     _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp],

@@ -30,8 +30,10 @@ struct EpiParams {
   long long gld0, gld1;
   int gc0;
   const float* gcoef;         // [N][Cout/2][4] = (ka0, ka1, kb0, kb1): z = x*ka + kb  (written by ddpm_gn_fwd)
-  float* gsums;               // [N][Cout][2] += (sum dz, sum dz*x)
+  float* gsums;               // [N][Cout][2] += (sum dz, sum dz*x)   (gstats: += (sum out, sum out^2))
   int gsilu;
+  int gstats;                 // 1: gsums receives the per-(sample, channel) moments of the STORED output -- the
+                              // statistics of the GroupNorm that consumes this tensor (no gx / gcoef involved)
   int wide;                   // every pointer / stride above allows 32-byte (256-bit) row accesses
 };
 
@@ -100,7 +102,7 @@ struct EpiX {
 // Issue the loads of the GroupNorm input for (pix, col .. col+31) -- call this EARLY (before waiting on the
 // accumulator / while the previous chunk is processed) so the latency is off the critical path.
 __device__ __forceinline__ void epi_load_x(const EpiParams& e, bool valid, long long pix, int col, EpiX& x) {
-  if (e.gsums != nullptr && valid && col < e.Cout) {
+  if (e.gsums != nullptr && !e.gstats && valid && col < e.Cout) {
     const __nv_bfloat16* xp = (col < e.gc0) ? e.gx0 + pix * e.gld0 + col : e.gx1 + pix * e.gld1 + (col - e.gc0);
     ld64B(xp, x.w, e.wide != 0);
   } else {
@@ -144,7 +146,18 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
       }
     }
   }
-  if (GN && e.gsums != nullptr) {
+  if (GN && e.gsums != nullptr && e.gstats) {
+    // ---- statistics of the consuming GroupNorm: moments of the bf16 values that are stored below ----
+    float s1[32], s2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float r = (valid && col_ok) ? __bfloat162float(__float2bfloat16(v[j])) : 0.f;
+      s1[j] = r;
+      s2[j] = r * r;
+    }
+    t1 += warp_column_sums(s1, lane);
+    t2 += warp_column_sums(s2, lane);
+  } else if (GN && e.gsums != nullptr) {
     // ---- GroupNorm backward, part 1 (warp-collective; packed fp32x2 math) ----
     float s2[32];
     if (valid && col_ok) {

@@ -570,6 +570,12 @@ int fill_epilogue(EpiParams* e, const ::ddpm_conv_args* a) {
     e->gsums = a->gn_sums;
     e->gsilu = a->gn_silu;
   }
+  if (a->out_csum != nullptr) {
+    DDPM_REQUIRE(a->gn_sums == nullptr && a->out_f32 == nullptr,
+                 "ddpm_conv_gemm: out_csum excludes gn_sums and fp32 output");
+    e->gsums = a->out_csum;
+    e->gstats = 1;
+  }
   auto ok32 = [](const void* ptr, long long ld_elems) {
     return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && (ld_elems * 2) % 32 == 0);
   };
@@ -812,7 +818,7 @@ extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream_) {
 
 extern "C" long long ddpm_conv_gemm_workspace_elems(const ddpm_conv_args* a) {
   // fp32 elements of split-K workspace ddpm_conv_gemm would use for this problem (0: no split)
-  if (!a || a->out_f32 || a->gn_sums || a->cout % 8) return 0;
+  if (!a || a->out_f32 || a->gn_sums || a->out_csum || a->cout % 8) return 0;
   if (a->ntaps == 9 && a->w >= env_int("DDPM_HALO_MIN_W", 64)) return 0;      // halo-resident kernel
   int wb, hb, nb;
   choose_box(a->n, a->h, a->w, &wb, &hb, &nb);

@@ -223,7 +223,7 @@ template <bool SILU>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                long long ldy, int pix_per_block, int V) {
+                long long ldy, int pix_per_block, int V, float* __restrict__ coef /*[N][C/2][4] or NULL*/) {
   const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
   const int n = blockIdx.y;
   const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
@@ -235,7 +235,32 @@ gn_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ 
   __nv_bfloat16* yp = y + static_cast<long long>(n) * hw * ldy + c;
   f2x4 ka, kb;
   gn_apply_coefs(stats + static_cast<long long>(n) * groups * 2, c, cpg, inv_m, eps, gamma, beta, false, &ka, &kb);
+  if (coef != nullptr && blockIdx.x == 0 && pl == 0) {     // affine table for the GroupNorm-backward conv fusion
+    float4* cp = reinterpret_cast<float4*>(coef) + (static_cast<long long>(n) * V * 8 + c) / 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cp[j] = make_float4(ka.p[j].x, ka.p[j].y, kb.p[j].x, kb.p[j].y);
+  }
   gn_apply_stream<SILU>(xp, ld, yp, ldy, p_begin + pl, p_end, ppb, ka, kb);
+}
+
+// stats[n][g] = (sum, sum of squares) over the group's channels of the per-(sample, channel) moments that the producing
+// conv epilogues accumulated (ddpm_conv_args.out_csum); the input may be a channel concat of two tensors
+__global__ void __launch_bounds__(256)
+gn_stats_from_csum_kernel(const float* __restrict__ cs0, int c0, const float* __restrict__ cs1, int c1, int n, int groups,
+                          float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * groups) return;
+  const int b = i / groups, g = i - b * groups;
+  const int cpg = (c0 + c1) / groups;
+  float a = 0.f, q = 0.f;
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    const float2 m = c < c0 ? *reinterpret_cast<const float2*>(cs0 + (static_cast<long long>(b) * c0 + c) * 2)
+                            : *reinterpret_cast<const float2*>(cs1 + (static_cast<long long>(b) * c1 + (c - c0)) * 2);
+    a += m.x;
+    q += m.y;
+  }
+  stats[i * 2] = a;
+  stats[i * 2 + 1] = q;
 }
 
 // =====================================================================================================
@@ -782,7 +807,7 @@ extern "C" int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* 
 
 extern "C" int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,
                              int hw, int groups, const float* stats, float eps, const float* gamma,
-                             const float* beta, int silu, void* y, long long ldy, void* stream_) {
+                             const float* beta, int silu, void* y, long long ldy, float* coef, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int e = gn_check(x0, c0, ld0, x1, c1, ld1, n, hw, groups, "ddpm_gn_apply")) return e;
   DDPM_REQUIRE(stats && gamma && beta && y && ldy % 8 == 0, "ddpm_gn_apply: bad argument");
@@ -793,11 +818,21 @@ extern "C" int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* 
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   if (silu)
     gn_apply_kernel<true><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma, beta,
-                                                                   yp, ldy, ppblk, V);
+                                                                   yp, ldy, ppblk, V, coef);
   else
     gn_apply_kernel<false><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma, beta,
-                                                                    yp, ldy, ppblk, V);
+                                                                    yp, ldy, ppblk, V, coef);
   return check_launch("gn_apply_kernel");
+}
+
+extern "C" int ddpm_gn_stats_from_csum(const float* csum0, int c0, const float* csum1, int c1, int n, int groups,
+                                       float* stats, void* stream) {
+  DDPM_REQUIRE(csum0 && stats && n > 0 && c0 > 0 && c1 >= 0 && (c1 == 0 || csum1) && groups > 0 &&
+                   (c0 + c1) % groups == 0,
+               "ddpm_gn_stats_from_csum: bad argument (c0=%d c1=%d groups=%d)", c0, c1, groups);
+  gn_stats_from_csum_kernel<<<(n * groups + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(csum0, c0, csum1, c1,
+                                                                                                     n, groups, stats);
+  return check_launch("gn_stats_from_csum_kernel");
 }
 
 extern "C" int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,

@@ -160,11 +160,22 @@ class CudaOps:
         hw = grid[1] * grid[2]
         return hw >= 4096
 
+    @staticmethod
+    def gn_stats_fusable(grid: Tuple[int, int, int]) -> bool:
+        """Should the conv that PRODUCES a tensor over this grid also reduce the per-(sample, channel) moments its
+        consuming GroupNorm needs (conv_gemm(csum=...))?  Same geometric rule and the same pay-off region as
+        gn_bwd_fusable: at >= 64x64 the GroupNorm forward is HBM-bound and drops from the two-phase team kernel
+        (0.139 ms at 128^2 x 128, 59 % of the copy peak) to one streaming pass (0.102 ms, 81 %)."""
+        hw = grid[1] * grid[2]
+        return hw >= 4096
+
     def conv_gemm(self, x0, x1, taps: Sequence[Tap], wgt, cout: int, grid: Tuple[int, int, int], bias=None,
-                  temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0, gn=None):
+                  temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0, gn=None, csum=None):
         """out[n,h,w,co] = bias + temb[n] + res + sum_taps X[pix+tap] . wgt[co, wk:wk+cin]; see ddpm_conv_gemm.
         gn = (x0, x1, coef, silu, sums) with coef from gn_fwd(want_coef=True): fuse the first half of the backward of
-        y = act(GroupNorm(x0|x1)) into the epilogue (out becomes dz, sums[n, c] += (sum dz, sum dz*x))."""
+        y = act(GroupNorm(x0|x1)) into the epilogue (out becomes dz, sums[n, c] += (sum dz, sum dz*x)).
+        csum [n, cout, 2] fp32 (zero-filled): += (sum out, sum out^2) per (sample, channel) -- the statistics of the
+        GroupNorm that consumes `out`, so that its forward is one streaming pass (gn_fwd_from_csum)."""
         n, h, w = grid
         _, _, _, c0, ld0 = _nhwc(x0, "x0")
         a = _capi.ConvArgs()
@@ -202,6 +213,12 @@ class CudaOps:
             if gsums.dtype != torch.float32 or not gsums.is_contiguous() or gsums.numel() != n * cout * 2:
                 raise ValueError("gn sums must be a contiguous fp32 [n, cout, 2] tensor")
             a.gn_sums = _ptr(gsums)
+        if csum is not None:
+            if gn is not None or out_f32:
+                raise ValueError("csum excludes the GroupNorm-backward fusion and fp32 output")
+            if csum.dtype != torch.float32 or not csum.is_contiguous() or csum.numel() != n * cout * 2:
+                raise ValueError("csum must be a contiguous fp32 [n, cout, 2] tensor")
+            a.out_csum = _ptr(csum)
         ws_elems = self.lib.ddpm_conv_gemm_workspace_elems(C.byref(a)) if gn is None and not out_f32 else 0
         if ws_elems > 0:      # low-resolution layer: split-K over idle SMs, fp32 partial sums in a workspace
             ws = torch.empty(ws_elems, device=x0.device, dtype=torch.float32)
@@ -294,7 +311,21 @@ class CudaOps:
         self.launches += 2
         return stats
 
-    def gn_apply(self, x0, x1, groups: int, stats, eps: float, gamma, beta, silu: bool, out=None):
+    def gn_fwd_from_csum(self, x0, x1, cs0, cs1, groups: int, eps: float, gamma, beta, silu: bool,
+                         want_coef: bool = False):
+        """GroupNorm forward whose statistics were already reduced by the producing convs (conv_gemm(csum=...)):
+        channel moments -> group stats (tiny kernel), then ONE streaming normalise pass.  Same returns as gn_fwd."""
+        n, h, w, c0, _ = _nhwc(x0, "x0")
+        c1 = x1.shape[-1] if x1 is not None else 0
+        stats = torch.empty((n, groups, 2), device=x0.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_gn_stats_from_csum(_ptr(cs0), c0, _ptr(cs1), c1, n, groups, _ptr(stats), _stream()),
+                    "ddpm_gn_stats_from_csum")
+        self.launches += 1
+        coef = torch.empty((n, (c0 + c1) // 2, 4), device=x0.device, dtype=torch.float32) if want_coef else None
+        out = self.gn_apply(x0, x1, groups, stats, eps, gamma, beta, silu, coef=coef)
+        return (stats, out, coef) if want_coef else (stats, out)
+
+    def gn_apply(self, x0, x1, groups: int, stats, eps: float, gamma, beta, silu: bool, out=None, coef=None):
         n, h, w, c0, ld0 = _nhwc(x0, "x0")
         c1, ld1 = 0, 0
         if x1 is not None:
@@ -303,7 +334,7 @@ class CudaOps:
             out = torch.empty((n, h, w, c0 + c1), device=x0.device, dtype=torch.bfloat16)
         _capi.check(self.lib.ddpm_gn_apply(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats), eps,
                                            _ptr(gamma), _ptr(beta), int(silu), _ptr(out), _nhwc(out, "out")[4],
-                                           _stream()), "ddpm_gn_apply")
+                                           _ptr(coef), _stream()), "ddpm_gn_apply")
         self.launches += 1
         return out
 

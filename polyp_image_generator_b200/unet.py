@@ -671,7 +671,9 @@ class UNet2DModel(nn.Module):
 
         # ---- conv_in ----
         patches = ops.im2col3(x)                                   # [N, H, W, 64] bf16, one k-block
-        h = ops.conv_gemm(patches, None, taps_1x1(), self._cin_wf, c0, (N, H, W), bias=self._aview(P.cin_b, (c0,)))
+        cs = self._csum_for(st, (N, H, W), c0)
+        h = self._tag(ops.conv_gemm(patches, None, taps_1x1(), self._cin_wf, c0, (N, H, W),
+                                    bias=self._aview(P.cin_b, (c0,)), csum=cs), cs)
         skips = [h]
 
         # ---- down ----
@@ -701,7 +703,7 @@ class UNet2DModel(nn.Module):
         # ---- out ----
         no = P.norm_out
         gam, bet = self._aview(no.g_off, (c0,)), self._aview(no.b_off, (c0,))
-        stats, a = ops.gn_fwd(h, None, no.groups, no.eps, gam, bet, True)
+        stats, a = self._gn_fwd(st, h, None, no.groups, no.eps, gam, bet, True)
         o32 = ops.conv_gemm(a, None, taps_3x3(c0), self._cout_wf, 32, (N, H, W), bias=self._cout_b32, out_f32=True)
         out = ops.nhwc_to_nchw_f32(o32, cfg.out_channels)
         if training:
@@ -714,6 +716,30 @@ class UNet2DModel(nn.Module):
         c = nobj.mod.num_channels
         return self._aview(nobj.g_off, (c,)), self._aview(nobj.b_off, (c,))
 
+    # GroupNorm statistics ride on the epilogue of the conv that PRODUCES the tensor (per-(sample, channel) moments,
+    # conv_gemm(csum=...)); the GroupNorm forward is then one streaming pass instead of the two-phase team kernel.
+    @staticmethod
+    def _csum_for(st, grid, cout):
+        ops = st.ops
+        if os.environ.get("DDPM_GN_STATS_FUSION", "1") == "0" or not ops.gn_stats_fusable(grid):
+            return None
+        return torch.zeros((grid[0], cout, 2), device=st.temb_all.device, dtype=torch.float32)
+
+    @staticmethod
+    def _tag(t, csum):
+        if csum is not None:
+            t._ddpm_csum = csum
+        return t
+
+    @staticmethod
+    def _gn_fwd(st, x0, x1, groups, eps, gam, bet, silu, want_coef=False):
+        ops = st.ops
+        cs0 = getattr(x0, "_ddpm_csum", None)
+        cs1 = getattr(x1, "_ddpm_csum", None) if x1 is not None else None
+        if cs0 is not None and (x1 is None or cs1 is not None):
+            return ops.gn_fwd_from_csum(x0, x1, cs0, cs1, groups, eps, gam, bet, silu, want_coef=want_coef)
+        return ops.gn_fwd(x0, x1, groups, eps, gam, bet, silu, want_coef=want_coef)
+
     def _resnet_fwd(self, st, r, x0, x1, in_skip=None, skip_idx=None):
         ops = st.ops
         N, H, W, _ = x0.shape
@@ -723,20 +749,24 @@ class UNet2DModel(nn.Module):
         fuse = st.tape is not None and ops.gn_bwd_fusable(grid)   # backward runs its first GN half in the dgrad epilogue
         coef1 = coef2 = None
         if fuse:
-            stats1, a, coef1 = ops.gn_fwd(x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True, want_coef=True)
+            stats1, a, coef1 = self._gn_fwd(st, x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True, want_coef=True)
         else:
-            stats1, a = ops.gn_fwd(x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True)
+            stats1, a = self._gn_fwd(st, x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True)
         temb = st.temb_all[:, r.temb_off:r.temb_off + r.cout]
-        h1 = ops.conv_gemm(a, None, taps_3x3(r.cin), r.conv1.wf, r.cout, grid, bias=self._bias(r.conv1), temb=temb)
+        cs = self._csum_for(st, grid, r.cout)
+        h1 = self._tag(ops.conv_gemm(a, None, taps_3x3(r.cin), r.conv1.wf, r.cout, grid, bias=self._bias(r.conv1),
+                                     temb=temb, csum=cs), cs)
         if fuse:
-            stats2, b, coef2 = ops.gn_fwd(h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True, want_coef=True)
+            stats2, b, coef2 = self._gn_fwd(st, h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True, want_coef=True)
         else:
-            stats2, b = ops.gn_fwd(h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True)
+            stats2, b = self._gn_fwd(st, h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True)
         if r.short is not None:
             sc = ops.conv_gemm(x0, x1, taps_1x1(), r.short.wf, r.cout, grid, bias=self._bias(r.short))
         else:
             sc = x0
-        out = ops.conv_gemm(b, None, taps_3x3(r.cout), r.conv2.wf, r.cout, grid, bias=self._bias(r.conv2), res=sc)
+        cs = self._csum_for(st, grid, r.cout)
+        out = self._tag(ops.conv_gemm(b, None, taps_3x3(r.cout), r.conv2.wf, r.cout, grid, bias=self._bias(r.conv2),
+                                      res=sc, csum=cs), cs)
         if st.tape is not None:
             st.tape.add(("resnet", r, SimpleNamespace(x0=x0, x1=x1, stats1=stats1, a=a, h1=h1, stats2=stats2, b=b,
                                                        in_skip=in_skip, skip_idx=skip_idx, grid=grid, coef1=coef1,
@@ -774,7 +804,9 @@ class UNet2DModel(nn.Module):
         N, H, W, C = x.shape
         s2d = ops.space_to_depth(x)
         grid = (N, H // 2, W // 2)
-        out = ops.conv_gemm(s2d, None, taps_s2d(C, N, d.pad), d.conv.wf, C, grid, bias=self._bias(d.conv), src_n=4 * N)
+        cs = self._csum_for(st, grid, C)
+        out = self._tag(ops.conv_gemm(s2d, None, taps_s2d(C, N, d.pad), d.conv.wf, C, grid, bias=self._bias(d.conv),
+                                      src_n=4 * N, csum=cs), cs)
         if st.tape is not None:
             st.tape.add(("down", d, SimpleNamespace(s2d=s2d, in_skip=in_skip, shape=(N, H, W, C), grid=grid)))
         return out
@@ -783,7 +815,9 @@ class UNet2DModel(nn.Module):
         ops = st.ops
         N, H, W, C = x.shape
         up = ops.upsample2x(x)
-        out = ops.conv_gemm(up, None, taps_3x3(C), u.conv.wf, C, (N, 2 * H, 2 * W), bias=self._bias(u.conv))
+        cs = self._csum_for(st, (N, 2 * H, 2 * W), C)
+        out = self._tag(ops.conv_gemm(up, None, taps_3x3(C), u.conv.wf, C, (N, 2 * H, 2 * W), bias=self._bias(u.conv),
+                                      csum=cs), cs)
         if st.tape is not None:
             st.tape.add(("up", u, SimpleNamespace(up=up, grid=(N, 2 * H, 2 * W))))
         return out

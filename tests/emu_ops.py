@@ -103,8 +103,25 @@ class EmuOps:
         hw = grid[1] * grid[2]
         return hw >= 128 or hw % 32 == 0      # the CPU emulation exercises the fused path wherever it is POSSIBLE
 
+    @staticmethod
+    def gn_stats_fusable(grid):
+        hw = grid[1] * grid[2]
+        return hw >= 128 or hw % 32 == 0      # exercised wherever it is POSSIBLE
+
+    def gn_fwd_from_csum(self, x0, x1, cs0, cs1, groups, eps, gamma, beta, silu, want_coef=False):
+        cs = cs0 if cs1 is None else torch.cat([cs0, cs1], 1)          # [n, C, 2]
+        n, C, _ = cs.shape
+        stats = cs.reshape(n, groups, C // groups, 2).sum(2)
+        # the fused statistics must agree with a direct reduction over the tensor itself
+        X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
+        want = torch.stack([X.reshape(n, -1, groups, C // groups).sum((1, 3)),
+                            (X ** 2).reshape(n, -1, groups, C // groups).sum((1, 3))], -1)
+        assert torch.allclose(stats, want, rtol=1e-4, atol=1e-3), "conv-epilogue statistics disagree with the tensor"
+        r = self.gn_fwd(x0, x1, groups, eps, gamma, beta, silu, want_coef=want_coef)
+        return r
+
     def conv_gemm(self, x0, x1, taps, wgt, cout, grid, bias=None, temb=None, res=None, out=None, out_f32=False,
-                  src_n=0, gn=None):
+                  src_n=0, gn=None, csum=None):
         n, h, w = grid
         X = x0 if x1 is None else torch.cat([x0, x1], -1)
         X = X.float()
@@ -134,6 +151,10 @@ class EmuOps:
             gsums[..., 0] += dzr.sum((1, 2))
             gsums[..., 1] += (dzr * Xg).sum((1, 2))
         r = acc if out_f32 else self._a(acc)
+        if csum is not None:
+            rf = r.float()
+            csum[..., 0] += rf.sum((1, 2))
+            csum[..., 1] += (rf * rf).sum((1, 2))
         if out is not None:
             out.copy_(r)
             return out

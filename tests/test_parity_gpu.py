@@ -333,6 +333,45 @@ def test_wide_head_attention_vs_sdpa(dev, b, t, heads, d):
         assert rel(dqkv[:, i * C:(i + 1) * C], ref.grad[:, i * C:(i + 1) * C]) < 1.5e-2, name
 
 
+@pytest.mark.parametrize("hw,cin,cout,k3,c1", [(64, 128, 128, True, 0), (64, 128, 256, False, 0), (32, 256, 256, True, 0),
+                                               (128, 128, 128, True, 64), (16, 128, 128, True, 0)])
+def test_conv_epilogue_statistics_and_single_pass_groupnorm(dev, hw, cin, cout, k3, c1):
+    """conv_gemm(csum=...): the producing conv reduces the per-(sample, channel) moments of its stored output (halo and
+    generic kernels); gn_fwd_from_csum then equals the two-phase gn_fwd (stats, y and the backward coef table)."""
+    from polyp_image_generator_b200 import ops as ops_mod
+    from polyp_image_generator_b200.ops import taps_1x1, taps_3x3
+    o = ops_mod.get()
+    torch.manual_seed(hw + cout)
+    n = 3
+    x0 = (torch.randn(n, hw, hw, cin - c1, device=dev) * 0.5).to(torch.bfloat16)
+    x1 = (torch.randn(n, hw, hw, c1, device=dev) * 0.5).to(torch.bfloat16) if c1 else None
+    taps = taps_3x3(cin) if k3 else taps_1x1()
+    w = (torch.randn(cout, len(taps) * cin, device=dev) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(cout, device=dev)
+    res = (torch.randn(n, hw, hw, cout, device=dev)).to(torch.bfloat16)
+    cs = torch.zeros(n, cout, 2, device=dev)
+    y = o.conv_gemm(x0, x1, taps, w, cout, (n, hw, hw), bias=bias, res=res, csum=cs)
+    y_plain = o.conv_gemm(x0, x1, taps, w, cout, (n, hw, hw), bias=bias, res=res)
+    # the statistics do not disturb the output (not bit-equal: the plain launch may take the split-K path, which
+    # accumulates in another order)
+    assert rel(y, y_plain) < 4e-3
+    yf = y.float()
+    want = torch.stack([yf.sum((1, 2)), (yf * yf).sum((1, 2))], -1)
+    assert rel(cs, want) < 1e-5
+    gam, bet = torch.randn(cout, device=dev), torch.randn(cout, device=dev)
+    st_a, ya, co_a = o.gn_fwd(y, None, 32, 1e-5, gam, bet, True, want_coef=True)
+    st_b, yb, co_b = o.gn_fwd_from_csum(y, None, cs, None, 32, 1e-5, gam, bet, True, want_coef=True)
+    assert rel(st_b, st_a) < 1e-5 and rel(co_b, co_a) < 1e-4
+    assert rel(yb, ya) < 4e-3                                          # bf16 outputs, fp32 statistics from two orders
+    # concat of two tensors whose statistics came from two different producers
+    cs2 = torch.zeros(n, cout, 2, device=dev)
+    y2 = o.conv_gemm(x0, x1, taps, w, cout, (n, hw, hw), csum=cs2)
+    g2, b2 = torch.randn(2 * cout, device=dev), torch.randn(2 * cout, device=dev)
+    st_c, yc = o.gn_fwd(y, y2, 32, 1e-6, g2, b2, False)
+    st_d, yd = o.gn_fwd_from_csum(y, y2, cs, cs2, 32, 1e-6, g2, b2, False)
+    assert rel(st_d, st_c) < 1e-5 and rel(yd, yc) < 4e-3
+
+
 def test_fused_adamw_vs_torch_adamw(dev):
     """clip_grad_norm_(1.0) + AdamW.step() (train_from_scratch.py:106-108) as two streaming kernels over the flat
     arena, against torch's own clip + AdamW on identical gradients: fp32, <= 1e-6 relative to the update size."""
