@@ -703,11 +703,16 @@ class UNet2DModel(nn.Module):
         # ---- out ----
         no = P.norm_out
         gam, bet = self._aview(no.g_off, (c0,)), self._aview(no.b_off, (c0,))
-        stats, a = self._gn_fwd(st, h, None, no.groups, no.eps, gam, bet, True)
+        coef_out = None
+        if training and ops.gn_bwd_fusable((N, H, W)):
+            stats, a, coef_out = self._gn_fwd(st, h, None, no.groups, no.eps, gam, bet, True, want_coef=True)
+        else:
+            stats, a = self._gn_fwd(st, h, None, no.groups, no.eps, gam, bet, True)
         o32 = ops.conv_gemm(a, None, taps_3x3(c0), self._cout_wf, 32, (N, H, W), bias=self._cout_b32, out_f32=True)
         out = ops.nhwc_to_nchw_f32(o32, cfg.out_channels)
         if training:
-            tape.head = SimpleNamespace(patches=patches, t_emb=t_emb, e1=e1, emb=emb, h_last=h, stats=stats, a=a)
+            tape.head = SimpleNamespace(patches=patches, t_emb=t_emb, e1=e1, emb=emb, h_last=h, stats=stats, a=a,
+                                        coef=coef_out)
         self.last_launches = ops.launches - l0
         return out
 
@@ -878,12 +883,19 @@ class UNet2DModel(nn.Module):
             R = torch.zeros((c0, 64), device=G.device, dtype=torch.float32)
             ops.conv_wgrad(hd.a, pd, None, taps_1x1(), R, grid0)
             self._gview(G, P.cout_w, (co, 9, c0)).add_(R[:, :9 * co].view(c0, 9, co).flip(1).permute(2, 1, 0))
-        d_a = ops.conv_gemm(pd, None, taps_1x1(), self._cout_wd, c0, grid0)
         gam, bet = self._norm_params(no)
         tr = no.trainable
-        g, _ = ops.gn_bwd(hd.h_last, None, no.groups, hd.stats, no.eps, gam, bet, True, d_a,
-                          dgamma=self._gview(G, no.g_off, (c0,)) if tr else None,
-                          dbeta=self._gview(G, no.b_off, (c0,)) if tr else None, **st.defer_kw)
+        dg_o = self._gview(G, no.g_off, (c0,)) if tr else None
+        db_o = self._gview(G, no.b_off, (c0,)) if tr else None
+        if hd.coef is not None:    # SiLU / GroupNorm derivative + per-(n, c) sums in the dgrad epilogue, one streaming pass
+            sums = torch.zeros((grid0[0], c0, 2), device=G.device, dtype=torch.float32)
+            dz = ops.conv_gemm(pd, None, taps_1x1(), self._cout_wd, c0, grid0, gn=(hd.h_last, None, hd.coef, True, sums))
+            g, _ = ops.gn_bwd_apply(hd.h_last, None, no.groups, hd.stats, no.eps, gam, dz, sums, dgamma=dg_o, dbeta=db_o,
+                                    **st.defer_kw)
+        else:
+            d_a = ops.conv_gemm(pd, None, taps_1x1(), self._cout_wd, c0, grid0)
+            g, _ = ops.gn_bwd(hd.h_last, None, no.groups, hd.stats, no.eps, gam, bet, True, d_a, dgamma=dg_o,
+                              dbeta=db_o, **st.defer_kw)
 
         prog = getattr(self, "_grad_progress_hook", None)
         for i in range(len(tape.steps) - 1, first_needed - 1, -1):
@@ -906,6 +918,8 @@ class UNet2DModel(nn.Module):
                 R = torch.zeros((c0, 64), device=G.device, dtype=torch.float32)
                 ops.conv_wgrad(g, hd.patches, None, taps_1x1(), R, tuple(g.shape[:3]))
                 self._gview(G, P.cin_w, (c0, 9 * cfg.in_channels)).add_(R[:, :9 * cfg.in_channels])
+        if st.wg_stream is not None:      # d_temb_all and every weight gradient are complete from here on
+            torch.cuda.current_stream().wait_stream(st.wg_stream)
         # ---- time-embedding MLP ----
         if self._temb_trainable() or self.time_embedding.linear_1.weight.requires_grad:
             wt = self._aview(P.temb_w_off, (P.temb_total, ted))
@@ -920,8 +934,6 @@ class UNet2DModel(nn.Module):
                 d_e1 = ops.linear_f32_dgrad(d_emb, w2, hd.e1, True)
                 ops.linear_f32_wgrad(hd.t_emb, d_e1, self._gview(G, P.te.w1, (ted, c0)),
                                      self._gview(G, P.te.b1, (ted,)), False)
-        if st.wg_stream is not None:
-            torch.cuda.current_stream().wait_stream(st.wg_stream)
         self.last_launches_bwd = ops.launches - l0
         return G, st
 
@@ -1000,9 +1012,9 @@ class UNet2DModel(nn.Module):
                                  dbeta=dbt, **st.defer_kw)
         # time embedding + conv1 bias share sum_hw(d_h1)
         dW1, db1 = self._wgrad_views(G, r.conv1)
-        if not fuse:
-            ops.reduce_hw(d_h1, st.d_temb_all[:, r.temb_off:r.temb_off + r.cout],
-                          db1 if r.conv1.bias_trainable else None)
+        if not fuse:     # consumed only by the time-embedding MLP backward at the very end: off the critical path
+            self._async_wgrad(st, lambda d_h1=d_h1: ops.reduce_hw(
+                d_h1, st.d_temb_all[:, r.temb_off:r.temb_off + r.cout], db1 if r.conv1.bias_trainable else None))
         if r.conv1.trainable:
             self._async_wgrad(st, lambda d_h1=d_h1: ops.conv_wgrad(d_h1, s.a, None, taps_3x3(r.cin), dW1, grid))
         g1, be1 = self._norm_params(r.norm1)
