@@ -404,7 +404,44 @@ def run_b200(args, rank, world, local_rank):
     all_ms = sum(cls_ms.values())
     all_tf = sum(prof["flops"].values()) / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0
     ops.conv_wgrad = orig_conv_wgrad
+    ops.conv_gemm = orig_conv_gemm
     step = eager_step
+    # HBM-bound kernel classes of the same single-stream eager step: algorithmic bytes over
+    # CUDA-event time, for the launches that are large enough to be bandwidth- rather than latency-sized (>= 64x64)
+    hbm_kernels = {}
+    if rank == 0:
+        pr = ops_mod.OpProfiler(ops)
+        pr.by_shape = True
+        pr.start()
+        for _ in range(2):
+            eager_step(clean_dev, noise_dev, t_dev)
+        table = pr.stop()
+        agg = {}
+        for key, v in table.items():
+            name, _, shape = key.partition("|")
+            if not v["bytes"] or v["ms"] <= 0:
+                continue
+            if name.startswith("gn_") and not (shape.startswith("128x128") or shape.startswith("64x64")):
+                continue
+            if name not in ("gn_fwd_from_csum", "gn_fwd", "gn_bwd_apply", "gn_bwd", "adamw_flat", "sumsq", "add_noise",
+                            "mse_fwd_bwd"):
+                continue
+            a = agg.setdefault(name, {"bytes": 0.0, "ms": 0.0, "calls": 0})
+            a["bytes"] += v["bytes"]; a["ms"] += v["ms"]; a["calls"] += v["calls"]
+        hbm_peak = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak = json.load(f).get("hbm_gbs")
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = hbm_peak or 6500.0
+        for name, a in agg.items():
+            gbps = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+            hbm_kernels[name] = {"gbps": round(gbps, 1), "frac_of_copy_peak": round(gbps / hbm_peak, 3),
+                                 "ms_per_step": round(a["ms"] / 2, 3), "calls_per_step": a["calls"] // 2}
+        hbm_kernels["_peak_gbs"] = hbm_peak
+        hbm_kernels["_note"] = ("GroupNorm rows: launches at >= 64x64 only (smaller maps are latency-sized); "
+                                "add_noise / mse at 12.6 MB are latency-sized too")
     os.environ.pop("DDPM_WGRAD_STREAM", None)
 
     # ---- secondary metric: reverse-diffusion sampling (BASELINE configs[2]: 256 images over 8 GPUs = 32 / GPU) ----
@@ -553,6 +590,7 @@ def run_b200(args, rank, world, local_rank):
                 "wgrad_ms_per_step": round(cls_ms["wgrad"] / n_prof_steps, 3),
                 "all_conv_gemms_tflops": round(all_tf, 1), "all_conv_gemms_frac_of_peak": round(all_tf / peak_tf, 4),
             },
+            "hbm_bound_kernels": hbm_kernels,
         },
         "cpu_baseline": cpu,
         "sampling": sampling,

@@ -626,9 +626,16 @@ class OpProfiler:
             if name == "gn_stats":
                 x0, x1 = args[0], args[1]
                 return 0.0, 2.0 * (x0.numel() + (x1.numel() if x1 is not None else 0))
+            if name == "gn_fwd_from_csum":
+                return 0.0, 4.0 * out[1].numel()              # one streaming pass: bf16 read + bf16 write
             if name in ("gn_bwd", "gn_bwd_apply"):
                 x0, x1 = args[0], args[1]
-                return 0.0, 6.0 * (x0.numel() + (x1.numel() if x1 is not None else 0))   # x, dy read + dx write
+                extra = sum(kwargs[k].numel() for k in ("add0", "add1") if kwargs.get(k) is not None)
+                return 0.0, 6.0 * (x0.numel() + (x1.numel() if x1 is not None else 0)) + 2.0 * extra  # x, dy, dx (+addends)
+            if name == "adamw_flat":
+                return 0.0, 28.0 * args[0].numel()            # p, g, m, v read; p, m, v written (fp32)
+            if name == "sumsq":
+                return 0.0, 4.0 * args[0].numel()
             if name in ("add_noise", "mse_fwd_bwd"):
                 return 0.0, 12.0 * args[0].numel()
             if name == "scheduler_step":
@@ -652,7 +659,7 @@ class OpProfiler:
                 dy, x0, x1, taps, dw, grid = args[:6]
                 cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
                 return f"|{grid[1]}x{grid[2]} c{cin}->{dy.shape[-1]} k{len(taps)}"
-            if name in ("gn_bwd", "gn_bwd_apply", "gn_apply", "gn_stats", "gn_fwd"):
+            if name in ("gn_bwd", "gn_bwd_apply", "gn_apply", "gn_stats", "gn_fwd", "gn_fwd_from_csum"):
                 x0, x1 = args[0], args[1]
                 c = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
                 return f"|{x0.shape[1]}x{x0.shape[2]} c{c}"
