@@ -30,6 +30,7 @@ namespace ddpm {
 
 constexpr int kHaloThreads = 352;
 constexpr int kHaloMaxBStages = 8;   // weight-tile ring depth is chosen at launch from the shared memory left over
+constexpr int kHaloMaxPairStages = 16;   // CTA-pair variant: half tiles (8 KB), twice the depth
 constexpr int kTileSlots = 256;
 constexpr int kHaloBBytes = 128 * 128;   // one weight tile: 128 cout rows x 64 ch
 
@@ -42,6 +43,7 @@ struct HaloParams {
   uint32_t halo_bytes;   // R * Wp * 128
   uint32_t halo_stride;  // halo_bytes rounded up to 1024
   int b_stages;          // weight-tile ring depth
+  int dbg;               // timing experiments only (DDPM_HALO_DBG)
   int mma_n;             // UMMA N: 128, or Cout rounded up to 16 for narrow outputs (conv_out: 3 -> 32 columns)
   EpiParams epi;
 };
@@ -249,6 +251,234 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 10) tmem_dealloc(tmem_base, 512);
 }
 
+// =====================================================================================================
+// CTA-pair variant (thread-block cluster of 2, tcgen05 cta_group::2).
+// The two CTAs of a pair work on the SAME tile position of two DIFFERENT images (img = 2*pair + rank), so their halo
+// buffers have identical geometry and one shared-memory descriptor addresses both.  The leader's MMA warp issues
+// M = 256 instructions: rows 0-127 come from its own halo and land in its own TMEM, rows 128-255 from the peer's halo
+// into the peer's TMEM; each CTA stages only HALF of every weight tile (64 of the 128 cout rows).  Per FLOP this halves
+// the issue cost (one issuing warp drives two tensor cores), the weight-tile L2 traffic and the weight shared-memory
+// footprint (the ring doubles in depth).  Barriers: "full" barriers live in the leader and count one arrival per CTA
+// (the peer's TMA signals them through their shared::cluster address); "empty" barriers live in both CTAs and are
+// released by multicast tcgen05.commit; the accumulator-empty barrier of the leader collects both epilogues.
+// =====================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // identical carve-up in both CTAs: offsets (not generic addresses) must match across the pair
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* halo = smem;                                   // 2 x halo_stride
+  uint8_t* bsm = smem + 2 * p.halo_stride;                // b_stages x 8 KB (this CTA's half of each weight tile)
+  const int kStages = p.b_stages;
+  constexpr int kHalfB = kHaloBBytes / 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + kStages * kHalfB);
+  uint64_t* halo_full = bars;            // [2]   (used in the leader)
+  uint64_t* halo_empty = bars + 2;       // [2]   (both CTAs)
+  uint64_t* b_full = bars + 4;           // [kHaloMaxPairStages] (leader)
+  uint64_t* b_empty = b_full + kHaloMaxPairStages;
+  uint64_t* tmem_full = b_empty + kHaloMaxPairStages;   // [2] (both CTAs)
+  uint64_t* tmem_empty = tmem_full + 2;                 // [2] (leader; 16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kbt = p.kb0 + p.kb1;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.kb1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&halo_full[i], 2);      // one arrival per CTA of the pair
+      mbar_init(&halo_empty[i], 1);
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 16);    // 8 epilogue warps x 2 CTAs
+    }
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&b_full[i], 2);
+      mbar_init(&b_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 10) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair tile -> (image of this CTA, first slot, cout tile)
+  auto decode = [&](int pt, int& img, bool& img_ok, int& q0, int& nt) {
+    nt = pt % p.n_tiles;
+    const int mt = pt / p.n_tiles;
+    const int ip = mt / p.tiles_per_img;
+    q0 = (mt - ip * p.tiles_per_img) * kTileSlots;
+    img = 2 * ip + static_cast<int>(rank);
+    img_ok = img < p.N;
+    if (!img_ok) img = p.N - 1;          // odd batch: the last peer recomputes the last image and stores nothing
+  };
+
+  if (warp == 8) {
+    // ---------------- halo producer (both CTAs; completion is signalled on the LEADER's barrier) ----------------
+    uint32_t hb = 0, hph = 0;
+    const uint32_t full0 = mapa_u32(smem_u32(&halo_full[0]), 0), full1 = mapa_u32(smem_u32(&halo_full[1]), 0);
+    for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
+      int img, q0, nt; bool ok;
+      decode(pt, img, ok, q0, nt);
+      const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
+      for (int c = 0; c < kbt; ++c) {
+        mbar_wait(&halo_empty[hb], hph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = hb ? full1 : full0;
+          if (c < p.kb0)
+            tma_load_4d_pair(halo + hb * p.halo_stride, &tmA0, fb, c * 64, -1, row_lo, img);
+          else
+            tma_load_4d_pair(halo + hb * p.halo_stride, &tmA1, fb, (c - p.kb0) * 64, -1, row_lo, img);
+          if (leader) mbar_expect_tx(&halo_full[hb], 2u * p.halo_bytes);   // arrive (1 of 2) + both CTAs' bytes
+          else mbar_arrive_cluster(fb);                                     // arrive (2 of 2)
+        }
+        __syncwarp();
+        hb ^= 1;
+        hph ^= (hb == 0);
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- weight-tile producer: this CTA's 64 cout rows of every tile ----------------
+    uint32_t bs = 0, bph = 0;
+    const uint32_t bfull0 = mapa_u32(smem_u32(&b_full[0]), 0);
+    for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
+      const int nt = pt % p.n_tiles;
+      const int row0 = nt * 128 + static_cast<int>(rank) * (p.mma_n / 2);   // this CTA's half of the N columns
+      for (int c = 0; c < kbt; ++c) {
+        int kcol = c * 64;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, kcol += p.Cin_total) {
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = bfull0 + bs * 8u;
+            tma_load_2d_pair(bsm + bs * kHalfB, &tmB, fb, kcol, row0);
+            if (leader) mbar_expect_tx(&b_full[bs], static_cast<uint32_t>(kHaloBBytes));
+            else mbar_arrive_cluster(fb);
+          }
+          __syncwarp();
+          if (++bs == static_cast<uint32_t>(kStages)) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    if (leader) {
+      // ---------------- MMA issuer (leader only): M = 256 across the pair ----------------
+      const uint32_t idesc = make_idesc_bf16(256, p.mma_n, false, false);
+      const uint64_t db_base = make_smem_desc_sw128(smem_u32(bsm), 16, 1024);
+      const uint32_t row_step = static_cast<uint32_t>(p.Wp) * 8u;
+      uint32_t bs = 0, bph = 0, hb = 0, hph = 0, acc = 0, aph = 0;
+      uint64_t db = db_base;
+      for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
+        int img, q0, nt; bool ok;
+        decode(pt, img, ok, q0, nt);
+        const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
+        const int rel00 = q0 - row_lo * p.Wp - p.Wp - 1;
+        mbar_wait(&tmem_empty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * 256;
+        for (int c = 0; c < kbt; ++c) {
+          mbar_wait(&halo_full[hb], hph);
+          const uint32_t h_addr = smem_u32(halo + hb * p.halo_stride);
+          const uint64_t da_c = make_smem_desc_sw128(h_addr + static_cast<uint32_t>(rel00) * 128u, 16, 1024);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint64_t da = da_c + static_cast<uint64_t>((tap / 3) * row_step + (tap % 3) * 8u);
+            const uint32_t first = (tap != 0 || c != 0) ? 1u : 0u;
+            if (elect_one()) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (p.dbg == 3 && u == 1) break;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_pair(d0 + u * 128, da + static_cast<uint64_t>(u * 1024 + k * 2),
+                                 db + static_cast<uint64_t>(k * 2), idesc, k == 0 ? first : 1u);
+              }
+              umma_commit_pair(&b_empty[bs]);
+            }
+            __syncwarp();
+            db += kHalfB >> 4;
+            if (++bs == static_cast<uint32_t>(kStages)) { bs = 0; bph ^= 1; db = db_base; }
+          }
+          if (elect_one()) umma_commit_pair(&halo_empty[hb]);
+          __syncwarp();
+          hb ^= 1;
+          hph ^= (hb == 0);
+        }
+        if (elect_one()) umma_commit_pair(&tmem_full[acc]);
+        __syncwarp();
+        acc ^= 1;
+        aph ^= (acc == 0);
+      }
+    }
+  } else {
+    // ---------------- epilogue (8 warps per CTA; each CTA drains its own TMEM = its own image) ----------------
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    uint32_t acc = 0, aph = 0;
+    const uint32_t empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
+      int img, q0, nt; bool img_ok;
+      decode(pt, img, img_ok, q0, nt);
+      auto geom = [&](int i, int& col, bool& valid, long long& pix, int& u) {
+        u = i & 1;
+        col = nt * 128 + (half * 2 + (i >> 1)) * 32;
+        const int slot = q0 + u * 128 + q * 32 + lane;
+        const int h = slot / p.Wp;
+        const int w = slot - h * p.Wp - 1;
+        valid = img_ok && (w >= 0) && (h < p.H);
+        pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
+      };
+      EpiX xcur, xnext;
+      {
+        int col, u; bool valid; long long pix;
+        geom(0, col, valid, pix, u);
+        epi_load_x(p.epi, valid, pix, col, xcur);
+      }
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        int col, u; bool valid; long long pix;
+        if (i + 1 < 4) {
+          geom(i + 1, col, valid, pix, u);
+          epi_load_x(p.epi, valid, pix, col, xnext);
+        }
+        geom(i, col, valid, pix, u);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + u * 128 + (half * 2 + (i >> 1)) * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        epi_chunk(p.epi, v, valid, img, pix, col, lane, t1, t2, xcur);
+        if (u == 1) {
+          epi_flush_sums(p.epi, img_ok ? img : -1, col, lane, t1, t2);
+          t1 = t2 = 0.f;
+        }
+        xcur = xnext;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty0 + acc * 8u);     // the LEADER's accumulator-empty barrier
+      acc ^= 1;
+      aph ^= (acc == 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 10) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // 4-D activation map with a caller-chosen box (not cached through make_act_map's (wb,hb,nb) key space clash:
 // the key includes the box, so the shared cache is safe to reuse)
 int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
@@ -280,6 +510,7 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
   bst = env_int("DDPM_HALO_BSTAGES", bst) < bst ? env_int("DDPM_HALO_BSTAGES", bst) : bst;
   if (bst < 2) return 1;
   p.b_stages = bst;
+  p.dbg = env_int("DDPM_HALO_DBG", 0);
   p.mma_n = a->cout >= 128 ? 128 : ((a->cout + 15) / 16) * 16;   // narrow outputs: do not multiply the zero rows
   const size_t smem = fixed + static_cast<size_t>(bst) * kHaloBBytes;
   p.tiles_per_img = (H * Wp + kTileSlots - 1) / kTileSlots;
@@ -295,6 +526,24 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
     ma1 = ma0;
   }
   const long long k_total = a->k_total > 0 ? a->k_total : a->ldw;
+  if (env_int("DDPM_HALO_PAIR", 1) != 0 && a->n >= 2) {
+    // CTA-pair variant: half weight tiles (8 KB per stage), pair tiles over image pairs
+    HaloParams pp = p;
+    int pst = static_cast<int>((227 * 1024 - fixed) / (kHaloBBytes / 2));
+    if (pst > kHaloMaxPairStages) pst = kHaloMaxPairStages;
+    pp.b_stages = pst;
+    pp.total_tiles = ((a->n + 1) / 2) * p.tiles_per_img * p.n_tiles;
+    const size_t psmem = fixed + static_cast<size_t>(pst) * (kHaloBBytes / 2);
+    if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 64)) return e;
+    static size_t pconfigured = 0;
+    if (psmem > pconfigured) {
+      DDPM_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      pconfigured = psmem;
+    }
+    int pgrid = 2 * pp.total_tiles < kNumSMs ? 2 * pp.total_tiles : (kNumSMs / 2) * 2;
+    conv_halo_pair_kernel<<<pgrid, kHaloThreads, psmem, stream>>>(ma0, ma1, mb, pp);
+    return check_launch("conv_halo_pair_kernel");
+  }
   if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 128)) return e;
   static size_t configured = 0;
   if (smem > configured) {
