@@ -671,9 +671,7 @@ class UNet2DModel(nn.Module):
 
         # ---- conv_in ----
         patches = ops.im2col3(x)                                   # [N, H, W, 64] bf16, one k-block
-        cs = self._csum_for(st, (N, H, W), c0)
-        h = self._tag(ops.conv_gemm(patches, None, taps_1x1(), self._cin_wf, c0, (N, H, W),
-                                    bias=self._aview(P.cin_b, (c0,)), csum=cs), cs)
+        h = ops.conv_gemm(patches, None, taps_1x1(), self._cin_wf, c0, (N, H, W), bias=self._aview(P.cin_b, (c0,)))
         skips = [h]
 
         # ---- down ----
@@ -721,8 +719,9 @@ class UNet2DModel(nn.Module):
         c = nobj.mod.num_channels
         return self._aview(nobj.g_off, (c,)), self._aview(nobj.b_off, (c,))
 
-    # GroupNorm statistics ride on the epilogue of the conv that PRODUCES the tensor (per-(sample, channel) moments,
+    # GroupNorm statistics ride on the epilogue of the 3x3 conv that PRODUCES the tensor (per-(sample, channel) moments,
     # conv_gemm(csum=...)); the GroupNorm forward is then one streaming pass instead of the two-phase team kernel.
+    # (Not for conv_in / the stride-2 convs: they run on the generic kernel, where the reductions are exposed.)
     @staticmethod
     def _csum_for(st, grid, cout):
         ops = st.ops
@@ -809,9 +808,7 @@ class UNet2DModel(nn.Module):
         N, H, W, C = x.shape
         s2d = ops.space_to_depth(x)
         grid = (N, H // 2, W // 2)
-        cs = self._csum_for(st, grid, C)
-        out = self._tag(ops.conv_gemm(s2d, None, taps_s2d(C, N, d.pad), d.conv.wf, C, grid, bias=self._bias(d.conv),
-                                      src_n=4 * N, csum=cs), cs)
+        out = ops.conv_gemm(s2d, None, taps_s2d(C, N, d.pad), d.conv.wf, C, grid, bias=self._bias(d.conv), src_n=4 * N)
         if st.tape is not None:
             st.tape.add(("down", d, SimpleNamespace(s2d=s2d, in_skip=in_skip, shape=(N, H, W, C), grid=grid)))
         return out
