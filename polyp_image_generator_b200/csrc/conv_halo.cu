@@ -43,7 +43,6 @@ struct HaloParams {
   uint32_t halo_bytes;   // R * Wp * 128
   uint32_t halo_stride;  // halo_bytes rounded up to 1024
   int b_stages;          // weight-tile ring depth
-  int dbg;               // timing experiments only (DDPM_HALO_DBG)
   int mma_n;             // UMMA N: 128, or Cout rounded up to 16 for narrow outputs (conv_out: 3 -> 32 columns)
   EpiParams epi;
 };
@@ -396,7 +395,6 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             if (elect_one()) {
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
-                if (p.dbg == 3 && u == 1) break;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_bf16_pair(d0 + u * 128, da + static_cast<uint64_t>(u * 1024 + k * 2),
@@ -510,7 +508,6 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
   bst = env_int("DDPM_HALO_BSTAGES", bst) < bst ? env_int("DDPM_HALO_BSTAGES", bst) : bst;
   if (bst < 2) return 1;
   p.b_stages = bst;
-  p.dbg = env_int("DDPM_HALO_DBG", 0);
   p.mma_n = a->cout >= 128 ? 128 : ((a->cout + 15) / 16) * 16;   // narrow outputs: do not multiply the zero rows
   const size_t smem = fixed + static_cast<size_t>(bst) * kHaloBBytes;
   p.tiles_per_img = (H * Wp + kTileSlots - 1) / kTileSlots;
