@@ -409,13 +409,16 @@ def run_b200(args, rank, world, local_rank):
     # HBM-bound kernel classes of the same single-stream eager step: algorithmic bytes over
     # CUDA-event time, for the launches that are large enough to be bandwidth- rather than latency-sized (>= 64x64)
     hbm_kernels = {}
+    # EVERY rank runs these steps: under DDP each step all-reduces the gradients, so a rank-0-only pass would leave
+    # rank 0 waiting in a collective the other ranks never enter
+    pr = ops_mod.OpProfiler(ops)
+    pr.by_shape = True
+    pr.start()
+    for _ in range(2):
+        eager_step(clean_dev, noise_dev, t_dev)
+    table = pr.stop()
+    barrier()
     if rank == 0:
-        pr = ops_mod.OpProfiler(ops)
-        pr.by_shape = True
-        pr.start()
-        for _ in range(2):
-            eager_step(clean_dev, noise_dev, t_dev)
-        table = pr.stop()
         agg = {}
         for key, v in table.items():
             name, _, shape = key.partition("|")
@@ -486,9 +489,10 @@ def run_b200(args, rank, world, local_rank):
         lora = run_lora_finetune(args, dev, world, rank, barrier)
 
     # ---- optional per-op breakdown (after the timed regions; CUDA events around every C-ABI op) ----
-    if args.breakdown and rank == 0:
+    if args.breakdown:       # all ranks step together (DDP collectives); rank 0 reports
         os.environ["DDPM_WGRAD_STREAM"] = "0"       # per-op events: one stream
         ops.conv_gemm = orig_conv_gemm
+        model.train()
         for _ in range(2):
             step(clean_dev, noise_dev, t_dev)
         pr = ops_mod.OpProfiler(ops)
@@ -500,23 +504,25 @@ def run_b200(args, rank, world, local_rank):
             step(clean_dev, noise_dev, t_dev)
         ev1.record()
         table = pr.stop()
-        wall = ev0.elapsed_time(ev1) / 2
-        rows = sorted(table.items(), key=lambda kv: -kv[1]["ms"])
-        acc = sum(v["ms"] for _, v in rows) / 2
-        out = {"ms_per_step_profiled": wall, "ms_in_ops": acc, "ops": {}}
-        print(f"[breakdown] step {wall:.2f} ms, in C-ABI ops {acc:.2f} ms (rest = torch optimizer/clip/alloc)",
-              file=sys.stderr)
-        for name, v in rows:
-            ms = v["ms"] / 2
-            tf = v["flops"] / 2 / (ms * 1e-3) / 1e12 if v["flops"] and ms > 0 else None
-            gb = v["bytes"] / 2 / (ms * 1e-3) / 1e9 if v["bytes"] and ms > 0 else None
-            out["ops"][name] = {"calls": v["calls"] // 2, "ms": round(ms, 3), "tflops": tf and round(tf, 1),
-                                "gbps": gb and round(gb, 1)}
-            print(f"[breakdown] {name:36s} calls {v['calls'] // 2:5d}  {ms:8.3f} ms  "
-                  f"{'%.1f TFLOP/s' % tf if tf else ''}{'%.0f GB/s' % gb if gb else ''}", file=sys.stderr)
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as f:
-            json.dump(out, f, indent=1)
+        barrier()
+        if rank == 0:
+            wall = ev0.elapsed_time(ev1) / 2
+            rows = sorted(table.items(), key=lambda kv: -kv[1]["ms"])
+            acc = sum(v["ms"] for _, v in rows) / 2
+            out = {"ms_per_step_profiled": wall, "ms_in_ops": acc, "ops": {}}
+            print(f"[breakdown] step {wall:.2f} ms, in C-ABI ops {acc:.2f} ms (rest = torch optimizer/clip/alloc)",
+                  file=sys.stderr)
+            for name, v in rows:
+                ms = v["ms"] / 2
+                tf = v["flops"] / 2 / (ms * 1e-3) / 1e12 if v["flops"] and ms > 0 else None
+                gb = v["bytes"] / 2 / (ms * 1e-3) / 1e9 if v["bytes"] and ms > 0 else None
+                out["ops"][name] = {"calls": v["calls"] // 2, "ms": round(ms, 3), "tflops": tf and round(tf, 1),
+                                    "gbps": gb and round(gb, 1)}
+                print(f"[breakdown] {name:36s} calls {v['calls'] // 2:5d}  {ms:8.3f} ms  "
+                      f"{'%.1f TFLOP/s' % tf if tf else ''}{'%.0f GB/s' % gb if gb else ''}", file=sys.stderr)
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as f:
+                json.dump(out, f, indent=1)
     os.environ.pop("DDPM_WGRAD_STREAM", None)
 
     tt = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
