@@ -387,3 +387,34 @@ def test_ddim_pipeline_matches_oracle_loop_and_round_trips(emu_backend, tmp_path
     pipe.save_pretrained(str(tmp_path / "p"))
     back = DDIMPipeline.from_pretrained(str(tmp_path / "p"))
     assert type(back.scheduler).__name__ == "DDIMScheduler" and back.scheduler.config.set_alpha_to_one is True
+
+
+def test_bench_has_no_rank_conditional_collectives():
+    """Every rank must walk bench.py's GPU arm through the same sequence of collectives: a training step (DDP
+    all-reduce), a barrier or a dist.* call under `if rank == 0` deadlocks the multi-GPU run (it did, once)."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    collective = {"step", "eager_step", "e2e_iter", "run_sampling", "run_lora_finetune", "barrier", "gstep", "net"}
+
+    def mentions_rank(node):
+        return any(isinstance(n, ast.Name) and n.id == "rank" for n in ast.walk(node))
+
+    def calls_in(nodes):
+        out = []
+        for st in nodes:
+            for n in ast.walk(st):
+                if isinstance(n, ast.Call):
+                    f = n.func
+                    if isinstance(f, ast.Name) and f.id in collective:
+                        out.append(f.id)
+                    if isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "dist":
+                        out.append("dist." + f.attr)
+        return out
+
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "run_b200")
+    bad = []
+    for node in ast.walk(fn):
+        if isinstance(node, ast.If) and mentions_rank(node.test):
+            # `if rank != 0: return` (no collective after it in that branch) is fine; anything else is checked
+            bad += [(node.lineno, c) for c in calls_in(node.body) + calls_in(node.orelse)]
+    assert not bad, f"collective-bearing calls under a rank condition: {bad}"
