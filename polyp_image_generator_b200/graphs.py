@@ -79,12 +79,21 @@ class GraphedTrainStep:
     """
 
     def __init__(self, net, noise_scheduler, optimizer, batch_shape, max_grad_norm: Optional[float] = 1.0,
-                 warmup_iters: int = 3):
+                 warmup_iters: int = 3, lr_scheduler=None):
         from .training import mse_loss
         params = [p for p in net.parameters() if p.requires_grad]
         dev = params[0].device
         if dev.type != "cuda":
             raise RuntimeError("CUDA graphs need the model on a CUDA device")
+        # The learning rate of a captured optimizer kernel is a launch constant unless it is read from device memory:
+        # with lr_scheduler (train_from_scratch.py:113, get_cosine_schedule_with_warmup) the rate lives in a device
+        # scalar that __call__ refreshes from the param group after every lr_scheduler.step().
+        self.lr_scheduler, self._lr_t, self._opt = lr_scheduler, None, optimizer
+        if lr_scheduler is not None:
+            if not hasattr(optimizer, "lr_tensor"):
+                raise NotImplementedError("lr_scheduler with a graphed step needs optim.FusedAdamW (device-resident lr)")
+            self._lr_t = torch.full((1,), float(optimizer.param_groups[0]["lr"]), device=dev, dtype=torch.float32)
+            optimizer.lr_tensor = self._lr_t
         self.clean = torch.zeros(tuple(batch_shape), device=dev, dtype=torch.float32)
         self.noise = torch.zeros(tuple(batch_shape), device=dev, dtype=torch.float32)
         self.t = torch.zeros((batch_shape[0],), device=dev, dtype=torch.int64)
@@ -122,4 +131,7 @@ class GraphedTrainStep:
         self.graph.replay()
         if self._invalidate is not None:        # replays update the weights without bumping autograd versions
             self._invalidate()
+        if self.lr_scheduler is not None:       # the reference steps the schedule once per iteration (:113)
+            self.lr_scheduler.step()
+            self._lr_t.fill_(float(self._opt.param_groups[0]["lr"]))
         return self.loss

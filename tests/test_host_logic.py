@@ -418,3 +418,33 @@ def test_bench_has_no_rank_conditional_collectives():
             # `if rank != 0: return` (no collective after it in that branch) is fine; anything else is checked
             bad += [(node.lineno, c) for c in calls_in(node.body) + calls_in(node.orelse)]
     assert not bad, f"collective-bearing calls under a rank condition: {bad}"
+
+
+def test_fused_adamw_device_lr_follows_a_schedule(emu_backend):
+    """lr_tensor (what GraphedTrainStep(lr_scheduler=...) refreshes between replays) overrides the group's lr, so a
+    captured optimizer kernel follows get_cosine_schedule_with_warmup (train_from_scratch.py:274-278, :113)."""
+    from polyp_image_generator_b200 import FusedAdamW, UNet2DModel
+    from polyp_image_generator_b200.training import get_cosine_schedule_with_warmup
+    cfg = _small_cfg(32)
+    torch.manual_seed(0)
+    a, b = UNet2DModel(**cfg), UNet2DModel(**cfg)
+    b.load_state_dict(a.state_dict())
+    oa = FusedAdamW(a.parameters(), lr=1e-3, max_grad_norm=1.0)
+    ob = FusedAdamW(b.parameters(), lr=1e-3, max_grad_norm=1.0)
+    sa = get_cosine_schedule_with_warmup(oa, 2, 6)
+    lr_t = torch.full((1,), float(ob.param_groups[0]["lr"]))
+    ob.lr_tensor = lr_t
+    ob.param_groups[0]["lr"] = 123.0            # must be ignored once the device scalar is set
+    x, t, tgt = torch.randn(2, 3, 32, 32), torch.tensor([3, 600]), torch.randn(2, 3, 32, 32)
+    for _ in range(4):
+        for m in (a, b):
+            torch.nn.functional.mse_loss(m(x, t).sample, tgt).backward()
+        oa.step(); ob.step()
+        oa.zero_grad(); ob.zero_grad()
+        sa.step()
+        ob.param_groups[0]["lr"] = oa.param_groups[0]["lr"]   # what lr_scheduler.step() leaves in the group ...
+        lr_t.fill_(float(oa.param_groups[0]["lr"]))           # ... copied into the device scalar
+        ob.param_groups[0]["lr"] = 123.0
+    assert sa.get_last_lr()[0] == pytest.approx(1e-3 * 0.5 * (1 + __import__("math").cos(__import__("math").pi * 0.5)))
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
