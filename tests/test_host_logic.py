@@ -432,7 +432,7 @@ def test_fused_adamw_device_lr_follows_a_schedule(emu_backend):
     oa = FusedAdamW(a.parameters(), lr=1e-3, max_grad_norm=1.0)
     ob = FusedAdamW(b.parameters(), lr=1e-3, max_grad_norm=1.0)
     sa = get_cosine_schedule_with_warmup(oa, 2, 6)
-    lr_t = torch.full((1,), float(ob.param_groups[0]["lr"]))
+    lr_t = torch.full((1,), float(oa.param_groups[0]["lr"]))     # LambdaLR already applied warm-up step 0 (lr = 0)
     ob.lr_tensor = lr_t
     ob.param_groups[0]["lr"] = 123.0            # must be ignored once the device scalar is set
     x, t, tgt = torch.randn(2, 3, 32, 32), torch.tensor([3, 600]), torch.randn(2, 3, 32, 32)
