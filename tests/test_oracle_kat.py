@@ -175,3 +175,35 @@ def test_oracle_ddim_closed_form_properties():
     assert s.timesteps[0].item() == 980 and s.timesteps[-1].item() == 0
     x1 = ac[0] ** 0.5 * x0 + (1 - ac[0]) ** 0.5 * eps
     assert torch.allclose(s.step(eps, torch.tensor(0), x1).prev_sample, x0, atol=2e-5)
+
+
+def test_ddim_golden_trajectory():
+    """tests/golden/ddim.json (make_golden_session3.py): the oracle reproduces its committed 25-step trajectory."""
+    gold = json.load(open(os.path.join(GOLD, "ddim.json")))
+    s = oracle.DDIMScheduler()
+    s.set_timesteps(25)
+    assert s.timesteps.tolist() == gold["timesteps"]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 3, 8, 8, generator=g)
+    for t, want in zip(s.timesteps, gold["trajectory_sums"]):
+        eps = torch.cos(x * 2.0 - float(t) * 0.02)
+        x = s.step(eps, t, x, eta=gold["eta"], use_clipped_model_output=True, generator=g).prev_sample
+        assert x.double().sum().item() == pytest.approx(want, rel=1e-5, abs=1e-5)
+    assert torch.allclose(x.flatten(), torch.tensor(gold["final"]), rtol=1e-5, atol=1e-6)
+
+
+def test_resize_golden_from_pillow():
+    """tests/golden/resize.json was written by Pillow / torchvision themselves; the oracle restatement must match it."""
+    import numpy as np
+    from oracle import preprocess as opre
+    sys_path_hack = os.path.join(GOLD)
+    gold = json.load(open(os.path.join(GOLD, "resize.json")))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk3", os.path.join(sys_path_hack, "make_golden_session3.py"))
+    mk3 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk3)
+    img = mk3.pattern(gold["h"], gold["w"])
+    assert np.array_equal(opre.resize_bilinear_u8(img, gold["size"], gold["size"]), np.array(gold["resized"], dtype=np.uint8))
+    t = opre.transform(img, gold["size"], True)
+    assert t.double().sum().item() == pytest.approx(gold["transform_flipped_sum"], abs=1e-9)
+    assert torch.equal(t[0, 0], torch.tensor(gold["transform_flipped_first_row"]))

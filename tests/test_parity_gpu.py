@@ -94,6 +94,24 @@ def test_ddim_step_bit_exact(dev, n_steps):
     assert torch.equal(a2.step(e.to(dev), 480, x.to(dev)).prev_sample.cpu(), want)
 
 
+def test_ddim_golden_trajectory_on_device(dev):
+    """The committed oracle trajectory (tests/golden/ddim.json) through the DDIM step kernel: bit-identical op order, so
+    the trajectory sums agree to fp32 rounding of the stand-in network."""
+    import json
+    from polyp_image_generator_b200 import DDIMScheduler
+    gold = json.load(open(os.path.join(GOLD, "ddim.json")))
+    s = DDIMScheduler()
+    s.set_timesteps(25)
+    assert s.timesteps.tolist() == gold["timesteps"]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 3, 8, 8, generator=g).to(dev)
+    for t, want in zip(s.timesteps.tolist(), gold["trajectory_sums"]):
+        eps = torch.cos(x.cpu() * 2.0 - float(t) * 0.02).to(dev)      # the stand-in runs on the CPU like the oracle's
+        x = s.step(eps, t, x, eta=gold["eta"], use_clipped_model_output=True, generator=g).prev_sample
+        assert x.double().sum().item() == pytest.approx(want, rel=1e-5, abs=1e-5)
+    assert torch.allclose(x.cpu().flatten(), torch.tensor(gold["final"]), rtol=1e-5, atol=1e-6)
+
+
 def test_scheduler_golden_trajectory(dev):
     """50-step trajectory with a deterministic stand-in for the UNet; CPU generator consumed in diffusers' order."""
     import json

@@ -107,3 +107,25 @@ def test_pinned_prefetcher_delivers_batches_in_order():
         seen.append(tag)
         assert pre(frames).shape == (4, 3, 64, 64)
     assert seen == [0, 1, 2, 3, 4]
+
+
+@pytest.mark.gpu
+def test_device_pipeline_matches_committed_pillow_golden():
+    """tests/golden/resize.json (written by Pillow / torchvision here): the CUDA transform reproduces it bit for bit."""
+    import importlib.util
+    import json
+    import os
+    from polyp_image_generator_b200.preprocess import DevicePreprocessor
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    gold = json.load(open(os.path.join(gdir, "resize.json")))
+    spec = importlib.util.spec_from_file_location("mk3", os.path.join(gdir, "make_golden_session3.py"))
+    mk3 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk3)
+    img = mk3.pattern(gold["h"], gold["w"])
+    dev = torch.device("cuda:0")
+    t = DevicePreprocessor(gold["size"])(torch.from_numpy(img)[None].to(dev), torch.tensor([True])).cpu()[0]
+    assert t.double().sum().item() == pytest.approx(gold["transform_flipped_sum"], abs=1e-9)
+    assert torch.equal(t[0, 0], torch.tensor(gold["transform_flipped_first_row"]))
+    plain = DevicePreprocessor(gold["size"])(torch.from_numpy(img)[None].to(dev), None).cpu()[0]
+    want = (torch.tensor(gold["resized"], dtype=torch.float32).permute(2, 0, 1) / 255 - 0.5) / 0.5
+    assert torch.equal(plain, want)
