@@ -74,12 +74,17 @@ class GraphedTrainStep:
         step = GraphedTrainStep(net, noise_scheduler, optimizer, batch_shape)   # net: UNet2DModel or its DDP wrapper
         loss = step(clean, noise, timesteps)          # device scalar (static buffer); no host sync
 
+    Construction runs `warmup_iters` eager steps plus the captured one on whatever the static buffers hold (pass
+    `warmup_batch=(clean, noise, timesteps)` to use real data instead of zeros): these ARE optimisation steps, exactly
+    like the first iterations of the reference loop -- count them in the schedule or construct the object before
+    loading a checkpoint.
+
     The optimizer must be capturable: optim.FusedAdamW (set its lr_tensor to a device scalar to drive a schedule from
     the host: lr_tensor.fill_(value) between replays) or torch.optim.AdamW(..., fused=True, capturable=True).
     """
 
     def __init__(self, net, noise_scheduler, optimizer, batch_shape, max_grad_norm: Optional[float] = 1.0,
-                 warmup_iters: int = 3, lr_scheduler=None):
+                 warmup_iters: int = 3, lr_scheduler=None, warmup_batch=None):
         from .training import mse_loss
         params = [p for p in net.parameters() if p.requires_grad]
         dev = params[0].device
@@ -97,6 +102,10 @@ class GraphedTrainStep:
         self.clean = torch.zeros(tuple(batch_shape), device=dev, dtype=torch.float32)
         self.noise = torch.zeros(tuple(batch_shape), device=dev, dtype=torch.float32)
         self.t = torch.zeros((batch_shape[0],), device=dev, dtype=torch.int64)
+        if warmup_batch is not None:
+            self.clean.copy_(warmup_batch[0])
+            self.noise.copy_(warmup_batch[1])
+            self.t.copy_(warmup_batch[2])
 
         def body():
             noisy = noise_scheduler.add_noise(self.clean, self.noise, self.t)
