@@ -573,16 +573,18 @@ def run_b200(args, rank, world, local_rank):
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches,
         "roofline": {
-            "kernel": "conv_halo_kernel (tcgen05 halo-resident 3x3 conv, fprop + dgrad, W >= 64: 77 % of the FLOPs)",
+            "kernel": "conv_halo_pair_kernel (tcgen05 cta_group::2 halo-resident 3x3 conv, fprop + dgrad, W >= 64: "
+                      "77 % of the FLOPs)",
             "bound": "tensor",
             "achieved": round(achieved_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
             "frac": round(achieved_tf / peak_tf, 4),
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (128->128 3x3 @128^2, batch 64) from the
-            # `ncu --set full` capture summarised in profiles/r1_conv_halo_lean.md; algorithmic bytes of that launch
-            # (bf16 input + bf16 output): 536.9 MB -- no wasted re-reads (halo / weight re-fetches are served by L2)
-            "traffic": 494.1e6 if (S == 128 and B == 64) else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (128->128 3x3 @128^2, batch 64) of the CTA-pair
+            # kernel, from the `ncu --set full` capture summarised in profiles/r1_halo_pair.md (single-CTA kernel:
+            # 494.1 MB, profiles/r1_conv_halo_lean.md); algorithmic bytes of that launch (bf16 input + bf16 output):
+            # 536.9 MB -- no wasted re-reads (halo / weight re-fetches are served by L2: 1.30 GB L2->SM per launch)
+            "traffic": 496.7e6 if (S == 128 and B == 64) else None,
             "traffic_note": "bytes per launch, 128->128 3x3 @128^2 batch 64 (ncu --set full, profiles/"
-                            "r1_conv_halo_lean.md); algorithmic 536.9e6",
+                            "r1_halo_pair.md); algorithmic 536.9e6",
             "peak_source": peak_src,
             "launches_timed": gemm_launches, "kernel_ms_per_step": round(gemm_ms / n_prof_steps, 3),
             "share_of_step": round(gemm_ms / ms_prof_total, 4),
