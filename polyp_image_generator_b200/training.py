@@ -86,6 +86,49 @@ def train_step(model, noise_scheduler, optimizer, clean_images: torch.Tensor, no
     return loss.detach()
 
 
+def train_epoch_with_accumulation(model, noise_scheduler, optimizer, batches, lr_scheduler=None,
+                                  accumulation_steps: int = 1, max_grad_norm: Optional[float] = 1.0,
+                                  draw=None) -> float:
+    """One epoch of the LoRA trainers' loop (train_with_lora_all_classes.py:123-176, train_with_lora_per_class.py
+    likewise), restated over the drop-in objects for the pixel-space UNet2DModel:
+
+        optimizer.zero_grad()
+        for step, batch: loss = mse(model(add_noise(x, noise, t), t), noise) / accumulation_steps; loss.backward()
+            every accumulation_steps: clip_grad_norm_(model.parameters(), 1.0); optimizer.step(); zero_grad();
+                                      lr_scheduler.step()
+        return mean over batches of loss * accumulation_steps
+
+    A trailing partial group of batches leaves its gradients unapplied, exactly as the reference does.  `batches` yields
+    image tensors (or tuples whose first element is one); `draw(x) -> (noise, timesteps)` lets tests inject the draws,
+    default: device randn / randint as the reference (:132-135).  (The VAE / text-encoder / auxiliary cosine loss of
+    the Stable-Diffusion scripts are out of scope: SURVEY.md §2.1 row 5.)"""
+    if accumulation_steps < 1:
+        raise ValueError("accumulation_steps must be >= 1")
+    total, count = 0.0, 0
+    optimizer.zero_grad()
+    T = noise_scheduler.config.num_train_timesteps
+    for step, batch in enumerate(batches):
+        x = batch[0] if isinstance(batch, (tuple, list)) else batch
+        if draw is not None:
+            noise, t = draw(x)
+        else:
+            noise = torch.randn_like(x)
+            t = torch.randint(0, T, (x.shape[0],), device=x.device)
+        pred = model(noise_scheduler.add_noise(x, noise, t), t).sample
+        loss = mse_loss(pred, noise) / accumulation_steps
+        loss.backward()
+        if (step + 1) % accumulation_steps == 0:
+            if max_grad_norm is not None and getattr(optimizer, "max_grad_norm", None) is None:
+                torch.nn.utils.clip_grad_norm_(list(model.parameters()), max_grad_norm)
+            optimizer.step()
+            optimizer.zero_grad()
+            if lr_scheduler is not None:
+                lr_scheduler.step()
+        total += loss.item() * accumulation_steps
+        count += 1
+    return total / max(count, 1)
+
+
 def get_cosine_schedule_with_warmup(optimizer, num_warmup_steps: int, num_training_steps: int,
                                     num_cycles: float = 0.5, last_epoch: int = -1):
     """diffusers.optimization.get_cosine_schedule_with_warmup (train_from_scratch.py:274-278); host-side scalar."""

@@ -130,3 +130,52 @@ def test_dropout_branch_is_consistent_between_forward_and_backward(emu_backend):
     with torch.no_grad():
         y1, y2 = m(x, t).sample, m(x, t).sample
     assert torch.equal(y1, y2)
+
+
+def test_accumulating_lora_epoch_matches_the_reference_loop(emu_backend):
+    """train_with_lora_all_classes.py:123-176 restated (training.train_epoch_with_accumulation) against the same loop
+    written over the oracle: loss / accumulation_steps, clip over ALL unet parameters, step + zero_grad + lr step every
+    accumulation_steps batches, the trailing batch's gradients left unapplied."""
+    from polyp_image_generator_b200 import DDPMScheduler, LoraConfig, UNet2DModel
+    from polyp_image_generator_b200.training import get_cosine_schedule_with_warmup, train_epoch_with_accumulation
+    cfg = oracle.polyp_unet_config(32)
+    cfg["block_out_channels"] = (64, 64, 64, 64, 128, 128)
+    tg = ["to_q", "to_k", "to_v", "to_out.0"]
+    torch.manual_seed(0)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    oracle.add_adapter(om, oracle.LoraConfig(r=4, lora_alpha=4, target_modules=tg, init_lora_weights="gaussian"))
+    m.add_adapter(LoraConfig(r=4, lora_alpha=4, target_modules=tg, init_lora_weights="gaussian"))
+    sd = {k: torch.randn_like(v) * 0.05 for k, v in oracle.lora_state_dict(om).items()}
+    om.load_state_dict(sd, strict=False)
+    m.load_state_dict(sd, strict=False)
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3)
+    oopt = torch.optim.AdamW([p for p in om.parameters() if p.requires_grad], lr=1e-3)
+    sch, osch = get_cosine_schedule_with_warmup(opt, 1, 4), get_cosine_schedule_with_warmup(oopt, 1, 4)
+    g = torch.Generator().manual_seed(3)
+    batches = [torch.randn(2, 3, 32, 32, generator=g).clamp(-1, 1) for _ in range(3)]
+    draws = [(torch.randn(2, 3, 32, 32, generator=g), torch.randint(0, 1000, (2,), generator=g)) for _ in range(3)]
+    it = iter(draws)
+    avg = train_epoch_with_accumulation(m, DDPMScheduler(), opt, batches, lr_scheduler=sch, accumulation_steps=2,
+                                        draw=lambda x: next(it))
+    # the reference loop over the oracle objects
+    ns, total = oracle.DDPMScheduler(), 0.0
+    oopt.zero_grad()
+    for step, (x, (noise, t)) in enumerate(zip(batches, draws)):
+        loss = torch.nn.functional.mse_loss(om(ns.add_noise(x, noise, t), t).sample, noise) / 2
+        loss.backward()
+        if (step + 1) % 2 == 0:
+            torch.nn.utils.clip_grad_norm_(list(om.parameters()), 1.0)
+            oopt.step()
+            oopt.zero_grad()
+            osch.step()
+        total += loss.item() * 2
+    assert avg == pytest.approx(total / 3, rel=1e-5)
+    assert sch.get_last_lr() == osch.get_last_lr()
+    osd = oracle.lora_state_dict(om)
+    from polyp_image_generator_b200.lora import lora_state_dict
+    for k, v in lora_state_dict(m).items():
+        assert torch.allclose(v, osd[k], rtol=1e-4, atol=2e-6), k
+    # the third batch's gradients are still pending, as in the reference
+    assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in m.parameters() if p.requires_grad)
