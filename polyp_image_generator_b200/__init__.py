@@ -14,7 +14,7 @@ def __getattr__(name):
     if name in ("UNet2DModel", "UNet2DOutput"):
         from . import unet
         return getattr(unet, name)
-    if name in ("LoraConfig", "lora_state_dict", "recover_lora_modules"):
+    if name in ("LoraConfig", "lora_state_dict", "recover_lora_modules", "save_lora_weights", "load_lora_weights"):
         from . import lora
         return getattr(lora, name)
     if name in ("mse_loss", "fused_train_step"):

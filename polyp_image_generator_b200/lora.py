@@ -125,6 +125,23 @@ def lora_state_dict(model: nn.Module) -> Dict[str, torch.Tensor]:
     return {k: v.detach().cpu() for k, v in model.state_dict().items() if "lora_" in k}
 
 
+def save_lora_weights(unet: nn.Module, save_path: str) -> str:
+    """train_with_lora_all_classes.py:29-34 / train_with_lora_per_class.py: `<save_path>/lora_weights.pth` holding only
+    the adapter tensors (CPU), the file the reference uploads to mlflow and reloads before sampling."""
+    import os
+    os.makedirs(save_path, exist_ok=True)
+    path = os.path.join(save_path, "lora_weights.pth")
+    torch.save(lora_state_dict(unet), path)
+    return path
+
+
+def load_lora_weights(device, unet: nn.Module, path: str) -> None:
+    """train_with_lora_all_classes.py:36-38: `load_state_dict(strict=False)` of `<path>/lora_weights.pth`."""
+    import os
+    weights = torch.load(os.path.join(path, "lora_weights.pth"), map_location=device)
+    unet.load_state_dict(weights, strict=False)
+
+
 def recover_lora_modules(state_dict: Dict[str, torch.Tensor]) -> List[str]:
     """get_lorarized_layers.py:12-24."""
     out = set()

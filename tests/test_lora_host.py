@@ -1,5 +1,6 @@
 """LoRA host logic on CPU (emulated op contracts): injection, key grammar, freezing, forward/backward wiring of the
 adapter folded into the projection GEMMs, merge, save/load -- against the oracle's peft restatement."""
+import os
 import pytest
 import torch
 
@@ -179,3 +180,33 @@ def test_accumulating_lora_epoch_matches_the_reference_loop(emu_backend):
         assert torch.allclose(v, osd[k], rtol=1e-4, atol=2e-6), k
     # the third batch's gradients are still pending, as in the reference
     assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in m.parameters() if p.requires_grad)
+
+
+def test_lora_weights_file_round_trip(emu_backend, tmp_path):
+    """save_lora_weights / load_lora_weights (train_with_lora_all_classes.py:29-38) and the module recovery of
+    get_lorarized_layers.py on the file they write."""
+    from polyp_image_generator_b200 import LoraConfig, UNet2DModel
+    from polyp_image_generator_b200.lora import load_lora_weights, recover_lora_modules, save_lora_weights
+    cfg = oracle.polyp_unet_config(32)
+    cfg["block_out_channels"] = (64, 64, 64, 64, 128, 128)
+    tg = ["to_q", "to_k", "to_v", "to_out.0"]
+    torch.manual_seed(1)
+    a, b = UNet2DModel(**cfg), UNet2DModel(**cfg)
+    b.load_state_dict(a.state_dict())
+    for m in (a, b):
+        m.add_adapter(LoraConfig(r=8, lora_alpha=8, target_modules=tg, lora_dropout=0.3, init_lora_weights="gaussian"))
+    with torch.no_grad():
+        for n, p in a.named_parameters():
+            if "lora_" in n:
+                p.normal_(0, 0.1)
+    path = save_lora_weights(a, str(tmp_path / "lora_AD"))
+    assert os.path.basename(path) == "lora_weights.pth"
+    sd = torch.load(path)
+    assert len(sd) == 48 and all("lora_" in k and v.device.type == "cpu" for k, v in sd.items())
+    mods = recover_lora_modules(sd)
+    assert len(mods) == 24 and "mid_block.attentions.0.to_out.0" in mods and "down_blocks.4.attentions.1.to_q" in mods
+    load_lora_weights("cpu", b, str(tmp_path / "lora_AD"))
+    x, t = torch.randn(1, 3, 32, 32), torch.tensor([7])
+    a.eval(); b.eval()
+    with torch.no_grad():
+        assert torch.equal(a(x, t).sample, b(x, t).sample)
