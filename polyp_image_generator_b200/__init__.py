@@ -20,6 +20,9 @@ def __getattr__(name):
     if name in ("mse_loss", "fused_train_step"):
         from . import training
         return getattr(training, name)
+    if name in ("PolypGeneratorModel",):
+        from . import model
+        return getattr(model, name)
     if name in ("FusedAdamW",):
         from . import optim
         return getattr(optim, name)

@@ -210,3 +210,46 @@ def test_lora_weights_file_round_trip(emu_backend, tmp_path):
     a.eval(); b.eval()
     with torch.no_grad():
         assert torch.equal(a(x, t).sample, b(x, t).sample)
+
+
+def test_polyp_generator_model_wrapper_lora_plus_unfreezing(emu_backend, capsys):
+    """PolypGeneratorModel.py:13-64: construction, add_lora_config's report, unfreeze_layers by name substring -- and
+    the backward program honouring the resulting mix of frozen / adapter / unfrozen parameters (the
+    'unconditional_with_lora_and_unfreezing' runs of the reference)."""
+    from polyp_image_generator_b200 import LoraConfig, PolypGeneratorModel
+    from polyp_image_generator_b200.training import mse_loss
+    torch.manual_seed(21)
+    wrap = PolypGeneratorModel("cpu", pretrained=False, add_lora=True, image_size=32)
+    m = wrap.get_model()
+    assert sum(p.numel() for p in m.parameters()) == 113_673_219 and m.config.sample_size == 32
+    with pytest.raises(NotImplementedError):
+        PolypGeneratorModel("cpu", pretrained=True, add_lora=False)
+    om = oracle.UNet2DModel(**oracle.polyp_unet_config(32))
+    om.load_state_dict(m.state_dict())
+    tg = ["to_q", "to_k", "to_v", "to_out.0"]
+    wrap.add_lora_config(LoraConfig(r=8, lora_alpha=8, target_modules=tg, init_lora_weights="gaussian"))
+    assert "Trainable params of unet: 196608 / 113869827 (0.17%)" in capsys.readouterr().out
+    oracle.add_adapter(om, oracle.LoraConfig(r=8, lora_alpha=8, target_modules=tg, init_lora_weights="gaussian"))
+    sd = {k: torch.randn_like(v) * 0.05 for k, v in oracle.lora_state_dict(om).items()}
+    om.load_state_dict(sd, strict=False)
+    m.load_state_dict(sd, strict=False)
+    unfreeze = ["conv_out", "up_blocks.5.resnets.2.conv2", "conv_norm_out"]
+    wrap.unfreeze_layers(unfreeze)
+    for n, p in om.named_parameters():
+        if any(x in n for x in unfreeze):
+            p.requires_grad = True
+    m.eval(); om.eval()
+    x, t, tgt = torch.randn(1, 3, 32, 32), torch.tensor([321]), torch.randn(1, 3, 32, 32)
+    mse_loss(m(x, t).sample, tgt).backward()
+    torch.nn.functional.mse_loss(om(x, t).sample, tgt).backward()
+    og = dict(om.named_parameters())
+    tot = sum(p.grad.norm() ** 2 for p in om.parameters() if p.grad is not None) ** 0.5
+    seen = 0
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            g = og[n].grad      # (q / k adapters of the 1-token mid-block attention have exactly zero gradient)
+            assert p.grad is not None and ((p.grad - g).norm() / (g.norm() + 1e-6 * tot)).item() < 2e-3, n
+            seen += 1
+        else:
+            assert p.grad is None, n
+    assert seen == 48 + 6
