@@ -86,6 +86,55 @@ def train_step(model, noise_scheduler, optimizer, clean_images: torch.Tensor, no
     return loss.detach()
 
 
+def train_loop(config, model, noise_scheduler, optimizer, train_dataloader, lr_scheduler, cls, imgs_to_generate,
+               device=None, evaluate_epochs=(199,), save_epochs=(199,), use_grad_scaler: Optional[bool] = None,
+               num_inference_steps: int = 1000, on_epoch_end=None):
+    """generator_model/train_from_scratch.py:68-133 over the drop-in objects (mlflow logging left to `on_epoch_end`).
+
+    Per batch, in the reference's order: noise / timesteps drawn on the device (:85-91), add_noise (:93), forward +
+    F.mse_loss (:95-101), scaler.scale(loss).backward() (:103), clip_grad_norm_(model.parameters(), 1.0) (:106 -- on
+    the still-scaled gradients, as the reference does), scaler.step / update, zero_grad, lr_scheduler.step (:110-113),
+    loss.item() (:115).  After each epoch a DDPMPipeline is built (:121); at `evaluate_epochs` the per-class images
+    are generated (sampling.evaluate = :39-66) and at `save_epochs` the pipeline is saved under
+    <output_dir>/models/model_<cls> (:128-131).  The reference hard-codes both lists to [199].
+    Returns the list of per-epoch average losses."""
+    import os
+    from .pipeline import DDPMPipeline
+    from .sampling import evaluate
+    if device is not None:
+        model.to(device)
+    dev = next(model.parameters()).device
+    if getattr(config, "output_dir", None) is not None:
+        os.makedirs(config.output_dir, exist_ok=True)
+    if use_grad_scaler is None:
+        use_grad_scaler = dev.type == "cuda"
+    scaler = torch.amp.GradScaler(dev.type) if use_grad_scaler else None
+    history = []
+    for epoch in range(config.num_epochs):
+        model.train()
+        total_loss, n_batches = 0.0, 0
+        for batch in train_dataloader:
+            clean_images = (batch[0] if isinstance(batch, (tuple, list)) else batch).to(dev)
+            loss = train_step(model, noise_scheduler, optimizer, clean_images, lr_scheduler=lr_scheduler,
+                              max_grad_norm=1.0, scaler=scaler)
+            total_loss += loss.item()
+            n_batches += 1
+        avg_loss = total_loss / max(n_batches, 1)
+        history.append(avg_loss)
+        print(f"Epoch {epoch + 1}: Loss = {avg_loss:.4f}")
+        pipeline = DDPMPipeline(unet=model, scheduler=noise_scheduler)
+        if epoch in evaluate_epochs:
+            model.eval()
+            evaluate(config, epoch, pipeline, cls, imgs_to_generate, num_inference_steps=num_inference_steps)
+        if epoch in save_epochs:
+            path_model = os.path.join(config.output_dir, "models", f"model_{cls}")
+            pipeline.save_pretrained(path_model)
+            print(f"  Model saved at {path_model}")
+        if on_epoch_end is not None:
+            on_epoch_end(epoch, avg_loss, pipeline)
+    return history
+
+
 def train_epoch_with_accumulation(model, noise_scheduler, optimizer, batches, lr_scheduler=None,
                                   accumulation_steps: int = 1, max_grad_norm: Optional[float] = 1.0,
                                   draw=None) -> float:

@@ -448,3 +448,32 @@ def test_fused_adamw_device_lr_follows_a_schedule(emu_backend):
     assert sa.get_last_lr()[0] == pytest.approx(1e-3 * 0.5 * (1 + __import__("math").cos(__import__("math").pi * 0.5)))
     for p, q in zip(a.parameters(), b.parameters()):
         assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+
+
+def test_train_loop_mirrors_train_from_scratch(emu_backend, tmp_path):
+    """training.train_loop = train_from_scratch.py:68-133: epochs x batches of the step recipe, a pipeline per epoch,
+    evaluate / save_pretrained at the listed epochs, files where the reference puts them."""
+    from types import SimpleNamespace
+    from polyp_image_generator_b200 import DDPMPipeline, DDPMScheduler, UNet2DModel
+    from polyp_image_generator_b200.training import get_cosine_schedule_with_warmup, train_loop
+    cfg = _small_cfg(32)
+    cfg["block_out_channels"] = (64, 64, 64, 64, 64, 64)
+    torch.manual_seed(0)
+    m = UNet2DModel(**cfg)
+    w0 = m.conv_out.weight.detach().clone()
+    g = torch.Generator().manual_seed(1)
+    loader = [(torch.randn(2, 3, 32, 32, generator=g).clamp(-1, 1), torch.zeros(2)) for _ in range(2)]
+    conf = SimpleNamespace(output_dir=str(tmp_path / "run"), num_epochs=2, eval_batch_size=2, seed=0)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4)
+    sched = get_cosine_schedule_with_warmup(opt, 1, 4)
+    seen = []
+    hist = train_loop(conf, m, DDPMScheduler(), opt, loader, sched, "AD", 3, evaluate_epochs=(1,), save_epochs=(1,),
+                      num_inference_steps=2, on_epoch_end=lambda e, l, p: seen.append((e, type(p).__name__)))
+    assert len(hist) == 2 and all(h > 0 for h in hist) and seen == [(0, "DDPMPipeline"), (1, "DDPMPipeline")]
+    assert sched.last_epoch == 4 and not torch.equal(m.conv_out.weight.detach(), w0)
+    samples = sorted(os.listdir(os.path.join(conf.output_dir, "samples", "AD")))
+    assert samples == ["1.png", "2.png", "3.png"]
+    saved = os.path.join(conf.output_dir, "models", "model_AD")
+    assert sorted(os.listdir(saved)) == ["model_index.json", "scheduler", "unet"]
+    back = DDPMPipeline.from_pretrained(saved)
+    assert torch.equal(back.unet.conv_out.weight.detach(), m.conv_out.weight.detach())
