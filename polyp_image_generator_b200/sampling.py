@@ -91,3 +91,27 @@ def top_up(config, pipeline, cls: str, target: int, folder: Optional[str] = None
     first = have + 1 if continue_numbering else 1
     return generate_images(config, pipeline, out_dir, missing, first_index=first, rank=rank, world=world,
                            num_inference_steps=num_inference_steps, verbose=verbose)
+
+
+def per_class_resume_plan(folder: str, classes, targets):
+    """The resume / skip decision of train_with_lora_per_class.py:252-293 for each class, as data:
+
+        "train"     no `lora_<cls>` + `model_<cls>` pair in `folder` yet: train (and sample) from scratch     (:292-)
+        "generate"  trained, but `samples/<cls>` does not exist: generate all `target` images              (:281-290)
+        "top_up"    trained, `samples/<cls>` holds fewer files than `target`: generate the difference     (:265-278)
+        "done"      trained and enough samples
+
+    Returns [(cls, action, n_images_to_generate)] in the order of `classes`."""
+    present = set(os.listdir(folder)) if os.path.isdir(folder) else set()
+    plan = []
+    for cls, target in zip(classes, targets):
+        if f"lora_{cls}" in present and f"model_{cls}" in present:
+            sdir = os.path.join(folder, "samples", cls)
+            if os.path.exists(sdir):
+                have = count_samples(sdir)
+                plan.append((cls, "top_up", target - have) if have < target else (cls, "done", 0))
+            else:
+                plan.append((cls, "generate", target))
+        else:
+            plan.append((cls, "train", target))
+    return plan

@@ -477,3 +477,20 @@ def test_train_loop_mirrors_train_from_scratch(emu_backend, tmp_path):
     assert sorted(os.listdir(saved)) == ["model_index.json", "scheduler", "unet"]
     back = DDPMPipeline.from_pretrained(saved)
     assert torch.equal(back.unet.conv_out.weight.detach(), m.conv_out.weight.detach())
+
+
+def test_per_class_resume_plan(tmp_path):
+    """train_with_lora_per_class.py:252-293: which classes still need training, full sampling, a top-up, or nothing."""
+    from polyp_image_generator_b200.sampling import per_class_resume_plan
+    root = tmp_path / "run"
+    for d in ("lora_AD", "model_AD", "lora_HP", "model_HP", "lora_ASS", "model_ASS", "lora_X"):
+        (root / d).mkdir(parents=True)
+    (root / "samples" / "AD").mkdir(parents=True)
+    for i in range(1, 6):
+        (root / "samples" / "AD" / f"{i}.png").write_bytes(b"x")
+    (root / "samples" / "HP").mkdir()
+    for i in range(1, 4):
+        (root / "samples" / "HP" / f"{i}.png").write_bytes(b"x")
+    plan = per_class_resume_plan(str(root), ["AD", "HP", "ASS", "X", "NEW"], [5, 10, 7, 4, 2])
+    assert plan == [("AD", "done", 0), ("HP", "top_up", 7), ("ASS", "generate", 7), ("X", "train", 4), ("NEW", "train", 2)]
+    assert per_class_resume_plan(str(tmp_path / "missing"), ["AD"], [3]) == [("AD", "train", 3)]
