@@ -195,12 +195,12 @@ def run_lora_finetune(args, dev, world, rank, barrier):
     downsample_padding 0), r=8 / alpha=8 / dropout 0.3 adapters on to_q, to_k, to_v, to_out.0, everything else frozen;
     add_noise -> forward -> MSE -> backward (LoRA gradients only) -> all-reduce -> clip 1.0 -> AdamW, graph-replayed."""
     import torch.distributed as dist
-    import oracle
     from polyp_image_generator_b200 import DDPMScheduler, LoraConfig, UNet2DModel
     from polyp_image_generator_b200.graphs import GraphedTrainStep
+    from polyp_image_generator_b200.model import celebahq_unet_config
     S, B = args.lora_size, args.lora_batch
     torch.manual_seed(1)
-    model = UNet2DModel(**oracle.celebahq_unet_config(S)).to(dev)
+    model = UNet2DModel(**celebahq_unet_config(S)).to(dev)
     model.add_adapter(LoraConfig(r=8, lora_alpha=8, target_modules=["to_q", "to_k", "to_v", "to_out.0"],
                                  lora_dropout=0.3, init_lora_weights="gaussian"))
     model.to(dev).train()
@@ -247,7 +247,7 @@ def run_b200(args, rank, world, local_rank):
     from polyp_image_generator_b200 import DDPMScheduler, UNet2DModel
     from polyp_image_generator_b200 import ops as ops_mod
     from polyp_image_generator_b200.training import mse_loss
-    import oracle  # only for polyp_unet_config (the reference's constructor kwargs) and the CPU baseline leg
+    from polyp_image_generator_b200.model import polyp_unet_config      # the reference's constructor kwargs
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
@@ -255,7 +255,7 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     S, B = args.size, args.batch
     torch.manual_seed(0)
-    model = UNet2DModel(**oracle.polyp_unet_config(S)).to(dev)
+    model = UNet2DModel(**polyp_unet_config(S)).to(dev)
     model.train()
     sched = DDPMScheduler(num_train_timesteps=1000)
     if args.torch_optimizer:

@@ -15,6 +15,24 @@ from typing import Iterable
 from .unet import UNet2DModel
 
 
+def polyp_unet_config(sample_size: int = 128) -> dict:
+    """The UNet2DModel keyword arguments exactly as PolypGeneratorModel.py:26-47 passes them (113 673 219 parameters)."""
+    return dict(
+        sample_size=sample_size, in_channels=3, out_channels=3, layers_per_block=2,
+        block_out_channels=(128, 128, 256, 256, 512, 512),
+        down_block_types=("DownBlock2D", "DownBlock2D", "DownBlock2D", "DownBlock2D", "AttnDownBlock2D", "DownBlock2D"),
+        up_block_types=("UpBlock2D", "AttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"))
+
+
+def celebahq_unet_config(sample_size: int = 256) -> dict:
+    """The google/ddpm-celebahq-256 architecture of BASELINE configs[3]/[4]: the same blocks with
+    ONE attention head as wide as the block, downsample_padding 0, [sin, cos] timestep order with freq_shift 1,
+    norm_eps 1e-6."""
+    cfg = polyp_unet_config(sample_size)
+    cfg.update(attention_head_dim=None, downsample_padding=0, flip_sin_to_cos=False, freq_shift=1, norm_eps=1e-6)
+    return cfg
+
+
 class PolypGeneratorModel:
     def __init__(self, device, pretrained: bool = False, add_lora: bool = False, image_size: int = 224):
         """image_size: `TrainingConfig.image_size` of the reference (config_diffusion.py:6 = 224)."""
@@ -23,12 +41,7 @@ class PolypGeneratorModel:
         if pretrained:
             raise NotImplementedError("pretrained=True (Stable Diffusion v1.4 components from the hub) is outside the "
                                       "B200 hot path; construct the from-scratch UNet2DModel with pretrained=False")
-        self.unet = UNet2DModel(
-            sample_size=image_size, in_channels=3, out_channels=3, layers_per_block=2,
-            block_out_channels=(128, 128, 256, 256, 512, 512),
-            down_block_types=("DownBlock2D", "DownBlock2D", "DownBlock2D", "DownBlock2D", "AttnDownBlock2D",
-                              "DownBlock2D"),
-            up_block_types=("UpBlock2D", "AttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"))
+        self.unet = UNet2DModel(**polyp_unet_config(image_size))
         if device is not None:
             self.unet.to(device)
 

@@ -494,3 +494,25 @@ def test_per_class_resume_plan(tmp_path):
     plan = per_class_resume_plan(str(root), ["AD", "HP", "ASS", "X", "NEW"], [5, 10, 7, 4, 2])
     assert plan == [("AD", "done", 0), ("HP", "top_up", 7), ("ASS", "generate", 7), ("X", "train", 4), ("NEW", "train", 2)]
     assert per_class_resume_plan(str(tmp_path / "missing"), ["AD"], [3]) == [("AD", "train", 3)]
+
+
+def test_product_configs_equal_the_oracle_configs_and_bench_gpu_arm_does_not_import_the_oracle():
+    import ast
+    from polyp_image_generator_b200.model import celebahq_unet_config, polyp_unet_config
+    for s in (64, 128, 256):
+        assert polyp_unet_config(s) == oracle.polyp_unet_config(s)
+        assert celebahq_unet_config(s) == oracle.celebahq_unet_config(s)
+    # only the CPU-baseline leg of bench.py (cpu_oracle_train) may touch oracle/
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in (n for n in tree.body if isinstance(n, ast.FunctionDef)):
+        uses = any(isinstance(n, (ast.Import, ast.ImportFrom)) and
+                   any((a.name or "").split(".")[0] == "oracle" for a in n.names) or
+                   (isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle")
+                   for n in ast.walk(fn))
+        assert uses == (fn.name == "cpu_oracle_train"), fn.name
+    # and the product package never imports it
+    pkg = os.path.join(ROOT, "polyp_image_generator_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f
