@@ -2,14 +2,14 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import oracle
+from polyp_image_generator_b200.model import polyp_unet_config
 from polyp_image_generator_b200 import UNet2DModel
 from polyp_image_generator_b200 import ops as ops_mod
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 S = 128
 torch.manual_seed(0)
-m = UNet2DModel(**oracle.polyp_unet_config(S)).to("cuda").eval()
+m = UNet2DModel(**polyp_unet_config(S)).to("cuda").eval()
 x = torch.randn(B, 3, S, S, device="cuda")
 t = torch.full((B,), 500, device="cuda", dtype=torch.int64)
 with torch.no_grad():
