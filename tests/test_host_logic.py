@@ -516,3 +516,13 @@ def test_product_configs_equal_the_oracle_configs_and_bench_gpu_arm_does_not_imp
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_get_num_images_to_generate_kat():
+    """train_from_scratch.py:140-169 by hand: AD target = max(real, 1000); total = int(AD / p_AD); others = int(total * p)."""
+    from polyp_image_generator_b200.sampling import get_num_images_to_generate
+    real = {"AD": 612, "HP": 321, "ASS": 95}
+    assert get_num_images_to_generate(real, (0.4, 0.3, 0.3)) == {"AD": 388, "HP": 429, "ASS": 655}
+    assert get_num_images_to_generate(real, (0.6, 0.4), one_vs_rest=True) == {"AD": 388, "REST": 250}
+    big = {"AD": 3000, "HP": 4000, "ASS": 10}
+    assert get_num_images_to_generate(big, (0.4, 0.3, 0.3)) == {"AD": 0, "HP": 0, "ASS": 2240}
