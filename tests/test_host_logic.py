@@ -140,11 +140,13 @@ def test_unet_state_dict_and_arena(emu_backend):
     assert torch.equal(m2.conv_out.weight, m.conv_out.weight)
 
 
-@pytest.mark.parametrize("variant", ["polyp", "celebahq", "celebahq_1head"])
+@pytest.mark.parametrize("variant", ["polyp", "celebahq", "celebahq_1head", "polyp_96"])
 def test_unet_forward_backward_programs_match_oracle(emu_backend, variant):
     from polyp_image_generator_b200 import UNet2DModel
     if variant == "polyp":
         cfg, S = _small_cfg(32), 32
+    elif variant == "polyp_96":      # like the reference's 224 = 7 * 32: odd maps (3x3) at the bottom, 36 / 9 tokens
+        cfg, S = _small_cfg(96), 96
     else:
         cfg = oracle.celebahq_unet_config(64)
         cfg["block_out_channels"] = (64, 64, 128, 128, 128, 128)
