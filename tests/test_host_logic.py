@@ -528,3 +528,38 @@ def test_get_num_images_to_generate_kat():
     assert get_num_images_to_generate(real, (0.6, 0.4), one_vs_rest=True) == {"AD": 388, "REST": 250}
     big = {"AD": 3000, "HP": 4000, "ASS": 10}
     assert get_num_images_to_generate(big, (0.4, 0.3, 0.3)) == {"AD": 0, "HP": 0, "ASS": 2240}
+
+
+def test_capi_argument_validation_of_session3_entry_points(built_lib):
+    """The entry points added for the optimizer, wide-head attention, samplers, input transform and the GroupNorm
+    statistics fusion reject bad arguments before touching the device (negative rc + message, no GPU needed)."""
+    from polyp_image_generator_b200 import _capi
+    lib = _capi.load()
+    fake = ctypes.c_void_p(0x1000)          # 16-byte aligned, never dereferenced: validation fails first
+    odd = ctypes.c_void_p(0x1004)
+
+    def bad(rc, needle):
+        assert rc < 0 and needle in _capi.last_error(), (rc, _capi.last_error())
+
+    bad(lib.ddpm_bgemm(None, 8, 0, 0, 0, fake, 8, 0, 0, 0, fake, 8, 0, 0, 0, 16, 16, 16, 1, 1, 1.0, None), "null pointer")
+    bad(lib.ddpm_bgemm(fake, 8, 0, 0, 0, fake, 8, 0, 0, 0, fake, 8, 0, 0, 0, 0, 16, 16, 1, 1, 1.0, None), "bad shape")
+    bad(lib.ddpm_bgemm(fake, 8, 0, 0, 0, fake, 8, 0, 0, 0, fake, 12, 0, 0, 0, 16, 16, 16, 1, 1, 1.0, None), "16-byte aligned")
+    bad(lib.ddpm_bgemm(fake, 8, 0, 0, 0, fake, 8, 0, 0, 0, fake, 8, 0, 0, 0, 16, 16, 16, 70000, 1, 1.0, None), "gridDim.z")
+    bad(lib.ddpm_softmax_rows(None, 8, fake, 8, 4, 8, None), "bad argument")
+    bad(lib.ddpm_softmax_rows(fake, 4, fake, 8, 4, 8, None), "bad argument")              # lds < t
+    bad(lib.ddpm_softmax_rows_bwd(fake, 8, None, 8, fake, 4, 8, 1.0, None), "bad argument")
+    bad(lib.ddpm_resize_h_u8(None, fake, 4, 8, 3, 4, fake, fake, 3, None), "null pointer")
+    bad(lib.ddpm_resize_h_u8(fake, fake, 4, 8, 2, 4, fake, fake, 3, None), "bad shape")   # c must be 1 or 3
+    bad(lib.ddpm_resize_v_normalize(fake, fake, 1, 8, 8, 3, 0, fake, fake, 3, None, None), "bad shape")
+    bad(lib.ddpm_ddim_step(None, fake, None, fake, None, 16, 1.0, 0.1, 1.0, 0.1, 0.0, 1.0, 0, None), "bad argument")
+    bad(lib.ddpm_ddim_step(fake, odd, None, fake, None, 16, 1.0, 0.1, 1.0, 0.1, 0.0, 1.0, 0, None), "16-byte aligned")
+    bad(lib.ddpm_adamw_flat(None, fake, fake, fake, 16, fake, None, 1.0, None, 1e-3, 0.9, 0.999, 1e-8, 0.01, None),
+        "bad argument")
+    bad(lib.ddpm_adamw_flat(fake, odd, fake, fake, 16, fake, None, 1.0, None, 1e-3, 0.9, 0.999, 1e-8, 0.01, None),
+        "16-byte aligned")
+    bad(lib.ddpm_sumsq_f32(odd, 16, fake, None), "16-byte aligned")
+    bad(lib.ddpm_gn_stats_from_csum(None, 128, None, 0, 2, 32, fake, None), "bad argument")
+    bad(lib.ddpm_gn_stats_from_csum(fake, 100, None, 0, 2, 32, fake, None), "bad argument")   # channels % groups
+    bad(lib.ddpm_gn_bwd_dparams(None, None, 2, 128, 32, 64, 1e-5, fake, fake, None), "bad argument")
+    a = _capi.ConvArgs()
+    assert lib.ddpm_conv_gemm_workspace_elems(ctypes.byref(a)) == 0
