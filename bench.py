@@ -414,9 +414,11 @@ def run_b200(args, rank, world, local_rank):
     pr = ops_mod.OpProfiler(ops)
     pr.by_shape = True
     pr.start()
-    for _ in range(2):
-        eager_step(clean_dev, noise_dev, t_dev)
-    table = pr.stop()
+    try:
+        for _ in range(2):
+            eager_step(clean_dev, noise_dev, t_dev)
+    finally:
+        table = pr.stop()
     barrier()
     if rank == 0:
         agg = {}
@@ -486,7 +488,10 @@ def run_b200(args, rank, world, local_rank):
     # ---- secondary metric: LoRA fine-tune step at 256x256 on the celebahq-architecture UNet (BASELINE configs[3]) ----
     lora = None
     if not args.no_lora:
-        lora = run_lora_finetune(args, dev, world, rank, barrier)
+        try:
+            lora = run_lora_finetune(args, dev, world, rank, barrier)
+        except Exception as e:  # noqa: BLE001 -- a secondary section must not take the headline line down with it
+            lora = {"error": repr(e)[:300]}
 
     # ---- optional per-op breakdown (after the timed regions; CUDA events around every C-ABI op) ----
     if args.breakdown:       # all ranks step together (DDP collectives); rank 0 reports
