@@ -563,3 +563,38 @@ def test_capi_argument_validation_of_session3_entry_points(built_lib):
     bad(lib.ddpm_gn_bwd_dparams(None, None, 2, 128, 32, 64, 1e-5, fake, fake, None), "bad argument")
     a = _capi.ConvArgs()
     assert lib.ddpm_conv_gemm_workspace_elems(ctypes.byref(a)) == 0
+
+
+def test_from_pretrained_reads_a_hub_style_celebahq_config(emu_backend, tmp_path):
+    """The on-disk layout of google/ddpm-celebahq-256 (config.json as written by an old diffusers,
+    lists instead of tuples, `attention_head_dim: null`, a `.bin` weight file) loads into the drop-in UNet."""
+    import json
+    from polyp_image_generator_b200 import UNet2DModel
+    d = tmp_path / "unet"
+    d.mkdir()
+    hub = {
+        "_class_name": "UNet2DModel", "_diffusers_version": "0.0.4", "act_fn": "silu", "attention_head_dim": None,
+        "block_out_channels": [64, 64, 128, 128, 128, 128], "center_input_sample": False,
+        "down_block_types": ["DownBlock2D", "DownBlock2D", "DownBlock2D", "DownBlock2D", "AttnDownBlock2D", "DownBlock2D"],
+        "downsample_padding": 0, "flip_sin_to_cos": False, "freq_shift": 1, "in_channels": 3, "layers_per_block": 2,
+        "mid_block_scale_factor": 1, "norm_eps": 1e-06, "norm_num_groups": 32, "out_channels": 3, "sample_size": 64,
+        "time_embedding_type": "positional",
+        "up_block_types": ["UpBlock2D", "AttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"],
+    }
+    (d / "config.json").write_text(json.dumps(hub, indent=2))
+    cfg = oracle.celebahq_unet_config(64)
+    cfg["block_out_channels"] = (64, 64, 128, 128, 128, 128)
+    torch.manual_seed(4)
+    om = oracle.UNet2DModel(**cfg)
+    torch.save(om.state_dict(), str(d / "diffusion_pytorch_model.bin"))
+    m = UNet2DModel.from_pretrained(str(d))
+    assert m.config.attention_head_dim is None and m.config.downsample_padding == 0 and m.config.freq_shift == 1
+    assert list(m.state_dict().keys()) == list(om.state_dict().keys())
+    x, t = torch.randn(1, 3, 64, 64), torch.tensor([77])
+    with torch.no_grad():
+        y, yo = m.eval()(x, t).sample, om.eval()(x, t).sample
+    assert ((y - yo).norm() / yo.norm()).item() < 1e-5
+    # and our own save -> load round trip keeps the architecture knobs
+    m.save_pretrained(str(tmp_path / "again"))
+    m2 = UNet2DModel.from_pretrained(str(tmp_path / "again"))
+    assert vars(m2.config) == vars(m.config)
