@@ -276,11 +276,6 @@ int ddpm_upsample2x(const void* x, long long ldx, void* out, int n, int h, int w
 int ddpm_sumpool2x(const void* dy, long long ldy, const void* add, long long ldadd, void* out, int n, int h, int w,
                    int c, void* stream);                    /* out[b][i][j] = sum 2x2 dy + add */
 
-/* Bring-up probe (not on the product path): D[128x64] = A[shift:shift+128, :64] * B[64x64]^T with the A operand
- * descriptor starting `shift` 128-byte rows into a SWIZZLE_128B tile; base_offset_mode 1 sets the descriptor's
- * base_offset field to (start >> 7) & 7.  Used to validate the shifted-descriptor tap trick on hardware. */
-int ddpm_debug_shift_probe(const void* a, const void* b, float* out, int shift, int base_offset_mode, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,9 @@ from typing import Dict, Iterable, List, Sequence, Union
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+from . import rounding as rq
 
 
 @dataclass
@@ -49,10 +52,18 @@ class LoraLinear(nn.Module):
         nn.init.zeros_(b)
 
     def forward(self, x):
+        n = self.adapter_name
+        if rq.enabled():
+            # rounding-matched mode (oracle/rounding.py): same graph, bf16 at the product's storage points -- the
+            # operand copies of W, A and (alpha/r) B, and the rank-r activation U = dropout(x) A^T
+            y = F.linear(x, rq.weight(self.base_layer.weight), self.base_layer.bias)
+            if self.merged:
+                return y
+            u = rq.act(F.linear(self.lora_dropout[n](x), rq.weight(self.lora_A[n].weight)))
+            return y + F.linear(u, rq.weight(self.lora_B[n].weight * self.scaling))
         y = self.base_layer(x)
         if self.merged:
             return y
-        n = self.adapter_name
         return y + self.lora_B[n](self.lora_A[n](self.lora_dropout[n](x))) * self.scaling
 
     def delta_weight(self):

@@ -20,6 +20,21 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import rounding as rq
+
+
+def _conv(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """m(x); in the rounding-matched mode (oracle/rounding.py) with the bf16 operand copy of the weight."""
+    if not rq.enabled():
+        return m(x)
+    return F.conv2d(x, rq.weight(m.weight), m.bias, m.stride, m.padding)
+
+
+def _linear(m, x: torch.Tensor) -> torch.Tensor:
+    if not rq.enabled() or not isinstance(m, nn.Linear):
+        return m(x)
+    return F.linear(x, rq.weight(m.weight), m.bias)
+
 
 @dataclass
 class UNet2DOutput:
@@ -89,13 +104,13 @@ class ResnetBlock2D(nn.Module):
             self.conv_shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, padding=0, bias=True)
 
     def forward(self, input_tensor, temb):
-        hidden_states = self.conv1(self.nonlinearity(self.norm1(input_tensor)))
+        hidden_states = _conv(self.conv1, rq.act(self.nonlinearity(self.norm1(input_tensor))))
         temb = self.time_emb_proj(self.nonlinearity(temb))[:, :, None, None]
-        hidden_states = hidden_states + temb
-        hidden_states = self.conv2(self.dropout(self.nonlinearity(self.norm2(hidden_states))))
+        hidden_states = rq.act(hidden_states + temb)
+        hidden_states = _conv(self.conv2, rq.act(self.dropout(self.nonlinearity(self.norm2(hidden_states)))))
         if self.conv_shortcut is not None:
-            input_tensor = self.conv_shortcut(input_tensor)
-        return (input_tensor + hidden_states) / self.output_scale_factor
+            input_tensor = rq.act(_conv(self.conv_shortcut, input_tensor))
+        return rq.act((input_tensor + hidden_states) / self.output_scale_factor)
 
 
 class Attention(nn.Module):
@@ -119,19 +134,19 @@ class Attention(nn.Module):
         residual = hidden_states
         b, c, h, w = hidden_states.shape
         x = hidden_states.view(b, c, h * w).transpose(1, 2)
-        x = self.group_norm(x.transpose(1, 2)).transpose(1, 2)
-        q, k, v = self.to_q(x), self.to_k(x), self.to_v(x)
+        x = rq.act(self.group_norm(x.transpose(1, 2)).transpose(1, 2))
+        q, k, v = rq.act(_linear(self.to_q, x)), rq.act(_linear(self.to_k, x)), rq.act(_linear(self.to_v, x))
 
         def split(t):
             return t.view(b, -1, self.heads, self.dim_head).transpose(1, 2)
 
         o = F.scaled_dot_product_attention(split(q), split(k), split(v), attn_mask=None, dropout_p=0.0,
                                            is_causal=False, scale=self.scale)
-        o = o.transpose(1, 2).reshape(b, -1, c).to(q.dtype)
-        o = self.to_out[1](self.to_out[0](o))
+        o = rq.act(o.transpose(1, 2).reshape(b, -1, c).to(q.dtype))
+        o = self.to_out[1](_linear(self.to_out[0], o))
         o = o.transpose(-1, -2).reshape(b, c, h, w)
         o = o + residual
-        return o / self.rescale_output_factor
+        return rq.act(o / self.rescale_output_factor)
 
 
 class Downsample2D(nn.Module):
@@ -143,7 +158,7 @@ class Downsample2D(nn.Module):
     def forward(self, x):
         if self.padding == 0:
             x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
-        return self.conv(x)
+        return rq.act(_conv(self.conv, x))
 
 
 class Upsample2D(nn.Module):
@@ -155,7 +170,7 @@ class Upsample2D(nn.Module):
         if x.shape[0] >= 64:
             x = x.contiguous()
         x = F.interpolate(x, scale_factor=2.0, mode="nearest")
-        return self.conv(x)
+        return rq.act(_conv(self.conv, x))
 
 
 class DownBlock2D(nn.Module):
@@ -349,7 +364,7 @@ class UNet2DModel(nn.Module):
         t_emb = self.time_proj(timesteps).to(dtype=self.dtype)
         emb = self.time_embedding(t_emb)
 
-        sample = self.conv_in(sample)
+        sample = rq.act(_conv(self.conv_in, rq.act(sample)))
         res = (sample,)
         for blk in self.down_blocks:
             sample, r = blk(sample, emb)
@@ -359,7 +374,7 @@ class UNet2DModel(nn.Module):
             n = len(blk.resnets)
             r, res = res[-n:], res[:-n]
             sample = blk(sample, r, emb)
-        sample = self.conv_out(self.conv_act(self.conv_norm_out(sample)))
+        sample = _conv(self.conv_out, rq.act(self.conv_act(self.conv_norm_out(sample))))
         if not return_dict:
             return (sample,)
         return UNet2DOutput(sample=sample)

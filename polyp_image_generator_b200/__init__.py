@@ -17,7 +17,7 @@ def __getattr__(name):
     if name in ("LoraConfig", "lora_state_dict", "recover_lora_modules", "save_lora_weights", "load_lora_weights"):
         from . import lora
         return getattr(lora, name)
-    if name in ("mse_loss", "fused_train_step"):
+    if name in ("mse_loss", "train_step", "train_loop"):
         from . import training
         return getattr(training, name)
     if name in ("PolypGeneratorModel",):

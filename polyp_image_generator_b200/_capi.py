@@ -107,7 +107,6 @@ SIGNATURES = {
     "ddpm_linear_f32_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "ddpm_linear_f32_dgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ddpm_reduce_hw": [_vp, _ll, _i, _i, _i, _vp, _ll, _vp, _vp],
-    "ddpm_debug_shift_probe": [_vp, _vp, _vp, _i, _i, _vp],
     "ddpm_dropout": [_vp, _vp, _vp, _ll, _f, _ull, _ull, _vp, _vp],
     "ddpm_space_to_depth": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _vp],
     "ddpm_zero_insert2x": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp],

@@ -17,11 +17,11 @@ INCLUDE = PKG.parent / "include"
 LIB = PKG / "libddpm_b200.so"
 OBJ = PKG / "build"
 
-SOURCES = ["elementwise.cu", "groupnorm.cu", "misc.cu", "attention.cu", "conv_igemm.cu", "conv_halo.cu", "conv_wgrad_row.cu", "bgemm.cu", "preprocess.cu",
-           "probe.cu"]
+SOURCES = ["elementwise.cu", "groupnorm.cu", "misc.cu", "attention.cu", "conv_igemm.cu", "conv_halo.cu", "conv_wgrad_row.cu", "bgemm.cu", "preprocess.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+    "-cudart", "shared",      # libcudart.so (torch's own): no statically linked runtime inside the product library
 ]
 
 
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-cudart", "shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -22,7 +22,7 @@ class DistributedDataParallel(nn.Module):
     """Wraps the B200 UNet2DModel; same call surface as torch's DDP for the reference's loop (`model(x, t)`,
     `.parameters()`, `.train()/.eval()`, `.module`)."""
 
-    def __init__(self, module: nn.Module, process_group=None, bucket_cap_mb: float = 128.0,
+    def __init__(self, module: nn.Module, process_group=None, bucket_cap_mb: float = 32.0,
                  broadcast_parameters: bool = True):
         super().__init__()
         if not dist.is_initialized():
@@ -34,7 +34,9 @@ class DistributedDataParallel(nn.Module):
         self._side = None
         self._pending: List[Tuple[int, int]] = []
         self._done_upto: Optional[int] = None
+        self._arena_trainable: Optional[bool] = None
         module._grad_ready_hook = self._finish
+        module._grad_begin_hook = self._begin
         module._grad_progress_hook = self._progress
         if broadcast_parameters:
             self.broadcast_parameters()
@@ -69,8 +71,16 @@ class DistributedDataParallel(nn.Module):
             self._side = torch.cuda.Stream(device=G.device)
         return self._side
 
+    def _begin(self):
+        """Start of a backward pass: forget bucket progress a previous (possibly aborted) pass left behind."""
+        self._done_upto = None
+
     def _progress(self, G: torch.Tensor, final_from: int):
         """Backward finished every tensor-core weight gradient at arena offsets >= final_from: ship full buckets."""
+        if self._arena_trainable is None:
+            self._arena_trainable = any(p.requires_grad for p, _, _ in self.module._plan.layout)
+        if not self._arena_trainable:      # LoRA runs: the arena holds no gradients, only the adapters are exchanged
+            return
         hi = self._done_upto if self._done_upto is not None else self.module._plan.temb_w_off
         if hi - final_from < self.bucket_elems:
             return
@@ -92,6 +102,7 @@ class DistributedDataParallel(nn.Module):
         """End of backward: reduce what is left (early layers, biases, norms, time MLP, LoRA) and join."""
         m = self.module
         arena_trainable = any(p.requires_grad for p, _, _ in m._plan.layout)
+        self._arena_trainable = None       # requires_grad flags may change between steps (unfreeze_layers)
         side = self._stream_ctx(G)
         if arena_trainable:
             hi = self._done_upto if self._done_upto is not None else m._plan.temb_w_off

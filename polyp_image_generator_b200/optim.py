@@ -49,6 +49,15 @@ class FusedAdamW(torch.optim.Optimizer):
         n = st.nbytes() // 4
         return torch.empty(0, dtype=torch.float32, device=tensors[0].device).set_(st, 0, (n,))
 
+    def load_state_dict(self, state_dict):
+        """torch.optim.Optimizer.load_state_dict; the flat moments / step counter are adopted at the next step()."""
+        super().load_state_dict(state_dict)
+        for st in self.state.values():          # torch keeps same-device tensors by reference: own the restored copies
+            for k in ("flat_exp_avg", "flat_exp_avg_sq", "flat_scalars"):
+                if torch.is_tensor(st.get(k)):
+                    st[k] = st[k].clone()
+        self._p = self._m = self._v = self._scal = None
+
     def _bind(self):
         ps = self.param_groups[0]["params"]
         if any(not p.requires_grad for p in ps):
@@ -59,7 +68,15 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._p is None or self._p.data_ptr() != flat.data_ptr():
             keep = self._m is not None and self._m.numel() == flat.numel() and self._m.device == flat.device
             self._p = flat
-            if not keep:
+            saved = self.state.get(ps[0], {})
+            if not keep and all(k in saved and torch.is_tensor(saved[k]) for k in
+                                ("flat_exp_avg", "flat_exp_avg_sq", "flat_scalars")) and \
+                    saved["flat_exp_avg"].numel() == flat.numel():
+                # restored by load_state_dict(): continue from the saved moments and step count
+                self._m = saved["flat_exp_avg"].to(device=flat.device, dtype=torch.float32).clone()
+                self._v = saved["flat_exp_avg_sq"].to(device=flat.device, dtype=torch.float32).clone()
+                self._scal = saved["flat_scalars"].to(device=flat.device, dtype=torch.float32).clone()
+            elif not keep:
                 self._m = torch.zeros_like(flat)
                 self._v = torch.zeros_like(flat)
                 self._scal = torch.zeros(4, dtype=torch.float32, device=flat.device)

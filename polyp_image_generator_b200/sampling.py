@@ -115,19 +115,3 @@ def per_class_resume_plan(folder: str, classes, targets):
         else:
             plan.append((cls, "train", target))
     return plan
-
-
-def get_num_images_to_generate(real_counts, distribution, ad_minimum: int = 1000, one_vs_rest: bool = False):
-    """train_from_scratch.py:140-169: how many synthetic images each class needs so that the AD class reaches
-    max(real AD count, ad_minimum) and the classes follow `distribution` ((AD, HP, ASS) or (AD, REST) fractions).
-    `real_counts` is the {'AD': n, 'HP': n, 'ASS': n} dictionary the reference reads from train.csv (:134-138)."""
-    ad_target = max(real_counts["AD"], ad_minimum)
-    total_target = int(ad_target / distribution[0])
-    if one_vs_rest:
-        rest_count = real_counts["HP"] + real_counts["ASS"]
-        rest_target = int(total_target * distribution[1])
-        return {"AD": max(0, ad_target - real_counts["AD"]), "REST": max(0, rest_target - rest_count)}
-    hp_target = int(total_target * distribution[1])
-    ass_target = int(total_target * distribution[2])
-    return {"AD": max(0, ad_target - real_counts["AD"]), "HP": max(0, hp_target - real_counts["HP"]),
-            "ASS": max(0, ass_target - real_counts["ASS"])}

@@ -161,6 +161,20 @@ class DDPMScheduler:
             self._coef_cache[t] = c
         return c
 
+    def _draw_philox_state(self, x: torch.Tensor):
+        """(seed, offset) of one in-kernel noise draw, taken from -- and advancing -- the device's default CUDA generator,
+        the way torch's own Philox consumers do: torch.manual_seed(s) makes the stream reproducible, consecutive draws
+        (any scheduler / pipeline instance, any class or epoch) never repeat, and ranks seeded differently draw
+        different noise.  (Ranks seeded identically draw identical noise, exactly as torch.randn would.)"""
+        if not x.is_cuda:
+            self._philox_offset += 1
+            return 0, self._philox_offset
+        idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        gen = torch.cuda.default_generators[idx]
+        off = gen.get_offset()
+        gen.set_offset(off + 4)           # one Philox counter block per draw: the kernel indexes elements itself
+        return gen.initial_seed(), off // 4 + 1
+
     def step(self, model_output: torch.Tensor, timestep: Union[int, torch.Tensor], sample: torch.Tensor,
              generator=None, return_dict: bool = True, variance_noise: Optional[torch.Tensor] = None,
              want_pred_original_sample: bool = True):
@@ -175,10 +189,9 @@ class DDPMScheduler:
             raise TypeError("scheduler step kernel computes in fp32 (the pipeline runs the scheduler in fp32)")
         eps, x = model_output.contiguous(), sample.contiguous()
         if t > 0 and variance_noise is None and generator is None:
-            seed = torch.cuda.default_generators[x.device.index or 0].initial_seed() if x.is_cuda else 0
-            self._philox_offset += 1
+            seed, offset = self._draw_philox_state(x)
             prev = ops.scheduler_step_philox(eps, x, c["sa"], c["sb"], c["c0"], c["ct"], c["sigma"], clip,
-                                             seed & 0xFFFFFFFFFFFFFFFF, self._philox_offset)
+                                             seed & 0xFFFFFFFFFFFFFFFF, offset)
             x0 = None
         else:
             z = None

@@ -73,12 +73,24 @@ def train_step(model, noise_scheduler, optimizer, clean_images: torch.Tensor, no
     else:
         loss.backward()
     params = [p for p in model.parameters() if p.requires_grad]
-    if max_grad_norm is not None and getattr(optimizer, "max_grad_norm", None) is None:
-        torch.nn.utils.clip_grad_norm_(params, max_grad_norm)       # optim.FusedAdamW clips inside its update
+    internal_clip = getattr(optimizer, "max_grad_norm", None)       # optim.FusedAdamW clips inside its update
     if scaler is not None:
-        scaler.step(optimizer)
+        # Reference order (train_from_scratch.py:103-111): clip_grad_norm_ runs on the STILL-SCALED gradients, then
+        # scaler.step unscales and steps.  Both optimizer paths follow it: FusedAdamW's internal clip (which would see
+        # the unscaled gradients) is switched off for this step and the explicit clip below takes its place.
+        if max_grad_norm is not None:
+            torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+        if internal_clip is not None:
+            optimizer.max_grad_norm = None
+        try:
+            scaler.step(optimizer)
+        finally:
+            if internal_clip is not None:
+                optimizer.max_grad_norm = internal_clip
         scaler.update()
     else:
+        if max_grad_norm is not None and internal_clip is None:
+            torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
         optimizer.step()
     optimizer.zero_grad()
     if lr_scheduler is not None:

@@ -187,6 +187,27 @@ def arena_written(data_ptr: int) -> None:
         m.invalidate_weight_cache()
 
 
+_DEPRECATED_ATTN = ((".query.", ".to_q."), (".key.", ".to_k."), (".value.", ".to_v."), (".proj_attn.", ".to_out.0."))
+
+
+def convert_deprecated_attention_keys(state_dict):
+    """diffusers' ModelMixin._convert_deprecated_attention_blocks, applied at load time: checkpoints saved before the
+    AttentionBlock -> Attention refactor (google/ddpm-celebahq-256 and the other google/ddpm-* repositories) store the
+    attention projections as `*.attentions.N.{query,key,value,proj_attn}.{weight,bias}`; the module tree names them
+    `to_q / to_k / to_v / to_out.0`.  Keys that already use the new names pass through unchanged."""
+    if not any(".attentions." in k and any(old in k for old, _ in _DEPRECATED_ATTN) for k in state_dict):
+        return state_dict
+    out = type(state_dict)()
+    for k, v in state_dict.items():
+        if ".attentions." in k:
+            for old, new in _DEPRECATED_ATTN:
+                if old in k:
+                    k = k.replace(old, new)
+                    break
+        out[k] = v
+    return out
+
+
 def _align(n, a=4):
     return (n + a - 1) // a * a
 
@@ -333,8 +354,13 @@ class UNet2DModel(nn.Module):
             sd = load_file(st)
         else:
             sd = torch.load(os.path.join(directory, "diffusion_pytorch_model.bin"), map_location="cpu")
-        model.load_state_dict(sd)
+        model.load_state_dict(convert_deprecated_attention_keys(sd))
         return model
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """nn.Module.load_state_dict, accepting the pre-0.14 attention-block key names of the hub's google/ddpm-*
+        checkpoints (see convert_deprecated_attention_keys)."""
+        return super().load_state_dict(convert_deprecated_attention_keys(state_dict), strict=strict, assign=assign)
 
     # ---------------------------------------------------------------------------------------------------------
     # plan: layer records in execution order + arena layout
@@ -847,7 +873,7 @@ class UNet2DModel(nn.Module):
         N = hd.patches.shape[0]
         c0 = cfg.block_out_channels[0]
         ted = self._temb_dim
-        G = torch.zeros(P.total, device=self._arena.device, dtype=torch.float32)
+        G = self._fresh_grad_arena()
         d_temb_all = torch.zeros((N, P.temb_total), device=G.device, dtype=torch.float32)
         st = SimpleNamespace(ops=ops, G=G, d_temb_all=d_temb_all, skip_grads={}, N=N, wg_stream=None, keep=[],
                              defer_kw={})
@@ -895,6 +921,9 @@ class UNet2DModel(nn.Module):
                               dbeta=db_o, **st.defer_kw)
 
         prog = getattr(self, "_grad_progress_hook", None)
+        begin = getattr(self, "_grad_begin_hook", None)
+        if begin is not None:
+            begin()
         for i in range(len(tape.steps) - 1, first_needed - 1, -1):
             kind, rec, s = tape.steps[i]
             if kind == "resnet":
@@ -933,6 +962,23 @@ class UNet2DModel(nn.Module):
                                      self._gview(G, P.te.b1, (ted,)), False)
         self.last_launches_bwd = ops.launches - l0
         return G, st
+
+    def _fresh_grad_arena(self) -> torch.Tensor:
+        """Zero-filled flat fp32 gradient arena.  The previous step's arena is reused (one memset, no allocation) unless a
+        parameter's .grad still aliases it -- gradient accumulation (train_epoch_with_accumulation) adds the new
+        gradients into the old ones, so those steps get a fresh buffer."""
+        P, dev = self._plan, self._arena.device
+        capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
+        G = getattr(self, "_grad_arena", None)
+        if G is not None and G.device == dev and G.numel() == P.total and not capturing:
+            lo, hi = G.data_ptr(), G.data_ptr() + 4 * G.numel()
+            live = any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p, _, _ in P.layout)
+            if not live:
+                return G.zero_()
+        G = torch.zeros(P.total, device=dev, dtype=torch.float32)
+        if not capturing:
+            self._grad_arena = G        # (a captured step owns its arena inside the graph's private pool)
+        return G
 
     @staticmethod
     def _async_wgrad(st, fn):

@@ -1,4 +1,4 @@
-"""Hardware probe: shifted (non-1024-aligned) SWIZZLE_128B UMMA operand descriptors (see csrc/probe.cu)."""
+"""Hardware probe: shifted (non-1024-aligned) SWIZZLE_128B UMMA operand descriptors (kernel: profiles/scratch/shift_probe.cu -- it was linked into the library during round-1 bring-up as ddpm_debug_shift_probe; it is no longer part of the product ABI, so this script is a record of the experiment, not a runnable tool)."""
 import os
 import sys
 
