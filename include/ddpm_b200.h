@@ -120,6 +120,10 @@ typedef struct ddpm_conv_args {
   float* splitk_ws; long long splitk_ws_elems;
 } ddpm_conv_args;
 int ddpm_conv_gemm(const ddpm_conv_args* args, void* stream);
+/* Number of column strips per image row the halo-resident 3x3 kernel (conv_halo.cu) uses at image width w, 0 when that
+ * width runs on the generic implicit-GEMM kernel.  The host uses it to decide where the GroupNorm statistics / backward
+ * fusions (out_csum, gn_sums) are free (their reductions hide behind the next tile's mainloop only in that kernel). */
+int ddpm_conv_halo_strips(int w);
 long long ddpm_conv_gemm_workspace_elems(const ddpm_conv_args* args);
 
 /* Conv / linear weight gradient on tcgen05:

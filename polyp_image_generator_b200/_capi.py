@@ -87,6 +87,7 @@ SIGNATURES = {
     "ddpm_to_uint8_nhwc": [_vp, _vp, _i, _i, _i, _i, _vp],
     "ddpm_conv_gemm": [C.POINTER(ConvArgs), _vp],
     "ddpm_conv_gemm_workspace_elems": [C.POINTER(ConvArgs)],
+    "ddpm_conv_halo_strips": [_i],
     "ddpm_conv_wgrad": [C.POINTER(WgradArgs), _vp],
     "ddpm_prep_weight": [_vp, _vp, _ll, _vp, _ll, _i, _i, _i, _vp],
     "ddpm_prep_weights_batched": [_vp, _i, _i, _i, _vp],

@@ -50,6 +50,8 @@ int make_map4(CUtensorMap* out, const void* ptr, const long long dims[4], const 
 int env_int(const char* name, int dflt);
 // halo-resident 3x3 conv: returns 1 when the problem is not eligible (caller falls back to the generic kernel)
 int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream);
+bool conv_uses_halo(const ::ddpm_conv_args* a);   // would ddpm_conv_gemm take the halo-resident kernel for this problem?
+int conv_halo_strips(int w);                      // column strips per image row at this width (0: not served)
 }
 struct ddpm_wgrad_args;
 namespace ddpm {

@@ -14,6 +14,13 @@
 // 128-byte-aligned start is valid).  L2->SM traffic per FLOP drops ~2.6x.  Slots that fall on a pad position
 // produce garbage accumulator rows that are simply not stored (W / (W + 1) efficiency).
 //
+// Wide images (W > ~140: the 224^2 default of the reference, the 256^2 LoRA configs) do not fit a double-buffered halo of
+// full rows in shared memory, so each row is cut into S column STRIPS of Ws = W / S pixels and a (image, strip) pair
+// becomes the unit that is tiled: the slot space of a unit has pitch Wp = Ws + 2 -- one halo column on EACH side, real
+// pixels of the neighbouring strip or TMA zero fill at the image border -- the box starts at w = strip * Ws - 1, and
+// the slots on the two halo columns are the garbage rows (Ws / (Ws + 2) efficiency: 98.5 % at 256^2).  S = 1 keeps the
+// shared pad slot (pitch W + 1).
+//
 // Structure: persistent CTAs (one per SM), static round-robin tile schedule, warp-specialised:
 //   warps 0-7  epilogue (TMEM -> registers -> bias / time-embedding / residual -> bf16 NHWC), overlapped with the
 //              next tile's mainloop through double-buffered accumulators (2 x 256 TMEM columns)
@@ -36,6 +43,8 @@ constexpr int kHaloBBytes = 128 * 128;   // one weight tile: 128 cout rows x 64 
 
 struct HaloParams {
   int N, H, W, Wp;
+  int S, Ws;             // column strips per row, pixels per strip (S * Ws == W); units = N * S
+  int units;
   int kb0, kb1;
   int Cout, Cin_total;
   int R;                 // padded rows per halo box
@@ -101,17 +110,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t hb = 0, hph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles;
-      const int img = mt / p.tiles_per_img;
-      const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
+      const int unit = mt / p.tiles_per_img;
+      const int q0 = (mt - unit * p.tiles_per_img) * kTileSlots;
+      const int img = unit / p.S;
+      const int x0 = (unit - img * p.S) * p.Ws - 1;      // first column of the box: the left halo column of the strip
       const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
       for (int c = 0; c < kbt; ++c) {
         mbar_wait(&halo_empty[hb], hph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&halo_full[hb], p.halo_bytes);
           if (c < p.kb0)
-            tma_load_4d(halo + hb * p.halo_stride, &tmA0, &halo_full[hb], c * 64, -1, row_lo, img);
+            tma_load_4d(halo + hb * p.halo_stride, &tmA0, &halo_full[hb], c * 64, x0, row_lo, img);
           else
-            tma_load_4d(halo + hb * p.halo_stride, &tmA1, &halo_full[hb], (c - p.kb0) * 64, -1, row_lo, img);
+            tma_load_4d(halo + hb * p.halo_stride, &tmA1, &halo_full[hb], (c - p.kb0) * 64, x0, row_lo, img);
         }
         __syncwarp();
         hb ^= 1;
@@ -146,8 +157,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint64_t db = db_base;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles;
-      const int img = mt / p.tiles_per_img;
-      const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
+      const int unit = mt / p.tiles_per_img;
+      const int q0 = (mt - unit * p.tiles_per_img) * kTileSlots;
       const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
       const int rel00 = q0 - row_lo * p.Wp - p.Wp - 1;   // slot of tap (-1, -1) of output slot q0 inside the halo buffer
       mbar_wait(&tmem_empty[acc], aph ^ 1);
@@ -196,8 +207,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
-      const int img = mt / p.tiles_per_img;
-      const int q0 = (mt - img * p.tiles_per_img) * kTileSlots;
+      const int unit = mt / p.tiles_per_img;
+      const int q0 = (mt - unit * p.tiles_per_img) * kTileSlots;
+      const int img = unit / p.S;
+      const int xs = (unit - img * p.S) * p.Ws;          // first image column of this strip
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       // step i = (cc, u): column chunk half*2 + i/2, row block i%2; the GroupNorm input of step i+1 is loaded while
       // step i is processed, and that of step 0 while the tile's mainloop is still running
@@ -207,8 +220,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int slot = q0 + u * 128 + q * 32 + lane;
         const int h = slot / p.Wp;
         const int w = slot - h * p.Wp - 1;
-        valid = (w >= 0) && (h < p.H);
-        pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
+        valid = (w >= 0) && (w < p.Ws) && (h < p.H);
+        pix = (static_cast<long long>(img) * p.H + h) * p.W + xs + w;
       };
       EpiX xcur, xnext;
       {
@@ -308,15 +321,18 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // pair tile -> (image of this CTA, first slot, cout tile)
-  auto decode = [&](int pt, int& img, bool& img_ok, int& q0, int& nt) {
+  // pair tile -> (image and first column of this CTA's strip, first slot, cout tile); the pair works on two
+  // consecutive (image, strip) units
+  auto decode = [&](int pt, int& img, int& xs, bool& img_ok, int& q0, int& nt) {
     nt = pt % p.n_tiles;
     const int mt = pt / p.n_tiles;
     const int ip = mt / p.tiles_per_img;
     q0 = (mt - ip * p.tiles_per_img) * kTileSlots;
-    img = 2 * ip + static_cast<int>(rank);
-    img_ok = img < p.N;
-    if (!img_ok) img = p.N - 1;          // odd batch: the last peer recomputes the last image and stores nothing
+    int unit = 2 * ip + static_cast<int>(rank);
+    img_ok = unit < p.units;
+    if (!img_ok) unit = p.units - 1;     // odd unit count: the last peer recomputes the last unit and stores nothing
+    img = unit / p.S;
+    xs = (unit - img * p.S) * p.Ws;
   };
 
   if (warp == 8) {
@@ -324,17 +340,17 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     uint32_t hb = 0, hph = 0;
     const uint32_t full0 = mapa_u32(smem_u32(&halo_full[0]), 0), full1 = mapa_u32(smem_u32(&halo_full[1]), 0);
     for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
-      int img, q0, nt; bool ok;
-      decode(pt, img, ok, q0, nt);
+      int img, xs, q0, nt; bool ok;
+      decode(pt, img, xs, ok, q0, nt);
       const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
       for (int c = 0; c < kbt; ++c) {
         mbar_wait(&halo_empty[hb], hph ^ 1);
         if (elect_one()) {
           const uint32_t fb = hb ? full1 : full0;
           if (c < p.kb0)
-            tma_load_4d_pair(halo + hb * p.halo_stride, &tmA0, fb, c * 64, -1, row_lo, img);
+            tma_load_4d_pair(halo + hb * p.halo_stride, &tmA0, fb, c * 64, xs - 1, row_lo, img);
           else
-            tma_load_4d_pair(halo + hb * p.halo_stride, &tmA1, fb, (c - p.kb0) * 64, -1, row_lo, img);
+            tma_load_4d_pair(halo + hb * p.halo_stride, &tmA1, fb, (c - p.kb0) * 64, xs - 1, row_lo, img);
           if (leader) mbar_expect_tx(&halo_full[hb], 2u * p.halo_bytes);   // arrive (1 of 2) + both CTAs' bytes
           else mbar_arrive_cluster(fb);                                     // arrive (2 of 2)
         }
@@ -375,8 +391,8 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       uint32_t bs = 0, bph = 0, hb = 0, hph = 0, acc = 0, aph = 0;
       uint64_t db = db_base;
       for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
-        int img, q0, nt; bool ok;
-        decode(pt, img, ok, q0, nt);
+        int img, xs, q0, nt; bool ok;
+        decode(pt, img, xs, ok, q0, nt);
         const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
         const int rel00 = q0 - row_lo * p.Wp - p.Wp - 1;
         mbar_wait(&tmem_empty[acc], aph ^ 1);
@@ -424,16 +440,16 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     uint32_t acc = 0, aph = 0;
     const uint32_t empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
-      int img, q0, nt; bool img_ok;
-      decode(pt, img, img_ok, q0, nt);
+      int img, xs, q0, nt; bool img_ok;
+      decode(pt, img, xs, img_ok, q0, nt);
       auto geom = [&](int i, int& col, bool& valid, long long& pix, int& u) {
         u = i & 1;
         col = nt * 128 + (half * 2 + (i >> 1)) * 32;
         const int slot = q0 + u * 128 + q * 32 + lane;
         const int h = slot / p.Wp;
         const int w = slot - h * p.Wp - 1;
-        valid = img_ok && (w >= 0) && (h < p.H);
-        pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
+        valid = img_ok && (w >= 0) && (w < p.Ws) && (h < p.H);
+        pix = (static_cast<long long>(img) * p.H + h) * p.W + xs + w;
       };
       EpiX xcur, xnext;
       {
@@ -477,32 +493,74 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   if (warp == 10) tmem_dealloc_pair(tmem_base, 512);
 }
 
-// 4-D activation map with a caller-chosen box (not cached through make_act_map's (wb,hb,nb) key space clash:
-// the key includes the box, so the shared cache is safe to reuse)
-int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
-  if (env_int("DDPM_HALO", 1) == 0) return 1;
-  if (a->ntaps != 9 || (a->out == nullptr && a->out_f32 == nullptr)) return 1;
-  if (a->src_n != 0 && a->src_n != a->n) return 1;
+// Strip plan for an image width: the smallest number of column strips S (S | W) whose double-buffered halo leaves room
+// for a weight-tile ring of >= 3 full (or 6 half) tiles.  Returns 0 when the width is not served by this kernel.
+struct HaloGeom {
+  int S, Ws, Wp, R;
+  uint32_t halo_bytes, halo_stride;
+  size_t fixed;
+};
+static bool halo_geometry(int W, HaloGeom* g) {
+  const int min_w = env_int("DDPM_HALO_MIN_W", 64);
+  if (W < min_w) return false;
+  for (int S = 1; S <= 8; ++S) {
+    if (W % S) continue;
+    const int Ws = W / S;
+    if (Ws < 32 || (S > 1 && Ws < min_w)) break;
+    const int Wp = (S == 1) ? W + 1 : Ws + 2;
+    if (Wp > 256) continue;                                  // TMA box extent limit
+    // rows covering [q0 - Wp - 1, q0 + 255 + Wp + 1] for any q0
+    const int R = (kTileSlots + 2 * Wp + 1) / Wp + 2;
+    if (R > 256) continue;
+    const uint32_t hbytes = static_cast<uint32_t>(R) * Wp * 128u;
+    const uint32_t hstride = (hbytes + 1023u) & ~1023u;
+    const size_t fixed = 2ull * hstride + 512 + 1024;
+    if (fixed + 3 * kHaloBBytes > 227 * 1024) continue;
+    g->S = S; g->Ws = Ws; g->Wp = Wp; g->R = R;
+    g->halo_bytes = hbytes; g->halo_stride = hstride; g->fixed = fixed;
+    return true;
+  }
+  return false;
+}
+
+int conv_halo_strips(int W) {
+  HaloGeom g;
+  if (env_int("DDPM_HALO", 1) == 0 || !halo_geometry(W, &g)) return 0;
+  return g.S;
+}
+
+static bool halo_taps_ok(const ::ddpm_conv_args* a) {
+  if (a->ntaps != 9 || (a->src_n != 0 && a->src_n != a->n)) return false;
   const int cin_total = a->c0 + a->c1;
   for (int t = 0; t < 9; ++t) {
     if (a->tap_dn[t] != 0 || a->tap_dh[t] != t / 3 - 1 || a->tap_dw[t] != t % 3 - 1 || a->tap_wk[t] != t * cin_total)
-      return 1;
+      return false;
   }
-  const int W = a->w, H = a->h, Wp = W + 1;
-  if (W < env_int("DDPM_HALO_MIN_W", 64) || Wp > 256) return 1;
+  return true;
+}
+
+// would ddpm_conv_gemm run this problem on the halo-resident kernel?
+bool conv_uses_halo(const ::ddpm_conv_args* a) {
+  return halo_taps_ok(a) && conv_halo_strips(a->w) > 0;
+}
+
+int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
+  if (env_int("DDPM_HALO", 1) == 0) return 1;
+  if (!halo_taps_ok(a) || (a->out == nullptr && a->out_f32 == nullptr)) return 1;
+  const int cin_total = a->c0 + a->c1;
+  const int W = a->w, H = a->h;
+  HaloGeom g;
+  if (!halo_geometry(W, &g)) return 1;
   HaloParams p;
   std::memset(&p, 0, sizeof(p));
-  p.N = a->n; p.H = H; p.W = W; p.Wp = Wp;
+  p.N = a->n; p.H = H; p.W = W; p.Wp = g.Wp;
+  p.S = g.S; p.Ws = g.Ws; p.units = a->n * g.S;
   p.kb0 = a->c0 / 64; p.kb1 = a->c1 / 64;
   p.Cout = a->cout; p.Cin_total = cin_total;
-  // rows covering [q0 - Wp - 1, q0 + 255 + Wp + 1] for any q0: floor((256 + 2*Wp + 1) / Wp) + 2, capped by the box limit
-  int R = (kTileSlots + 2 * Wp + 1) / Wp + 2;
-  if (R > 256) return 1;
-  p.R = R;
-  p.halo_bytes = static_cast<uint32_t>(R) * Wp * 128u;
-  p.halo_stride = (p.halo_bytes + 1023u) & ~1023u;
-  const size_t fixed = 2ull * p.halo_stride + 512 + 1024;
-  if (fixed + 2 * kHaloBBytes > 227 * 1024) return 1;
+  p.R = g.R;
+  p.halo_bytes = g.halo_bytes;
+  p.halo_stride = g.halo_stride;
+  const size_t fixed = g.fixed;
   int bst = static_cast<int>((227 * 1024 - fixed) / kHaloBBytes);
   if (bst > kHaloMaxBStages) bst = kHaloMaxBStages;
   bst = env_int("DDPM_HALO_BSTAGES", bst) < bst ? env_int("DDPM_HALO_BSTAGES", bst) : bst;
@@ -510,26 +568,26 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
   p.b_stages = bst;
   p.mma_n = a->cout >= 128 ? 128 : ((a->cout + 15) / 16) * 16;   // narrow outputs: do not multiply the zero rows
   const size_t smem = fixed + static_cast<size_t>(bst) * kHaloBBytes;
-  p.tiles_per_img = (H * Wp + kTileSlots - 1) / kTileSlots;
+  p.tiles_per_img = (H * g.Wp + kTileSlots - 1) / kTileSlots;     // tiles per (image, strip) unit
   p.n_tiles = (a->cout + 127) / 128;
-  p.total_tiles = a->n * p.tiles_per_img * p.n_tiles;
+  p.total_tiles = p.units * p.tiles_per_img * p.n_tiles;
   if (int e = fill_epilogue(&p.epi, a)) return e;
 
   CUtensorMap ma0, ma1, mb;
-  if (int e = make_act_map(&ma0, a->x0, a->c0, a->ld0, a->n, H, W, Wp, R, 1)) return e;
+  if (int e = make_act_map(&ma0, a->x0, a->c0, a->ld0, a->n, H, W, g.Wp, g.R, 1)) return e;
   if (a->c1 > 0) {
-    if (int e = make_act_map(&ma1, a->x1, a->c1, a->ld1, a->n, H, W, Wp, R, 1)) return e;
+    if (int e = make_act_map(&ma1, a->x1, a->c1, a->ld1, a->n, H, W, g.Wp, g.R, 1)) return e;
   } else {
     ma1 = ma0;
   }
   const long long k_total = a->k_total > 0 ? a->k_total : a->ldw;
-  if (env_int("DDPM_HALO_PAIR", 1) != 0 && a->n >= 2) {
-    // CTA-pair variant: half weight tiles (8 KB per stage), pair tiles over image pairs
+  if (env_int("DDPM_HALO_PAIR", 1) != 0 && p.units >= 2) {
+    // CTA-pair variant: half weight tiles (8 KB per stage), pair tiles over pairs of (image, strip) units
     HaloParams pp = p;
     int pst = static_cast<int>((227 * 1024 - fixed) / (kHaloBBytes / 2));
     if (pst > kHaloMaxPairStages) pst = kHaloMaxPairStages;
     pp.b_stages = pst;
-    pp.total_tiles = ((a->n + 1) / 2) * p.tiles_per_img * p.n_tiles;
+    pp.total_tiles = ((p.units + 1) / 2) * p.tiles_per_img * p.n_tiles;
     const size_t psmem = fixed + static_cast<size_t>(pst) * (kHaloBBytes / 2);
     if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 64)) return e;
     static size_t pconfigured = 0;
@@ -553,3 +611,5 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
 }
 
 }  // namespace ddpm
+
+extern "C" int ddpm_conv_halo_strips(int w) { return ddpm::conv_halo_strips(w); }

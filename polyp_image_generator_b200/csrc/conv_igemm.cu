@@ -820,7 +820,7 @@ extern "C" long long ddpm_conv_gemm_workspace_elems(const ddpm_conv_args* a) {
   // fp32 elements of split-K workspace ddpm_conv_gemm would use for this problem (0: no split)
   if (!a || a->out_f32 || a->gn_sums || a->out_csum || a->cout % 8) return 0;
   if (a->n <= 0 || a->h <= 0 || a->w <= 0 || a->cout <= 0 || a->ntaps <= 0) return 0;   // ddpm_conv_gemm rejects these
-  if (a->ntaps == 9 && a->w >= env_int("DDPM_HALO_MIN_W", 64)) return 0;      // halo-resident kernel
+  if (conv_uses_halo(a)) return 0;                                             // halo-resident kernel
   int wb, hb, nb;
   choose_box(a->n, a->h, a->w, &wb, &hb, &nb);
   const long long mt = static_cast<long long>((a->w + wb - 1) / wb) * ((a->h + hb - 1) / hb) * ((a->n + nb - 1) / nb);

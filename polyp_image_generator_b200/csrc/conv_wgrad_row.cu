@@ -194,8 +194,10 @@ int launch_wgrad_row(const ::ddpm_wgrad_args* a, cudaStream_t stream) {
   }
   const int W = a->w;
   if (W < env_int("DDPM_WGRAD_ROW_MIN_W", 16) || W % 16) return 1;
-  const int kw = W < 128 ? W : 128;
-  if (W % kw) return 1;
+  // pixels per segment row: the largest multiple of 16 up to 128 that divides W (128 at 128^2 / 256^2, 112 at 224^2)
+  int kw = W < 128 ? W : 128;
+  while (kw >= 16 && W % kw) kw -= 16;
+  if (kw < 16 || (W >= 128 && kw < 64)) return 1;
   int hb = 1;
   if (W < 128) {
     hb = 128 / W;

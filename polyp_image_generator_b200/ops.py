@@ -82,6 +82,7 @@ class CudaOps:
         self.lib = _capi.load()
         self.launches = 0  # kernels launched through this object (bench.py reports it)
         self._freqs = {}
+        self._halo_strips = {}
 
     # ---- scheduler / loss ----------------------------------------------------------------------------
     def add_noise(self, x0, noise, t, sqrt_ac, sqrt_1mac):
@@ -160,16 +161,21 @@ class CudaOps:
         hw = grid[1] * grid[2]
         return hw >= 4096
 
-    @staticmethod
-    def gn_stats_fusable(grid: Tuple[int, int, int]) -> bool:
+    def gn_stats_fusable(self, grid: Tuple[int, int, int]) -> bool:
         """Should a 3x3 stride-1 conv that PRODUCES a tensor over this grid also reduce the per-(sample, channel) moments
         its consuming GroupNorm needs (conv_gemm(csum=...))?  At >= 64x64 the GroupNorm forward is HBM-bound and drops
         from the two-phase team kernel (0.139 ms at 128^2 x 128, 59 % of the copy peak) to one streaming pass (0.102 ms,
-        81 %).  Only where the conv runs on the halo-resident kernel (64 <= W <= 255), whose epilogue overlaps the next
-        tile's mainloop: in the generic kernel the extra warp reductions are exposed (measured: +1.6 ms on the 256^2
-        LoRA step)."""
+        81 %).  Only where the conv runs on the halo-resident kernel (ddpm_conv_halo_strips(w) > 0), whose epilogue
+        overlaps the next tile's mainloop: in the generic kernel the extra warp reductions are exposed (measured: +1.6 ms
+        on the 256^2 LoRA step)."""
         hw = grid[1] * grid[2]
-        return hw >= 4096 and 64 <= grid[2] <= 255
+        return hw >= 4096 and self.halo_strips(grid[2]) > 0
+
+    def halo_strips(self, w: int) -> int:
+        s = self._halo_strips.get(w)
+        if s is None:
+            s = self._halo_strips[w] = int(self.lib.ddpm_conv_halo_strips(int(w)))
+        return s
 
     def conv_gemm(self, x0, x1, taps: Sequence[Tap], wgt, cout: int, grid: Tuple[int, int, int], bias=None,
                   temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0, gn=None, csum=None):

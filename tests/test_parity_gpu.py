@@ -168,22 +168,16 @@ def _small_cfg(S=32):
     return cfg
 
 
-def _grad_report(m, om):
-    og = dict(om.named_parameters())
-    tot = sum(p.grad.norm() ** 2 for p in om.parameters()) ** 0.5
-    num = den = 0.0
-    worst, worst_name = 0.0, ""
-    for n, p in m.named_parameters():
-        g = og[n].grad
-        d = (p.grad.detach().cpu() - g)
-        num += d.norm().item() ** 2
-        den += g.norm().item() ** 2
-        # per-tensor error measured against max(|g_n|, 5% of the whole-gradient norm): the gradients of tiny deep
-        # layers (1-16 tokens, batch 2-4) are dominated by bf16 noise compounded over ~70 layers at random init
-        r = (d.norm() / (g.norm() + 5e-2 * tot)).item()
-        if r > worst:
-            worst, worst_name = r, n
-    return (num / den) ** 0.5, worst, worst_name
+def _grad_report(m, om, x, t, noise):
+    """-> (whole-gradient rel error vs the fp32 oracle, worst per-tensor noise-floor ratio, its name).  The ratio is
+    (product vs fp32 oracle) / max(rounding-matched oracle vs fp32 oracle, 5e-3) per tensor, over every tensor that
+    carries >= 1e-6 of the gradient norm: see tests/parity_util.py and tests/test_parity_full_gpu.py."""
+    from parity_util import _grad_table, _noise_floor_ratio, _oracle_grads
+    _, g_o = _oracle_grads(om, x, t, noise, rounded=False)
+    _, g_r = _oracle_grads(om, x, t, noise, rounded=True)
+    whole, rows = _grad_table(m, g_o)
+    ratio, name, _ = _noise_floor_ratio(rows, g_r, g_o)
+    return whole, ratio, name
 
 
 def test_unet_golden_small_case(dev):
@@ -208,9 +202,10 @@ def test_unet_golden_small_case(dev):
     for n, p in params.items():      # whole-gradient norm check via the stored per-tensor norms
         num += (p.grad.norm().item() - gold["grad_norms"][n]) ** 2
     assert (num ** 0.5) / tot < 2e-2
-    for k, g in gold["grads"].items():
-        d = (params[k].grad.detach().cpu() - g).norm().item()
-        assert d / (g.norm().item() + 5e-2 * tot) < 5e-2, k
+    for k, g in gold["grads"].items():       # the stored tensors that carry >= 1 % of the gradient norm each
+        if g.norm().item() >= 1e-2 * tot:
+            print(f"golden grad {k}: rel {rel(params[k].grad, g):.4f}")
+            assert rel(params[k].grad, g) < 2e-2, k
 
 
 @pytest.mark.parametrize("variant,S,B", [("polyp_small", 32, 3), ("celebahq_small", 64, 2), ("celebahq_1head", 64, 3),
@@ -245,10 +240,9 @@ def test_unet_forward_backward_vs_oracle(dev, variant, S, B):
     assert rel(pred, pred_o) < 2e-2
     loss = mse_loss(pred, noise.to(dev))
     loss.backward()
-    F.mse_loss(pred_o, noise).backward()
-    total, worst, name = _grad_report(m, om)
+    total, worst, name = _grad_report(m, om, x, t, noise)
     assert total < 2e-2, f"whole-gradient rel error {total}"
-    assert worst < 6e-2, f"{name}: {worst}"
+    assert worst < 2.0, f"{name}: {worst} x the bf16-storage noise floor of that tensor"
     # inference path (no tape) gives the same prediction; python-int timestep broadcast
     with torch.no_grad():
         p2 = m(x.to(dev), t.to(dev)).sample
@@ -469,33 +463,25 @@ def test_lora_forward_backward_and_merge_vs_oracle(dev):
     pred_o = om(x, t).sample
     assert rel(pred, pred_o) < 2e-2
     mse_loss(pred, nz.to(dev)).backward()
-    F.mse_loss(pred_o, nz).backward()
-    og = dict(om.named_parameters())
-    tot = sum(p.grad.norm() ** 2 for p in om.parameters() if p.grad is not None) ** 0.5
-    num = den = 0.0
-    per_tensor = {}
     for n, p in m.named_parameters():
-        if not p.requires_grad:
-            assert p.grad is None
-            continue
-        g = og[n].grad
-        e = (p.grad.cpu() - g).norm().item()
-        num += e ** 2
-        den += g.norm().item() ** 2
-        per_tensor[n] = (e / tot.item(), e / max(g.norm().item(), 1e-30),
-                         F.cosine_similarity(p.grad.cpu().reshape(1, -1), g.reshape(1, -1)).item())
-    worst = sorted(per_tensor.items(), key=lambda kv: -kv[1][0])[:6]
-    print("worst LoRA tensors (err/total, err/own, cos):", worst)
-    # Noise floor, measured (profiles/scratch/debug_lora.py): the adapters sit in the 1..16-token
-    # attentions at the bottom of the UNet, where the gradient has crossed ~120 bf16-rounded activations; per tensor
-    # the bf16 path differs from the fp32 oracle by 6-10 % (more for the 1-token mid-block attention of this 32x32
-    # case), and by the SAME amount from our own full-weight wgrad on the merged model -- activation rounding, not
-    # the LoRA path.  Against the oracle we therefore only check the whole LoRA gradient loosely; the LoRA path
-    # itself is checked tightly below against the full-weight gradient of the SAME backward pass.
-    g_all = torch.cat([p.grad.cpu().reshape(-1) for n, p in m.named_parameters() if p.requires_grad])
-    o_all = torch.cat([og[n].grad.reshape(-1) for n, p in m.named_parameters() if p.requires_grad])
-    assert F.cosine_similarity(g_all[None], o_all[None]).item() > 0.95, worst
-    assert (num / den) ** 0.5 < 0.35, worst
+        assert p.requires_grad or p.grad is None, n
+    # Adapter gradients.  The adapters sit in the 1..16-token attentions at the bottom of the UNet, behind ~60 bf16
+    # storage points in each direction: ANY bf16 realisation of the graph (the rounding-matched oracle) differs from
+    # the fp32 oracle by several per cent per adapter tensor at random init.  End to end the product must stay within
+    # 2x of that floor, tensor by tensor; the LoRA path itself is checked tightly below (self-consistency) and
+    # layer-locally at 256x256 in tests/test_parity_full_gpu.py::test_celebahq_256_lora_step_vs_oracle.
+    from parity_util import _grad_table, _noise_floor_ratio, _oracle_grads
+    _, g_o = _oracle_grads(om, x, t, nz, rounded=False)
+    _, g_r = _oracle_grads(om, x, t, nz, rounded=True)
+    whole, rows = _grad_table(m, g_o)
+    ratio, worst_name, cnt = _noise_floor_ratio(rows, g_r, g_o, floor=1e-6)
+    floor_whole = (sum((g_r[n] - g_o[n]).norm().item() ** 2 for n in g_o) /
+                   sum(g_o[n].norm().item() ** 2 for n in g_o)) ** 0.5
+    print(f"LoRA gradients: whole vs fp32 {whole:.4f}, bf16-storage floor {floor_whole:.4f}, worst tensor ratio "
+          f"{ratio:.2f} ({worst_name}), {cnt} tensors")
+    assert len(rows) == 48
+    assert whole < 2.0 * max(floor_whole, 1e-2), (whole, floor_whole)
+    assert ratio < 2.0, (worst_name, ratio)
 
     # Self-consistency (common-mode noise cancels): with the base projections ALSO trainable, the same backward
     # yields dW = dY^T x, and the adapter gradients must equal dA = s B^T dW, dB = s dW A^T  (s = alpha / r = 1).
