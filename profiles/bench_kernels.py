@@ -94,6 +94,56 @@ def bench_convgn(ops, B, iters, pk, first=None):
               f"fused {ms_f:7.3f} ms {fl / ms_f / 1e9:7.1f} TFLOP/s  (+{ms_f - ms_p:.3f} ms)", flush=True)
 
 
+def bench_epi(ops, B, iters, pk, first=None):
+    """Halo conv 3x3 with each epilogue fusion switched on separately: which one costs what (the epilogue warps have one
+    tile's mainloop -- 9216 tensor clocks at 128->128 -- to drain 256 x 128 accumulators)."""
+    print(f"# conv_gemm 3x3 epilogue variants, batch {B}")
+    for (h, cin, cout) in [(128, 128, 128), (128, 256, 128), (64, 128, 128), (64, 256, 256)][:first]:
+        nb = B if h <= 128 else max(2, B // 4)
+        x = bf(nb, h, h, cin)
+        w = bf(cout, 9 * cin) * 0.1
+        bias = torch.randn(cout, device="cuda")
+        temb = torch.randn(nb, cout, device="cuda")
+        res = bf(nb, h, h, cout)
+        gx = bf(nb, h, h, cout)
+        gam, bet = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+        _, _, coef = ops.gn_fwd(gx, None, 32, 1e-5, gam, bet, True, want_coef=True)
+        out = torch.empty(nb, h, h, cout, device="cuda", dtype=torch.bfloat16)
+        cs = torch.zeros(nb, cout, 2, device="cuda")
+        tp = taps_3x3(cin)
+        grid = (nb, h, h)
+        variants = [
+            ("plain", {}), ("bias", dict(bias=bias)), ("bias+temb", dict(bias=bias, temb=temb)),
+            ("bias+res", dict(bias=bias, res=res)), ("bias+temb+csum", dict(bias=bias, temb=temb, csum=cs)),
+            ("bias+res+csum", dict(bias=bias, res=res, csum=cs)), ("gn-bwd fusion", dict(gn=(gx, None, coef, True, cs))),
+        ]
+        fl = 2.0 * nb * h * h * cout * cin * 9
+        for name, kw in variants:
+            ms = timeit(lambda i: ops.conv_gemm(x, None, tp, w, cout, grid, out=out, **kw), iters, 1)
+            print(f"epi {h:3d}x{h:<3d} {cin:4d}->{cout:<4d} {name:16s} {ms:7.3f} ms {fl / ms / 1e9:7.1f} TFLOP/s "
+                  f"{fl / ms / 1e9 / pk['bf16_tflops']:.3f} of peak", flush=True)
+
+
+def bench_hires(ops, B, iters, pk, first=None):
+    """224^2 / 256^2 shapes of BASELINE configs[3]/[4] and the reference's default image_size (batch 8)."""
+    nb = 8
+    print(f"# conv_gemm / conv_wgrad at 224^2 and 256^2, batch {nb}")
+    for (h, cin, cout, taps) in [(256, 128, 128, 9), (256, 256, 128, 9), (224, 128, 128, 9), (112, 128, 128, 9),
+                                 (256, 256, 128, 1), (128, 128, 128, 9)][:first]:
+        x = bf(nb, h, h, cin)
+        w = bf(cout, taps * cin) * 0.1
+        bias = torch.randn(cout, device="cuda")
+        out = torch.empty(nb, h, h, cout, device="cuda", dtype=torch.bfloat16)
+        tp = taps_3x3(cin) if taps == 9 else taps_1x1()
+        fl = 2.0 * nb * h * h * cout * cin * taps
+        ms = timeit(lambda i: ops.conv_gemm(x, None, tp, w, cout, (nb, h, h), bias=bias, out=out), iters, 1)
+        dy = bf(nb, h, h, cout)
+        dw = torch.zeros(cout, taps * cin, device="cuda")
+        ms_w = timeit(lambda i: ops.conv_wgrad(dy, x, None, tp, dw, (nb, h, h)), iters, 1)
+        print(f"hires {h:3d}x{h:<3d} {cin:4d}->{cout:<4d} k{taps} conv {ms:7.3f} ms {fl / ms / 1e9:7.1f} TFLOP/s | "
+              f"wgrad {ms_w:7.3f} ms {fl / ms_w / 1e9:7.1f} TFLOP/s", flush=True)
+
+
 def bench_wgrad(ops, B, iters, pk, first=None):
     print(f"# conv_wgrad, batch {B}")
     for (h, cin, cout, taps) in CONV_SHAPES[:first]:
@@ -182,6 +232,10 @@ if __name__ == "__main__":
         bench_convgn(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("wgrad", "all"):
         bench_wgrad(ops, a.batch, a.iters, pk, a.first)
+    if a.what in ("epi", "all"):
+        bench_epi(ops, a.batch, a.iters, pk, a.first)
+    if a.what in ("hires", "all"):
+        bench_hires(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("gn", "all"):
         bench_gn(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("small", "all"):
