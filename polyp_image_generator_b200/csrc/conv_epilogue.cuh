@@ -97,14 +97,20 @@ __device__ __forceinline__ float warp_column_sums(float (&a)[32], int lane) {
 }
 
 struct EpiX {
-  uint32_t w[16];   // 32 bf16 channels of the GroupNorm input at this thread's pixel
+  uint32_t w[16];   // 32 bf16 channels at this thread's pixel: the GroupNorm input (backward fusion) or the residual
 };
-// Issue the loads of the GroupNorm input for (pix, col .. col+31) -- call this EARLY (before waiting on the
-// accumulator / while the previous chunk is processed) so the latency is off the critical path.
+// does the prefetch slot carry the GroupNorm input (true) or the residual (false)?
+__device__ __forceinline__ bool epi_slot_is_gn(const EpiParams& e) { return e.gsums != nullptr && !e.gstats; }
+// Issue the loads of the per-pixel side input of (pix, col .. col+31) -- the GroupNorm input of the backward fusion, or
+// else the residual -- EARLY (before waiting on the accumulator / while the previous chunk is processed) so that the
+// DRAM latency is off the epilogue's critical path.  (A residual loaded inside epi_chunk cost +0.055 ms on a 0.21 ms
+// 128->128 conv at 128^2: four exposed ~1 us round trips per tile against a 4.8 us mainloop.)
 __device__ __forceinline__ void epi_load_x(const EpiParams& e, bool valid, long long pix, int col, EpiX& x) {
-  if (e.gsums != nullptr && !e.gstats && valid && col < e.Cout) {
+  if (epi_slot_is_gn(e) && valid && col < e.Cout) {
     const __nv_bfloat16* xp = (col < e.gc0) ? e.gx0 + pix * e.gld0 + col : e.gx1 + pix * e.gld1 + (col - e.gc0);
     ld64B(xp, x.w, e.wide != 0);
+  } else if (!epi_slot_is_gn(e) && e.res != nullptr && valid && col < e.Cout) {
+    ld64B(e.res + pix * e.ldr + col, x.w, e.wide != 0);
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) x.w[j] = 0u;
@@ -116,7 +122,9 @@ __device__ __forceinline__ void epi_load_x(const EpiParams& e, bool valid, long 
 // together when GN fusion is on (shuffles), and the warp's valid rows must belong to ONE sample (host-checked).
 // With GroupNorm fusion, this lane's column totals are ADDED to (t1, t2); the caller flushes them with
 // epi_flush_sums once all row blocks sharing these columns (and this sample) have been processed.
-template <bool GN = true>
+// PREF: xin was filled by epi_load_x for this (pix, col) -- the residual, when there is one and the slot is not taken by
+// the GroupNorm input, comes from there instead of a load issued here.
+template <bool GN = true, bool PREF = GN>
 __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bool valid, int n, long long pix, int col,
                                           int lane, float& t1, float& t2, const EpiX& xin) {
   const bool col_ok = col < e.Cout;
@@ -137,12 +145,20 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
       }
     }
     if (e.res) {
-      uint32_t rw[16];
-      ld64B(e.res + pix * e.ldr + col, rw, e.wide != 0);
+      if (PREF && !epi_slot_is_gn(e)) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[2 * j] += bf16lo_f(rw[j]);
-        v[2 * j + 1] += bf16hi_f(rw[j]);
+        for (int j = 0; j < 16; ++j) {
+          v[2 * j] += bf16lo_f(xin.w[j]);
+          v[2 * j + 1] += bf16hi_f(xin.w[j]);
+        }
+      } else {
+        uint32_t rw[16];
+        ld64B(e.res + pix * e.ldr + col, rw, e.wide != 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[2 * j] += bf16lo_f(rw[j]);
+          v[2 * j + 1] += bf16hi_f(rw[j]);
+        }
       }
     }
   }

@@ -501,7 +501,9 @@ struct HaloGeom {
   size_t fixed;
 };
 static bool halo_geometry(int W, HaloGeom* g) {
-  const int min_w = env_int("DDPM_HALO_MIN_W", 64);
+  // 32x32 maps included: measured on the 128^2 training step, 35.80 -> 35.39 ms against the generic kernel (L2-bound
+  // tap-by-tap refetch); below that a 256-slot tile wastes too many slots on the last partial tile of an image
+  const int min_w = env_int("DDPM_HALO_MIN_W", 32);
   if (W < min_w) return false;
   for (int S = 1; S <= 8; ++S) {
     if (W % S) continue;

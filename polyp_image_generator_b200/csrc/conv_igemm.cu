@@ -173,13 +173,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int col0 = nt * BLOCK_N;
 
     EpiX xcur, xnext;
-    if (GN) epi_load_x(p.epi, valid, pix, col0, xcur);   // in flight while the mainloop runs
+    const bool pref = GN || (p.epi.res != nullptr && p.splitk_ws == nullptr);   // side input: GroupNorm x or residual
+    if (pref) epi_load_x(p.epi, valid, pix, col0, xcur);   // in flight while the mainloop runs
+    else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) xcur.w[j] = xnext.w[j] = 0u;
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int n_warp = (GN && p.epi.gsums) ? epi_warp_sample(valid, n) : -1;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
-      if (GN && c + 1 < BLOCK_N / 32) epi_load_x(p.epi, valid, pix, col0 + (c + 1) * 32, xnext);
+      if (pref && c + 1 < BLOCK_N / 32) epi_load_x(p.epi, valid, pix, col0 + (c + 1) * 32, xnext);
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
       tmem_ld_wait();
@@ -199,11 +204,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       float t1 = 0.f, t2 = 0.f;
-      epi_chunk<GN>(p.epi, v, valid, n, pix, col0 + c * 32, lane, t1, t2, xcur);
-      if (GN) {
-        epi_flush_sums(p.epi, n_warp, col0 + c * 32, lane, t1, t2);
-        xcur = xnext;
-      }
+      epi_chunk<GN, true>(p.epi, v, valid, n, pix, col0 + c * 32, lane, t1, t2, xcur);
+      if (GN) epi_flush_sums(p.epi, n_warp, col0 + c * 32, lane, t1, t2);
+      xcur = xnext;
     }
   }
   tc_fence_before();

@@ -296,6 +296,7 @@ class CudaOps:
         out = torch.empty((n, h, w, 64), device=x.device, dtype=torch.bfloat16)
         _capi.check(self.lib.ddpm_im2col3(_ptr(x), _ptr(out), n, h, w, cin, _ptr(chan_sum), _stream()), "ddpm_im2col3")
         self.launches += 1
+        out._ddpm_alg_k = 9 * cin          # columns that carry data (FLOP accounting only)
         return out
 
     def nhwc_to_nchw_f32(self, src, cout: int):
@@ -583,6 +584,7 @@ class CudaOps:
         _capi.check(self.lib.ddpm_zero_insert2x(_ptr(dy), ld, _ptr(out), n, ho, wo, c, h, w, _stream()),
                     "ddpm_zero_insert2x")
         self.launches += 1
+        out._ddpm_alg_pixels_div = 4       # 75 % structural zeros (FLOP accounting only)
         return out
 
     def upsample2x(self, x):
@@ -599,6 +601,22 @@ class CudaOps:
                                             _ptr(out), n, h2 // 2, w2 // 2, c, _stream()), "ddpm_sumpool2x")
         self.launches += 1
         return out
+
+
+def algorithmic_conv_flops(x0, x1, taps, cout, grid, out_f32: bool = False) -> float:
+    """ALGORITHMIC FLOPs of one conv_gemm / conv_wgrad launch (2 * B * Ho * Wo * Cout * Cin * k^2 of the
+    convolution the launch implements), not the FLOPs the tensor cores execute:
+      * the stride-2 dgrad runs as a stride-1 correlation over a zero-inserted gradient (4x the pixels, 75 % zeros):
+        tensors produced by zero_insert2x carry `_ddpm_alg_pixels_div = 4`;
+      * the 3-channel boundary convs run on padded operands: im2col3 patches (64 columns, 9 * cin used) carry
+        `_ddpm_alg_k`, and conv_out's 32 padded output columns count as its real `out_channels` (tagged on the weight
+        operand as `_ddpm_alg_cout`)."""
+    n, h, w = grid
+    cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+    k = getattr(x0, "_ddpm_alg_k", None)
+    kk = float(k) if k is not None else float(cin * len(taps))
+    pix = float(n) * h * w / float(getattr(x0, "_ddpm_alg_pixels_div", 1))
+    return 2.0 * pix * float(cout) * kk
 
 
 class OpProfiler:
@@ -619,14 +637,10 @@ class OpProfiler:
         try:
             if name == "conv_gemm":
                 x0, x1, taps, wgt, cout, grid = args[:6]
-                cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
-                n, h, w = grid
-                return 2.0 * n * h * w * cout * cin * len(taps), 0.0
+                return algorithmic_conv_flops(x0, x1, taps, getattr(wgt, "_ddpm_alg_cout", cout), grid), 0.0
             if name == "conv_wgrad":
                 dy, x0, x1, taps, dw, grid = args[:6]
-                cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
-                n, h, w = grid
-                return 2.0 * n * h * w * dy.shape[-1] * cin * len(taps), 0.0
+                return algorithmic_conv_flops(x0, x1, taps, getattr(dy, "_ddpm_alg_k", dy.shape[-1]), grid), 0.0
             if name == "gn_apply":
                 return 0.0, 4.0 * out.numel()                 # bf16 read + bf16 write
             if name == "gn_fwd":

@@ -546,6 +546,7 @@ class UNet2DModel(nn.Module):
         c0 = self.conv_in.out_channels
         self._cin_wf = self._bf16[P.cin_wf_off:P.cin_wf_off + c0 * 64].view(c0, 64)
         self._cout_wf = self._bf16[P.cout_wf_off:P.cout_wf_off + 32 * 9 * c0].view(32, 9 * c0)
+        self._cout_wf._ddpm_alg_cout = self.conv_out.out_channels      # rows that carry data (FLOP accounting only)
         self._cout_wd = self._bf16[P.cout_wd_off:P.cout_wd_off + c0 * 64].view(c0, 64)
         self._cout_b32 = torch.zeros(32, device=dev, dtype=torch.float32)
         self._prep_table = None
