@@ -29,8 +29,11 @@ def peaks():
         return {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
 
 
+WARMUP = 3
+
+
 def timeit(fn, iters, nbuf):
-    for i in range(3):
+    for i in range(WARMUP):
         fn(i % nbuf)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -222,7 +225,9 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--first", type=int, default=None, help="only the first N conv shapes (short ncu runs)")
+    ap.add_argument("--warmup", type=int, default=3, help="untimed launches per shape (0 for ncu captures)")
     a = ap.parse_args()
+    WARMUP = a.warmup
     ops = ops_mod.get()
     pk = peaks()
     torch.manual_seed(0)
