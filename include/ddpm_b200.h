@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 #define DDPM_MAX_TAPS 9
-#define DDPM_ABI_VERSION 2
+#define DDPM_ABI_VERSION 3
 
 const char* ddpm_last_error(void);
 int ddpm_abi_version(void);
@@ -118,6 +118,13 @@ typedef struct ddpm_conv_args {
    * SMs split the reduction over blockIdx.z, accumulate fp32 partial sums here and finish in a second pass.
    * ddpm_conv_gemm_workspace_elems() says how many elements this problem would use (0 = it does not split). */
   float* splitk_ws; long long splitk_ws_elems;
+  /* fp32-faithful inference (split-bf16, see "fp32-faithful mode" below): 1 = `out` and `res` are SPLIT tensors --
+   * per pixel cout "hi" channels followed by cout "lo" channels (ldo / ldr >= 2*cout), value = hi + lo; the fp32
+   * accumulator is stored as hi = bf16(v), lo = bf16(v - hi).  Excludes gn_sums / out_csum.  The A operand of such a
+   * conv is a split tensor passed as x0 = [hi | lo] (c0 = 2*cin) and x1 = its hi half (c1 = cin), with the weight
+   * operand [W_hi | W_hi | W_lo] per tap: (A_hi + A_lo) W_hi + A_hi W_lo, fp32 accumulation -- three bf16 MMAs per
+   * product instead of one, ~2^-17 relative error instead of 2^-9. */
+  int split_io;
 } ddpm_conv_args;
 int ddpm_conv_gemm(const ddpm_conv_args* args, void* stream);
 /* Number of column strips per image row the halo-resident 3x3 kernel (conv_halo.cu) uses at image width w, 0 when that
@@ -164,6 +171,25 @@ int ddpm_prep_weights_batched(const ddpm_prep_desc* table_dev, int n_entries, in
  *   ddpm_nhwc_to_nchw_f32: out[n][k][h][w] = src[pix][k], k < cout <= 4 (src fp32 NHWC, pixel stride ld). */
 int ddpm_im2col3(const float* src, void* patches, int n, int h, int w, int cin, float* chan_sum, void* stream);
 int ddpm_nhwc_to_nchw_f32(const float* src, long long ld, float* out, int n, int h, int w, int cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32-faithful mode (reference: the sampling loop of train_from_scratch.py:39-66,121-125 and the LoRA trainers run
+ * WITHOUT autocast, i.e. in fp32).  Activations travel as "split-bf16" tensors: per pixel C hi channels then C lo
+ * channels, value = hi + lo (16 mantissa bits).  The tensor cores stay the compute engine (ddpm_conv_args.split_io);
+ * the *_split entry points below are the same ops as their bf16 namesakes on split tensors, with exact (non-approx)
+ * transcendental arithmetic.  c0 / c1 / ld* count LOGICAL channels / elements of the split row (ld >= 2*c).
+ * ---------------------------------------------------------------------------------------------- */
+int ddpm_gn_stats_split(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
+                        int groups, float* stats, void* stream);
+int ddpm_gn_apply_split(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
+                        int groups, const float* stats, float eps, const float* gamma, const float* beta, int silu,
+                        void* y, long long ldy, void* stream);
+/* qkv: split rows [q k v hi (3*heads*d) | q k v lo]; o: split rows [hi (heads*d) | lo]; narrow heads (d = 8..64). */
+int ddpm_attn_fwd_split(const void* qkv, long long ldqkv, void* o, long long ldo, int b, int t, int heads, int d,
+                        float scale, void* stream);
+/* patches[pix][128] bf16: columns [0, 9cin) hi, [32, 32 + 9cin) lo, [64, 64 + 9cin) hi again (the three MMA terms of
+ * conv_in as ONE two-k-block GEMM against [W_hi | W_hi | W_lo] laid out the same way), zero elsewhere; cin <= 3. */
+int ddpm_im2col3_split(const float* src, void* patches, int n, int h, int w, int cin, void* stream);
 
 /* GroupNorm statistics: stats[n][g] = (sum, sumsq) over the (possibly concatenated) channels of group g. */
 int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,

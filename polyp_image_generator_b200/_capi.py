@@ -12,7 +12,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libddpm_b200.so"
 
 MAX_TAPS = 9
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _ll = C.c_longlong
 _vp = C.c_void_p
@@ -41,6 +41,7 @@ class ConvArgs(C.Structure):
         ("gn_sums", _vp),
         ("out_csum", _vp),
         ("splitk_ws", _vp), ("splitk_ws_elems", _ll),
+        ("split_io", _i),
     ]
 
 
@@ -96,6 +97,10 @@ SIGNATURES = {
     "ddpm_gn_stats": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _vp],
     "ddpm_gn_apply": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp, _vp],
     "ddpm_gn_stats_from_csum": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
+    "ddpm_gn_stats_split": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _vp],
+    "ddpm_gn_apply_split": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp],
+    "ddpm_attn_fwd_split": [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp],
+    "ddpm_im2col3_split": [_vp, _vp, _i, _i, _i, _i, _vp],
     "ddpm_gn_fwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp, _vp],
     "ddpm_gn_bwd": [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp, _ll, _vp, _ll, _vp, _ll,
                     _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp],

@@ -80,6 +80,70 @@ __global__ void attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long
   }
 }
 
+// fp32-faithful mode (include/ddpm_b200.h): the same core on SPLIT rows -- qkv rows are [q k v hi (3C) | q k v lo (3C)],
+// o rows [hi (C) | lo (C)], value = hi + lo; exact exp2f / division.  Inference only (no log-sum-exp output).
+__device__ __forceinline__ void ld8_split(const __nv_bfloat16* hp, int lo_off, float* dst, float scale = 1.0f) {
+  float f[8], g[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(hp), f);
+  unpack8(*reinterpret_cast<const bf16x8*>(hp + lo_off), g);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) dst[u] = (f[u] + g[u]) * scale;
+}
+
+template <int D>
+__global__ void attn_fwd_split_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldqkv,
+                                      __nv_bfloat16* __restrict__ o, long long ldo, int T, int heads, float scale_log2) {
+  extern __shared__ __align__(16) float sm[];
+  float* ks = sm;            // [T][D]
+  float* vs = sm + T * D;    // [T][D]
+  const int b = blockIdx.x / heads, hd = blockIdx.x - b * heads;
+  const int C = heads * D;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * ldqkv + hd * D;
+  for (int i = threadIdx.x; i < T * (D / 8); i += blockDim.x) {
+    const int j = i / (D / 8), e = (i - j * (D / 8)) * 8;
+    ld8_split(base + j * ldqkv + C + e, 3 * C, ks + j * D + e);
+    ld8_split(base + j * ldqkv + 2 * C + e, 3 * C, vs + j * D + e);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    float q[D], acc[D];
+#pragma unroll
+    for (int e = 0; e < D; e += 8) ld8_split(base + i * ldqkv + e, 3 * C, q + e, scale_log2);
+#pragma unroll
+    for (int e = 0; e < D; ++e) acc[e] = 0.f;
+    float m = -INFINITY;
+    for (int j = 0; j < T; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < D; ++e) s = fmaf(q[e], ks[j * D + e], s);
+      m = fmaxf(m, s);
+    }
+    float l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < D; ++e) s = fmaf(q[e], ks[j * D + e], s);
+      const float p = exp2f(s - m);
+      l += p;
+#pragma unroll
+      for (int e = 0; e < D; ++e) acc[e] = fmaf(p, vs[j * D + e], acc[e]);
+    }
+    __nv_bfloat16* op = o + (static_cast<long long>(b) * T + i) * ldo + hd * D;
+#pragma unroll
+    for (int e = 0; e < D; e += 8) {
+      float f[8], h[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = acc[e + u] / l;
+      const bf16x8 hi = pack8(f);
+      unpack8(hi, h);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] -= h[u];
+      *reinterpret_cast<bf16x8*>(op + e) = hi;
+      *reinterpret_cast<bf16x8*>(op + C + e) = pack8(f);
+    }
+  }
+}
+
 template <int D>
 __global__ void attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldqkv,
                                 const __nv_bfloat16* __restrict__ o, long long ldo,
@@ -224,6 +288,27 @@ extern "C" int ddpm_attn_fwd(const void* qkv, long long ldqkv, void* o, long lon
                                                                 scale * kLog2e);
   });
   return check_launch("attn_fwd_kernel");
+}
+
+extern "C" int ddpm_attn_fwd_split(const void* qkv, long long ldqkv, void* o, long long ldo, int b, int t, int heads,
+                                   int d, float scale, void* stream) {
+  DDPM_REQUIRE(qkv && o && b > 0 && t > 0 && heads > 0, "ddpm_attn_fwd_split: bad argument");
+  DDPM_REQUIRE(ldqkv % 8 == 0 && ldo % 8 == 0 && d % 8 == 0 && ldqkv >= 6LL * heads * d && ldo >= 2LL * heads * d,
+               "ddpm_attn_fwd_split: rows must be 16-byte aligned split rows [hi | lo]");
+  const size_t smem = sizeof(float) * 2 * t * d;
+  DDPM_REQUIRE(smem <= 200 * 1024, "ddpm_attn_fwd_split: t=%d d=%d does not fit shared memory", t, d);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ATTN_DISPATCH(d, {
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      DDPM_CUDA(cudaFuncSetAttribute(attn_fwd_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    attn_fwd_split_kernel<D><<<b * heads, attn_threads(t), smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), ldqkv,
+                                                                      static_cast<__nv_bfloat16*>(o), ldo, t, heads,
+                                                                      scale * kLog2e);
+  });
+  return check_launch("attn_fwd_split_kernel");
 }
 
 extern "C" int ddpm_attn_bwd(const void* qkv, long long ldqkv, const void* o, long long ldo, const void* d_o,

@@ -35,6 +35,7 @@ struct EpiParams {
   int gstats;                 // 1: gsums receives the per-(sample, channel) moments of the STORED output -- the
                               // statistics of the GroupNorm that consumes this tensor (no gx / gcoef involved)
   int wide;                   // every pointer / stride above allows 32-byte (256-bit) row accesses
+  int split;                  // fp32-faithful mode: out / res rows are [hi (Cout) | lo (Cout)], value = hi + lo
 };
 
 // 256-bit global accesses (sm_100: LDG/STG.E.256).  One thread owns one pixel row here, so a warp-wide access touches
@@ -160,6 +161,15 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
           v[2 * j + 1] += bf16hi_f(rw[j]);
         }
       }
+      if (e.split) {      // low halves of the split residual
+        uint32_t rw[16];
+        ld64B(e.res + pix * e.ldr + e.Cout + col, rw, e.wide != 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[2 * j] += bf16lo_f(rw[j]);
+          v[2 * j + 1] += bf16hi_f(rw[j]);
+        }
+      }
     }
   }
   if (GN && e.gsums != nullptr && e.gstats) {
@@ -224,6 +234,13 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
 #pragma unroll
       for (int j = 0; j < 16; ++j) ow[j] = pack2_bf16_(v[2 * j], v[2 * j + 1]);
       st64B(e.out + pix * e.ldo + col, ow, e.wide != 0);
+      if (e.split) {      // lo = bf16(v - hi): together 16 mantissa bits of the fp32 accumulator
+        uint32_t lw[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          lw[j] = pack2_bf16_(v[2 * j] - bf16lo_f(ow[j]), v[2 * j + 1] - bf16hi_f(ow[j]));
+        st64B(e.out + pix * e.ldo + e.Cout + col, lw, e.wide != 0);
+      }
     }
   }
 }

@@ -579,6 +579,12 @@ int fill_epilogue(EpiParams* e, const ::ddpm_conv_args* a) {
     e->gsums = a->out_csum;
     e->gstats = 1;
   }
+  if (a->split_io) {
+    DDPM_REQUIRE(a->gn_sums == nullptr && a->out_csum == nullptr && a->out_f32 == nullptr && a->out != nullptr &&
+                     a->ldo >= 2LL * a->cout && (a->res == nullptr || a->ldr >= 2LL * a->cout) && a->cout % 32 == 0,
+                 "ddpm_conv_gemm: split_io needs a bf16 split output (ldo >= 2*cout) and excludes the GroupNorm fusions");
+    e->split = 1;
+  }
   auto ok32 = [](const void* ptr, long long ld_elems) {
     return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && (ld_elems * 2) % 32 == 0);
   };
@@ -612,8 +618,21 @@ splitk_finalize_kernel(const float* __restrict__ ws, EpiParams e, long long pixe
     unpack8(*reinterpret_cast<const bf16x8*>(e.res + pix * e.ldr + col), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += f[j];
+    if (e.split) {
+      unpack8(*reinterpret_cast<const bf16x8*>(e.res + pix * e.ldr + e.Cout + col), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += f[j];
+    }
   }
-  *reinterpret_cast<bf16x8*>(e.out + pix * e.ldo + col) = pack8(v);
+  const bf16x8 hi = pack8(v);
+  *reinterpret_cast<bf16x8*>(e.out + pix * e.ldo + col) = hi;
+  if (e.split) {
+    float h[8];
+    unpack8(hi, h);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] -= h[j];
+    *reinterpret_cast<bf16x8*>(e.out + pix * e.ldo + e.Cout + col) = pack8(v);
+  }
 }
 
 // Split-K plan for a problem with `ctas` output tiles and `iters` (tap, k-block) iterations: engage idle SMs when the

@@ -712,6 +712,92 @@ gn_bwd_dparam_raw_kernel(const float* __restrict__ sums, const float* __restrict
   }
 }
 
+// =====================================================================================================
+// fp32-faithful mode (include/ddpm_b200.h): the same statistics / apply passes on SPLIT tensors -- a row holds C "hi"
+// channels then C "lo" channels, value = hi + lo -- with exact sigmoid arithmetic.  Thread mapping as above; each
+// thread moves its 8-channel vector twice (hi and lo).  Inference only: no backward, no conv fusions.
+// =====================================================================================================
+__device__ __forceinline__ void gn_load_split(const __nv_bfloat16* hp, int c_src, float* f) {
+  float lo[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(hp), f);
+  unpack8(*reinterpret_cast<const bf16x8*>(hp + c_src), lo);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] += lo[j];
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_split_kernel(GnSrc s, int hw, int cpg, int groups, float* __restrict__ stats, int pix_per_block, int V) {
+  __shared__ float sm[64 * 2];
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = v * 8;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(hw, p_begin + pix_per_block);
+  long long ld;
+  const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
+  const int c_src = c < s.c0 ? s.c0 : s.c1;
+  float sum[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  for (int p = p_begin + pl; p < p_end; p += ppb) {
+    float f[8];
+    gn_load_split(xp + p * ld, c_src, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sum[j] += f[j];
+      sq[j] = fmaf(f[j], f[j], sq[j]);
+    }
+  }
+  f2x4 s4, q4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s4.p[j] = make_float2(sum[2 * j], sum[2 * j + 1]);
+    q4.p[j] = make_float2(sq[2 * j], sq[2 * j + 1]);
+  }
+  gn_fold_groups(s4, q4, c, cpg, sm);
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+    atomicAdd(&stats[static_cast<long long>(n) * groups * 2 + i], sm[i]);
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_split_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                      long long ldy, int pix_per_block, int V) {
+  const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+  const int n = blockIdx.y;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = v * 8, C = V * 8;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(hw, p_begin + pix_per_block);
+  long long ld;
+  const __nv_bfloat16* xp = gn_base(s, n, hw, c, &ld);
+  const int c_src = c < s.c0 ? s.c0 : s.c1;
+  __nv_bfloat16* yp = y + static_cast<long long>(n) * hw * ldy + c;
+  f2x4 ka, kb;
+  gn_apply_coefs(stats + static_cast<long long>(n) * groups * 2, c, cpg, inv_m, eps, gamma, beta, false, &ka, &kb);
+  const float a8[8] = {ka.p[0].x, ka.p[0].y, ka.p[1].x, ka.p[1].y, ka.p[2].x, ka.p[2].y, ka.p[3].x, ka.p[3].y};
+  const float b8[8] = {kb.p[0].x, kb.p[0].y, kb.p[1].x, kb.p[1].y, kb.p[2].x, kb.p[2].y, kb.p[3].x, kb.p[3].y};
+  for (int p = p_begin + pl; p < p_end; p += ppb) {
+    float f[8], hi[8];
+    gn_load_split(xp + p * ld, c_src, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(f[j], a8[j], b8[j]);
+      f[j] = SILU ? z / (1.0f + expf(-z)) : z;
+    }
+    const bf16x8 h = pack8(f);
+    unpack8(h, hi);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] -= hi[j];
+    *reinterpret_cast<bf16x8*>(yp + p * ldy) = h;
+    *reinterpret_cast<bf16x8*>(yp + p * ldy + C) = pack8(f);
+  }
+}
+
 static int gn_check(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                     int groups, const char* who) {
   if (!x0 || n <= 0 || hw <= 0 || groups <= 0 || groups > 64) {
@@ -963,4 +1049,40 @@ extern "C" int ddpm_gn_bwd_apply(const void* x0, int c0, long long ld0, const vo
     return check_launch("gn_bwd_dparam_raw_kernel");
   }
   return DDPM_OK;
+}
+
+extern "C" int ddpm_gn_stats_split(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,
+                                   int hw, int groups, float* stats, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = gn_check(x0, c0, ld0, x1, c1, ld1, n, hw, groups, "ddpm_gn_stats_split")) return e;
+  DDPM_REQUIRE(stats && ld0 >= 2LL * c0 && (c1 == 0 || ld1 >= 2LL * c1), "ddpm_gn_stats_split: rows must hold [hi | lo]");
+  const int C = c0 + c1;
+  GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
+  int V, threads, ppblk, chunks;
+  gn_geometry(C, hw, n, 16, &V, &threads, &ppblk, &chunks);
+  DDPM_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
+  gn_stats_split_kernel<<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, ppblk, V);
+  return check_launch("gn_stats_split_kernel");
+}
+
+extern "C" int ddpm_gn_apply_split(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n,
+                                   int hw, int groups, const float* stats, float eps, const float* gamma,
+                                   const float* beta, int silu, void* y, long long ldy, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = gn_check(x0, c0, ld0, x1, c1, ld1, n, hw, groups, "ddpm_gn_apply_split")) return e;
+  const int C = c0 + c1;
+  DDPM_REQUIRE(stats && gamma && beta && y && ldy % 8 == 0 && ldy >= 2LL * C && ld0 >= 2LL * c0 &&
+                   (c1 == 0 || ld1 >= 2LL * c1),
+               "ddpm_gn_apply_split: bad argument (rows must hold [hi | lo])");
+  GnSrc s{static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), ld0, ld1, c0, c1};
+  int V, threads, ppblk, chunks;
+  gn_geometry(C, hw, n, 16, &V, &threads, &ppblk, &chunks);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  if (silu)
+    gn_apply_split_kernel<true><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma,
+                                                                         beta, yp, ldy, ppblk, V);
+  else
+    gn_apply_split_kernel<false><<<dim3(chunks, n), threads, 0, stream>>>(s, hw, C / groups, groups, stats, eps, gamma,
+                                                                          beta, yp, ldy, ppblk, V);
+  return check_launch("gn_apply_split_kernel");
 }

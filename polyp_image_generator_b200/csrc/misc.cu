@@ -555,6 +555,56 @@ extern "C" int ddpm_im2col3(const float* src, void* patches, int n, int h, int w
   return check_launch("im2col3_kernel");
 }
 
+// fp32-faithful conv_in: 128-column patch rows [hi (9cin) @0 | lo (9cin) @32 | hi again @64], one thread = one pixel
+__global__ void __launch_bounds__(256)
+im2col3_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ patches, int N, int H, int W, int cin,
+                     long long npix) {
+  const long long hw = static_cast<long long>(H) * W;
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int n = static_cast<int>(pix / hw);
+  const int rem = static_cast<int>(pix - n * hw);
+  const int h = rem / W, w = rem - h * W;
+  const float* sn = src + static_cast<long long>(n) * cin * hw;
+  float hi[32], lo[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) hi[j] = lo[j] = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+    const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < cin) {
+        const float x = in ? __ldg(sn + k * hw + static_cast<long long>(hh) * W + ww) : 0.f;
+        const float xh = __bfloat162float(__float2bfloat16(x));
+        // dense [tap * cin + k] order; cin is 1..3 here, so the index is resolved per compile-time (tap, k) pair
+        const int idx = tap * cin + k;
+#pragma unroll
+        for (int j = 0; j < 27; ++j)
+          if (j == idx) { hi[j] = xh; lo[j] = x - xh; }
+      }
+    }
+  }
+  uint4* row = reinterpret_cast<uint4*>(patches + pix * 128);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bf16x8 vh = pack8(hi + q * 8), vl = pack8(lo + q * 8);
+    row[q] = vh;
+    row[4 + q] = vl;
+    row[8 + q] = vh;
+    row[12 + q] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+extern "C" int ddpm_im2col3_split(const float* src, void* patches, int n, int h, int w, int cin, void* stream) {
+  DDPM_REQUIRE(src && patches && n > 0 && h > 0 && w > 0 && cin >= 1 && cin <= 3, "ddpm_im2col3_split: bad argument");
+  const long long npix = static_cast<long long>(n) * h * w;
+  im2col3_split_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(patches), n, h, w, cin, npix);
+  return check_launch("im2col3_split_kernel");
+}
+
 extern "C" int ddpm_nhwc_to_nchw_f32(const float* src, long long ld, float* out, int n, int h, int w, int cout,
                                      void* stream) {
   DDPM_REQUIRE(src && out && n > 0 && h > 0 && w > 0 && cout >= 1 && cout <= 4 && ld % 4 == 0 && ld >= 4,

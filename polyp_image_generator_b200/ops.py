@@ -178,7 +178,8 @@ class CudaOps:
         return s
 
     def conv_gemm(self, x0, x1, taps: Sequence[Tap], wgt, cout: int, grid: Tuple[int, int, int], bias=None,
-                  temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0, gn=None, csum=None):
+                  temb=None, res=None, out=None, out_f32: bool = False, src_n: int = 0, gn=None, csum=None,
+                  split_io: bool = False):
         """out[n,h,w,co] = bias + temb[n] + res + sum_taps X[pix+tap] . wgt[co, wk:wk+cin]; see ddpm_conv_gemm.
         gn = (x0, x1, coef, silu, sums) with coef from gn_fwd(want_coef=True): fuse the first half of the backward of
         y = act(GroupNorm(x0|x1)) into the epilogue (out becomes dz, sums[n, c] += (sum dz, sum dz*x)).
@@ -198,6 +199,12 @@ class CudaOps:
         if wgt.dtype != torch.bfloat16 or wgt.dim() != 2 or wgt.stride(1) != 1:
             raise ValueError("wgt must be a bf16 [cout, K] matrix with unit inner stride")
         a.wgt, a.cout, a.ldw, a.k_total = _ptr(wgt), cout, wgt.stride(0), wgt.shape[1]
+        if split_io:          # fp32-faithful mode: out / res rows are [hi (cout) | lo (cout)] (ddpm_conv_args.split_io)
+            if gn is not None or csum is not None or out_f32:
+                raise ValueError("split_io excludes the GroupNorm fusions and fp32 output")
+            a.split_io = 1
+            if out is None:
+                out = torch.empty((n, h, w, 2 * cout), device=x0.device, dtype=torch.bfloat16)
         if out is None:
             out = torch.empty((n, h, w, cout), device=x0.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
         if out_f32:
@@ -288,6 +295,48 @@ class CudaOps:
         _capi.check(self.lib.ddpm_prep_weights_batched(_ptr(table), n_entries, total_tiles, int(with_d), _stream()),
                     "ddpm_prep_weights_batched")
         self.launches += 1
+
+    # ---- fp32-faithful mode: the same ops on split-bf16 tensors (rows [hi (C) | lo (C)], value = hi + lo) -----------
+    def im2col3_split(self, x):
+        n, cin, h, w = x.shape
+        out = torch.empty((n, h, w, 128), device=x.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_im2col3_split(_ptr(x), _ptr(out), n, h, w, cin, _stream()), "ddpm_im2col3_split")
+        self.launches += 1
+        return out
+
+    @staticmethod
+    def _split_src(t, what):
+        n, h, w, c2, ld = _nhwc(t, what)
+        if c2 % 2:
+            raise ValueError(f"{what}: a split tensor has an even number of stored channels")
+        return n, h, w, c2 // 2, ld
+
+    def gn_fwd_split(self, x0, x1, groups: int, eps: float, gamma, beta, silu: bool):
+        """GroupNorm(+SiLU) on split tensors: statistics pass + apply pass (exact sigmoid) -> split y [n, h, w, 2C]."""
+        n, h, w, c0, ld0 = self._split_src(x0, "x0")
+        c1, ld1 = 0, 0
+        if x1 is not None:
+            _, _, _, c1, ld1 = self._split_src(x1, "x1")
+        C_ = c0 + c1
+        stats = torch.empty((n, groups, 2), device=x0.device, dtype=torch.float32)
+        _capi.check(self.lib.ddpm_gn_stats_split(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats),
+                                                 _stream()), "ddpm_gn_stats_split")
+        y = torch.empty((n, h, w, 2 * C_), device=x0.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_gn_apply_split(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, n, h * w, groups, _ptr(stats),
+                                                 eps, _ptr(gamma), _ptr(beta), int(silu), _ptr(y), 2 * C_, _stream()),
+                    "ddpm_gn_apply_split")
+        self.launches += 3
+        return y
+
+    def attn_fwd_split(self, qkv, b: int, t: int, heads: int, d: int, scale: float):
+        """qkv: split rows [b*t, 6*heads*d] -> split o [b*t, 2*heads*d] (narrow heads only)."""
+        if d not in self.NARROW_HEAD_DIMS:
+            raise NotImplementedError(f"fp32-faithful attention supports head_dim in {self.NARROW_HEAD_DIMS}, got {d}")
+        o = torch.empty((b * t, 2 * heads * d), device=qkv.device, dtype=torch.bfloat16)
+        _capi.check(self.lib.ddpm_attn_fwd_split(_ptr(qkv), qkv.stride(0), _ptr(o), o.stride(0), b, t, heads, d, scale,
+                                                 _stream()), "ddpm_attn_fwd_split")
+        self.launches += 1
+        return o
 
     # ---- 3-channel boundary convs (as GEMMs) --------------------------------------------------------------
     def im2col3(self, x, chan_sum=None):

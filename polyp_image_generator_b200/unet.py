@@ -312,6 +312,11 @@ class UNet2DModel(nn.Module):
         self._wcache_key = None
         self._lora_layers: Dict[str, object] = {}
         self.last_launches = 0
+        # Inference arithmetic (no-grad forward, i.e. sampling): "bf16" = bf16 tensor-core operands and bf16 activations
+        # (fast path); "fp32" = fp32-faithful split-bf16 path (_run_forward_split): what the reference does when it
+        # samples outside autocast (train_from_scratch.py:121-125, 39-66).  Training always runs the bf16 path.
+        self.inference_precision = "bf16"
+        self._w3_cache = None
 
     # ---- nn.Module conveniences expected by call sites ------------------------------------------------------
     @property
@@ -667,6 +672,8 @@ class UNet2DModel(nn.Module):
         params = [p for p in self.parameters() if p.requires_grad]
         if torch.is_grad_enabled() and params:
             out = _UNetFunction.apply(self, x, ts, len(params), *params)
+        elif self.inference_precision == "fp32":
+            out = self._run_forward_split(x, ts)
         else:
             out = self._run_forward(x, ts, None)
         if not return_dict:
@@ -754,6 +761,163 @@ class UNet2DModel(nn.Module):
         if training:
             tape.head = SimpleNamespace(patches=patches, t_emb=t_emb, e1=e1, emb=emb, h_last=h, stats=stats, a=a,
                                         coef=coef_out)
+        self.last_launches = ops.launches - l0
+        return out
+
+    # ---------------------------------------------------------------------------------------------------------
+    # fp32-faithful inference (north_star: eps within 1e-4 of the fp32 reference; SURVEY.md App. A.6: sampling and the
+    # LoRA trainers run without autocast).  Activations are split-bf16 tensors [N, H, W, 2C] = [hi | lo]; every conv /
+    # linear is ONE tcgen05 GEMM over the K-concat [A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo] (fp32 accumulation, the
+    # dropped A_lo W_lo term is 2^-18 relative); GroupNorm / SiLU / softmax read hi + lo, compute in fp32 with exact
+    # transcendentals and write split results.  3x the tensor work and 2x the activation bytes of the bf16 path.
+    # ---------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _split3(w2d: torch.Tensor, taps: int, cin: int) -> torch.Tensor:
+        """fp32 [cout, taps*cin] (physical [cout][tap][cin]) -> bf16 [cout, taps*3*cin]: per tap [W_hi | W_hi | W_lo]."""
+        w = w2d.reshape(w2d.shape[0], taps, cin).float()
+        hi = w.to(torch.bfloat16)
+        lo = (w - hi.float()).to(torch.bfloat16)
+        return torch.stack([hi, hi, lo], dim=2).reshape(w2d.shape[0], taps * 3 * cin).contiguous()
+
+    def _effective_weight(self, gobj: _Gemm) -> torch.Tensor:
+        """fp32 [cout, taps*cin] master weight of a GEMM layer, LoRA update (alpha/r) B A folded in when unmerged."""
+        k = gobj.taps * gobj.cin
+        rows = []
+        o = gobj.w_off
+        for w in gobj.weights:
+            rows.append(self._arena[o:o + w.numel()].view(gobj.cout_each, k))
+            o = _align(o + w.numel())
+        W = torch.cat(rows, 0) if len(rows) > 1 else rows[0]
+        if gobj.lora is not None and gobj.lora.active:
+            W = W.clone()
+            for i, m, _ in gobj.lora.slots:
+                if not m.merged:
+                    W[i * gobj.cout_each:(i + 1) * gobj.cout_each] += m.scaling * (m.B.detach().float() @ m.A.detach().float())
+        return W
+
+    def _split_weights(self):
+        """Split operands of every layer, cached on the parameter versions."""
+        P = self._plan
+        key = (getattr(self, "_weights_epoch", 0),) + tuple(p._version for p in self.parameters())
+        if self._w3_cache is not None and self._w3_cache[0] == key:
+            return self._w3_cache[1]
+        cfg = self.config
+        c0, ci, co = cfg.block_out_channels[0], cfg.in_channels, cfg.out_channels
+        W3 = {}
+        with torch.no_grad():
+            for gobj in P.gemms:
+                W3[gobj.name] = self._split3(self._effective_weight(gobj), gobj.taps, gobj.cin)
+            # conv_in: [c0, 128] against the im2col3_split rows: W_hi @0, W_hi @32, W_lo @64
+            w_in = self._aview(P.cin_w, (c0, 9 * ci)).float()
+            hi = w_in.to(torch.bfloat16)
+            lo = (w_in - hi.float()).to(torch.bfloat16)
+            wi = torch.zeros((c0, 128), device=w_in.device, dtype=torch.bfloat16)
+            wi[:, :9 * ci], wi[:, 32:32 + 9 * ci], wi[:, 64:64 + 9 * ci] = hi, hi, lo
+            W3["conv_in"] = wi
+            w_out = torch.zeros((32, 9 * c0), device=w_in.device, dtype=torch.float32)
+            w_out[:co] = self._aview(P.cout_w, (co, 9 * c0))
+            W3["conv_out"] = self._split3(w_out, 9, c0)
+            b32 = torch.zeros(32, device=w_in.device, dtype=torch.float32)
+            b32[:co] = self._aview(P.cout_b, (co,))
+            W3["conv_out.bias"] = b32
+        self._w3_cache = (key, W3)
+        return W3
+
+    def _w3_slice(self, W3, gobj: _Gemm, lo_ch: int, n_ch: int) -> torch.Tensor:
+        """Split operand of a 1x1 layer restricted to input channels [lo_ch, lo_ch + n_ch) (one source of a concat)."""
+        key = (gobj.name, lo_ch, n_ch)
+        w = W3.get(key)
+        if w is None:
+            with torch.no_grad():
+                w = W3[key] = self._split3(self._effective_weight(gobj)[:, lo_ch:lo_ch + n_ch].contiguous(), 1, n_ch)
+        return w
+
+    def _run_forward_split(self, x: torch.Tensor, ts: torch.Tensor) -> torch.Tensor:
+        ops = _ops.get()
+        l0 = ops.launches
+        P, cfg = self._plan, self.config
+        W3 = self._split_weights()
+        N, _, H, W = x.shape
+        ted, c0 = self._temb_dim, cfg.block_out_channels[0]
+        t_emb = ops.timestep_embedding(ts, c0, cfg.flip_sin_to_cos, float(cfg.freq_shift))
+        e1 = ops.linear_f32(t_emb, self._aview(P.te.w1, (ted, c0)), self._aview(P.te.b1, (ted,)), False)
+        emb = ops.linear_f32(e1, self._aview(P.te.w2, (ted, ted)), self._aview(P.te.b2, (ted,)), True)
+        temb_all = ops.linear_f32(emb, self._aview(P.temb_w_off, (P.temb_total, ted)),
+                                  self._aview(P.temb_b_off, (P.temb_total,)), True)
+
+        def conv(xs, gobj, taps_fn, cout, grid, **kw):
+            """xs: split tensor [.., 2*cin]; one GEMM over [hi | lo | hi] against the layer's split operand."""
+            cin = xs.shape[-1] // 2
+            return ops.conv_gemm(xs, xs[..., :cin], taps_fn(3 * cin), W3[gobj.name], cout, grid,
+                                 bias=self._bias(gobj), split_io=True, **kw)
+
+        def resnet(r, x0, x1):
+            n_, h_, w_, _ = x0.shape
+            grid = (n_, h_, w_)
+            g1, be1 = self._norm_params(r.norm1)
+            g2, be2 = self._norm_params(r.norm2)
+            a = ops.gn_fwd_split(x0, x1, r.norm1.groups, r.norm1.eps, g1, be1, True)
+            temb = temb_all[:, r.temb_off:r.temb_off + r.cout]
+            h1 = conv(a, r.conv1, taps_3x3, r.cout, grid, temb=temb)
+            b = ops.gn_fwd_split(h1, None, r.norm2.groups, r.norm2.eps, g2, be2, True)
+            if r.short is None:
+                sc = x0
+            else:
+                ca = x0.shape[-1] // 2
+                sc = ops.conv_gemm(x0, x0[..., :ca], taps_1x1(), self._w3_slice(W3, r.short, 0, ca), r.cout, grid,
+                                   bias=self._bias(r.short), split_io=True)
+                if x1 is not None:     # the concat's second source accumulates onto the first through the residual input
+                    cb = x1.shape[-1] // 2
+                    sc = ops.conv_gemm(x1, x1[..., :cb], taps_1x1(), self._w3_slice(W3, r.short, ca, cb), r.cout, grid,
+                                       res=sc, split_io=True)
+            return conv(b, r.conv2, taps_3x3, r.cout, grid, res=sc)
+
+        def attn(at, xs):
+            n_, h_, w_, c2 = xs.shape
+            C, T = c2 // 2, h_ * w_
+            M = n_ * T
+            gam, bet = self._norm_params(at.norm)
+            xn = ops.gn_fwd_split(xs, None, at.norm.groups, at.norm.eps, gam, bet, False).view(1, 1, M, 2 * C)
+            qkv = conv(xn, at.qkv, lambda k: taps_1x1(), 3 * C, (1, 1, M))
+            o = ops.attn_fwd_split(qkv.view(M, 6 * C), n_, T, at.heads, at.d, at.d ** -0.5).view(1, 1, M, 2 * C)
+            return conv(o, at.out, lambda k: taps_1x1(), C, (1, 1, M), res=xs.view(1, 1, M, 2 * C)).view(n_, h_, w_, 2 * C)
+
+        patches = ops.im2col3_split(x)
+        h = ops.conv_gemm(patches, None, taps_1x1(), W3["conv_in"], c0, (N, H, W), bias=self._aview(P.cin_b, (c0,)),
+                          split_io=True)
+        skips = [h]
+        for b in P.down:
+            for j, r in enumerate(b.resnets):
+                h = resnet(r, h, None)
+                if b.attns:
+                    h = attn(b.attns[j], h)
+                skips.append(h)
+            if b.down is not None:
+                n_, h_, w_, c2 = h.shape
+                s2d = ops.space_to_depth(h)
+                C = c2 // 2
+                h = ops.conv_gemm(s2d, s2d[..., :C], taps_s2d(3 * C, n_, b.down.pad), W3[b.down.conv.name], C,
+                                  (n_, h_ // 2, w_ // 2), bias=self._bias(b.down.conv), src_n=4 * n_, split_io=True)
+                skips.append(h)
+        h = resnet(P.mid.r0, h, None)
+        if P.mid.attn is not None:
+            h = attn(P.mid.attn, h)
+        h = resnet(P.mid.r1, h, None)
+        for b in P.up:
+            for j, r in enumerate(b.resnets):
+                h = resnet(r, h, skips.pop())
+                if b.attns:
+                    h = attn(b.attns[j], h)
+            if b.up is not None:
+                up = ops.upsample2x(h)
+                n_, h_, w_, _ = up.shape
+                h = conv(up, b.up.conv, taps_3x3, b.up.c, (n_, h_, w_))
+        no = P.norm_out
+        gam, bet = self._aview(no.g_off, (c0,)), self._aview(no.b_off, (c0,))
+        a = ops.gn_fwd_split(h, None, no.groups, no.eps, gam, bet, True)
+        o32 = ops.conv_gemm(a, a[..., :c0], taps_3x3(3 * c0), W3["conv_out"], 32, (N, H, W),
+                            bias=W3["conv_out.bias"], out_f32=True)
+        out = ops.nhwc_to_nchw_f32(o32, cfg.out_channels)
         self.last_launches = ops.launches - l0
         return out
 

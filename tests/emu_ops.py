@@ -120,8 +120,51 @@ class EmuOps:
         r = self.gn_fwd(x0, x1, groups, eps, gamma, beta, silu, want_coef=want_coef)
         return r
 
+    # ---- fp32-faithful mode: split tensors [.., 2C] = [hi | lo], value = hi + lo (the emulation splits at bf16) -------
+    @staticmethod
+    def _to_split(v):
+        hi = v.to(torch.bfloat16).float()
+        lo = (v - hi).to(torch.bfloat16).float()
+        return torch.cat([hi, lo], -1)
+
+    @staticmethod
+    def _from_split(t):
+        c = t.shape[-1] // 2
+        return t[..., :c].float() + t[..., c:].float()
+
+    def im2col3_split(self, x):
+        n, cin, h, w = x.shape
+        pat = F.unfold(x.float(), 3, padding=1).view(n, cin, 9, h, w).permute(0, 3, 4, 2, 1).reshape(n, h, w, 9 * cin)
+        sp = self._to_split(pat)
+        out = torch.zeros((n, h, w, 128), dtype=torch.float32)
+        k = 9 * cin
+        out[..., :k], out[..., 32:32 + k], out[..., 64:64 + k] = sp[..., :k], sp[..., k:], sp[..., :k]
+        return out
+
+    def gn_fwd_split(self, x0, x1, groups, eps, gamma, beta, silu):
+        x = self._from_split(x0)
+        if x1 is not None:
+            x = torch.cat([x, self._from_split(x1)], -1)
+        y = F.group_norm(x.permute(0, 3, 1, 2), groups, gamma, beta, eps)
+        if silu:
+            y = F.silu(y)
+        return self._to_split(y.permute(0, 2, 3, 1).contiguous())
+
+    def attn_fwd_split(self, qkv, b, t, heads, d, scale):
+        C = heads * d
+        x = self._from_split(qkv)
+        q, k, v = [z.reshape(b, t, heads, d).transpose(1, 2) for z in x.split(C, dim=1)]
+        o = F.scaled_dot_product_attention(q, k, v, scale=scale).transpose(1, 2).reshape(b * t, C)
+        return self._to_split(o)
+
     def conv_gemm(self, x0, x1, taps, wgt, cout, grid, bias=None, temb=None, res=None, out=None, out_f32=False,
-                  src_n=0, gn=None, csum=None):
+                  src_n=0, gn=None, csum=None, split_io=False):
+        if split_io:
+            assert gn is None and csum is None and not out_f32 and out is None
+            acc = self.conv_gemm(x0, x1, taps, wgt, cout, grid, bias=bias, temb=temb, out_f32=True, src_n=src_n)
+            if res is not None:
+                acc = acc + self._from_split(res).reshape(acc.shape)
+            return self._to_split(acc)
         n, h, w = grid
         X = x0 if x1 is None else torch.cat([x0, x1], -1)
         X = X.float()

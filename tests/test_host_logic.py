@@ -672,3 +672,34 @@ def test_ddp_skips_arena_buckets_for_frozen_models_and_resets_progress():
     assert fake._done_upto is None
     D._progress(fake, torch.zeros(8), 0)
     assert calls == [] and fake._done_upto is None
+
+
+def test_fp32_faithful_inference_program_matches_fp32_oracle(emu_backend):
+    """inference_precision = "fp32" (north_star: eps within 1e-4 of the fp32 reference): the split-bf16 forward program
+    -- K-concat [hi | lo | hi] x [W_hi | W_hi | W_lo] convs, split GroupNorm / attention, two-call shortcut over a
+    channel concat, stride-2 taps, LoRA folded into the effective weight -- against the fp32 oracle through the CPU
+    emulation of the op contracts."""
+    from polyp_image_generator_b200 import LoraConfig, UNet2DModel
+    for variant in ("polyp", "polyp_lora"):
+        cfg = _small_cfg(32)
+        torch.manual_seed(3)
+        om = oracle.UNet2DModel(**cfg)
+        m = UNet2DModel(**cfg)
+        m.load_state_dict(om.state_dict())
+        if variant == "polyp_lora":
+            oracle.add_adapter(om, oracle.LoraConfig(r=8, lora_alpha=8, init_lora_weights="gaussian"))
+            m.add_adapter(LoraConfig(r=8, lora_alpha=8, init_lora_weights="gaussian"))
+            sd = {k: torch.randn_like(v) * 0.05 for k, v in oracle.lora_state_dict(om).items()}
+            om.load_state_dict(sd, strict=False)
+            m.load_state_dict(sd, strict=False)
+        m.eval()
+        m.inference_precision = "fp32"
+        x, t = torch.randn(2, 3, 32, 32), torch.tensor([7, 903])
+        with torch.no_grad():
+            got = m(x, t).sample
+            want = om(x, t).sample
+        r = ((got - want).norm() / want.norm()).item()
+        assert r < 1e-4, (variant, r)
+        m.inference_precision = "bf16"
+        with torch.no_grad():
+            assert ((m(x, t).sample - want).norm() / want.norm()).item() < 1e-3     # emulation runs the bf16 path in fp32

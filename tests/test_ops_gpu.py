@@ -563,3 +563,87 @@ def test_wgrad_concat_and_stride2(ops):
             F.conv2d(xin, wr, None, stride=2, padding=pad).backward(dy.float().permute(0, 3, 1, 2))
             ck(f"conv3x3 stride2 wgrad pad={pad} {h}x{w_}", dw, wr.grad.permute(0, 2, 3, 1).reshape(c, -1), 2e-3)
     ck.done()
+
+
+# ---- fp32-faithful mode: split-bf16 kernels (include/ddpm_b200.h "fp32-faithful mode") ----------------------------------
+def _to_split(v):
+    hi = v.to(torch.bfloat16)
+    lo = (v - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], -1).contiguous()
+
+
+def _from_split(t):
+    c = t.shape[-1] // 2
+    return t[..., :c].float() + t[..., c:].float()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 128, 128, 128, 128), (2, 64, 64, 256, 128), (3, 32, 32, 256, 256),
+                                            (4, 8, 8, 512, 512), (2, 16, 16, 128, 256), (1, 7, 7, 64, 128)])
+def test_split_conv_is_fp32_faithful(ops, n, h, w, cin, cout):
+    """conv over a split tensor as ONE GEMM [hi | lo | hi] x [W_hi | W_hi | W_lo] (+ fp32 bias, temb, split residual, split
+    output): against F.conv2d in fp32 (TF32 off) on the SAME fp32 values -- 1e-5, i.e. fp32-level, not bf16-level."""
+    from polyp_image_generator_b200.ops import taps_3x3
+    from polyp_image_generator_b200.unet import UNet2DModel
+    ck = Check()
+    torch.manual_seed(8)
+    xv = torch.randn(n, h, w, cin, device=DEV)
+    w4 = torch.randn(cout, cin, 3, 3, device=DEV) * 0.03
+    b = torch.randn(cout, device=DEV)
+    temb = torch.randn(n, cout, device=DEV)
+    resv = torch.randn(n, h, w, cout, device=DEV)
+    xs, rs = _to_split(xv), _to_split(resv)
+    xq, rq = _from_split(xs), _from_split(rs)                      # the values the split tensors actually hold
+    w3 = UNet2DModel._split3(w4.permute(0, 2, 3, 1).reshape(cout, 9 * cin), 9, cin)
+    out = ops.conv_gemm(xs, xs[..., :cin], taps_3x3(3 * cin), w3, cout, (n, h, w), bias=b, temb=temb, res=rs,
+                        split_io=True)
+    want = F.conv2d(xq.permute(0, 3, 1, 2), w4, b, padding=1).permute(0, 2, 3, 1) + temb[:, None, None, :] + rq
+    assert out.shape == (n, h, w, 2 * cout)
+    ck("split conv3x3 +bias+temb+res", _from_split(out), want, 1e-5)
+    ck("   (its bf16 hi half alone is only bf16-accurate)", out[..., :cout].float(), want, 4e-3)
+    ck.done()
+    assert rel(out[..., :cout].float(), want) > 5e-4
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1,silu", [(2, 64, 64, 128, 0, True), (2, 16, 16, 256, 128, True),
+                                              (3, 8, 8, 512, 512, True), (2, 4, 4, 512, 0, False),
+                                              (2, 128, 128, 128, 128, True)])
+def test_split_groupnorm_is_fp32_faithful(ops, n, h, w, c0, c1, silu):
+    torch.manual_seed(9)
+    C = c0 + c1
+    xa = torch.randn(n, h, w, c0, device=DEV) * 1.5 + 0.3
+    xb = torch.randn(n, h, w, c1, device=DEV) - 0.2 if c1 else None
+    gamma = torch.randn(C, device=DEV) * 0.5 + 1
+    beta = torch.randn(C, device=DEV) * 0.2
+    sa, sb = _to_split(xa), (_to_split(xb) if c1 else None)
+    y = ops.gn_fwd_split(sa, sb, 32, 1e-5, gamma, beta, silu)
+    xq = _from_split(sa) if not c1 else torch.cat([_from_split(sa), _from_split(sb)], -1)
+    want = F.group_norm(xq.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)
+    if silu:
+        want = F.silu(want)
+    assert y.shape == (n, h, w, 2 * C)
+    assert rel(_from_split(y), want.permute(0, 2, 3, 1)) < 2e-5
+
+
+@pytest.mark.parametrize("b,t,heads,d", [(2, 64, 64, 8), (3, 16, 64, 8), (2, 196, 64, 8), (2, 49, 4, 16)])
+def test_split_attention_is_fp32_faithful(ops, b, t, heads, d):
+    torch.manual_seed(10)
+    C = heads * d
+    qkv = torch.randn(b * t, 3 * C, device=DEV)
+    qs = _to_split(qkv)
+    o = ops.attn_fwd_split(qs, b, t, heads, d, d ** -0.5)
+    q, k, v = [z.reshape(b, t, heads, d).transpose(1, 2) for z in _from_split(qs).split(C, 1)]
+    want = F.scaled_dot_product_attention(q, k, v, scale=d ** -0.5).transpose(1, 2).reshape(b * t, C)
+    assert o.shape == (b * t, 2 * C)
+    assert rel(_from_split(o), want) < 2e-5
+
+
+def test_split_im2col3_layout(ops):
+    torch.manual_seed(11)
+    x = torch.randn(2, 3, 9, 13, device=DEV)
+    pat = ops.im2col3_split(x)
+    want = F.unfold(x, 3, padding=1).view(2, 3, 9, 9, 13).permute(0, 3, 4, 2, 1).reshape(2, 9, 13, 27)
+    assert pat.shape == (2, 9, 13, 128)
+    assert torch.equal(pat[..., :27], pat[..., 64:91])
+    assert rel(pat[..., :27].float() + pat[..., 32:59].float(), want) < 1e-5
+    assert float(pat[..., 27:32].float().abs().sum() + pat[..., 59:64].float().abs().sum() +
+                 pat[..., 91:].float().abs().sum()) == 0.0

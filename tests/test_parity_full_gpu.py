@@ -188,6 +188,32 @@ def test_celebahq_256_lora_step_vs_oracle(dev):
     assert local["conv_wgrad_launches"] == 2 * 12
 
 
+@pytest.mark.parametrize("S,B", [(128, 2), (64, 4), (224, 1)])
+def test_fp32_faithful_inference_within_1e4_of_the_fp32_oracle(dev, S, B):
+    """Row n1 (north_star: "1e-4 in fp32"; the reference samples outside autocast, train_from_scratch.py:121-125): the
+    full 113.7 M-parameter model with inference_precision = "fp32" -- split-bf16 activations, three-term tensor-core
+    GEMMs, exact transcendentals -- against the fp32 oracle, next to the bf16 fast path on the same inputs."""
+    from polyp_image_generator_b200 import UNet2DModel
+    cfg = oracle.polyp_unet_config(S)
+    torch.manual_seed(0)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    m.to(dev).eval()
+    x, t, _ = _polyp_like_batch(B, S, 300 + S)
+    with torch.no_grad():
+        want = om(x, t).sample
+        m.inference_precision = "fp32"
+        got32 = m(x.to(dev), t.to(dev)).sample
+        m.inference_precision = "bf16"
+        got16 = m(x.to(dev), t.to(dev)).sample
+    rec = {"case": f"fp32-faithful inference polyp {S}x{S} B={B}", "eps_fp32_mode_vs_fp32_oracle": rel(got32, want),
+           "eps_bf16_mode_vs_fp32_oracle": rel(got16, want)}
+    _report(rec)
+    assert rec["eps_fp32_mode_vs_fp32_oracle"] < 1e-4, rec
+    assert rec["eps_bf16_mode_vs_fp32_oracle"] < 2e-2, rec
+
+
 def test_sampling_chain_250_steps_full_model(dev):
     """DDPMPipeline on the full 113.7 M-parameter UNet, 250 strided reverse steps from the same CPU generator as the
     oracle pipeline (the reference's RNG contract): image-level agreement after the whole chain."""
@@ -210,8 +236,16 @@ def test_sampling_chain_250_steps_full_model(dev):
     with bf16_storage_points():
         ic = pb(batch_size=B, generator=torch.Generator("cpu").manual_seed(11), num_inference_steps=steps,
                 output_type="np").images
+    m.inference_precision = "fp32"      # the reference's sampling arithmetic (no autocast): fp32-faithful split path
+    raw32 = DDPMPipeline(unet=m, scheduler=DDPMScheduler())(
+        batch_size=B, generator=torch.Generator("cpu").manual_seed(11), num_inference_steps=steps,
+        output_type="pt_raw").images
+    m.inference_precision = "bf16"
+    i32 = (raw32 / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()
     u8 = lambda im: (im * 255).round().astype("int32")
     rec = {"case": f"sampling chain polyp {S}x{S} B={B} {steps} steps",
+           "fp32_mode_mean_abs_vs_fp32": float(abs(i32 - ib).mean()), "fp32_mode_max_abs_vs_fp32": float(abs(i32 - ib).max()),
+           "fp32_mode_uint8_identical_frac": float((u8(i32) == u8(ib)).mean()),
            "mean_abs_vs_fp32": float(abs(ia - ib).mean()), "max_abs_vs_fp32": float(abs(ia - ib).max()),
            "mean_abs_vs_rounded": float(abs(ia - ic).mean()),
            "mean_abs_rounded_vs_fp32": float(abs(ic - ib).mean()),
@@ -219,8 +253,9 @@ def test_sampling_chain_250_steps_full_model(dev):
            "uint8_frac_within_2_levels": float((abs(u8(ia) - u8(ib)) <= 2).mean())}
     _report(rec)
     assert ia.shape == ib.shape == (B, S, S, 3)
-    assert rec["mean_abs_vs_fp32"] < 1e-2, rec        # images in [0, 1]
-    assert rec["uint8_frac_within_2_levels"] > 0.9, rec
+    assert rec["mean_abs_vs_fp32"] < 2e-3, rec        # bf16 path; images in [0, 1] (measured 5e-4)
+    assert rec["uint8_frac_within_2_levels"] > 0.99, rec
+    assert rec["fp32_mode_mean_abs_vs_fp32"] < 2e-5 and rec["fp32_mode_uint8_identical_frac"] > 0.99, rec
 
 
 def test_two_rank_nccl_gradients_equal_single_rank(dev):
