@@ -110,9 +110,10 @@ typedef struct ddpm_conv_args {
   const float* gn_coef;
   int gn_silu;
   float* gn_sums;
-  /* Optional statistics of the GroupNorm that CONSUMES this output: out_csum[n][co][0..1] += (sum out, sum out^2) over
-   * the sample's pixels, of the bf16 values actually stored (zero-filled by the caller; same h*w rule as gn_sums;
-   * excludes gn_sums / out_f32).  ddpm_gn_stats_from_csum + ddpm_gn_apply then replace the two-phase ddpm_gn_fwd. */
+  /* Optional statistics of the GroupNorm that CONSUMES this output: out_csum[n][co / 4][0..1] += (sum out, sum out^2)
+   * over the sample's pixels and the 4 channels of a granule, of the bf16 values actually stored (zero-filled by the
+   * caller; same h*w rule as gn_sums; excludes gn_sums / out_f32; GroupNorm groups are multiples of 4 channels).
+   * ddpm_gn_stats_from_csum + ddpm_gn_apply then replace the two-phase ddpm_gn_fwd. */
   float* out_csum;
   /* Optional split-K workspace (fp32, caller-owned): low-resolution layers whose tile grid covers less than half the
    * SMs split the reduction over blockIdx.z, accumulate fp32 partial sums here and finish in a second pass.
@@ -199,7 +200,7 @@ int ddpm_gn_stats(const void* x0, int c0, long long ld0, const void* x1, int c1,
 int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* x1, int c1, long long ld1, int n, int hw,
                   int groups, const float* stats, float eps, const float* gamma, const float* beta, int silu,
                   void* y, long long ldy, float* coef, void* stream);
-/* stats (as ddpm_gn_stats) from the per-(sample, channel) moments accumulated by the producing conv epilogues
+/* stats (as ddpm_gn_stats) from the per-(sample, 4-channel granule) moments accumulated by the producing conv epilogues
  * (ddpm_conv_args.out_csum), for an input that may be the concat of two tensors: with it the GroupNorm forward is ONE
  * streaming pass (ddpm_gn_apply, 4 B/elem) instead of the two-phase ddpm_gn_fwd. */
 int ddpm_gn_stats_from_csum(const float* csum0, int c0, const float* csum1, int c1, int n, int groups, float* stats,

@@ -215,6 +215,183 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
+// fprop / dgrad / linear, PERSISTENT variant (problems with many output tiles)
+// ---------------------------------------------------------------------------------------------
+// The kernel above gives every output tile its own CTA: barrier init, TMEM allocation, descriptor prefetch and the
+// pipeline fill are paid per tile, and the epilogue of a tile overlaps nothing of its own CTA.  For the short-K GEMMs of
+// the UNet -- the 1x1 shortcut convs (2-6 k-blocks), conv_in / conv_out's dgrad (ONE k-block), the attention projections
+// -- that overhead IS the kernel: they are memory-bound by bytes (0.12 ms for 256->128 1x1 @128^2, batch 64) and ran at
+// 0.19 ms.  Here one CTA per SM walks a static round-robin of tiles with the TMA ring running ahead across tile
+// boundaries and two TMEM accumulators, so tile i's epilogue (8 warps) runs under tile i+1's loads and MMAs.
+constexpr int kPersistThreads = 320;   // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int kPersistMaxStages = 8;
+
+struct PersistParams {
+  GemmParams g;
+  int n_tiles, total_tiles, stages;
+};
+
+template <int BLOCK_N, bool GN>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PersistParams pp) {
+  const GemmParams& p = pp.g;
+  constexpr int kABytes = kBlockM * kBlockK * 2;
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = pp.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * kStageBytes);
+  uint64_t* empty_bar = full_bar + kPersistMaxStages;
+  uint64_t* tmem_full = empty_bar + kPersistMaxStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.kb1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);     // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, 2 * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int kbt = p.kb0 + p.kb1;
+  const int tiles_hw = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    uint32_t s = 0, ph = 1;
+    for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x) {
+      const int nt = tile % pp.n_tiles;
+      const int mt = tile / pp.n_tiles;
+      const int tn = mt / tiles_hw;
+      const int r2 = mt - tn * tiles_hw;
+      const int th = r2 / p.tiles_w;
+      const int w0 = (r2 - th * p.tiles_w) * p.wb, h0 = th * p.hb, n0 = tn * p.nb;
+      for (int t = 0; t < p.taps.ntaps; ++t) {
+        const int cw = w0 + p.taps.dw[t], ch = h0 + p.taps.dh[t], cn = n0 + p.taps.dn[t], wk = p.taps.wk[t];
+        for (int kb = 0; kb < kbt; ++kb) {
+          mbar_wait(&empty_bar[s], ph);
+          if (elect_one()) {
+            uint8_t* sa = smem + s * kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(&full_bar[s], p.a_bytes + kBBytes);
+            if (kb < p.kb0)
+              tma_load_4d(sa, &tmA0, &full_bar[s], kb * kBlockK, cw, ch, cn);
+            else
+              tma_load_4d(sa, &tmA1, &full_bar[s], (kb - p.kb0) * kBlockK, cw, ch, cn);
+            tma_load_2d(sb, &tmB, &full_bar[s], wk + kb * kBlockK, nt * BLOCK_N);
+          }
+          __syncwarp();
+          if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, false, false);
+    const uint64_t da_base = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    const int iters = p.taps.ntaps * kbt;
+    uint64_t da0 = da_base;
+    uint32_t s = 0, ph = 0, acc = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * BLOCK_N;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t db0 = da0 + (kABytes >> 4);
+        const uint32_t first = it != 0 ? 1u : 0u;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(d0, da0 + static_cast<uint64_t>((k * kUmmaK * 2) >> 4),
+                      db0 + static_cast<uint64_t>((k * kUmmaK * 2) >> 4), idesc, k == 0 ? first : 1u);
+          umma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+        da0 += kStageBytes >> 4;
+        if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; da0 = da_base; }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      aph ^= (acc == 0);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; two warps per lane quarter split the columns
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kChunks = BLOCK_N / 64;          // 32-column chunks per warp
+    const int row = q * 32 + lane;
+    const int rows_per_img = p.wb * p.hb;
+    const int ni = row / rows_per_img;
+    const int rem = row - ni * rows_per_img;
+    const int hi = rem / p.wb;
+    const int wi = rem - hi * p.wb;
+    uint32_t acc = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x) {
+      const int nt = tile % pp.n_tiles;
+      const int mt = tile / pp.n_tiles;
+      const int tn = mt / tiles_hw;
+      const int r2 = mt - tn * tiles_hw;
+      const int th = r2 / p.tiles_w;
+      const int n = tn * p.nb + ni, h = th * p.hb + hi, w = (r2 - th * p.tiles_w) * p.wb + wi;
+      const bool valid = (ni < p.nb) && (n < p.N) && (h < p.H) && (w < p.W);
+      const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+      const int col0 = nt * BLOCK_N + half * (BLOCK_N / 2);
+      EpiX xcur, xnext;
+      const bool pref = GN || p.epi.res != nullptr;
+      if (pref) epi_load_x(p.epi, valid, pix, col0, xcur);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xcur.w[j] = xnext.w[j] = 0u;
+      }
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      const int n_warp = (GN && p.epi.gsums) ? epi_warp_sample(valid, n) : -1;
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        if (pref && c + 1 < kChunks) epi_load_x(p.epi, valid, pix, col0 + (c + 1) * 32, xnext);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2) + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        float t1 = 0.f, t2 = 0.f;
+        epi_chunk<GN, true>(p.epi, v, valid, n, pix, col0 + c * 32, lane, t1, t2, xcur);
+        if (GN) epi_flush_sums(p.epi, n_warp, col0 + c * 32, lane, t1, t2);
+        xcur = xnext;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      aph ^= (acc == 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+}
+
+// ---------------------------------------------------------------------------------------------
 // wgrad
 // ---------------------------------------------------------------------------------------------
 struct WgradParams {
@@ -662,6 +839,29 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   return check_launch("conv_gemm_kernel");
 }
 
+template <int BLOCK_N, bool GN>
+static int launch_gemm_persist(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
+                               cudaStream_t stream) {
+  PersistParams pp;
+  pp.g = p;
+  pp.n_tiles = (p.epi.Cout + BLOCK_N - 1) / BLOCK_N;
+  pp.total_tiles = pp.n_tiles * p.tiles_w * p.tiles_h * p.tiles_n;
+  const int stage_bytes = kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2;
+  int stages = (227 * 1024 - 1024 - 512) / stage_bytes;
+  if (stages > kPersistMaxStages) stages = kPersistMaxStages;
+  pp.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 512 + 1024;
+  auto kern = conv_gemm_persist_kernel<BLOCK_N, GN>;
+  static bool configured = false;
+  if (!configured) {
+    DDPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = pp.total_tiles < kNumSMs ? pp.total_tiles : kNumSMs;
+  kern<<<grid, kPersistThreads, smem, stream>>>(a0, a1, b, pp);
+  return check_launch("conv_gemm_persist_kernel");
+}
+
 template <int BLOCK_N, int STAGES>
 static int launch_wgrad(const CUtensorMap& y, const CUtensorMap& x0, const CUtensorMap& x1, const WgradParams& p,
                         int splits, cudaStream_t stream) {
@@ -733,6 +933,20 @@ extern "C" int ddpm_conv_gemm(const ddpm_conv_args* a, void* stream_) {
     if (a->ntaps * (p.kb0 + p.kb1) <= 8) block_n = 128;
   }
   long long k_total = a->k_total > 0 ? a->k_total : a->ldw;
+  {
+    // many tiles: the persistent kernel (tile i's epilogue under tile i+1's mainloop, no per-tile CTA setup)
+    const long long mtiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_n;
+    const int pbn = (block_n == 256) ? 256 : 128;
+    const long long ptiles = mtiles * ((a->cout + pbn - 1) / pbn);
+    if (env_int("DDPM_PERSIST", 1) != 0 && ptiles >= env_int("DDPM_PERSIST_MIN_TILES", 2 * kNumSMs)) {
+      if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, pbn)) return e;
+      if (pbn == 256)
+        return p.epi.gsums ? launch_gemm_persist<256, true>(ma0, ma1, mb, p, stream)
+                           : launch_gemm_persist<256, false>(ma0, ma1, mb, p, stream);
+      return p.epi.gsums ? launch_gemm_persist<128, true>(ma0, ma1, mb, p, stream)
+                         : launch_gemm_persist<128, false>(ma0, ma1, mb, p, stream);
+    }
+  }
   if (block_n == 256) {
     if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 256)) return e;
     return p.epi.gsums ? launch_gemm<256, 4, true>(ma0, ma1, mb, p, stream)

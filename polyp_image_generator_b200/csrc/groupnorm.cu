@@ -243,19 +243,21 @@ gn_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ 
   gn_apply_stream<SILU>(xp, ld, yp, ldy, p_begin + pl, p_end, ppb, ka, kb);
 }
 
-// stats[n][g] = (sum, sum of squares) over the group's channels of the per-(sample, channel) moments that the producing
-// conv epilogues accumulated (ddpm_conv_args.out_csum); the input may be a channel concat of two tensors
+// stats[n][g] = (sum, sum of squares) over the group's channels of the per-(sample, 4-channel granule) moments that the
+// producing conv epilogues accumulated (ddpm_conv_args.out_csum: [n][c / 4][2]); the input may be a channel concat of two
+// tensors.  Group sizes are multiples of 4 channels (host-checked), so granules never straddle a group.
 __global__ void __launch_bounds__(256)
 gn_stats_from_csum_kernel(const float* __restrict__ cs0, int c0, const float* __restrict__ cs1, int c1, int n, int groups,
                           float* __restrict__ stats) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * groups) return;
   const int b = i / groups, g = i - b * groups;
-  const int cpg = (c0 + c1) / groups;
+  const int gpg = (c0 + c1) / groups / 4;       // granules per group
+  const int q0 = c0 / 4, q1 = c1 / 4;
   float a = 0.f, q = 0.f;
-  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-    const float2 m = c < c0 ? *reinterpret_cast<const float2*>(cs0 + (static_cast<long long>(b) * c0 + c) * 2)
-                            : *reinterpret_cast<const float2*>(cs1 + (static_cast<long long>(b) * c1 + (c - c0)) * 2);
+  for (int k = g * gpg; k < (g + 1) * gpg; ++k) {
+    const float2 m = k < q0 ? *reinterpret_cast<const float2*>(cs0 + (static_cast<long long>(b) * q0 + k) * 2)
+                            : *reinterpret_cast<const float2*>(cs1 + (static_cast<long long>(b) * q1 + (k - q0)) * 2);
     a += m.x;
     q += m.y;
   }
@@ -914,8 +916,9 @@ extern "C" int ddpm_gn_apply(const void* x0, int c0, long long ld0, const void* 
 extern "C" int ddpm_gn_stats_from_csum(const float* csum0, int c0, const float* csum1, int c1, int n, int groups,
                                        float* stats, void* stream) {
   DDPM_REQUIRE(csum0 && stats && n > 0 && c0 > 0 && c1 >= 0 && (c1 == 0 || csum1) && groups > 0 &&
-                   (c0 + c1) % groups == 0,
-               "ddpm_gn_stats_from_csum: bad argument (c0=%d c1=%d groups=%d)", c0, c1, groups);
+                   (c0 + c1) % groups == 0 && c0 % 4 == 0 && c1 % 4 == 0 && ((c0 + c1) / groups) % 4 == 0,
+               "ddpm_gn_stats_from_csum: bad argument (c0=%d c1=%d groups=%d; channels per group must be a multiple "
+               "of 4)", c0, c1, groups);
   gn_stats_from_csum_kernel<<<(n * groups + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(csum0, c0, csum1, c1,
                                                                                                      n, groups, stats);
   return check_launch("gn_stats_from_csum_kernel");

@@ -183,8 +183,8 @@ class CudaOps:
         """out[n,h,w,co] = bias + temb[n] + res + sum_taps X[pix+tap] . wgt[co, wk:wk+cin]; see ddpm_conv_gemm.
         gn = (x0, x1, coef, silu, sums) with coef from gn_fwd(want_coef=True): fuse the first half of the backward of
         y = act(GroupNorm(x0|x1)) into the epilogue (out becomes dz, sums[n, c] += (sum dz, sum dz*x)).
-        csum [n, cout, 2] fp32 (zero-filled): += (sum out, sum out^2) per (sample, channel) -- the statistics of the
-        GroupNorm that consumes `out`, so that its forward is one streaming pass (gn_fwd_from_csum)."""
+        csum [n, cout / 4, 2] fp32 (zero-filled): += (sum out, sum out^2) per (sample, 4-channel granule) -- the
+        statistics of the GroupNorm that consumes `out`, so that its forward is one streaming pass (gn_fwd_from_csum)."""
         n, h, w = grid
         _, _, _, c0, ld0 = _nhwc(x0, "x0")
         a = _capi.ConvArgs()
@@ -231,8 +231,8 @@ class CudaOps:
         if csum is not None:
             if gn is not None or out_f32:
                 raise ValueError("csum excludes the GroupNorm-backward fusion and fp32 output")
-            if csum.dtype != torch.float32 or not csum.is_contiguous() or csum.numel() != n * cout * 2:
-                raise ValueError("csum must be a contiguous fp32 [n, cout, 2] tensor")
+            if csum.dtype != torch.float32 or not csum.is_contiguous() or csum.numel() != n * (cout // 4) * 2:
+                raise ValueError("csum must be a contiguous fp32 [n, cout / 4, 2] tensor")
             a.out_csum = _ptr(csum)
         ws_elems = self.lib.ddpm_conv_gemm_workspace_elems(C.byref(a)) if gn is None and not out_f32 else 0
         if ws_elems > 0:      # low-resolution layer: split-K over idle SMs, fp32 partial sums in a workspace

@@ -929,12 +929,15 @@ class UNet2DModel(nn.Module):
     # GroupNorm statistics ride on the epilogue of the 3x3 conv that PRODUCES the tensor (per-(sample, channel) moments,
     # conv_gemm(csum=...)); the GroupNorm forward is then one streaming pass instead of the two-phase team kernel.
     # (Not for conv_in / the stride-2 convs: they run on the generic kernel, where the reductions are exposed.)
-    @staticmethod
-    def _csum_for(st, grid, cout):
+    def _csum_for(self, st, grid, cout):
         ops = st.ops
         if os.environ.get("DDPM_GN_STATS_FUSION", "1") == "0" or not ops.gn_stats_fusable(grid):
             return None
-        return torch.zeros((grid[0], cout, 2), device=st.temb_all.device, dtype=torch.float32)
+        # the statistics are kept per 4-channel granule: usable when the consuming GroupNorm's groups are whole granules,
+        # which holds whenever every concatenated source is a multiple of 4 * norm_num_groups channels (128 here)
+        if cout % (4 * self.config.norm_num_groups):
+            return None
+        return torch.zeros((grid[0], cout // 4, 2), device=st.temb_all.device, dtype=torch.float32)
 
     @staticmethod
     def _tag(t, csum):

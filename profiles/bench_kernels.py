@@ -112,13 +112,14 @@ def bench_epi(ops, B, iters, pk, first=None):
         gam, bet = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
         _, _, coef = ops.gn_fwd(gx, None, 32, 1e-5, gam, bet, True, want_coef=True)
         out = torch.empty(nb, h, h, cout, device="cuda", dtype=torch.bfloat16)
-        cs = torch.zeros(nb, cout, 2, device="cuda")
+        cs = torch.zeros(nb, cout // 4, 2, device="cuda")      # forward statistics: per 4-channel granule
+        gs = torch.zeros(nb, cout, 2, device="cuda")           # backward fusion sums: per channel
         tp = taps_3x3(cin)
         grid = (nb, h, h)
         variants = [
             ("plain", {}), ("bias", dict(bias=bias)), ("bias+temb", dict(bias=bias, temb=temb)),
             ("bias+res", dict(bias=bias, res=res)), ("bias+temb+csum", dict(bias=bias, temb=temb, csum=cs)),
-            ("bias+res+csum", dict(bias=bias, res=res, csum=cs)), ("gn-bwd fusion", dict(gn=(gx, None, coef, True, cs))),
+            ("bias+res+csum", dict(bias=bias, res=res, csum=cs)), ("gn-bwd fusion", dict(gn=(gx, None, coef, True, gs))),
         ]
         fl = 2.0 * nb * h * h * cout * cin * 9
         for name, kw in variants:

@@ -109,9 +109,10 @@ class EmuOps:
         return hw >= 128 or hw % 32 == 0      # exercised wherever it is POSSIBLE
 
     def gn_fwd_from_csum(self, x0, x1, cs0, cs1, groups, eps, gamma, beta, silu, want_coef=False):
-        cs = cs0 if cs1 is None else torch.cat([cs0, cs1], 1)          # [n, C, 2]
-        n, C, _ = cs.shape
-        stats = cs.reshape(n, groups, C // groups, 2).sum(2)
+        cs = cs0 if cs1 is None else torch.cat([cs0, cs1], 1)          # [n, C / 4, 2]: 4-channel granules
+        n, Q, _ = cs.shape
+        C = 4 * Q
+        stats = cs.reshape(n, groups, Q // groups, 2).sum(2)
         # the fused statistics must agree with a direct reduction over the tensor itself
         X = (x0 if x1 is None else torch.cat([x0, x1], -1)).float()
         want = torch.stack([X.reshape(n, -1, groups, C // groups).sum((1, 3)),
@@ -196,8 +197,8 @@ class EmuOps:
         r = acc if out_f32 else self._a(acc)
         if csum is not None:
             rf = r.float()
-            csum[..., 0] += rf.sum((1, 2))
-            csum[..., 1] += (rf * rf).sum((1, 2))
+            csum[..., 0] += rf.sum((1, 2)).reshape(csum.shape[0], -1, 4).sum(-1)
+            csum[..., 1] += (rf * rf).sum((1, 2)).reshape(csum.shape[0], -1, 4).sum(-1)
         if out is not None:
             out.copy_(r)
             return out

@@ -122,7 +122,7 @@ class Recorder:
                     extra = _rel(sums, want)       # sums are zero-filled by the caller before the launch
                 if kw.get("csum") is not None:
                     o = out.float()
-                    want = torch.stack([o.sum((1, 2)), (o * o).sum((1, 2))], -1)
+                    want = torch.stack([o.sum((1, 2)), (o * o).sum((1, 2))], -1).reshape(n, cout // 4, 4, 2).sum(2)
                     extra = _rel(kw["csum"], want)
                 desc = f"{h}x{w} n{n} c{cin}->{cout} k{len(taps)}" + \
                     "".join(f" +{k}" for k in ("bias", "temb", "res", "gn", "csum") if kw.get(k) is not None)

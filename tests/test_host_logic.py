@@ -23,7 +23,7 @@ def test_capi_exports_every_declared_symbol(built_lib):
         assert hasattr(lib, name), f"{name} declared in include/ddpm_b200.h but not exported"
     from polyp_image_generator_b200 import _capi
     assert set(_capi.SIGNATURES) | {"ddpm_last_error"} == declared
-    assert _capi.load().ddpm_abi_version() == 2
+    assert _capi.load().ddpm_abi_version() == _capi.ABI_VERSION == 3
 
 
 def test_capi_argument_validation_without_gpu(built_lib):

@@ -361,14 +361,14 @@ def test_conv_epilogue_statistics_and_single_pass_groupnorm(dev, hw, cin, cout, 
     w = (torch.randn(cout, len(taps) * cin, device=dev) * 0.05).to(torch.bfloat16)
     bias = torch.randn(cout, device=dev)
     res = (torch.randn(n, hw, hw, cout, device=dev)).to(torch.bfloat16)
-    cs = torch.zeros(n, cout, 2, device=dev)
+    cs = torch.zeros(n, cout // 4, 2, device=dev)          # per (sample, 4-channel granule)
     y = o.conv_gemm(x0, x1, taps, w, cout, (n, hw, hw), bias=bias, res=res, csum=cs)
     y_plain = o.conv_gemm(x0, x1, taps, w, cout, (n, hw, hw), bias=bias, res=res)
     # the statistics do not disturb the output (not bit-equal: the plain launch may take the split-K path, which
     # accumulates in another order)
     assert rel(y, y_plain) < 4e-3
     yf = y.float()
-    want = torch.stack([yf.sum((1, 2)), (yf * yf).sum((1, 2))], -1)
+    want = torch.stack([yf.sum((1, 2)), (yf * yf).sum((1, 2))], -1).reshape(n, cout // 4, 4, 2).sum(2)
     assert rel(cs, want) < 1e-5
     gam, bet = torch.randn(cout, device=dev), torch.randn(cout, device=dev)
     st_a, ya, co_a = o.gn_fwd(y, None, 32, 1e-5, gam, bet, True, want_coef=True)
@@ -376,7 +376,7 @@ def test_conv_epilogue_statistics_and_single_pass_groupnorm(dev, hw, cin, cout, 
     assert rel(st_b, st_a) < 1e-5 and rel(co_b, co_a) < 1e-4
     assert rel(yb, ya) < 4e-3                                          # bf16 outputs, fp32 statistics from two orders
     # concat of two tensors whose statistics came from two different producers
-    cs2 = torch.zeros(n, cout, 2, device=dev)
+    cs2 = torch.zeros(n, cout // 4, 2, device=dev)
     y2 = o.conv_gemm(x0, x1, taps, w, cout, (n, hw, hw), csum=cs2)
     g2, b2 = torch.randn(2 * cout, device=dev), torch.randn(2 * cout, device=dev)
     st_c, yc = o.gn_fwd(y, y2, 32, 1e-6, g2, b2, False)
