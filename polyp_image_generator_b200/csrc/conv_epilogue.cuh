@@ -141,6 +141,22 @@ __device__ __forceinline__ void epi_load_x(const EpiParams& e, bool valid, long 
   }
 }
 
+// L2 prefetch of the side input (GroupNorm x or residual) of one pixel row, `ncols` channels from `col`: no register
+// destination, so it can run a whole tile ahead.  ncu (profiles/r2_epilogue_stalls.md): with the register prefetch one
+// 32-column chunk ahead the epilogue warps still sat in long-scoreboard stalls on the first use of these loads -- a chunk
+// takes ~700 clk, a DRAM round trip under load ~2000 -- and the fused epilogues cost +25 ... +60 % of the kernel.
+__device__ __forceinline__ void epi_prefetch_side(const EpiParams& e, bool valid, long long pix, int col, int ncols) {
+  if (!valid || col >= e.Cout) return;
+  const __nv_bfloat16* p0 = nullptr;
+  if (epi_slot_is_gn(e))
+    p0 = (col < e.gc0) ? e.gx0 + pix * e.gld0 + col : e.gx1 + pix * e.gld1 + (col - e.gc0);
+  else if (e.res != nullptr)
+    p0 = e.res + pix * e.ldr + col;
+  if (p0 == nullptr) return;
+  for (int b = 0; b < ncols * 2; b += 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p0) + b));
+}
+
 // v[32]: fp32 accumulators of (row = this thread's pixel, columns col .. col+31).  `n`, `pix` describe the pixel;
 // rows with valid == false are not stored and contribute zero to the sums.  All 32 lanes of the warp must call this
 // together when GN fusion is on (shuffles), and the warp's valid rows must belong to ONE sample (host-checked).

@@ -229,6 +229,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         geom(0, col, valid, pix, u);
         epi_load_x(p.epi, valid, pix, col, xcur);
       }
+      if (p.epi.res != nullptr || epi_slot_is_gn(p.epi)) {
+        // side input of the NEXT tile of this CTA -> L2, one whole tile ahead of its first use
+        const int tn = tile + gridDim.x;
+        if (tn < p.total_tiles) {
+          const int nt2 = tn % p.n_tiles, mt2 = tn / p.n_tiles;
+          const int unit2 = mt2 / p.tiles_per_img;
+          const int q02 = (mt2 - unit2 * p.tiles_per_img) * kTileSlots;
+          const int img2 = unit2 / p.S, xs2 = (unit2 - img2 * p.S) * p.Ws;
+#pragma unroll
+          for (int u2 = 0; u2 < 2; ++u2) {
+            const int slot = q02 + u2 * 128 + q * 32 + lane;
+            const int h2 = slot / p.Wp, w2 = slot - h2 * p.Wp - 1;
+            epi_prefetch_side(p.epi, (w2 >= 0) && (w2 < p.Ws) && (h2 < p.H),
+                              (static_cast<long long>(img2) * p.H + h2) * p.W + xs2 + w2, nt2 * 128 + half * 64, 64);
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
       float t1 = 0.f, t2 = 0.f;
@@ -456,6 +473,18 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         int col, u; bool valid; long long pix;
         geom(0, col, valid, pix, u);
         epi_load_x(p.epi, valid, pix, col, xcur);
+      }
+      if ((p.epi.res != nullptr || epi_slot_is_gn(p.epi)) && pt + n_pairs < p.total_tiles) {
+        // side input of the NEXT tile of this CTA -> L2, one whole tile ahead of its first use
+        int img2, xs2, q02, nt2; bool ok2;
+        decode(pt + n_pairs, img2, xs2, ok2, q02, nt2);
+#pragma unroll
+        for (int u2 = 0; u2 < 2; ++u2) {
+          const int slot = q02 + u2 * 128 + q * 32 + lane;
+          const int h2 = slot / p.Wp, w2 = slot - h2 * p.Wp - 1;
+          epi_prefetch_side(p.epi, ok2 && (w2 >= 0) && (w2 < p.Ws) && (h2 < p.H),
+                            (static_cast<long long>(img2) * p.H + h2) * p.W + xs2 + w2, nt2 * 128 + half * 64, 64);
+        }
       }
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();

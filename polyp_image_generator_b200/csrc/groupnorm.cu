@@ -220,7 +220,7 @@ __device__ __forceinline__ void gn_apply_stream(const __nv_bfloat16* xp, long lo
 }
 
 template <bool SILU>
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, 4)
 gn_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                 long long ldy, int pix_per_block, int V, float* __restrict__ coef /*[N][C/2][4] or NULL*/) {
@@ -557,7 +557,7 @@ gn_bwd_dparam_kernel(const float* __restrict__ sums, int N, int C, float* __rest
 
 // ---- backward, second half only (first half fused into the dgrad conv epilogue, conv_epilogue.cuh) ---------------
 // grid (chunks, N).  sums[n][c] = (S1 = sum dz, S2 = sum dz*x) raw moments.  dx = dz*k1 + x*nk4 + nk5 (+ addends).
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, 3)
 gn_bwd_apply_kernel(GnSrc s, int hw, int cpg, int groups, const float* __restrict__ stats, float eps,
                     const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dz, long long lddz,
                     const float* __restrict__ sums, GnDst o, int pix_per_block, int V,
