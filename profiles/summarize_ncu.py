@@ -2,6 +2,7 @@
 
     python profiles/summarize_ncu.py rep  gpurun_out/X.ncu-rep  > profiles/r1_X.md     # --set full capture(s)
     python profiles/summarize_ncu.py list gpurun_out/launches.csv > profiles/r1_launches.md  # gpu__time_duration list
+    python profiles/summarize_ncu.py table gpurun_out/X_raw.csv [label ...] > profiles/r2_X.md  # CSV exported on the box
 """
 import csv
 import subprocess
@@ -42,6 +43,44 @@ def rep(path):
         print()
 
 
+TABLE_KEYS = [
+    ("time us", "gpu__time_duration.sum"), ("tensor %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+    ("L2 %", "lts__throughput.avg.pct_of_peak_sustained_elapsed"), ("L2->SM", "l1tex__m_xbar2l1tex_read_bytes.sum"),
+    ("DRAM rd", "dram__bytes_read.sum"), ("DRAM wr", "dram__bytes_write.sum"),
+    ("DRAM %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+    ("warps %", "sm__warps_active.avg.pct_of_peak_sustained_active"), ("grid", "launch__grid_size"),
+    ("regs", "launch__registers_per_thread"), ("waves", "launch__waves_per_multiprocessor"),
+]
+
+
+def table(path, labels=None):
+    """Raw-metrics CSV exported ON THE GPU BOX (`ncu -i X.ncu-rep --page raw --csv`) -> one markdown row per launch."""
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    print(f"# ncu --set full, one row per launch, from `{path}`\n")
+    print("(per launch, cold-cache, serialised under the profiler: ratios and shares are meaningful, absolute times are "
+          "not bench numbers)\n")
+    print("| # | kernel | " + " | ".join(k for k, _ in TABLE_KEYS) + " |")
+    print("|---|---|" + "---|" * len(TABLE_KEYS))
+    for n, r in enumerate(rows[2:]):
+        name = r[ki].split("(")[0].replace("void ", "").replace("ddpm::", "")
+        if labels and n < len(labels):
+            name += f" -- {labels[n]}"
+        cells = []
+        for _, k in TABLE_KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                v = r[i].replace(",", "")
+                try:
+                    cells.append(f"{float(v):.4g} {units[i]}".strip())
+                except ValueError:
+                    cells.append(v)
+            else:
+                cells.append("-")
+        print(f"| {n} | `{name}` | " + " | ".join(cells) + " |")
+
+
 def lst(path):
     rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
     hdr = rows[0]
@@ -65,4 +104,7 @@ def lst(path):
 
 
 if __name__ == "__main__":
-    (rep if sys.argv[1] == "rep" else lst)(sys.argv[2])
+    if sys.argv[1] == "table":
+        table(sys.argv[2], sys.argv[3:])
+    else:
+        (rep if sys.argv[1] == "rep" else lst)(sys.argv[2])
