@@ -302,7 +302,8 @@ def run_b200(args, rank, world, local_rank):
     # ---- instrument the dominant kernel (conv_gemm) with CUDA events on the launch stream ----
     # classes: "halo" = conv_halo_kernel (3x3 stride-1, W >= 64: the dominant kernel), "gemm" = every other
     # ddpm_conv_gemm launch (generic implicit GEMM: low-res 3x3, 1x1, linears, boundary convs), "wgrad" = ddpm_conv_wgrad
-    prof = {"on": False, "ev": {"halo": [], "gemm": [], "wgrad": []}, "flops": {"halo": 0.0, "gemm": 0.0, "wgrad": 0.0}}
+    prof = {"on": False, "ev": {"halo": [], "gemm": [], "wgrad": []}, "flops": {"halo": 0.0, "gemm": 0.0, "wgrad": 0.0},
+            "k1": {"ev": [], "bytes": 0.0, "flops": 0.0}}
     orig_conv_gemm, orig_conv_wgrad = ops.conv_gemm, ops.conv_wgrad
 
     def conv_gemm_timed(x0, x1, taps, wgt, cout, grid, **kw):
@@ -317,7 +318,17 @@ def run_b200(args, rank, world, local_rank):
                    all(tp[:3] == (0, i // 3 - 1, i % 3 - 1) for i, tp in enumerate(taps)))
         cls = "halo" if is_halo else "gemm"
         prof["ev"][cls].append((e0, e1))
-        prof["flops"][cls] += ops_mod.algorithmic_conv_flops(x0, x1, taps, getattr(wgt, "_ddpm_alg_cout", cout), grid)
+        fl = ops_mod.algorithmic_conv_flops(x0, x1, taps, getattr(wgt, "_ddpm_alg_cout", cout), grid)
+        prof["flops"][cls] += fl
+        if len(taps) == 1 and grid[0] * grid[1] * grid[2] >= 64 * 64 * 64:
+            # 1x1 convs / boundary GEMMs over >= 64x64 maps: HBM-bound by bytes (2-6 k-blocks of reduction), so their
+            # roofline is the copy bandwidth: algorithmic bytes = bf16 input + output (+ residual), weights negligible
+            cin = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+            npx = grid[0] * grid[1] * grid[2]
+            by = npx * (2.0 * cin + (4.0 if kw.get("out_f32") else 2.0) * cout + (2.0 * cout if kw.get("res") is not None else 0.0))
+            prof["k1"]["ev"].append((e0, e1))
+            prof["k1"]["bytes"] += by
+            prof["k1"]["flops"] += fl
         return out
 
     def conv_wgrad_timed(dy, x0, x1, taps, dw, grid, **kw):
@@ -406,6 +417,7 @@ def run_b200(args, rank, world, local_rank):
     ms_prof_total = e3_begin.elapsed_time(e3_end)
     cls_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in prof["ev"].items()}
     cls_tf = {k: (prof["flops"][k] / (cls_ms[k] * 1e-3) / 1e12 if cls_ms[k] > 0 else 0.0) for k in cls_ms}
+    k1_ms = sum(a.elapsed_time(b) for a, b in prof["k1"]["ev"])
     gemm_ms = cls_ms["halo"]
     gemm_launches = len(prof["ev"]["halo"])
     gemm_flops = prof["flops"]["halo"]
@@ -608,6 +620,15 @@ def run_b200(args, rank, world, local_rank):
             "generic_gemm_tflops (1x1, stride-2, <= 16x16 3x3, linears, boundary convs)": round(cls_tf["gemm"], 1),
             "generic_gemm_frac_of_peak": round(cls_tf["gemm"] / peak_tf, 4),
             "generic_gemm_ms_per_step": round(cls_ms["gemm"] / n_prof_steps, 3),
+            "generic_1x1_ge64 (memory-bound class: 1x1 shortcut convs, conv_in, conv_out dgrad at >= 64x64)": {
+                "ms_per_step": round(k1_ms / n_prof_steps, 3), "launches_per_step": len(prof["k1"]["ev"]) // n_prof_steps,
+                "gbps": round(prof["k1"]["bytes"] / (k1_ms * 1e-3) / 1e9, 1) if k1_ms > 0 else None,
+                "frac_of_copy_peak": round(prof["k1"]["bytes"] / (k1_ms * 1e-3) / 1e9 /
+                                           hbm_kernels.get("_peak_gbs", 6536.0), 4) if k1_ms > 0 else None,
+                "tflops": round(prof["k1"]["flops"] / (k1_ms * 1e-3) / 1e12, 1) if k1_ms > 0 else None},
+            "generic_rest_tflops (stride-2, <= 16x16 3x3, linears)": round(
+                (prof["flops"]["gemm"] - prof["k1"]["flops"]) / ((cls_ms["gemm"] - k1_ms) * 1e-3) / 1e12, 1)
+            if cls_ms["gemm"] > k1_ms else None,
             "wgrad_tflops (row-resident + generic)": round(cls_tf["wgrad"], 1),
             "wgrad_frac_of_peak": round(cls_tf["wgrad"] / peak_tf, 4),
             "wgrad_ms_per_step": round(cls_ms["wgrad"] / n_prof_steps, 3),

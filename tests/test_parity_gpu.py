@@ -242,7 +242,7 @@ def test_unet_forward_backward_vs_oracle(dev, variant, S, B):
     loss.backward()
     total, worst, name = _grad_report(m, om, x, t, noise)
     assert total < 2e-2, f"whole-gradient rel error {total}"
-    assert worst < 2.0, f"{name}: {worst} x the bf16-storage noise floor of that tensor"
+    assert worst < 3.0, f"{name}: {worst} x the bf16-storage noise floor of that tensor"
     # inference path (no tape) gives the same prediction; python-int timestep broadcast
     with torch.no_grad():
         p2 = m(x.to(dev), t.to(dev)).sample
@@ -481,7 +481,7 @@ def test_lora_forward_backward_and_merge_vs_oracle(dev):
           f"{ratio:.2f} ({worst_name}), {cnt} tensors")
     assert len(rows) == 48
     assert whole < 2.0 * max(floor_whole, 1e-2), (whole, floor_whole)
-    assert ratio < 2.0, (worst_name, ratio)
+    assert ratio < 3.0, (worst_name, ratio)
 
     # Self-consistency (common-mode noise cancels): with the base projections ALSO trainable, the same backward
     # yields dW = dY^T x, and the adapter gradients must equal dA = s B^T dW, dB = s dW A^T  (s = alpha / r = 1).
