@@ -79,6 +79,10 @@ class GraphedTrainStep:
     like the first iterations of the reference loop -- count them in the schedule or construct the object before
     loading a checkpoint.
 
+    Do not keep an autograd graph of the same model alive across construction (e.g. the `loss` of an earlier eager step
+    that was never freed): its AccumulateGrad nodes are bound to the stream of that step, and CUDA refuses a capture
+    that makes the legacy default stream wait on the capturing one (cudaErrorStreamCaptureImplicit).
+
     The optimizer must be capturable: optim.FusedAdamW (set its lr_tensor to a device scalar to drive a schedule from
     the host: lr_tensor.fill_(value) between replays) or torch.optim.AdamW(..., fused=True, capturable=True).
     """

@@ -70,6 +70,9 @@ def main():
     same = all(torch.equal(gathered[0], x) for x in gathered)
 
     # ---- CUDA-graph DDP step (lr = 0: weights stay put, gradients of the replay are comparable) ----
+    # (drop the eager autograd graph first: while it lives, the parameters' AccumulateGrad nodes stay bound to the stream
+    # of that eager step -- the legacy default stream -- and a capture that reuses them is refused by CUDA)
+    del loss
     opt = FusedAdamW(model.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0)
     model.zero_grad(set_to_none=True)
     step = GraphedTrainStep(ddp, sched, opt, clean[sl].shape, max_grad_norm=1.0, warmup_iters=2,
