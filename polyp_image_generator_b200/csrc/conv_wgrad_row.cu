@@ -43,6 +43,7 @@ struct WgradRowParams {
   uint32_t stage_bytes;
   float* dw;
   long long ldw;
+  int noflush;             // timing experiment only (DDPM_WGRAD_NOFLUSH=1): skip the red.add epilogue
 };
 
 __global__ void __launch_bounds__(kWrThreads, 1)
@@ -159,7 +160,7 @@ conv_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
     const int co = cot * 128 + q * 32 + lane;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    if (n_iters > 0) {
+    if (n_iters > 0 && !p.noflush) {
 #pragma unroll 1
       for (int t = 0; t < 3; ++t) {
         float* row = p.dw + static_cast<long long>(co) * p.ldw + (r * 3 + t) * p.Cin_total + cit * 128;
@@ -229,6 +230,7 @@ int launch_wgrad_row(const ::ddpm_wgrad_args* a, cudaStream_t stream) {
   if (stages < 2) return 1;
   p.stages = stages;
   p.dw = a->dw; p.ldw = a->ldw;
+  p.noflush = env_int("DDPM_WGRAD_NOFLUSH", 0);
 
   const long long out_tiles = 3LL * p.cin_tiles * p.cout_tiles;
   int splits = a->splits;
