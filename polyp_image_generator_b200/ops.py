@@ -17,6 +17,10 @@ from . import _capi
 
 Tap = Tuple[int, int, int, int]  # (dn, dh, dw, wk)
 
+# smallest map (pixels per sample) at which the GroupNorm statistics / backward fusions ride on the conv epilogues
+import os as _os
+_GN_FUSE_MIN_HW = int(_os.environ.get("DDPM_GN_FUSE_MIN_HW", "4096"))
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -159,7 +163,7 @@ class CudaOps:
         measured on B200 (profiles/bench_kernels.py convgn) the fused epilogue costs +0.058 ms at 128^2 against
         0.19 ms saved in the GroupNorm pass, but +0.040 ms at 32^2 against 0.01 ms saved."""
         hw = grid[1] * grid[2]
-        return hw >= 4096
+        return hw >= _GN_FUSE_MIN_HW
 
     def gn_stats_fusable(self, grid: Tuple[int, int, int]) -> bool:
         """Should a 3x3 stride-1 conv that PRODUCES a tensor over this grid also reduce the per-(sample, channel) moments
@@ -169,7 +173,7 @@ class CudaOps:
         overlaps the next tile's mainloop: in the generic kernel the extra warp reductions are exposed (measured: +1.6 ms
         on the 256^2 LoRA step)."""
         hw = grid[1] * grid[2]
-        return hw >= 4096 and self.halo_strips(grid[2]) > 0
+        return hw >= _GN_FUSE_MIN_HW and self.halo_strips(grid[2]) > 0
 
     def halo_strips(self, w: int) -> int:
         s = self._halo_strips.get(w)
