@@ -36,6 +36,7 @@
 namespace ddpm {
 
 constexpr int kHaloThreads = 352;
+constexpr int kHaloPairThreads = 384;   // pair kernel: 8 epilogue warps + 3 role warps + 1 idle warp = 3 full warpgroups
 constexpr int kHaloMaxBStages = 8;   // weight-tile ring depth is chosen at launch from the shared memory left over
 constexpr int kHaloMaxPairStages = 16;   // CTA-pair variant: half tiles (8 KB), twice the depth
 constexpr int kTileSlots = 256;
@@ -291,7 +292,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // (the peer's TMA signals them through their shared::cluster address); "empty" barriers live in both CTAs and are
 // released by multicast tcgen05.commit; the accumulator-empty barrier of the leader collects both epilogues.
 // =====================================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloPairThreads, 1)
 conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -338,6 +339,14 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register split (ncu, profiles/r2_epilogue_stalls.md: the fused epilogues stalled on the first use of their side-input
+  // loads, one 32-column chunk of prefetch was all that 168 registers allowed).  The four role warps (one issuing lane
+  // each) shrink to 56 registers, the eight epilogue warps grow to 224 and hold the side input of ALL FOUR chunks of a
+  // tile, loaded before they wait for the accumulator.
+  // (the setmaxnreg instructions sit at the top of the two role regions below so that ptxas allocates each region
+  // against its own budget)
+
+
   // pair tile -> (image and first column of this CTA's strip, first slot, cout tile); the pair works on two
   // consecutive (image, strip) units
   auto decode = [&](int pt, int& img, int& xs, bool& img_ok, int& q0, int& nt) {
@@ -352,6 +361,8 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     xs = (unit - img * p.S) * p.Ws;
   };
 
+  if (warp >= 8) {
+  setmaxnreg_dec<56>();
   if (warp == 8) {
     // ---------------- halo producer (both CTAs; completion is signalled on the LEADER's barrier) ----------------
     uint32_t hb = 0, hph = 0;
@@ -450,7 +461,9 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         aph ^= (acc == 0);
       }
     }
+  }
   } else {
+    setmaxnreg_inc<224>();
     // ---------------- epilogue (8 warps per CTA; each CTA drains its own TMEM = its own image) ----------------
     const int q = warp & 3;
     const int half = warp >> 2;
@@ -468,11 +481,18 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         valid = img_ok && (w >= 0) && (w < p.Ws) && (h < p.H);
         pix = (static_cast<long long>(img) * p.H + h) * p.W + xs + w;
       };
-      EpiX xcur, xnext;
+      // side input (GroupNorm x or residual) of all four chunks, in flight while the tile's mainloop still runs
+      EpiX x0, x1, x2, x3;
       {
         int col, u; bool valid; long long pix;
         geom(0, col, valid, pix, u);
-        epi_load_x(p.epi, valid, pix, col, xcur);
+        epi_load_x(p.epi, valid, pix, col, x0);
+        geom(1, col, valid, pix, u);
+        epi_load_x(p.epi, valid, pix, col, x1);
+        geom(2, col, valid, pix, u);
+        epi_load_x(p.epi, valid, pix, col, x2);
+        geom(3, col, valid, pix, u);
+        epi_load_x(p.epi, valid, pix, col, x3);
       }
       if ((p.epi.res != nullptr || epi_slot_is_gn(p.epi)) && pt + n_pairs < p.total_tiles) {
         // side input of the NEXT tile of this CTA -> L2, one whole tile ahead of its first use
@@ -492,10 +512,6 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
         int col, u; bool valid; long long pix;
-        if (i + 1 < 4) {
-          geom(i + 1, col, valid, pix, u);
-          epi_load_x(p.epi, valid, pix, col, xnext);
-        }
         geom(i, col, valid, pix, u);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + u * 128 + (half * 2 + (i >> 1)) * 32, r);
@@ -503,12 +519,14 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epi_chunk(p.epi, v, valid, img, pix, col, lane, t1, t2, xcur);
+        epi_chunk(p.epi, v, valid, img, pix, col, lane, t1, t2, x0);
         if (u == 1) {
           epi_flush_sums(p.epi, img_ok ? img : -1, col, lane, t1, t2);
           t1 = t2 = 0.f;
         }
-        xcur = xnext;
+        x0 = x1;
+        x1 = x2;
+        x2 = x3;
       }
       tc_fence_before();
       __syncwarp();
@@ -627,7 +645,7 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
       pconfigured = psmem;
     }
     int pgrid = 2 * pp.total_tiles < kNumSMs ? 2 * pp.total_tiles : (kNumSMs / 2) * 2;
-    conv_halo_pair_kernel<<<pgrid, kHaloThreads, psmem, stream>>>(ma0, ma1, mb, pp);
+    conv_halo_pair_kernel<<<pgrid, kHaloPairThreads, psmem, stream>>>(ma0, ma1, mb, pp);
     return check_launch("conv_halo_pair_kernel");
   }
   if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 128)) return e;
