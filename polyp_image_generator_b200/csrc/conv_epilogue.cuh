@@ -157,16 +157,26 @@ __device__ __forceinline__ void epi_prefetch_side(const EpiParams& e, bool valid
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p0) + b));
 }
 
+// Per-thread column partials of the fused reductions, accumulated over the row blocks that share a 32-column chunk and
+// reduced across the warp ONCE (epi_reduce): GroupNorm-backward fusion a[j] = dz, b[j] = dz * x per column;
+// forward statistics a[k] = sum, b[k] = sum of squares per 4-channel granule (k < 8).
+struct EpiAcc {
+  float a[32];
+  float b[32];
+};
+__device__ __forceinline__ void epi_acc_zero(EpiAcc& acc) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc.a[j] = acc.b[j] = 0.f;
+}
+
 // v[32]: fp32 accumulators of (row = this thread's pixel, columns col .. col+31).  `n`, `pix` describe the pixel;
-// rows with valid == false are not stored and contribute zero to the sums.  All 32 lanes of the warp must call this
-// together when GN fusion is on (shuffles), and the warp's valid rows must belong to ONE sample (host-checked).
-// With GroupNorm fusion, this lane's column totals are ADDED to (t1, t2); the caller flushes them with
-// epi_flush_sums once all row blocks sharing these columns (and this sample) have been processed.
+// rows with valid == false are not stored and contribute zero to the sums.  Applies bias / temb / residual and, with
+// GroupNorm fusion, turns v into dz; the fused reductions' per-column partials are ADDED to acc.
 // PREF: xin was filled by epi_load_x for this (pix, col) -- the residual, when there is one and the slot is not taken by
 // the GroupNorm input, comes from there instead of a load issued here.
-template <bool GN = true, bool PREF = GN>
-__device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bool valid, int n, long long pix, int col,
-                                          int lane, float& t1, float& t2, const EpiX& xin) {
+template <bool GN, bool PREF>
+__device__ __forceinline__ void epi_math(const EpiParams& e, float (&v)[32], bool valid, int n, long long pix, int col,
+                                         const EpiX& xin, EpiAcc& acc) {
   const bool col_ok = col < e.Cout;
   if (valid && col_ok) {
     if (e.bias) {
@@ -212,27 +222,24 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
     }
   }
   if (GN && e.gsums != nullptr && e.gstats) {
-    // ---- statistics of the consuming GroupNorm: moments of the bf16 values that are stored below, per 4-channel
-    // granule (in-thread fold of 4 columns, then a 9-shuffle granule butterfly; +0.046 ms -> see profiles/ for the
-    // per-channel version this replaced) ----
-    float g1[8], g2[8];
+    // ---- statistics of the consuming GroupNorm: moments of the bf16 values that are stored, per 4-channel granule
+    // (in-thread fold of 4 columns; the 9-shuffle granule butterfly runs once per chunk in epi_reduce) ----
+    if (valid && col_ok) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float a = 0.f, q = 0.f;
+      for (int k = 0; k < 8; ++k) {
+        float a = 0.f, q = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float r = (valid && col_ok) ? __bfloat162float(__float2bfloat16(v[4 * k + j])) : 0.f;
-        a += r;
-        q = fmaf(r, r, q);
+        for (int j = 0; j < 4; ++j) {
+          const float r = __bfloat162float(__float2bfloat16(v[4 * k + j]));
+          a += r;
+          q = fmaf(r, r, q);
+        }
+        acc.a[k] += a;
+        acc.b[k] += q;
       }
-      g1[k] = a;
-      g2[k] = q;
     }
-    t1 += warp_granule_sums(g1, lane);
-    t2 += warp_granule_sums(g2, lane);
   } else if (GN && e.gsums != nullptr) {
-    // ---- GroupNorm backward, part 1 (warp-collective; packed fp32x2 math) ----
-    float s2[32];
+    // ---- GroupNorm backward, part 1 (packed fp32x2 math) ----
     if (valid && col_ok) {
       float x[32];
 #pragma unroll
@@ -257,39 +264,62 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bo
         }
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) s2[j] = v[j] * x[j];
-    } else {
-#pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] = 0.f;
-        s2[j] = 0.f;
-      }
-    }
-    float keep[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) keep[j] = v[j];
-    t1 += warp_column_sums(keep, lane);
-    t2 += warp_column_sums(s2, lane);
-  }
-  if (valid && col_ok) {
-    if (e.out_f32) {
-      float4* op = reinterpret_cast<float4*>(e.out_f32 + pix * e.ldo + col);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-      uint32_t ow[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) ow[j] = pack2_bf16_(v[2 * j], v[2 * j + 1]);
-      st64B(e.out + pix * e.ldo + col, ow, e.wide != 0);
-      if (e.split) {      // lo = bf16(v - hi): together 16 mantissa bits of the fp32 accumulator
-        uint32_t lw[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          lw[j] = pack2_bf16_(v[2 * j] - bf16lo_f(ow[j]), v[2 * j + 1] - bf16hi_f(ow[j]));
-        st64B(e.out + pix * e.ldo + e.Cout + col, lw, e.wide != 0);
+        acc.a[j] += v[j];
+        acc.b[j] = fmaf(v[j], x[j], acc.b[j]);
       }
     }
   }
+}
+
+// stores v (after epi_math) as bf16 (or fp32 / split-bf16) at (pix, col .. col+31)
+__device__ __forceinline__ void epi_store(const EpiParams& e, const float (&v)[32], bool valid, long long pix, int col) {
+  if (!(valid && col < e.Cout)) return;
+  if (e.out_f32) {
+    float4* op = reinterpret_cast<float4*>(e.out_f32 + pix * e.ldo + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    uint32_t ow[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ow[j] = pack2_bf16_(v[2 * j], v[2 * j + 1]);
+    st64B(e.out + pix * e.ldo + col, ow, e.wide != 0);
+    if (e.split) {      // lo = bf16(v - hi): together 16 mantissa bits of the fp32 accumulator
+      uint32_t lw[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        lw[j] = pack2_bf16_(v[2 * j] - bf16lo_f(ow[j]), v[2 * j + 1] - bf16hi_f(ow[j]));
+      st64B(e.out + pix * e.ldo + e.Cout + col, lw, e.wide != 0);
+    }
+  }
+}
+
+// Cross-lane reduction of the per-column partials: this lane's totals are ADDED to (t1, t2) (the layout epi_flush_sums
+// expects).  All 32 lanes of the warp must call this together, and the warp's valid rows must belong to ONE sample.
+template <bool GN>
+__device__ __forceinline__ void epi_reduce(const EpiParams& e, int lane, EpiAcc& acc, float& t1, float& t2) {
+  if (!GN || e.gsums == nullptr) return;
+  if (e.gstats) {
+    float g1[8], g2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g1[k] = acc.a[k]; g2[k] = acc.b[k]; }
+    t1 += warp_granule_sums(g1, lane);
+    t2 += warp_granule_sums(g2, lane);
+  } else {
+    t1 += warp_column_sums(acc.a, lane);
+    t2 += warp_column_sums(acc.b, lane);
+  }
+}
+
+// One chunk, one row block: math + reduction + store (kernels whose row blocks do not share a chunk's columns).
+template <bool GN = true, bool PREF = GN>
+__device__ __forceinline__ void epi_chunk(const EpiParams& e, float (&v)[32], bool valid, int n, long long pix, int col,
+                                          int lane, float& t1, float& t2, const EpiX& xin) {
+  EpiAcc acc;
+  if (GN) epi_acc_zero(acc);
+  epi_math<GN, PREF>(e, v, valid, n, pix, col, xin, acc);
+  epi_reduce<GN>(e, lane, acc, t1, t2);
+  epi_store(e, v, valid, pix, col);
 }
 
 // Adds this lane's column totals to gsums[n][col + lane][0..1].  `n_valid` < 0: the warp had no valid row.

@@ -508,25 +508,31 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       }
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
-      float t1 = 0.f, t2 = 0.f;
+      // two column chunks per warp; the two row blocks (u = 0, 1) of a chunk share its columns, so their per-column
+      // partials of the fused reductions are added in registers and cross the warp ONCE
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        int col, u; bool valid; long long pix;
-        geom(i, col, valid, pix, u);
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + u * 128 + (half * 2 + (i >> 1)) * 32, r);
-        tmem_ld_wait();
-        float v[32];
+      for (int cc = 0; cc < 2; ++cc) {
+        EpiAcc racc;
+        epi_acc_zero(racc);
+        int col = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epi_chunk(p.epi, v, valid, img, pix, col, lane, t1, t2, x0);
-        if (u == 1) {
-          epi_flush_sums(p.epi, img_ok ? img : -1, col, lane, t1, t2);
-          t1 = t2 = 0.f;
+        for (int u = 0; u < 2; ++u) {
+          int uu; bool valid; long long pix;
+          geom(2 * cc + u, col, valid, pix, uu);
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + u * 128 + (half * 2 + cc) * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epi_math<true, true>(p.epi, v, valid, img, pix, col, u == 0 ? x0 : x1, racc);
+          epi_store(p.epi, v, valid, pix, col);
         }
-        x0 = x1;
-        x1 = x2;
-        x2 = x3;
+        float t1 = 0.f, t2 = 0.f;
+        epi_reduce<true>(p.epi, lane, racc, t1, t2);
+        epi_flush_sums(p.epi, img_ok ? img : -1, col, lane, t1, t2);
+        x0 = x2;
+        x1 = x3;
       }
       tc_fence_before();
       __syncwarp();
