@@ -48,17 +48,22 @@ def main():
     single.load_state_dict(model.state_dict())
     sl = slice(rank * per, (rank + 1) * per)
 
+    def mark(what):
+        print(f"[rank {rank}] {what}", file=sys.stderr, flush=True)
+
     def flat_grads(m):
         return torch.cat([p.grad.reshape(-1).float() for p in m.parameters()])
 
     def rel(a, b):
         return ((a - b).norm() / (b.norm() + 1e-30)).item()
 
+    mark("setup done")
     # ---- reference: one process, whole batch ----
     noisy = sched.add_noise(clean, noise, t)
     mse_loss(single(noisy, t, return_dict=False)[0], noise).backward()
     g_ref = flat_grads(single)
 
+    mark("reference done")
     # ---- eager DDP ----
     loss = mse_loss(ddp(noisy[sl], t[sl], return_dict=False)[0], noise[sl])
     loss.backward()
@@ -72,13 +77,16 @@ def main():
     # ---- CUDA-graph DDP step (lr = 0: weights stay put, gradients of the replay are comparable) ----
     # (drop the eager autograd graph first: while it lives, the parameters' AccumulateGrad nodes stay bound to the stream
     # of that eager step -- the legacy default stream -- and a capture that reuses them is refused by CUDA)
+    mark("eager DDP done")
     del loss
     opt = FusedAdamW(model.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0)
     model.zero_grad(set_to_none=True)
     step = GraphedTrainStep(ddp, sched, opt, clean[sl].shape, max_grad_norm=1.0, warmup_iters=2,
                             warmup_batch=(clean[sl], noise[sl], t[sl]))
+    mark("graph captured")
     loss_g = step(clean[sl], noise[sl], t[sl])
     torch.cuda.synchronize()
+    mark("graph replayed")
     g_graph = flat_grads(model)
     r_graph = rel(g_graph, g_ref)
     # mean of the rank losses == whole-batch loss
@@ -86,6 +94,7 @@ def main():
     dist.all_reduce(lt, op=dist.ReduceOp.AVG)
     loss_ref = mse_loss(single(noisy, t, return_dict=False)[0].detach(), noise)
 
+    mark("loss reduced")
     # ---- replicas stay identical through real optimizer steps ----
     opt2 = FusedAdamW(model.parameters(), lr=1e-3, max_grad_norm=1.0)
     for _ in range(3):
@@ -93,6 +102,7 @@ def main():
         mse_loss(ddp(noisy[sl], t[sl], return_dict=False)[0], noise[sl]).backward()
         opt2.step()
     torch.cuda.synchronize()
+    mark("3 eager optimizer steps done")
     w = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     ws = [torch.empty_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
