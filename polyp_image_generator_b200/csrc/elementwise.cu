@@ -275,6 +275,15 @@ to_uint8_nhwc_kernel(const float* __restrict__ x, unsigned char* __restrict__ ou
 // train_from_scratch.py:106-108: clip_grad_norm_(params, 1.0); optimizer.step().  With every parameter, gradient and
 // moment in ONE flat fp32 buffer the update is two streaming kernels (sum of squares; update) instead of ~30
 // multi-tensor launches; the clip coefficient is applied on the fly, so the gradients are read once.
+// Deterministic: every block writes its partial sum to a fixed slot, the block that finishes last adds the slots in
+// index order.  (An atomicAdd per block made the global norm -- and with it the clip coefficient -- differ in the last
+// bit between the ranks of a data-parallel job that hold bit-identical gradients, so the replicas drifted apart:
+// tests/nccl_worker.py.)  The scratch below is per device and not re-entrant across streams; the optimizer step is the
+// only caller and runs on one stream.
+constexpr int kSumsqMaxBlocks = kNumSMs * 16;
+__device__ float g_sumsq_partials[kSumsqMaxBlocks];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(kEwThreads)
 sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -287,13 +296,35 @@ sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) 
   for (long long i = (nvec << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     acc += x[i] * x[i];
   __shared__ float red[kEwThreads / 32];
+  __shared__ bool last;
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
     float v = threadIdx.x < kEwThreads / 32 ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+    if (threadIdx.x == 0) {
+      g_sumsq_partials[blockIdx.x] = v;
+      __threadfence();
+      last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // fixed-order final reduction: thread t adds slots t, t + 256, ... then the usual shuffle tree
+  float tot = 0.f;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += kEwThreads) tot += __ldcg(&g_sumsq_partials[i]);
+  tot = warp_sum(tot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kEwThreads / 32 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      *out += v;
+      g_sumsq_ticket = 0;
+    }
   }
 }
 

@@ -115,9 +115,11 @@ def main():
               f"ranks bit-identical {same}, replicas bit-identical after 3 steps {replicas_same}, "
               f"loss {lt.item():.6f} vs {loss_ref.item():.6f}", flush=True)
         print("NCCL_PARITY_OK" if ok else "NCCL_PARITY_FAIL", flush=True)
+    okt = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)          # every rank leaves with the same exit code (no torchrun hang)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.exit(0 if int(okt.item()) == 1 else 1)
 
 
 if __name__ == "__main__":
