@@ -77,6 +77,17 @@ int ddpm_ddim_step(const float* eps, const float* x, const float* z, float* prev
                    float sqrt_alpha_prod, float sqrt_beta_prod, float sqrt_alpha_prod_prev, float dir_coef, float sigma,
                    float clip, int use_clipped_model_output, void* stream);
 
+/* UniPCMultistepScheduler.step (the sampler the LoRA scripts build at train_with_lora_all_classes.py:314 /
+ * train_with_lora_per_class.py:308; diffusers defaults: solver_order 2, epsilon, predict_x0, "bh2", lower_order_final).
+ * Scalars are computed on the host in fp32 in diffusers' op order; the two kernels keep torch's elementwise op order:
+ *   ddpm_unipc_x0:     out = (x - sigma_t * eps) / alpha_t                           (convert_model_output)
+ *   ddpm_unipc_update: out = (cx * x - cm * m0) - cb * res,
+ *                      res = rho0 * ((m1 - m0) / rk)  [m1 != NULL]   (+)   rho_t * (mt - m0)  [mt != NULL]
+ *                      (predictor: m1 = previous x0 prediction at order 2; corrector: mt = this step's x0 prediction) */
+int ddpm_unipc_x0(const float* eps, const float* x, float* out, long long n, float sigma_t, float alpha_t, void* stream);
+int ddpm_unipc_update(const float* x, const float* m0, const float* m1, const float* mt, float* out, long long n,
+                      float cx, float cm, float cb, float rk, float rho0, float rho_t, void* stream);
+
 /* DDPMPipeline post-processing: (x/2+0.5).clamp(0,1) -> NHWC uint8 via round(x*255). x: NCHW fp32. */
 int ddpm_to_uint8_nhwc(const float* x, unsigned char* out, int n, int c, int h, int w, void* stream);
 

@@ -300,3 +300,190 @@ def numpy_to_pil(images):
         images = images[None, ...]
     images = (images * 255).round().astype("uint8")
     return [Image.fromarray(im) for im in images]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UniPC: the multistep predictor-corrector sampler the LoRA scripts build with
+# UniPCMultistepScheduler.from_config(...) (train_with_lora_all_classes.py:314, train_with_lora_per_class.py:308).
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class SchedulerOutput:
+    prev_sample: torch.Tensor
+
+
+class UniPCMultistepScheduler:
+    """Restatement of diffusers==0.33.1 schedulers/scheduling_unipc_multistep.py for its default configuration
+    (solver_order 2, epsilon prediction, predict_x0, solver_type "bh2", lower_order_final, timestep_spacing "linspace",
+    final_sigmas_type "zero", no thresholding / Karras / flow sigmas) -- every tensor expression in diffusers' op order,
+    0-dim fp32 tensors for the scalars, so that a kernel implementation can be held bit-exact to it.  PARITY UNPINNED
+    like the rest of the oracle (the diffusers source is not available offline); the algorithm is UniPC (Zhao et al.
+    2023): B(h) = expm1(h) ("bh2"), order-1 corrector / order-2 predictor use the closed-form rho = 1/2."""
+
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", solver_order: int = 2, prediction_type: str = "epsilon",
+                 thresholding: bool = False, predict_x0: bool = True, solver_type: str = "bh2",
+                 lower_order_final: bool = True, disable_corrector=(), timestep_spacing: str = "linspace",
+                 steps_offset: int = 0, final_sigmas_type: str = "zero"):
+        if prediction_type != "epsilon" or thresholding or not predict_x0 or solver_type not in ("bh1", "bh2") or \
+                timestep_spacing != "linspace" or final_sigmas_type != "zero":
+            raise NotImplementedError("oracle covers the default UniPC configuration only")
+        self.config = SimpleNamespace(
+            num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+            beta_schedule=beta_schedule, solver_order=solver_order, prediction_type=prediction_type,
+            thresholding=thresholding, predict_x0=predict_x0, solver_type=solver_type,
+            lower_order_final=lower_order_final, disable_corrector=list(disable_corrector),
+            timestep_spacing=timestep_spacing, steps_offset=steps_offset, final_sigmas_type=final_sigmas_type)
+        self.betas = make_betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.sigmas = ((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5
+        self.init_noise_sigma = 1.0
+        self.predict_x0 = predict_x0
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(
+            np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=np.float32)[::-1].copy())
+        self.model_outputs = [None] * solver_order
+        self.timestep_list = [None] * solver_order
+        self.lower_order_nums = 0
+        self.disable_corrector = list(disable_corrector)
+        self.last_sample = None
+        self._step_index = None
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    def scale_model_input(self, sample, *a, **k):
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        T = self.config.num_train_timesteps
+        timesteps = np.linspace(0, T - 1, num_inference_steps + 1).round()[::-1][:-1].copy().astype(np.int64)
+        sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
+        sigmas = np.interp(timesteps, np.arange(0, len(sigmas)), sigmas)
+        sigmas = np.concatenate([sigmas, [0.0]]).astype(np.float32)
+        self.sigmas = torch.from_numpy(sigmas)
+        self.timesteps = torch.from_numpy(timesteps).to(device=device, dtype=torch.int64)
+        self.num_inference_steps = len(timesteps)
+        self.model_outputs = [None] * self.config.solver_order
+        self.lower_order_nums = 0
+        self.last_sample = None
+        self._step_index = None
+
+    @staticmethod
+    def _sigma_to_alpha_sigma_t(sigma):
+        alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
+        sigma_t = sigma * alpha_t
+        return alpha_t, sigma_t
+
+    def convert_model_output(self, model_output, sample):
+        sigma = self.sigmas[self.step_index]
+        alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma)
+        return (sample - sigma_t * model_output) / alpha_t
+
+    def _rb(self, rks, order, hh):
+        """R, b, h_phi_1, B_h of the UniPC update (shared by predictor and corrector)."""
+        R, b = [], []
+        h_phi_1 = torch.expm1(hh)
+        h_phi_k = h_phi_1 / hh - 1
+        factorial_i = 1
+        B_h = hh if self.config.solver_type == "bh1" else torch.expm1(hh)
+        for i in range(1, order + 1):
+            R.append(torch.pow(rks, i - 1))
+            b.append(h_phi_k * factorial_i / B_h)
+            factorial_i *= i + 1
+            h_phi_k = h_phi_k / hh - 1 / factorial_i
+        return torch.stack(R), torch.tensor(b), h_phi_1, B_h
+
+    def multistep_uni_p_bh_update(self, sample, order):
+        m0, x = self.model_outputs[-1], sample
+        sigma_t, sigma_s0 = self.sigmas[self.step_index + 1], self.sigmas[self.step_index]
+        alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma_t)
+        alpha_s0, sigma_s0 = self._sigma_to_alpha_sigma_t(sigma_s0)
+        lambda_t = torch.log(alpha_t) - torch.log(sigma_t)
+        lambda_s0 = torch.log(alpha_s0) - torch.log(sigma_s0)
+        h = lambda_t - lambda_s0
+        rks, D1s = [], []
+        for i in range(1, order):
+            si = self.step_index - i
+            mi = self.model_outputs[-(i + 1)]
+            alpha_si, sigma_si = self._sigma_to_alpha_sigma_t(self.sigmas[si])
+            lambda_si = torch.log(alpha_si) - torch.log(sigma_si)
+            rk = (lambda_si - lambda_s0) / h
+            rks.append(rk)
+            D1s.append((mi - m0) / rk)
+        rks.append(1.0)
+        rks = torch.tensor(rks)
+        hh = -h
+        R, b, h_phi_1, B_h = self._rb(rks, order, hh)
+        if len(D1s) > 0:
+            D1s = torch.stack(D1s, dim=1)
+            rhos_p = torch.tensor([0.5], dtype=x.dtype) if order == 2 else torch.linalg.solve(R[:-1, :-1], b[:-1]).to(x.dtype)
+        else:
+            D1s = None
+        x_t_ = sigma_t / sigma_s0 * x - alpha_t * h_phi_1 * m0
+        pred_res = torch.einsum("k,bkc...->bc...", rhos_p, D1s) if D1s is not None else 0
+        x_t = x_t_ - alpha_t * B_h * pred_res
+        return x_t.to(x.dtype)
+
+    def multistep_uni_c_bh_update(self, this_model_output, last_sample, this_sample, order):
+        m0, x, model_t = self.model_outputs[-1], last_sample, this_model_output
+        sigma_t, sigma_s0 = self.sigmas[self.step_index], self.sigmas[self.step_index - 1]
+        alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma_t)
+        alpha_s0, sigma_s0 = self._sigma_to_alpha_sigma_t(sigma_s0)
+        lambda_t = torch.log(alpha_t) - torch.log(sigma_t)
+        lambda_s0 = torch.log(alpha_s0) - torch.log(sigma_s0)
+        h = lambda_t - lambda_s0
+        rks, D1s = [], []
+        for i in range(1, order):
+            si = self.step_index - (i + 1)
+            mi = self.model_outputs[-(i + 1)]
+            alpha_si, sigma_si = self._sigma_to_alpha_sigma_t(self.sigmas[si])
+            lambda_si = torch.log(alpha_si) - torch.log(sigma_si)
+            rk = (lambda_si - lambda_s0) / h
+            rks.append(rk)
+            D1s.append((mi - m0) / rk)
+        rks.append(1.0)
+        rks = torch.tensor(rks)
+        hh = -h
+        R, b, h_phi_1, B_h = self._rb(rks, order, hh)
+        D1s = torch.stack(D1s, dim=1) if len(D1s) > 0 else None
+        rhos_c = torch.tensor([0.5], dtype=x.dtype) if order == 1 else torch.linalg.solve(R, b).to(x.dtype)
+        x_t_ = sigma_t / sigma_s0 * x - alpha_t * h_phi_1 * m0
+        corr_res = torch.einsum("k,bkc...->bc...", rhos_c[:-1], D1s) if D1s is not None else 0
+        D1_t = model_t - m0
+        x_t = x_t_ - alpha_t * B_h * (corr_res + rhos_c[-1] * D1_t)
+        return x_t.to(x.dtype)
+
+    def step(self, model_output, timestep, sample, return_dict: bool = True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating "
+                             "the scheduler")
+        if self._step_index is None:
+            self._step_index = int((self.timesteps == int(timestep)).nonzero()[0])
+        use_corrector = self.step_index > 0 and self.step_index - 1 not in self.disable_corrector and \
+            self.last_sample is not None
+        model_output_convert = self.convert_model_output(model_output, sample)
+        if use_corrector:
+            sample = self.multistep_uni_c_bh_update(model_output_convert, self.last_sample, sample, self.this_order)
+        for i in range(self.config.solver_order - 1):
+            self.model_outputs[i] = self.model_outputs[i + 1]
+            self.timestep_list[i] = self.timestep_list[i + 1]
+        self.model_outputs[-1] = model_output_convert
+        self.timestep_list[-1] = timestep
+        if self.config.lower_order_final:
+            this_order = min(self.config.solver_order, len(self.timesteps) - self.step_index)
+        else:
+            this_order = self.config.solver_order
+        self.this_order = min(this_order, self.lower_order_nums + 1)
+        assert self.this_order > 0
+        self.last_sample = sample
+        prev_sample = self.multistep_uni_p_bh_update(sample, self.this_order)
+        if self.lower_order_nums < self.config.solver_order:
+            self.lower_order_nums += 1
+        self._step_index += 1
+        if not return_dict:
+            return (prev_sample,)
+        return SchedulerOutput(prev_sample=prev_sample)

@@ -5,8 +5,9 @@
 All tensor arithmetic runs in hand-written sm_100a kernels behind the C-ABI in include/ddpm_b200.h
 (libddpm_b200.so, built in-tree by `python -m polyp_image_generator_b200.build`).  There is no CPU fallback.
 """
-from .scheduler import DDIMScheduler, DDIMSchedulerOutput, DDPMScheduler, DDPMSchedulerOutput  # noqa: F401
-from .pipeline import DDIMPipeline, DDPMPipeline, ImagePipelineOutput, randn_tensor  # noqa: F401
+from .scheduler import (DDIMScheduler, DDIMSchedulerOutput, DDPMScheduler, DDPMSchedulerOutput,  # noqa: F401
+                        UniPCMultistepScheduler)
+from .pipeline import DDIMPipeline, DDPMPipeline, ImagePipelineOutput, UniPCPipeline, randn_tensor  # noqa: F401
 
 
 def __getattr__(name):

@@ -86,6 +86,8 @@ SIGNATURES = {
     "ddpm_ddim_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _i, _vp],
     "ddpm_scheduler_step_philox": [_vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _ull, _ull, _vp],
     "ddpm_to_uint8_nhwc": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "ddpm_unipc_x0": [_vp, _vp, _vp, _ll, _f, _f, _vp],
+    "ddpm_unipc_update": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _vp],
     "ddpm_conv_gemm": [C.POINTER(ConvArgs), _vp],
     "ddpm_conv_gemm_workspace_elems": [C.POINTER(ConvArgs)],
     "ddpm_conv_halo_strips": [_i],

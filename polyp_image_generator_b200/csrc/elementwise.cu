@@ -271,6 +271,38 @@ to_uint8_nhwc_kernel(const float* __restrict__ x, unsigned char* __restrict__ ou
   }
 }
 
+// ---- UniPC multistep sampler (train_with_lora_all_classes.py:314) -------------------------------
+// Two single-pass kernels with the scalars (sigma / alpha / lambda arithmetic, B(h), rho) computed on the host as 0-dim
+// fp32 tensors exactly as diffusers does; every elementwise expression below keeps torch's op order and rounding
+// (explicit _rn intrinsics: no FMA contraction), so the sampler is bit-identical to the oracle's torch expressions.
+//   x0  = (x - sigma_t * eps) / alpha_t                                  (convert_model_output, epsilon / predict_x0)
+//   out = (cx * x - cm * m0) - cb * res,   res = rho0 * ((m1 - m0) / rk)  [has_d1]  (+)  rho_t * (mt - m0)  [has_t]
+__global__ void __launch_bounds__(kEwThreads)
+unipc_x0_kernel(const float* __restrict__ eps, const float* __restrict__ x, float* __restrict__ out, long long n,
+                float sigma_t, float alpha_t) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sigma_t, eps[i])), alpha_t);
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+unipc_update_kernel(const float* __restrict__ x, const float* __restrict__ m0, const float* __restrict__ m1,
+                    const float* __restrict__ mt, float* __restrict__ out, long long n, float cx, float cm, float cb,
+                    float rk, float rho0, float rho_t, int has_d1, int has_t) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float a = m0[i];
+    const float base = __fsub_rn(__fmul_rn(cx, x[i]), __fmul_rn(cm, a));
+    float res = 0.f;
+    if (has_d1) res = __fmul_rn(rho0, __fdiv_rn(__fsub_rn(m1[i], a), rk));
+    if (has_t) {
+      const float dt = __fmul_rn(rho_t, __fsub_rn(mt[i], a));
+      res = has_d1 ? __fadd_rn(res, dt) : dt;
+    }
+    out[i] = (has_d1 || has_t) ? __fsub_rn(base, __fmul_rn(cb, res)) : base;
+  }
+}
+
 // ---- fused global-norm clip + AdamW over the flat parameter arena -----------------------
 // train_from_scratch.py:106-108: clip_grad_norm_(params, 1.0); optimizer.step().  With every parameter, gradient and
 // moment in ONE flat fp32 buffer the update is two streaming kernels (sum of squares; update) instead of ~30
@@ -554,4 +586,22 @@ extern "C" int ddpm_adamw_flat(float* p, const float* g, float* m, float* v, lon
   adamw_flat_kernel<<<ew_blocks(n / 4 + 1), kEwThreads, 0, stream>>>(p, g, m, v, n, scal, lr_dev, lr, beta1, beta2, eps,
                                                                      weight_decay);
   return check_launch("adamw_flat_kernel");
+}
+
+extern "C" int ddpm_unipc_x0(const float* eps, const float* x, float* out, long long n, float sigma_t, float alpha_t,
+                             void* stream) {
+  DDPM_REQUIRE(eps && x && out && n >= 0, "ddpm_unipc_x0: bad argument");
+  if (n == 0) return DDPM_OK;
+  unipc_x0_kernel<<<ew_blocks(n), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(eps, x, out, n, sigma_t, alpha_t);
+  return check_launch("unipc_x0_kernel");
+}
+
+extern "C" int ddpm_unipc_update(const float* x, const float* m0, const float* m1, const float* mt, float* out,
+                                 long long n, float cx, float cm, float cb, float rk, float rho0, float rho_t,
+                                 void* stream) {
+  DDPM_REQUIRE(x && m0 && out && n >= 0, "ddpm_unipc_update: bad argument");
+  if (n == 0) return DDPM_OK;
+  unipc_update_kernel<<<ew_blocks(n), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, m0, m1, mt, out, n, cx, cm, cb, rk, rho0, rho_t, m1 != nullptr ? 1 : 0, mt != nullptr ? 1 : 0);
+  return check_launch("unipc_update_kernel");
 }

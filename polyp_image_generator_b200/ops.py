@@ -148,6 +148,22 @@ class CudaOps:
         self.launches += 1
         return prev
 
+    def unipc_x0(self, eps, x, sigma_t: float, alpha_t: float):
+        out = torch.empty_like(x)
+        _capi.check(self.lib.ddpm_unipc_x0(_ptr(eps), _ptr(x), _ptr(out), x.numel(), sigma_t, alpha_t, _stream()),
+                    "ddpm_unipc_x0")
+        self.launches += 1
+        return out
+
+    def unipc_update(self, x, m0, m1, mt, cx: float, cm: float, cb: float, rk: float = 1.0, rho0: float = 0.0,
+                     rho_t: float = 0.0):
+        """(cx x - cm m0) - cb [rho0 (m1 - m0) / rk  (+)  rho_t (mt - m0)]; m1 / mt may be None."""
+        out = torch.empty_like(x)
+        _capi.check(self.lib.ddpm_unipc_update(_ptr(x), _ptr(m0), _ptr(m1), _ptr(mt), _ptr(out), x.numel(), cx, cm, cb,
+                                               rk, rho0, rho_t, _stream()), "ddpm_unipc_update")
+        self.launches += 1
+        return out
+
     def to_uint8_nhwc(self, x):
         n, c, h, w = x.shape
         out = torch.empty((n, h, w, c), device=x.device, dtype=torch.uint8)

@@ -142,3 +142,23 @@ class DDIMPipeline(DDPMPipeline):
                                         use_clipped_model_output=bool(use_clipped_model_output), generator=generator,
                                         want_pred_original_sample=False).prev_sample
         return self._finish(image, output_type, return_dict)
+
+
+class UniPCPipeline(DDPMPipeline):
+    """The unconditional reverse loop driven by UniPCMultistepScheduler (the sampler of the LoRA scripts,
+    train_with_lora_all_classes.py:314; 25 steps there, :56-61) -- SURVEY.md §8(f) rank 4.  Deterministic given x_T:
+    the generator is consumed once, for the initial noise."""
+
+    @torch.no_grad()
+    def __call__(self, batch_size: int = 1, generator=None, num_inference_steps: int = 25,
+                 output_type: Optional[str] = "pil", return_dict: bool = True):
+        s = self.unet.config.sample_size
+        hw = (s, s) if isinstance(s, int) else tuple(s)
+        image_shape = (batch_size, self.unet.config.in_channels, *hw)
+        image = randn_tensor(image_shape, generator=generator, device=self.device, dtype=torch.float32)
+        self.scheduler.set_timesteps(num_inference_steps)
+        fwd = self._graphed_forward(image) if self.use_cuda_graph else None
+        for t in self.scheduler._ts_list:
+            model_output = fwd(image, t) if fwd is not None else self.unet(image, t).sample
+            image = self.scheduler.step(model_output, t, image).prev_sample
+        return self._finish(image, output_type, return_dict)

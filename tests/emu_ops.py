@@ -47,6 +47,21 @@ class EmuOps:
             prev = prev + f(sigma) * z
         return prev, (x0 if want_x0 else None)
 
+    def unipc_x0(self, eps, x, sigma_t, alpha_t):
+        f = lambda v: torch.tensor(v, dtype=torch.float32)
+        return (x - f(sigma_t) * eps) / f(alpha_t)
+
+    def unipc_update(self, x, m0, m1, mt, cx, cm, cb, rk=1.0, rho0=0.0, rho_t=0.0):
+        f = lambda v: torch.tensor(v, dtype=torch.float32)
+        base = f(cx) * x - f(cm) * m0
+        res = None
+        if m1 is not None:
+            res = f(rho0) * ((m1 - m0) / f(rk))
+        if mt is not None:
+            d = f(rho_t) * (mt - m0)
+            res = d if res is None else res + d
+        return base if res is None else base - f(cb) * res
+
     def scheduler_step(self, eps, x, z, sa, sb, c0, ct, sigma, clip, want_x0=False):
         f = lambda v: torch.tensor(v, dtype=torch.float32)
         x0 = (x - f(sb) * eps) / f(sa)

@@ -391,6 +391,58 @@ def test_ddim_pipeline_matches_oracle_loop_and_round_trips(emu_backend, tmp_path
     assert type(back.scheduler).__name__ == "DDIMScheduler" and back.scheduler.config.set_alpha_to_one is True
 
 
+def test_unipc_scheduler_and_pipeline_match_oracle(emu_backend, tmp_path):
+    """UniPCMultistepScheduler (train_with_lora_all_classes.py:314) -- the tabulated-coefficient
+    host logic against the oracle restatement, bit for bit on the emulated kernels; add_noise; the sampling loop."""
+    from polyp_image_generator_b200 import UNet2DModel, UniPCMultistepScheduler, UniPCPipeline
+    sd = dict(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, steps_offset=1)
+    for kw in (dict(), sd, dict(solver_order=1), dict(disable_corrector=[0, 3])):
+        for n in (25, 4, 2, 1):
+            a, b = UniPCMultistepScheduler(**kw), oracle.UniPCMultistepScheduler(**kw)
+            a.set_timesteps(n)
+            b.set_timesteps(n)
+            assert torch.equal(a.timesteps, b.timesteps) and torch.equal(a.sigmas, b.sigmas)
+            g = torch.Generator().manual_seed(n)
+            xa = xb = torch.randn(2, 3, 8, 8, generator=g)
+            for t in a.timesteps:
+                eps = torch.randn(2, 3, 8, 8, generator=g)
+                xa, xb = a.step(eps, t, xa).prev_sample, b.step(eps, t, xb).prev_sample
+                assert torch.equal(xa, xb), (kw, n, int(t))
+            assert a.step_index == b.step_index == n
+    with pytest.raises(ValueError, match="set_timesteps"):
+        UniPCMultistepScheduler().step(xa, 10, xa)
+    for bad in (dict(solver_type="bh1"), dict(prediction_type="v_prediction"), dict(solver_order=3),
+                dict(use_karras_sigmas=True)):
+        with pytest.raises(NotImplementedError):
+            UniPCMultistepScheduler(**bad)
+    # forward noising on the UniPC scheduler (train_with_lora_all_classes.py:137): alpha_t x0 + sigma_t noise
+    a = UniPCMultistepScheduler(**sd)
+    x, e, t = torch.randn(3, 4, 8, 8), torch.randn(3, 4, 8, 8), torch.tensor([0, 500, 999])
+    ac = a.alphas_cumprod[t].view(-1, 1, 1, 1)
+    assert torch.allclose(a.add_noise(x, e, t), ac ** 0.5 * x + (1 - ac) ** 0.5 * e, rtol=1e-5, atol=1e-6)
+    # sampling loop + on-disk round trip
+    cfg = _small_cfg(32)
+    cfg["block_out_channels"] = (64, 64, 64, 64, 64, 64)
+    torch.manual_seed(0)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    pipe = UniPCPipeline(unet=m, scheduler=UniPCMultistepScheduler())
+    got = pipe(batch_size=2, generator=torch.Generator("cpu").manual_seed(4), num_inference_steps=5,
+               output_type="np").images
+    osch = oracle.UniPCMultistepScheduler()
+    img = oracle.randn_tensor((2, 3, 32, 32), generator=torch.Generator("cpu").manual_seed(4))
+    osch.set_timesteps(5)
+    with torch.no_grad():
+        for t in osch.timesteps:
+            img = osch.step(om(img, t).sample, t, img).prev_sample
+    want = (img / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).numpy()
+    assert abs(got - want).max() <= 1.0 / 255 + 1e-6
+    pipe.save_pretrained(str(tmp_path / "p"))
+    back = UniPCPipeline.from_pretrained(str(tmp_path / "p"))
+    assert type(back.scheduler).__name__ == "UniPCMultistepScheduler" and back.scheduler.config.solver_order == 2
+
+
 def test_bench_has_no_rank_conditional_collectives():
     """Every rank must walk bench.py's GPU arm through the same sequence of collectives: a training step (DDP
     all-reduce), a barrier or a dist.* call under `if rank == 0` deadlocks the multi-GPU run (it did, once)."""

@@ -192,6 +192,43 @@ def test_ddim_golden_trajectory():
     assert torch.allclose(x.flatten(), torch.tensor(gold["final"]), rtol=1e-5, atol=1e-6)
 
 
+def test_oracle_unipc_closed_form_and_golden():
+    """UniPC (Zhao et al. 2023) integrates the data-prediction ODE exactly when the x0 prediction is constant: fed the
+    TRUE noise of a fixed (x0, e) line, every iterate is alpha_t x0 + sigma_t e and the final sample (sigma = 0) is x0 --
+    for both solver orders, any step count; plus the committed 12-step trajectory (make_golden_unipc.py)."""
+    torch.manual_seed(0)
+    x0, e = torch.randn(2, 3, 8, 8).double(), torch.randn(2, 3, 8, 8).double()
+    for order in (1, 2):
+        for n in (25, 7, 2):
+            s = oracle.UniPCMultistepScheduler(solver_order=order)
+            s.set_timesteps(n)
+            a, sg = s._sigma_to_alpha_sigma_t(s.sigmas[0].double())
+            x = (a * x0 + sg * e).float()
+            for i, t in enumerate(s.timesteps):
+                a, sg = s._sigma_to_alpha_sigma_t(s.sigmas[i].double())
+                eps = ((x.double() - a * x0) / sg).float()         # the noise that makes the x0 prediction exact
+                x = s.step(eps, t, x).prev_sample
+                a, sg = s._sigma_to_alpha_sigma_t(s.sigmas[i + 1].double())
+                assert torch.allclose(x.double(), a * x0 + sg * e, atol=5e-4), (order, n, i)
+            assert torch.allclose(x.double(), x0, atol=5e-4)
+    # timestep / sigma grid of the default configuration: linspace over [0, T-1], rounded, descending, last dropped
+    s = oracle.UniPCMultistepScheduler()
+    s.set_timesteps(25)
+    assert s.timesteps.tolist()[:3] == [999, 959, 919] and s.timesteps[-1].item() == 40 and s.sigmas[-1].item() == 0.0
+    ac = s.alphas_cumprod
+    assert s.sigmas[0].item() == pytest.approx(float(((1 - ac[999]) / ac[999]) ** 0.5), rel=1e-6)
+    gold = json.load(open(os.path.join(GOLD, "unipc.json")))
+    s = oracle.UniPCMultistepScheduler(**gold["kwargs"])
+    s.set_timesteps(gold["steps"])
+    assert s.timesteps.tolist() == gold["timesteps"]
+    assert torch.allclose(s.sigmas, torch.tensor(gold["sigmas"]), rtol=1e-6)
+    x = torch.randn(1, 3, 8, 8, generator=torch.Generator().manual_seed(13))
+    for t, want in zip(s.timesteps, gold["trajectory_sums"]):
+        x = s.step(torch.cos(x * 2.0 - float(t) * 0.02), t, x).prev_sample
+        assert x.double().sum().item() == pytest.approx(want, rel=1e-5, abs=1e-5)
+    assert torch.allclose(x.flatten(), torch.tensor(gold["final"]), rtol=1e-5, atol=1e-6)
+
+
 def test_resize_golden_from_pillow():
     """tests/golden/resize.json was written by Pillow / torchvision themselves; the oracle restatement must match it."""
     import numpy as np

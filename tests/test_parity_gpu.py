@@ -94,6 +94,36 @@ def test_ddim_step_bit_exact(dev, n_steps):
     assert torch.equal(a2.step(e.to(dev), 480, x.to(dev)).prev_sample.cpu(), want)
 
 
+@pytest.mark.parametrize("n_steps", [25, 3])
+def test_unipc_step_bit_exact(dev, n_steps):
+    """UniPCMultistepScheduler.step (train_with_lora_all_classes.py:314): x0 conversion, corrector
+    and predictor kernels, whole trajectories bit-identical to the oracle's torch expressions; ragged size; golden."""
+    import json
+    from polyp_image_generator_b200 import UniPCMultistepScheduler
+    sd = dict(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, steps_offset=1)
+    for kw, shape in ((dict(), (4, 3, 32, 32)), (sd, (1, 3, 7, 5)), (dict(solver_order=1), (2, 3, 16, 16))):
+        a, b = UniPCMultistepScheduler(**kw), oracle.UniPCMultistepScheduler(**kw)
+        a.set_timesteps(n_steps)
+        b.set_timesteps(n_steps)
+        g = torch.Generator().manual_seed(5)
+        xb = torch.randn(shape, generator=g)
+        xa = xb.to(dev)
+        for t in a.timesteps.tolist():
+            eps = torch.randn(shape, generator=g)
+            xa = a.step(eps.to(dev), t, xa).prev_sample
+            xb = b.step(eps, torch.tensor(t), xb).prev_sample
+            assert torch.equal(xa.cpu(), xb), (kw, t)
+    gold = json.load(open(os.path.join(GOLD, "unipc.json")))
+    s = UniPCMultistepScheduler(**gold["kwargs"])
+    s.set_timesteps(gold["steps"])
+    assert s.timesteps.tolist() == gold["timesteps"]
+    x = torch.randn(1, 3, 8, 8, generator=torch.Generator().manual_seed(13)).to(dev)
+    for t, want in zip(s.timesteps.tolist(), gold["trajectory_sums"]):
+        x = s.step(torch.cos(x.cpu() * 2.0 - float(t) * 0.02).to(dev), t, x).prev_sample
+        assert x.double().sum().item() == pytest.approx(want, rel=1e-5, abs=1e-5)
+    assert torch.allclose(x.cpu().flatten(), torch.tensor(gold["final"]), rtol=1e-5, atol=1e-6)
+
+
 def test_ddim_golden_trajectory_on_device(dev):
     """The committed oracle trajectory (tests/golden/ddim.json) through the DDIM step kernel: bit-identical op order, so
     the trajectory sums agree to fp32 rounding of the stand-in network."""
