@@ -145,8 +145,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 24)) {
-      printf("ddpm_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x);
+      printf("ddpm_b200: mbarrier wait timed out (block %d,%d thread %d, barrier @smem 0x%x, parity %u)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
@@ -265,6 +265,39 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
 // peer's producer warp spent ~700 clk per tap in it and became the pipeline's bottleneck (profiles/r1_halo_pair.md)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Publishing a word to the other CTA of the pair through (distributed) shared memory: the writer stores it, then
+// arrives with RELEASE at CLUSTER scope on a barrier in the reader's CTA; the reader waits with ACQUIRE at cluster scope
+// and loads the word through its shared::cluster address.  (One fence per published word on the writer -- affordable
+// once per tile, not once per tap: see mbar_arrive_cluster above.)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_acquire_cluster(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      printf("ddpm_b200: mbarrier wait timed out (block %d,%d thread %d, barrier @smem 0x%x, parity %u, cluster scope)\n",
+             blockIdx.x, blockIdx.y, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ uint32_t ld_shared_cluster_u32(uint32_t cluster_addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+  return v;
 }
 // TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are signalled on a barrier
 // that may live in the peer CTA (shared::cluster address)

@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "conv_epilogue.cuh"
 
+#include <atomic>
 #include <cstring>
 
 #include "../../include/ddpm_b200.h"
@@ -54,8 +55,59 @@ struct HaloParams {
   uint32_t halo_stride;  // halo_bytes rounded up to 1024
   int b_stages;          // weight-tile ring depth
   int mma_n;             // UMMA N: 128, or Cout rounded up to 16 for narrow outputs (conv_out: 3 -> 32 columns)
+  unsigned int* sched_ctr;   // pair kernel: global tile counter of the dynamic schedule (nullptr: static round-robin)
   EpiParams epi;
 };
+
+// ---- dynamic tile schedule of the CTA-pair kernel ---------------------------------------------------------------
+// A static round-robin makes the kernel as slow as its LAST-STARTED pair: when some SMs are still held by a kernel of
+// another stream (the weight-gradient GEMMs of the second stream, NCCL's all-reduce CTAs under DDP -- neither can
+// co-reside with a 200 KB / 59 K-register CTA) those pairs start late and still own a full share of the tiles.  With
+// the dynamic schedule the first tile of a pair is static (tile = pair index, no latency) and every further tile is
+// drawn from a global counter by the otherwise idle 12th warp of the leader CTA; it hands the tile index to the role
+// warps of BOTH CTAs through a 4-deep ring in the LEADER's shared memory (plain store, then a release arrive on a
+// barrier in each CTA; readers acquire at cluster scope and load the word over its shared::cluster address), running up
+// to 4 tiles ahead of the slowest consumer, so the ~1 us atomic never sits on the critical path.  The counter resets
+// itself: the draws of one launch number exactly total_tiles (every pair draws until it gets a value past the end), so
+// the draw that returns total_tiles - 1 is the last one.
+constexpr int kSchedDepth = 4;
+constexpr uint32_t kSchedConsumers = 21;   // role warps that read a tile index: 8 epilogue + halo + weight producer in
+                                           // both CTAs, + the leader's MMA warp
+
+struct TileFeed {
+  uint64_t* full;        // [kSchedDepth], this CTA
+  uint32_t tiles0;       // shared::cluster address of the LEADER's tile ring
+  uint32_t empty0;       // shared::cluster address of the LEADER's empty[0]
+  uint32_t s, ph;
+  int pt, step, total;   // static schedule (dyn == false)
+  bool dyn;
+
+  // next tile of this pair, or -1; called by all lanes of a converged warp
+  __device__ __forceinline__ int next() {
+    if (!dyn) {
+      const int t = pt;
+      pt += step;
+      return t < total ? t : -1;
+    }
+    mbar_wait_acquire_cluster(&full[s], ph);
+    const int t = static_cast<int>(ld_shared_cluster_u32(tiles0 + s * 4u));
+    __syncwarp();
+    // the slot may be refilled once every consumer warp of the pair has read it; the (always true) test on the loaded
+    // value keeps the arrive behind the completion of the load
+    if (elect_one() && t >= -1) mbar_arrive_cluster(empty0 + s * 8u);
+    if (++s == static_cast<uint32_t>(kSchedDepth)) { s = 0; ph ^= 1; }
+    return t;
+  }
+  // the tile after the one next() returned last, without consuming it (-1: none)
+  __device__ __forceinline__ int peek() {
+    if (!dyn) return pt < total ? pt : -1;
+    mbar_wait_acquire_cluster(&full[s], ph);
+    return static_cast<int>(ld_shared_cluster_u32(tiles0 + s * 4u));
+  }
+};
+
+constexpr unsigned int kTileCtrPool = 256;
+__device__ unsigned int g_halo_tile_ctr[kTileCtrPool];   // zero at load; every launch leaves its counter at zero
 
 __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
@@ -310,12 +362,16 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   uint64_t* tmem_full = b_empty + kHaloMaxPairStages;   // [2] (both CTAs)
   uint64_t* tmem_empty = tmem_full + 2;                 // [2] (leader; 16 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* sched_full = tmem_empty + 3;                // [kSchedDepth] (both CTAs)
+  uint64_t* sched_empty = sched_full + kSchedDepth;     // [kSchedDepth] (leader)
+  int* sched_tiles = reinterpret_cast<int*>(sched_empty + kSchedDepth);   // [kSchedDepth] (both CTAs)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kbt = p.kb0 + p.kb1;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const bool dyn = p.sched_ctr != nullptr && p.total_tiles > n_pairs;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
@@ -330,6 +386,10 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&b_full[i], 2);
       mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < kSchedDepth; ++i) {
+      mbar_init(&sched_full[i], 1);                 // the scheduler's release arrive
+      mbar_init(&sched_empty[i], kSchedConsumers);
     }
     fence_barrier_init();
   }
@@ -361,13 +421,21 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     xs = (unit - img * p.S) * p.Ws;
   };
 
+  TileFeed feed;
+  feed.full = sched_full;
+  feed.tiles0 = mapa_u32(smem_u32(&sched_tiles[0]), 0);
+  feed.empty0 = mapa_u32(smem_u32(&sched_empty[0]), 0);
+  feed.s = 0; feed.ph = 0;
+  feed.pt = pair_id; feed.step = n_pairs; feed.total = p.total_tiles;
+  feed.dyn = dyn;
+
   if (warp >= 8) {
   setmaxnreg_dec<56>();
   if (warp == 8) {
     // ---------------- halo producer (both CTAs; completion is signalled on the LEADER's barrier) ----------------
     uint32_t hb = 0, hph = 0;
     const uint32_t full0 = mapa_u32(smem_u32(&halo_full[0]), 0), full1 = mapa_u32(smem_u32(&halo_full[1]), 0);
-    for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
+    for (int pt = feed.next(); pt >= 0; pt = feed.next()) {
       int img, xs, q0, nt; bool ok;
       decode(pt, img, xs, ok, q0, nt);
       const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
@@ -391,7 +459,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     // ---------------- weight-tile producer: this CTA's 64 cout rows of every tile ----------------
     uint32_t bs = 0, bph = 0;
     const uint32_t bfull0 = mapa_u32(smem_u32(&b_full[0]), 0);
-    for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
+    for (int pt = feed.next(); pt >= 0; pt = feed.next()) {
       const int nt = pt % p.n_tiles;
       const int row0 = nt * 128 + static_cast<int>(rank) * (p.mma_n / 2);   // this CTA's half of the N columns
       for (int c = 0; c < kbt; ++c) {
@@ -418,7 +486,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       const uint32_t row_step = static_cast<uint32_t>(p.Wp) * 8u;
       uint32_t bs = 0, bph = 0, hb = 0, hph = 0, acc = 0, aph = 0;
       uint64_t db = db_base;
-      for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
+      for (int pt = feed.next(); pt >= 0; pt = feed.next()) {
         int img, xs, q0, nt; bool ok;
         decode(pt, img, xs, ok, q0, nt);
         const int row_lo = floor_div(q0 - p.Wp - 1, p.Wp);
@@ -461,6 +529,37 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         aph ^= (acc == 0);
       }
     }
+  } else if (dyn && leader) {
+    // ---------------- tile scheduler (warp 11 of the leader) ----------------
+    // The WHOLE warp walks the loop (lane 0 draws and publishes): the kernel ends in an .aligned cluster barrier, which a
+    // warp must reach converged -- a one-lane loop let lanes 1-31 arrive there early and lane 0 a second time.
+    uint32_t s = 0, ph = 0;
+    const uint32_t full_p = mapa_u32(smem_u32(&sched_full[0]), 1);
+    const unsigned int total = static_cast<unsigned int>(p.total_tiles);
+    bool first = true;
+    for (;;) {
+      mbar_wait(&sched_empty[s], ph ^ 1);
+      uint32_t done = 0;
+      if (lane == 0) {
+        unsigned int t;
+        if (first) {
+          t = static_cast<unsigned int>(pair_id);
+        } else {
+          const unsigned int old = atomicAdd(p.sched_ctr, 1u);
+          if (old == total - 1u) *reinterpret_cast<volatile unsigned int*>(p.sched_ctr) = 0u;   // the launch's last draw
+          t = static_cast<unsigned int>(n_pairs) + old;
+        }
+        done = t >= total ? 1u : 0u;
+        *reinterpret_cast<volatile int*>(&sched_tiles[s]) = done ? -1 : static_cast<int>(t);
+        mbar_arrive_release_cluster(full_p + s * 8u);     // peer's consumers
+        mbar_arrive(&sched_full[s]);                      // this CTA's consumers (release.cta)
+      }
+      first = false;
+      done = __shfl_sync(0xffffffffu, done, 0);
+      if (done) break;
+      if (++s == static_cast<uint32_t>(kSchedDepth)) { s = 0; ph ^= 1; }
+    }
+    __syncwarp();
   }
   } else {
     setmaxnreg_inc<224>();
@@ -469,7 +568,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     const int half = warp >> 2;
     uint32_t acc = 0, aph = 0;
     const uint32_t empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
-    for (int pt = pair_id; pt < p.total_tiles; pt += n_pairs) {
+    for (int pt = feed.next(); pt >= 0; pt = feed.next()) {
       int img, xs, q0, nt; bool img_ok;
       decode(pt, img, xs, img_ok, q0, nt);
       auto geom = [&](int i, int& col, bool& valid, long long& pix, int& u) {
@@ -494,10 +593,11 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         geom(3, col, valid, pix, u);
         epi_load_x(p.epi, valid, pix, col, x3);
       }
-      if ((p.epi.res != nullptr || epi_slot_is_gn(p.epi)) && pt + n_pairs < p.total_tiles) {
+      const int pt_next = (p.epi.res != nullptr || epi_slot_is_gn(p.epi)) ? feed.peek() : -1;
+      if (pt_next >= 0) {
         // side input of the NEXT tile of this CTA -> L2, one whole tile ahead of its first use
         int img2, xs2, q02, nt2; bool ok2;
-        decode(pt + n_pairs, img2, xs2, ok2, q02, nt2);
+        decode(pt_next, img2, xs2, ok2, q02, nt2);
 #pragma unroll
         for (int u2 = 0; u2 < 2; ++u2) {
           const int slot = q02 + u2 * 128 + q * 32 + lane;
@@ -651,6 +751,15 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
       pconfigured = psmem;
     }
     int pgrid = 2 * pp.total_tiles < kNumSMs ? 2 * pp.total_tiles : (kNumSMs / 2) * 2;
+    pp.sched_ctr = nullptr;
+    if (env_int("DDPM_HALO_DYNAMIC", 1) != 0 && pp.total_tiles > pgrid / 2) {
+      // one self-resetting counter per launch, round-robin over a small pool: launches on ONE stream never overlap,
+      // and a captured graph keeps the slot it was captured with
+      static unsigned int* pool = nullptr;
+      static std::atomic<unsigned int> seq{0};
+      if (pool == nullptr) DDPM_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&pool), g_halo_tile_ctr));
+      pp.sched_ctr = pool + (seq.fetch_add(1) % kTileCtrPool);
+    }
     conv_halo_pair_kernel<<<pgrid, kHaloPairThreads, psmem, stream>>>(ma0, ma1, mb, pp);
     return check_launch("conv_halo_pair_kernel");
   }

@@ -19,7 +19,11 @@ Tap = Tuple[int, int, int, int]  # (dn, dh, dw, wk)
 
 # smallest map (pixels per sample) at which the GroupNorm statistics / backward fusions ride on the conv epilogues
 import os as _os
-_GN_FUSE_MIN_HW = int(_os.environ.get("DDPM_GN_FUSE_MIN_HW", "4096"))
+
+
+def _gn_fuse_min_hw() -> int:
+    # read per call (not at import) so that profiles/ab_step.py can capture one CUDA graph per setting in one process
+    return int(_os.environ.get("DDPM_GN_FUSE_MIN_HW", "1024"))
 
 
 def _stream() -> int:
@@ -179,7 +183,7 @@ class CudaOps:
         measured on B200 (profiles/bench_kernels.py convgn) the fused epilogue costs +0.058 ms at 128^2 against
         0.19 ms saved in the GroupNorm pass, but +0.040 ms at 32^2 against 0.01 ms saved."""
         hw = grid[1] * grid[2]
-        return hw >= _GN_FUSE_MIN_HW
+        return hw >= _gn_fuse_min_hw()
 
     def gn_stats_fusable(self, grid: Tuple[int, int, int]) -> bool:
         """Should a 3x3 stride-1 conv that PRODUCES a tensor over this grid also reduce the per-(sample, channel) moments
@@ -189,7 +193,7 @@ class CudaOps:
         overlaps the next tile's mainloop: in the generic kernel the extra warp reductions are exposed (measured: +1.6 ms
         on the 256^2 LoRA step)."""
         hw = grid[1] * grid[2]
-        return hw >= _GN_FUSE_MIN_HW and self.halo_strips(grid[2]) > 0
+        return hw >= _gn_fuse_min_hw() and self.halo_strips(grid[2]) > 0
 
     def halo_strips(self, w: int) -> int:
         s = self._halo_strips.get(w)

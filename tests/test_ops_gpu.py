@@ -430,6 +430,49 @@ def test_conv3x3_fprop_with_fused_epilogue(ops, n, h, w, cin, cout):
     ck.done()
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(8, 128, 128, 128, 128), (5, 128, 128, 256, 128), (16, 64, 64, 256, 256),
+                                            (3, 256, 256, 128, 128), (24, 32, 32, 256, 512)])
+def test_halo_pair_dynamic_schedule_matches_static(ops, n, h, w, cin, cout):
+    """The CTA-pair halo conv draws its tiles from a self-resetting global counter (conv_halo.cu, TileFeed): same
+    outputs, bit for bit, as the static round-robin -- plain, +residual (next-tile L2 prefetch through peek()) and the
+    GroupNorm-backward epilogue -- over repeated launches (the counter must be back at zero after each) and against
+    F.conv2d."""
+    from polyp_image_generator_b200.ops import taps_3x3
+    ck = Check()
+    torch.manual_seed(3)
+    x = bf(torch.randn(n, h, w, cin, device=DEV))
+    w4 = bf(torch.randn(cout, cin, 3, 3, device=DEV) * 0.03)
+    wk = w4.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    b = torch.randn(cout, device=DEV)
+    res = bf(torch.randn(n, h, w, cout, device=DEV))
+    want = conv_ref(x, w4, b)
+    with env(DDPM_HALO_DYNAMIC=0):
+        s_plain = ops.conv_gemm(x, None, taps_3x3(cin), wk, cout, (n, h, w), bias=b)
+        s_res = ops.conv_gemm(x, None, taps_3x3(cin), wk, cout, (n, h, w), bias=b, res=res)
+    ck("static vs F.conv2d", s_plain, want, 4e-3)
+    for rep in range(3):
+        d_plain = ops.conv_gemm(x, None, taps_3x3(cin), wk, cout, (n, h, w), bias=b)
+        d_res = ops.conv_gemm(x, None, taps_3x3(cin), wk, cout, (n, h, w), bias=b, res=res)
+        assert torch.equal(d_plain, s_plain), f"dynamic != static (plain, launch {rep})"
+        assert torch.equal(d_res, s_res), f"dynamic != static (+residual, launch {rep})"
+    ck("dynamic +res vs F.conv2d", d_res, want + res.float(), 4e-3)
+    # GroupNorm-backward epilogue: dz and the per-(n, c) sums (atomics: order differs, values agree to fp32 rounding)
+    gamma, beta = torch.randn(cout, device=DEV) * 0.5 + 1, torch.randn(cout, device=DEV) * 0.2
+    xg = bf(torch.randn(n, h, w, cout, device=DEV))
+    _, _, coef = ops.gn_fwd(xg, None, 32, 1e-5, gamma, beta, True, want_coef=True)
+    outs = []
+    for dyn in (0, 1, 1):
+        with env(DDPM_HALO_DYNAMIC=dyn):
+            sums = torch.zeros(n, cout, 2, device=DEV)
+            dz = ops.conv_gemm(x, None, taps_3x3(cin), wk, cout, (n, h, w), gn=(xg, None, coef, True, sums))
+            outs.append((dz, sums))
+    for dz, sums in outs[1:]:
+        assert torch.equal(dz, outs[0][0]), "dynamic != static (GroupNorm-backward epilogue)"
+        ck("   fused sums", sums, outs[0][1], 1e-5)
+    torch.cuda.synchronize()
+    ck.done()
+
+
 def test_conv_concat_slices_stride2_and_dgrad(ops):
     from polyp_image_generator_b200.ops import taps_1x1, taps_3x3, taps_s2d
     ck = Check()
