@@ -167,11 +167,13 @@ int ddpm_prep_weight(const float* w, void* wf, long long ldwf, void* wd, long lo
                      void* stream);
 
 /* The same for ALL layers of the model in one launch: a device-resident table of descriptors (pointers into the
- * fp32 parameter arena and the bf16 operand arena), tile_begin = running count of 32x32 tiles (ascending). */
+ * fp32 parameter arena and the bf16 operand arena), tile_begin = running count of DDPM_PREP_TILE x DDPM_PREP_TILE
+ * tiles (ascending). */
+#define DDPM_PREP_TILE 64
 typedef struct ddpm_prep_desc {
   const float* w; void* wf; long long ldwf; void* wd; long long ldwd;
   int cout, taps, cin;
-  int tile_begin, tiles_x, tiles_y;   /* tiles_x = ceil(cin/32), tiles_y = ceil(cout/32); taps tiles in z */
+  int tile_begin, tiles_x, tiles_y;   /* tiles_x = ceil(cin/TILE), tiles_y = ceil(cout/TILE); taps tiles in z */
 } ddpm_prep_desc;
 int ddpm_prep_weights_batched(const ddpm_prep_desc* table_dev, int n_entries, int total_tiles, int with_d,
                               void* stream);
@@ -270,6 +272,16 @@ int ddpm_bgemm(const void* a, long long lda, long long a_head, long long a_batch
 int ddpm_softmax_rows(const float* s, long long lds, void* p, long long ldp, long long rows, int t, void* stream);
 int ddpm_softmax_rows_bwd(const void* p, long long ldp, const float* dp, long long lddp, void* ds, long long rows,
                           int t, float scale, void* stream);
+
+/* The same attention core as ONE fused tcgen05 kernel (attn_wide.cu) where it fits: t <= 256 tokens and head_dim a
+ * multiple of 128 (the 16x16 / 8x8 blocks of the celebahq architecture at 256^2: t = 256 / 64, one head of 512).
+ * S = Q K^T accumulates in TMEM, the softmax runs from TMEM into shared memory, O = P V follows from there; S and P
+ * never travel through L2 / HBM.  qkv as in ddpm_attn_fwd; o bf16 [b*t][heads*d] (row stride ldo);
+ * probs: NULL (inference) or bf16 [b][heads][t][ldp] receiving softmax(scale * Q K^T) for the backward pass
+ * (ddpm_bgemm / ddpm_softmax_rows_bwd).  ddpm_attn_wide_supported -> 1 when (t, heads, d) fits the fused kernel. */
+int ddpm_attn_wide_supported(int t, int heads, int d);
+int ddpm_attn_wide_fwd(const void* qkv, long long ldqkv, void* o, long long ldo, void* probs, long long ldp, int b,
+                       int t, int heads, int d, float scale, void* stream);
 
 /* Timesteps(128) sinusoid -> fp32 [b][dim]; t int64[b] (device); freqs fp32[dim/2] (device) =
  * exp(-ln(10000) * j / (dim/2 - freq_shift)) tabulated by the host. */

@@ -110,6 +110,8 @@ SIGNATURES = {
                           _vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp],
     "ddpm_attn_fwd": [_vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
     "ddpm_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _f, _vp],
+    "ddpm_attn_wide_supported": [_i, _i, _i],
+    "ddpm_attn_wide_fwd": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp],
     "ddpm_timestep_embedding": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "ddpm_linear_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "ddpm_linear_f32_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

@@ -17,7 +17,7 @@ INCLUDE = PKG.parent / "include"
 LIB = PKG / "libddpm_b200.so"
 OBJ = PKG / "build"
 
-SOURCES = ["elementwise.cu", "groupnorm.cu", "misc.cu", "attention.cu", "conv_igemm.cu", "conv_halo.cu", "conv_wgrad_row.cu", "bgemm.cu", "preprocess.cu"]
+SOURCES = ["elementwise.cu", "groupnorm.cu", "misc.cu", "attention.cu", "conv_igemm.cu", "conv_halo.cu", "conv_wgrad_row.cu", "bgemm.cu", "attn_wide.cu", "preprocess.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

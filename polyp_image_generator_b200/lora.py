@@ -241,14 +241,18 @@ class GemmLora:
         u = ops.conv_gemm(xd, None, taps_1x1(), self.a_ext, LORA_K, (1, 1, M))
         return SimpleNamespace(u=u, xd=xd, p=p, seed=seed, offset=offset, tick=tick)
 
-    def backward(self, ops, s, x2, dy2, d_x):
-        """Adds the adapter's contribution to d_x and stores dA / dB in self.grads (keyed by id(param))."""
+    def backward(self, ops, s, x2, dy2, d_x, zeros=None):
+        """Adds the adapter's contribution to d_x and stores dA / dB in self.grads (keyed by id(param)).
+        zeros(shape, device): the caller's zero-filled fp32 scratch (unet._ZeroPool.take), else torch.zeros."""
         M = x2.shape[2]
         dev = dy2.device
+        if zeros is None:
+            def zeros(shape, device):
+                return torch.zeros(shape, device=device, dtype=torch.float32)
         dU = ops.conv_gemm(dy2, None, taps_1x1(), self.bt_ext, LORA_K, (1, 1, M))
-        dA_ext = torch.zeros((LORA_K, self.cin), device=dev, dtype=torch.float32)
+        dA_ext = zeros((LORA_K, self.cin), dev)
         ops.conv_wgrad(dU, s.xd, None, taps_1x1(), dA_ext, (1, 1, M), accumulate=True)
-        dB_ext = torch.zeros((self.cout, LORA_K), device=dev, dtype=torch.float32)
+        dB_ext = zeros((self.cout, LORA_K), dev)
         ops.conv_wgrad(dy2, s.u, None, taps_1x1(), dB_ext, (1, 1, M), accumulate=True)
         for i, m, off in self.slots:
             if m.merged:

@@ -16,6 +16,7 @@ import torch
 from . import _capi
 
 Tap = Tuple[int, int, int, int]  # (dn, dh, dw, wk)
+PREP_TILE = 64                   # DDPM_PREP_TILE of include/ddpm_b200.h (tile edge of ddpm_prep_weights_batched)
 
 # smallest map (pixels per sample) at which the GroupNorm statistics / backward fusions ride on the conv epilogues
 import os as _os
@@ -309,7 +310,7 @@ class CudaOps:
             d.w, d.wf, d.ldwf = _ptr(w), _ptr(wf), wf.stride(0)
             d.wd, d.ldwd = _ptr(wd), wd.stride(0)
             d.cout, d.taps, d.cin = cout, taps, cin
-            d.tiles_x, d.tiles_y = (cin + 31) // 32, (cout + 31) // 32
+            d.tiles_x, d.tiles_y = (cin + PREP_TILE - 1) // PREP_TILE, (cout + PREP_TILE - 1) // PREP_TILE   # ddpm_b200.h
             d.tile_begin = tiles
             tiles += d.tiles_x * d.tiles_y * taps
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
@@ -505,8 +506,17 @@ class CudaOps:
                                         m, n, k, heads, batch, float(alpha), _stream()), "ddpm_bgemm")
         self.launches += 1
 
-    def _attn_wide_fwd(self, qkv, b, t, heads, d, scale):
+    def _attn_wide_fwd(self, qkv, b, t, heads, d, scale, keep_probs: bool = True):
         C, ld, tp = heads * d, qkv.stride(0), (t + 7) // 8 * 8
+        if _os.environ.get("DDPM_ATTN_FUSED", "1") != "0" and self.lib.ddpm_attn_wide_supported(t, heads, d):
+            # ONE kernel: S in TMEM, softmax into shared memory, O = P V from there (attn_wide.cu); the probabilities
+            # are written out only when a backward pass will read them
+            o = torch.empty((b * t, C), device=qkv.device, dtype=torch.bfloat16)
+            p = torch.empty((b, heads, t, tp), device=qkv.device, dtype=torch.bfloat16) if keep_probs else None
+            _capi.check(self.lib.ddpm_attn_wide_fwd(_ptr(qkv), ld, _ptr(o), C, _ptr(p), tp, b, t, heads, d,
+                                                    float(scale), _stream()), "ddpm_attn_wide_fwd")
+            self.launches += 1
+            return o, p
         q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:3 * C]
         s = torch.empty((b, heads, t, tp), device=qkv.device, dtype=torch.float32)
         p = torch.empty((b, heads, t, tp), device=qkv.device, dtype=torch.bfloat16)
@@ -540,13 +550,14 @@ class CudaOps:
         self.bgemm(ds, tp, ps, pb, 1, q, ld, d, t * ld, 1, dk, ldd, d, t * ldd, t, d, t, heads, b)
         return dqkv
 
-    def attn_fwd(self, qkv, b: int, t: int, heads: int, d: int, scale: float):
+    def attn_fwd(self, qkv, b: int, t: int, heads: int, d: int, scale: float, need_aux: bool = True):
         """qkv: bf16 [b*t, 3*heads*d] -> (o bf16 [b*t, heads*d], aux).  aux (kept for backward) is the fp32 log-sum-exp
-        [b, heads, t] for narrow heads and the bf16 probabilities [b, heads, t, t8] for wide ones."""
+        [b, heads, t] for narrow heads and the bf16 probabilities [b, heads, t, t8] for wide ones (None when
+        need_aux is False and the fused wide-head kernel ran: inference)."""
         if d not in self.NARROW_HEAD_DIMS:
             if d % 8 or d < 64:
                 raise NotImplementedError(f"attention head_dim={d}: supported are 8/16/32/64 and multiples of 8 above")
-            return self._attn_wide_fwd(qkv, b, t, heads, d, scale)
+            return self._attn_wide_fwd(qkv, b, t, heads, d, scale, keep_probs=need_aux)
         o = torch.empty((b * t, heads * d), device=qkv.device, dtype=torch.bfloat16)
         lse = torch.empty((b, heads, t), device=qkv.device, dtype=torch.float32)
         _capi.check(self.lib.ddpm_attn_fwd(_ptr(qkv), qkv.stride(0), _ptr(o), o.stride(0), _ptr(lse), b, t, heads, d,

@@ -208,6 +208,39 @@ def convert_deprecated_attention_keys(state_dict):
     return out
 
 
+class _ZeroPool:
+    """Zero-filled fp32 scratch for the reduction targets of ONE pass (per-conv GroupNorm moments, per-norm backward
+    sums, d_temb): one fill per pass instead of one fill kernel per target (~70 launches of ~2.4 us in a training step,
+    ~130 in a LoRA step).  The pass's total is learned on the first pass; a pass that asks for more gets an extra chunk."""
+
+    ALIGN = 32      # floats: every slice starts on a 128-byte boundary
+
+    def __init__(self):
+        self.need = 0
+        self.buf = None
+        self.off = 0
+        self.taken = 0
+
+    def begin(self, device):
+        self.need = max(self.need, self.taken)
+        self.taken = 0
+        self.off = 0
+        self.buf = torch.zeros(self.need, device=device, dtype=torch.float32) if self.need else None
+        return self
+
+    def take(self, shape, device) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        na = (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.taken += na
+        if self.buf is None or self.buf.device != device or self.off + na > self.buf.numel():
+            return torch.zeros(tuple(shape), device=device, dtype=torch.float32)     # first pass / grown pass
+        out = self.buf[self.off:self.off + n].view(tuple(shape))
+        self.off += na
+        return out
+
+
 def _align(n, a=4):
     return (n + a - 1) // a * a
 
@@ -710,7 +743,7 @@ class UNet2DModel(nn.Module):
         emb = ops.linear_f32(e1, w2, b2, True)
         temb_all = ops.linear_f32(emb, wt, bt, True)           # [N, sum C] fp32
         st = SimpleNamespace(temb_all=temb_all, N=N, tape=tape, ops=ops,
-                             d_temb_all=None, rng_tick=None)
+                             d_temb_all=None, rng_tick=None, zeros=self._zero_pool("fwd", training, x.device))
         if training and any(g.lora is not None and g.lora.active and g.lora.p > 0.0 for g in P.gemms):
             # device-resident step counter for the adapter dropout: a CUDA-graph replay of the step draws new masks
             tick = getattr(self, "_rng_tick", None)
@@ -937,7 +970,7 @@ class UNet2DModel(nn.Module):
         # which holds whenever every concatenated source is a multiple of 4 * norm_num_groups channels (128 here)
         if cout % (4 * self.config.norm_num_groups):
             return None
-        return torch.zeros((grid[0], cout // 4, 2), device=st.temb_all.device, dtype=torch.float32)
+        return st.zeros.take((grid[0], cout // 4, 2), st.temb_all.device)
 
     @staticmethod
     def _tag(t, csum):
@@ -998,7 +1031,7 @@ class UNet2DModel(nn.Module):
             if (at.qkv.lora and at.qkv.lora.active) else None
         qkv = ops.conv_gemm(xn2, lora_qkv.u if lora_qkv else None, self._lin_taps(at.qkv), at.qkv.wf, 3 * C,
                             (1, 1, N * T), bias=self._bias(at.qkv))
-        o, lse = ops.attn_fwd(qkv.view(N * T, 3 * C), N, T, at.heads, at.d, at.d ** -0.5)
+        o, lse = ops.attn_fwd(qkv.view(N * T, 3 * C), N, T, at.heads, at.d, at.d ** -0.5, need_aux=st.tape is not None)
         o2 = o.view(1, 1, N * T, C)
         lora_o = at.out.lora.forward_extra(ops, o2, self.training, st.rng_tick) \
             if (at.out.lora and at.out.lora.active) else None
@@ -1058,9 +1091,10 @@ class UNet2DModel(nn.Module):
         c0 = cfg.block_out_channels[0]
         ted = self._temb_dim
         G = self._fresh_grad_arena()
-        d_temb_all = torch.zeros((N, P.temb_total), device=G.device, dtype=torch.float32)
+        zp = self._zero_pool("bwd", True, G.device)
+        d_temb_all = zp.take((N, P.temb_total), G.device)
         st = SimpleNamespace(ops=ops, G=G, d_temb_all=d_temb_all, skip_grads={}, N=N, wg_stream=None, keep=[],
-                             defer_kw={})
+                             defer_kw={}, zeros=zp)
         if G.is_cuda and os.environ.get("DDPM_WGRAD_STREAM", "1") != "0":
             # Weight gradients feed nothing downstream in backward, so they run on a second stream: the tensor-bound
             # wgrad GEMMs overlap the HBM-bound GroupNorm-backward kernels and the latency-bound low-resolution layers
@@ -1087,18 +1121,22 @@ class UNet2DModel(nn.Module):
         train_out = self.conv_out.weight.requires_grad
         pd = ops.im2col3(d_out, chan_sum=self._gview(G, P.cout_b, (co,)) if train_out else None)
         if train_out:   # R[ci][tap'*co_n + co] = sum_pix a[pix, ci] * d_out[pix + off(tap'), co]
-            R = torch.zeros((c0, 64), device=G.device, dtype=torch.float32)
+            R = zp.take((c0, 64), G.device)
             ops.conv_wgrad(hd.a, pd, None, taps_1x1(), R, grid0)
             self._gview(G, P.cout_w, (co, 9, c0)).add_(R[:, :9 * co].view(c0, 9, co).flip(1).permute(2, 1, 0))
         gam, bet = self._norm_params(no)
         tr = no.trainable
         dg_o = self._gview(G, no.g_off, (c0,)) if tr else None
         db_o = self._gview(G, no.b_off, (c0,)) if tr else None
+        n_steps = len(tape.steps)
+        st.bias_done = False
         if hd.coef is not None:    # SiLU / GroupNorm derivative + per-(n, c) sums in the dgrad epilogue, one streaming pass
-            sums = torch.zeros((grid0[0], c0, 2), device=G.device, dtype=torch.float32)
+            sums = zp.take((grid0[0], c0, 2), G.device)
             dz = ops.conv_gemm(pd, None, taps_1x1(), self._cout_wd, c0, grid0, gn=(hd.h_last, None, hd.coef, True, sums))
+            st.next_bias = self._colsum_target(G, tape, n_steps - 1, first_needed)
             g, _ = ops.gn_bwd_apply(hd.h_last, None, no.groups, hd.stats, no.eps, gam, dz, sums, dgamma=dg_o, dbeta=db_o,
-                                    **st.defer_kw)
+                                    out_c=st.next_bias, **st.defer_kw)
+            st.bias_done = st.next_bias is not None
         else:
             d_a = ops.conv_gemm(pd, None, taps_1x1(), self._cout_wd, c0, grid0)
             g, _ = ops.gn_bwd(hd.h_last, None, no.groups, hd.stats, no.eps, gam, bet, True, d_a, dgamma=dg_o,
@@ -1110,6 +1148,9 @@ class UNet2DModel(nn.Module):
             begin()
         for i in range(len(tape.steps) - 1, first_needed - 1, -1):
             kind, rec, s = tape.steps[i]
+            # the bias gradient of the conv that consumes this step's result (= the column sums of the gradient this step
+            # returns) rides on the step's last streaming kernel where it has one: no separate pass over that tensor
+            st.next_bias = self._colsum_target(G, tape, i - 1, first_needed)
             if kind == "resnet":
                 g = self._resnet_bwd(st, rec, s, g)
             elif kind == "attn":
@@ -1124,8 +1165,9 @@ class UNet2DModel(nn.Module):
         if first_needed == 0 and self._head_trainable():
             # g is now the gradient of conv_in's output (skip 0 already folded in by the first resnet)
             if self.conv_in.weight.requires_grad:
-                ops.reduce_hw(g, None, self._gview(G, P.cin_b, (c0,)))
-                R = torch.zeros((c0, 64), device=G.device, dtype=torch.float32)
+                if not st.bias_done:
+                    ops.reduce_hw(g, None, self._gview(G, P.cin_b, (c0,)))
+                R = zp.take((c0, 64), G.device)
                 ops.conv_wgrad(g, hd.patches, None, taps_1x1(), R, tuple(g.shape[:3]))
                 self._gview(G, P.cin_w, (c0, 9 * cfg.in_channels)).add_(R[:, :9 * cfg.in_channels])
         if st.wg_stream is not None:      # d_temb_all and every weight gradient are complete from here on
@@ -1146,6 +1188,32 @@ class UNet2DModel(nn.Module):
                                      self._gview(G, P.te.b1, (ted,)), False)
         self.last_launches_bwd = ops.launches - l0
         return G, st
+
+    def _colsum_target(self, G, tape, i: int, first_needed: int):
+        """The bias gradient that equals the pixel sums of the gradient ENTERING tape step i (i = -1: conv_in), or None."""
+        if os.environ.get("DDPM_BIAS_FUSION", "1") == "0":
+            return None
+        if i < first_needed:
+            if i == -1 and first_needed == 0 and self.conv_in.weight.requires_grad:
+                return self._gview(G, self._plan.cin_b, (self.config.block_out_channels[0],))
+            return None
+        kind, rec, _ = tape.steps[i]
+        if kind == "resnet":
+            if rec.conv2.bias_trainable:
+                return self._wgrad_views(G, rec.conv2)[1]
+            if rec.short is not None and rec.short.bias_trainable:
+                return self._wgrad_views(G, rec.short)[1]
+            return None
+        gobj = rec.out if kind == "attn" else rec.conv
+        return self._wgrad_views(G, gobj)[1] if gobj.bias_trainable else None
+
+    def _zero_pool(self, which: str, training: bool, device) -> _ZeroPool:
+        pools = self.__dict__.setdefault("_zero_pools", {})
+        key = (which, training)
+        zp = pools.get(key)
+        if zp is None:
+            zp = pools[key] = _ZeroPool()
+        return zp.begin(device)
 
     def _fresh_grad_arena(self) -> torch.Tensor:
         """Zero-filled flat fp32 gradient arena.  The previous step's arena is reused (one memset, no allocation) unless a
@@ -1204,8 +1272,11 @@ class UNet2DModel(nn.Module):
         grid = s.grid
         # conv2 (+ shortcut bias shares the same column sums)
         dW2, db2 = self._wgrad_views(G, r.conv2)
-        fold_bias = r.conv2.trainable and r.conv2.bias_trainable     # bias gradient rides on the wgrad GEMM
-        if r.conv2.bias_trainable and not fold_bias:
+        done, st.bias_done = st.bias_done, False     # the producer of g already added its pixel sums to the bias gradient
+        fold_bias = r.conv2.trainable and r.conv2.bias_trainable and not done    # bias gradient rides on the wgrad GEMM
+        if done:
+            pass
+        elif r.conv2.bias_trainable and not fold_bias:
             ops.reduce_hw(g, None, db2)
         elif not r.conv2.bias_trainable and r.short is not None and r.short.bias_trainable:
             ops.reduce_hw(g, None, self._wgrad_views(G, r.short)[1])
@@ -1216,7 +1287,7 @@ class UNet2DModel(nn.Module):
                 ops.conv_wgrad(g, s.b, None, taps_3x3(r.cout), dW2, grid, dbias=db2 if fold_bias else None)
             if share_bias:
                 self._wgrad_views(G, r.short)[1].copy_(db2)       # the shortcut bias sees the same column sums
-        if fold_bias or not r.conv2.bias_trainable:
+        if fold_bias or done or not r.conv2.bias_trainable:
             self._async_wgrad(st, wgrad2)
         else:
             wgrad2()        # db2 came from reduce_hw on the main stream: keep the copy ordered behind it
@@ -1224,7 +1295,7 @@ class UNet2DModel(nn.Module):
         dg, dbt = self._norm_grads(G, r.norm2)
         fuse = s.coef2 is not None
         if fuse:   # SiLU/GroupNorm derivative + per-(n, c) sums in the dgrad epilogue, then one streaming pass
-            sums = torch.zeros((grid[0], r.cout, 2), device=g.device, dtype=torch.float32)
+            sums = st.zeros.take((grid[0], r.cout, 2), g.device)
             dz = ops.conv_gemm(g, None, taps_3x3(r.cout), r.conv2.wd, r.cout, grid,
                                gn=(s.h1, None, s.coef2, True, sums))
             # the pixel sums of d_h1 (time-embedding gradient per sample, conv1 bias gradient) come out of the same pass
@@ -1246,7 +1317,7 @@ class UNet2DModel(nn.Module):
             self._async_wgrad(st, lambda d_h1=d_h1: ops.conv_wgrad(d_h1, s.a, None, taps_3x3(r.cin), dW1, grid))
         g1, be1 = self._norm_params(r.norm1)
         if fuse:
-            sums1 = torch.zeros((grid[0], r.cin, 2), device=g.device, dtype=torch.float32)
+            sums1 = st.zeros.take((grid[0], r.cin, 2), g.device)
             d_a = ops.conv_gemm(d_h1, None, taps_3x3(r.cout), r.conv1.wd, r.cin, grid,
                                 gn=(s.x0, s.x1, s.coef1, True, sums1))
         else:
@@ -1261,8 +1332,16 @@ class UNet2DModel(nn.Module):
         extra = st.skip_grads.pop(s.in_skip, None) if s.in_skip is not None else None
         dg, dbt = self._norm_grads(G, r.norm1)
         if fuse:
+            nb = st.next_bias
+            oc = nb
+            if nb is not None and s.x1 is not None:      # the kernel sums all c0 + c1 channels: keep the first c0
+                oc = st.zeros.take((r.cin,), g.device)
             dx0, dx1 = ops.gn_bwd_apply(s.x0, s.x1, r.norm1.groups, s.stats1, r.norm1.eps, g1, d_a, sums1, add0=d_sc,
-                                        add1=extra, dgamma=dg, dbeta=dbt, **st.defer_kw)
+                                        add1=extra, dgamma=dg, dbeta=dbt, out_c=oc, **st.defer_kw)
+            if nb is not None:
+                if oc is not nb:
+                    nb.add_(oc[:nb.numel()])
+                st.bias_done = True
         else:
             dx0, dx1 = ops.gn_bwd(s.x0, s.x1, r.norm1.groups, s.stats1, r.norm1.eps, g1, be1, True, d_a, add0=d_sc,
                                   add1=extra, dgamma=dg, dbeta=dbt, **st.defer_kw)
@@ -1277,14 +1356,15 @@ class UNet2DModel(nn.Module):
         M = N * T
         g2 = g.view(1, 1, M, C)
         dWo, dbo = self._wgrad_views(G, at.out)
-        if at.out.bias_trainable:
+        done, st.bias_done = st.bias_done, False
+        if at.out.bias_trainable and not done:
             ops.reduce_hw(g2, None, dbo)
         o2 = s.o.view(1, 1, M, C)
         if at.out.trainable:
             self._async_wgrad(st, lambda: ops.conv_wgrad(g2, o2, None, taps_1x1(), dWo, (1, 1, M)))
         d_o = ops.conv_gemm(g2, None, taps_1x1(), at.out.wd, C, (1, 1, M))
         if s.lora_o is not None:
-            d_o = at.out.lora.backward(ops, s.lora_o, o2, g2, d_o)
+            d_o = at.out.lora.backward(ops, s.lora_o, o2, g2, d_o, zeros=st.zeros.take)
         dqkv = ops.attn_bwd(s.qkv.view(M, 3 * C), s.o, d_o.view(M, C), s.lse, N, T, at.heads, at.d, at.d ** -0.5)
         dq2 = dqkv.view(1, 1, M, 3 * C)
         dWq, dbq = self._wgrad_views(G, at.qkv)
@@ -1295,7 +1375,7 @@ class UNet2DModel(nn.Module):
             self._async_wgrad(st, lambda: ops.conv_wgrad(dq2, xn2, None, taps_1x1(), dWq, (1, 1, M)))
         d_xn = ops.conv_gemm(dq2, None, taps_1x1(), at.qkv.wd, C, (1, 1, M))
         if s.lora_qkv is not None:
-            d_xn = at.qkv.lora.backward(ops, s.lora_qkv, xn2, dq2, d_xn)
+            d_xn = at.qkv.lora.backward(ops, s.lora_qkv, xn2, dq2, d_xn, zeros=st.zeros.take)
         extra = st.skip_grads.pop(s.in_skip, None) if s.in_skip is not None else None
         gam, bet = self._norm_params(at.norm)
         dg, dbt = self._norm_grads(G, at.norm)
@@ -1307,8 +1387,9 @@ class UNet2DModel(nn.Module):
         ops, G = st.ops, st.G
         N, H, W, C = s.shape
         dW, db = self._wgrad_views(G, d.conv)
-        fold_bias = d.conv.trainable and d.conv.bias_trainable
-        if d.conv.bias_trainable and not fold_bias:
+        done, st.bias_done = st.bias_done, False
+        fold_bias = d.conv.trainable and d.conv.bias_trainable and not done
+        if d.conv.bias_trainable and not fold_bias and not done:
             ops.reduce_hw(g, None, db)
         if d.conv.trainable:
             self._async_wgrad(st, lambda g=g: ops.conv_wgrad(g, s.s2d, None, taps_s2d(C, N, d.pad), dW, s.grid,
@@ -1324,8 +1405,9 @@ class UNet2DModel(nn.Module):
         ops, G = st.ops, st.G
         C = u.c
         dW, db = self._wgrad_views(G, u.conv)
-        fold_bias = u.conv.trainable and u.conv.bias_trainable
-        if u.conv.bias_trainable and not fold_bias:
+        done, st.bias_done = st.bias_done, False
+        fold_bias = u.conv.trainable and u.conv.bias_trainable and not done
+        if u.conv.bias_trainable and not fold_bias and not done:
             ops.reduce_hw(g, None, db)
         if u.conv.trainable:
             self._async_wgrad(st, lambda g=g: ops.conv_wgrad(g, s.up, None, taps_3x3(C), dW, s.grid,

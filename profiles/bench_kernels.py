@@ -220,6 +220,26 @@ def bench_small(ops, B, iters, pk):
     print(f"step (philox)    {ms:7.4f} ms  {12 * x.numel() / ms / 1e6:6.0f} GB/s ({12 * x.numel() / ms / 1e6 / pk['hbm_gbs']:.2f})")
 
 
+def bench_linear(ops, B, iters, pk):
+    """The fp32 time-embedding linears at the sizes of the step; weights rotate through > L2 of buffers (cold reads)."""
+    print(f"# time-embedding linears (fp32 SIMT), batch {B}")
+    for k, n in ((128, 512), (512, 512), (512, 9984)):
+        nbuf = max(2, int(200e6 // (n * k * 4)) + 1) if n * k * 4 > 4e6 else 2
+        ws = [torch.randn(n, k, device="cuda") * 0.05 for _ in range(nbuf)]
+        dws = [torch.zeros(n, k, device="cuda") for _ in range(min(nbuf, 4))]
+        x = torch.randn(B, k, device="cuda")
+        dy = torch.randn(B, n, device="cuda")
+        b = torch.randn(n, device="cuda")
+        db = torch.zeros(n, device="cuda")
+        wbytes = n * k * 4
+        ms = timeit(lambda i: ops.linear_f32(x, ws[i % nbuf], b, True), iters, nbuf)
+        print(f"linear  {B}x{k}->{n}  fwd   {ms * 1e3:8.1f} us  ({wbytes / ms / 1e6:6.0f} GB/s of weights)")
+        ms = timeit(lambda i: ops.linear_f32_wgrad(x, dy, dws[i % len(dws)], db, True), iters, len(dws))
+        print(f"linear  {B}x{k}->{n}  wgrad {ms * 1e3:8.1f} us  ({2 * wbytes / ms / 1e6:6.0f} GB/s of dW read+write)")
+        ms = timeit(lambda i: ops.linear_f32_dgrad(dy, ws[i % nbuf], x, True), iters, nbuf)
+        print(f"linear  {B}x{k}->{n}  dgrad {ms * 1e3:8.1f} us  ({wbytes / ms / 1e6:6.0f} GB/s of weights)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -246,3 +266,5 @@ if __name__ == "__main__":
         bench_gn(ops, a.batch, a.iters, pk, a.first)
     if a.what in ("small", "all"):
         bench_small(ops, a.batch, a.iters, pk)
+    if a.what in ("linear", "all"):
+        bench_linear(ops, a.batch, a.iters, pk)

@@ -388,7 +388,7 @@ class EmuOps:
         C = heads * d
         return [z.reshape(b, t, heads, d).transpose(1, 2) for z in qkv.float().split(C, 1)]
 
-    def attn_fwd(self, qkv, b, t, heads, d, scale):
+    def attn_fwd(self, qkv, b, t, heads, d, scale, need_aux=True):
         q, k, v = self._split(qkv, b, t, heads, d)
         s = (q @ k.transpose(-1, -2)) * scale
         lse = torch.logsumexp(s, -1) * 1.4426950408889634

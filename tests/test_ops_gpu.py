@@ -280,6 +280,61 @@ def test_time_embedding_linears_and_layout_helpers(ops):
     ck.done()
 
 
+# ---- time-embedding linears at the sizes of the step (tiled fp32 SIMT GEMM, split reduction in the input gradient) ----
+@pytest.mark.parametrize("m,k,n", [(64, 512, 9984), (32, 512, 9984), (64, 128, 512), (64, 512, 512), (70, 100, 333),
+                                   (1, 8, 16), (130, 40, 65), (512, 8, 512)])
+def test_time_embedding_linears_at_step_sizes(ops, m, k, n):
+    ck = Check()
+    torch.manual_seed(m * 7 + n)
+    x = torch.randn(m, k, device=DEV)
+    w = torch.randn(n, k, device=DEV) / k ** 0.5
+    b = torch.randn(n, device=DEV)
+    for silu in (False, True):
+        xr = x.double().requires_grad_(True)
+        wr = w.double().requires_grad_(True)
+        yr = F.linear(F.silu(xr) if silu else xr, wr, b.double())
+        ck(f"linear_f32 {m}x{k}->{n} silu={silu}", ops.linear_f32(x, w, b, silu), yr, 1e-5)
+        ck("   no bias", ops.linear_f32(x, w, None, silu), yr - b.double(), 1e-5)
+        dy = torch.randn(m, n, device=DEV)
+        yr.backward(dy.double())
+        dw = torch.zeros_like(w)
+        db = torch.zeros_like(b)
+        ops.linear_f32_wgrad(x, dy, dw, db, silu)
+        ck("   wgrad", dw, wr.grad, 1e-5)
+        ck("   bgrad", db, dy.double().sum(0), 1e-5)
+        ops.linear_f32_wgrad(x, dy, dw, db, silu)          # accumulates
+        ck("   wgrad accumulates", dw, 2 * wr.grad, 1e-5)
+        ck("   dgrad", ops.linear_f32_dgrad(dy, w, x, silu), xr.grad, 1e-5)
+    ck.done()
+
+
+def test_batched_weight_preparation_pairs_and_scalar_paths(ops):
+    """ddpm_prep_weights_batched over a table mixing even (bf16x2 path) and odd (scalar path) layer shapes, ragged
+    against the 64x64 tile, against the per-layer definition: wf[co][tap][ci], wd[ci][T-1-tap][co], both rounded once."""
+    ck = Check()
+    torch.manual_seed(5)
+    shapes = [(128, 9, 128), (96, 9, 160), (512, 1, 1024), (70, 9, 66), (33, 3, 65), (64, 9, 64), (256, 9, 384)]
+    entries, keep = [], []
+    for cout, taps, cin in shapes:
+        wm = torch.randn(cout, taps, cin, device=DEV)
+        wf = torch.full((cout, taps * cin + 64), 7.0, device=DEV, dtype=torch.bfloat16)     # wider row: ldwf > K
+        wd = torch.full((cin, taps * cout), 7.0, device=DEV, dtype=torch.bfloat16)
+        entries.append((wm.reshape(-1), wf[:, :taps * cin], wd, cout, taps, cin))
+        keep.append((wm, wf, wd))
+    table = ops.build_prep_table(entries, torch.device(DEV))
+    for with_d in (True, False):
+        for _, wf, wd in keep:
+            wf.fill_(7.0)
+            wd.fill_(7.0)
+        ops.prep_weights_batched(*table, with_d)
+        for (cout, taps, cin), (wm, wf, wd) in zip(shapes, keep):
+            ck(f"wf {cout}x{taps}x{cin} with_d={with_d}", wf[:, :taps * cin], bf(wm).reshape(cout, -1), 0.0)
+            ck("   wf padding untouched", wf[:, taps * cin:], torch.full_like(wf[:, taps * cin:], 7.0), 0.0)
+            want_d = bf(wm).flip(1).permute(2, 1, 0).reshape(cin, -1) if with_d else torch.full_like(wd, 7.0)
+            ck("   wd", wd, want_d, 0.0)
+    ck.done()
+
+
 # ---- 3-channel boundary convs -------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,h,w,C", [(2, 16, 24, 128), (3, 64, 64, 128), (1, 7, 5, 64), (2, 128, 128, 128),
                                      (1, 224, 224, 128), (1, 256, 256, 128)])

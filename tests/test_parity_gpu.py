@@ -375,6 +375,38 @@ def test_wide_head_attention_vs_sdpa(dev, b, t, heads, d):
         assert rel(dqkv[:, i * C:(i + 1) * C], ref.grad[:, i * C:(i + 1) * C]) < 1.5e-2, name
 
 
+@pytest.mark.parametrize("b,t,heads,d", [(8, 256, 1, 512), (8, 64, 1, 512), (2, 256, 2, 256), (1, 130, 1, 128),
+                                         (1, 100, 3, 384), (2, 7, 1, 128), (1, 256, 1, 1024), (3, 129, 2, 128)])
+def test_fused_wide_head_attention_matches_unfused_and_sdpa(dev, b, t, heads, d, monkeypatch):
+    """attn_wide.cu (ONE tcgen05 kernel: S in TMEM, softmax into shared memory, O = P V) against the three-launch
+    composition it replaces (bgemm + softmax_rows + bgemm) and against fp32 SDPA: output, the probabilities kept for
+    the backward pass, and the inference call that keeps none."""
+    from polyp_image_generator_b200 import ops as ops_mod
+    o = ops_mod.get()
+    assert o.lib.ddpm_attn_wide_supported(t, heads, d) == 1
+    torch.manual_seed(3 * t + d)
+    C = heads * d
+    qkv = (torch.randn(b * t, 3 * C) * 0.7).to(torch.bfloat16)
+    scale = d ** -0.5
+    monkeypatch.setenv("DDPM_ATTN_FUSED", "0")
+    l0 = o.launches
+    out_u, p_u = o.attn_fwd(qkv.to(dev), b, t, heads, d, scale)
+    monkeypatch.setenv("DDPM_ATTN_FUSED", "1")
+    l1 = o.launches
+    out_f, p_f = o.attn_fwd(qkv.to(dev), b, t, heads, d, scale)
+    assert o.launches - l1 == 1 and l1 - l0 > 1          # the fused path IS one launch
+    out_i, p_i = o.attn_fwd(qkv.to(dev), b, t, heads, d, scale, need_aux=False)
+    assert p_i is None and torch.equal(out_i, out_f)
+    q, k, v = [x.reshape(b, t, heads, d).transpose(1, 2) for x in qkv.float().split(C, dim=1)]
+    want = F.scaled_dot_product_attention(q, k, v, scale=scale).transpose(1, 2).reshape(b * t, C)
+    want_p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    assert rel(out_f, want) < 1e-2
+    assert rel(out_f, out_u) < 6e-3                      # both round P and O to bf16 once
+    assert rel(p_f[..., :t], want_p) < 6e-3
+    assert rel(p_f[..., :t], p_u[..., :t]) < 6e-3
+    assert torch.isfinite(out_f.float()).all()
+
+
 @pytest.mark.parametrize("hw,cin,cout,k3,c1", [(64, 128, 128, True, 0), (64, 128, 256, False, 0), (32, 256, 256, True, 0),
                                                (128, 128, 128, True, 64), (16, 128, 128, True, 0)])
 def test_conv_epilogue_statistics_and_single_pass_groupnorm(dev, hw, cin, cout, k3, c1):
