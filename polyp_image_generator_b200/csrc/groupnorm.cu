@@ -301,6 +301,7 @@ __device__ __forceinline__ void gn_team_barrier(int* counter, int expected) {
 struct GnTeam {
   int N, hw, cpg, groups, V, team_size, pix_per_cta;
   float eps;
+  int slab_ch;   // solo launches (team_size == 1) only: channels per CTA, blockIdx.y = slab (whole groups); 0 = all
 };
 
 // ---- forward: statistics + normalise/affine/SiLU --------------------------------------------------------------
@@ -314,8 +315,12 @@ gn_fwd_fused_kernel(GnSrc s, GnTeam t, float* __restrict__ stats /*[N][groups][2
   const int team = blockIdx.x / t.team_size, rank = blockIdx.x - team * t.team_size;
   const int nteams = gridDim.x / t.team_size;
   const int V = t.V, hw = t.hw, cpg = t.cpg, groups = t.groups;
-  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
-  const int c = v * 8;
+  // solo launches may cut a sample into channel slabs of whole groups (blockIdx.y): groups are independent, so the
+  // slabs need no exchange at all and a 64-sample batch of small maps fills the GPU instead of 64 SMs
+  const int Vt = t.slab_ch ? t.slab_ch / 8 : V;                   // threads per pixel
+  const int c_base = t.slab_ch ? static_cast<int>(blockIdx.y) * t.slab_ch : 0;
+  const int v = threadIdx.x % Vt, pl = threadIdx.x / Vt, ppb = blockDim.x / Vt;
+  const int c = c_base + v * 8;
   const int p_begin = rank * t.pix_per_cta;
   const int p_end = min(hw, p_begin + t.pix_per_cta);
   const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
@@ -333,8 +338,9 @@ gn_fwd_fused_kernel(GnSrc s, GnTeam t, float* __restrict__ stats /*[N][groups][2
     float* st = stats + static_cast<long long>(n) * groups * 2;
     f2x4 ka, kb;
     if (t.team_size == 1) {
-      // small maps: the CTA owns the whole sample -- statistics stay in shared memory, written out once
-      for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) st[i] = sm[i];
+      // small maps: the CTA owns the whole sample (or slab) -- statistics stay in shared memory, written out once
+      const int i_lo = (c_base / cpg) * 2, i_hi = t.slab_ch ? ((c_base + t.slab_ch) / cpg) * 2 : groups * 2;
+      for (int i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) st[i] = sm[i];
       gn_apply_coefs(sm, c, cpg, inv_m, t.eps, gamma, beta, false, &ka, &kb);
     } else {
       for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&st[i], sm[i]);
@@ -367,8 +373,10 @@ gn_bwd_fused_kernel(GnSrc s, GnTeam t, const float* __restrict__ stats, const fl
   const int V = t.V, hw = t.hw, cpg = t.cpg, groups = t.groups;
   const int C = V * 8;
   float* scoef = smc + C * 2;
-  const int v = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
-  const int c = v * 8;
+  const int Vt = t.slab_ch ? t.slab_ch / 8 : V;                   // channel slabs of a solo launch: see the forward
+  const int c_base = t.slab_ch ? static_cast<int>(blockIdx.y) * t.slab_ch : 0;
+  const int v = threadIdx.x % Vt, pl = threadIdx.x / Vt, ppb = blockDim.x / Vt;
+  const int c = c_base + v * 8;
   const int p_begin = rank * t.pix_per_cta;
   const int p_end = min(hw, p_begin + t.pix_per_cta);
   const float inv_m = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
@@ -435,14 +443,15 @@ gn_bwd_fused_kernel(GnSrc s, GnTeam t, const float* __restrict__ stats, const fl
     __syncthreads();
     float* sn = sums + static_cast<long long>(n) * C * 2;
     const bool solo = t.team_size == 1;
+    const int c_end = t.slab_ch ? c_base + t.slab_ch : C;        // this CTA's channels: [c_base, c_end)
     if (solo) {
-      for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sn[i] = smc[i];   // kept for dgamma / dbeta
+      for (int i = c_base * 2 + threadIdx.x; i < c_end * 2; i += blockDim.x) sn[i] = smc[i];   // kept for dgamma / dbeta
     } else {
       for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(&sn[i], smc[i]);
       gn_team_barrier(&counters[n], t.team_size);
     }
     // ---- group coefficients: (sum_c gamma*A, sum_c gamma*B) / m ----
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    for (int g = c_base / cpg + threadIdx.x; g < c_end / cpg; g += blockDim.x) {
       float s1 = 0.f, s2 = 0.f;
       for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
         const float2 ab = solo ? *reinterpret_cast<const float2*>(smc + cc * 2)
@@ -835,9 +844,32 @@ static void gn_geometry(int C, int hw, int n, int min_iters, int* V, int* thread
 // Team geometry for the fused kernels.  `resident` = co-resident CTAs of the kernel (occupancy * SMs);
 // `sample_bytes` = bytes of one sample that phase 2 re-reads.  Teams are sized so that teams * sample_bytes stays
 // within the L2 budget and every CTA still has >= 2 loop trips.
+// Channel slab of a solo launch: whole GroupNorm groups and whole 8-channel vectors (a multiple of lcm(cpg, 8)), rows of
+// at least 128 bytes, and no more slabs than it takes to put ~3 CTAs on every SM.  Returns C when one slab is enough.
+static int gn_slab_channels(int C, int cpg, int n) {
+  if (env_int("DDPM_GN_SLABS", 1) == 0) return C;
+  int u = cpg;
+  while (u % 8) u += cpg;
+  if (C % u) return C;
+  const int units = C / u;
+  int want = (3 * kNumSMs + n - 1) / n;
+  if (want < 1) want = 1;
+  int best = C;
+  for (int k = 1; k <= units; ++k) {
+    if (units % k) continue;
+    const int ch = k * u;
+    if (ch < 64 && k < units) continue;
+    best = ch;
+    if (units / k <= want) break;
+  }
+  return best;
+}
+
 static void gn_team_geometry(int C, int hw, int n, int resident, double sample_bytes, GnTeam* t, int* threads,
-                             int* grid) {
+                             int* grid, int* grid_y) {
   const int V = C / 8;
+  *grid_y = 1;
+  t->slab_ch = 0;
   int ppb = kGnThreads / V;
   if (ppb < 1) ppb = 1;
   *threads = V * ppb;
@@ -854,9 +886,23 @@ static void gn_team_geometry(int C, int hw, int n, int resident, double sample_b
   if (team_size < 1) team_size = 1;
   teams = resident / team_size;
   if (teams > n) teams = n;
-  if (static_cast<long long>(hw) * C <= env_int("DDPM_GN_SOLO_ELEMS", 65536)) {
+  const int slab = gn_slab_channels(C, t->cpg, n);
+  const bool solo_whole = static_cast<long long>(hw) * C <= env_int("DDPM_GN_SOLO_ELEMS", 65536);
+  const bool solo_slabs = slab < C && static_cast<long long>(hw) * slab <= env_int("DDPM_GN_SOLO_SLAB_ELEMS", 32768);
+  if (solo_whole || solo_slabs) {
     team_size = 1;                       // latency-sized sample: one CTA, no atomics / barrier / memsets
     teams = resident < n ? resident : n;
+    if (slab < C) {                      // ... per channel slab
+      const int slabs = C / slab;
+      t->slab_ch = slab;
+      *grid_y = slabs;
+      teams = resident / slabs < n ? resident / slabs : n;
+      if (teams < 1) teams = 1;
+      const int vt = slab / 8;
+      int ppb_s = kGnThreads / vt;
+      if (ppb_s < 1) ppb_s = 1;
+      *threads = vt * ppb_s;
+    }
   }
   int ppc = (hw + team_size - 1) / team_size;
   ppc = (ppc + ppb - 1) / ppb * ppb;
@@ -939,8 +985,8 @@ extern "C" int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1
   if (!resident[ki])
     resident[ki] = silu ? gn_resident_ctas(gn_fwd_fused_kernel<true>, kGnThreads, 0)
                         : gn_resident_ctas(gn_fwd_fused_kernel<false>, kGnThreads, 0);
-  int threads, grid;
-  gn_team_geometry(C, hw, n, resident[ki], 2.0 * hw * C, &t, &threads, &grid);
+  int threads, grid, grid_y;
+  gn_team_geometry(C, hw, n, resident[ki], 2.0 * hw * C, &t, &threads, &grid, &grid_y);
   if (t.team_size > 1) {
     DDPM_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
     DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * n, stream));
@@ -954,7 +1000,7 @@ extern "C" int ddpm_gn_fwd(const void* x0, int c0, long long ld0, const void* x1
   if (t.team_size > 1)
     DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, stream));
   else
-    DDPM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, 0, stream));
+    DDPM_CUDA(cudaLaunchKernel(fn, dim3(grid, grid_y), dim3(threads), args, 0, stream));
   return check_launch("gn_fwd_fused_kernel");
 }
 
@@ -984,9 +1030,9 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
   if (!resident[ki])
     resident[ki] = silu ? gn_resident_ctas(gn_bwd_fused_kernel<true>, kGnThreads, sizeof(float) * (kMaxC * 2 + 128))
                         : gn_resident_ctas(gn_bwd_fused_kernel<false>, kGnThreads, sizeof(float) * (kMaxC * 2 + 128));
-  int threads, grid;
+  int threads, grid, grid_y;
   const double sample_bytes = 2.0 * hw * C * (2 + (add0 ? 1 : 0) + (add1 ? 1 : 0));
-  gn_team_geometry(C, hw, n, resident[ki], sample_bytes, &t, &threads, &grid);
+  gn_team_geometry(C, hw, n, resident[ki], sample_bytes, &t, &threads, &grid, &grid_y);
   if (t.team_size > 1)
     DDPM_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * static_cast<size_t>(n) * C * 2 + sizeof(int) * n, stream));
   void* args[] = {&s, &t, &stats, &gamma, &beta, &dyp, &lddy, &sums, &counters, &o};
@@ -995,7 +1041,7 @@ extern "C" int ddpm_gn_bwd(const void* x0, int c0, long long ld0, const void* x1
   if (t.team_size > 1)
     DDPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, stream));
   else
-    DDPM_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, stream));
+    DDPM_CUDA(cudaLaunchKernel(fn, dim3(grid, grid_y), dim3(threads), args, smem, stream));
   if (int e = check_launch("gn_bwd_fused_kernel")) return e;
   if (dgamma || dbeta) {
     gn_bwd_dparam_kernel<<<(C + 7) / 8, kGnThreads, 0, stream>>>(sums, n, C, dgamma, dbeta);
