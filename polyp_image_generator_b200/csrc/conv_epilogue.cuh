@@ -120,6 +120,58 @@ __device__ __forceinline__ float warp_granule_sums(float (&a)[8], int lane) {
 }
 __device__ __forceinline__ int epi_granule_of(int lane) { return (lane >> 2) & 7; }
 
+// Build-time switches of the epilogue arithmetic.  All four cut the static instruction count of a chunk row (902 -> 805
+// SASS instructions with all of them on), and none of them paid: timed against each other in one process per library
+// (profiles/epi_variants.sh, profiles/r2_epilogue_variants.md) they move the fused variants of the 128->128 conv by
+// -5 ... +15 %, mostly in branches they do not touch -- the kernel is ONE function whose variants share a register
+// allocation (168 registers, 13-22 spilled), so an edit in one branch reshuffles the spills of the others.  They stay
+// off; what did pay is the two-element conversion in the forward-statistics branch below (-17 / -22 us).
+#ifndef EPI_PACKED_ADDS
+#define EPI_PACKED_ADDS 0      // bias / temb / residual adds as packed fp32x2 instructions
+#endif
+#ifndef EPI_PACKED_GNACC
+#define EPI_PACKED_GNACC 0     // GroupNorm-backward column partials with packed fp32x2 instructions
+#endif
+#ifndef EPI_CSUM_PAIRS
+#define EPI_CSUM_PAIRS 0       // forward-statistics partials kept as pairs until the per-chunk reduction
+#endif
+#ifndef EPI_SILU_FORM2
+#define EPI_SILU_FORM2 0       // silu'(z) = (1 + t + (z/2)(1 - t^2)) / 2 instead of the sigmoid form
+#endif
+
+// (a, b) += (x, y) as ONE packed fp32x2 add
+__device__ __forceinline__ void epi_add2(float& a, float& b, float x, float y) {
+#if EPI_PACKED_ADDS
+  const float2 r = __fadd2_rn(make_float2(a, b), make_float2(x, y));
+  a = r.x;
+  b = r.y;
+#else
+  a += x;
+  b += y;
+#endif
+}
+
+// Epilogue specialisation of a kernel instantiation: the fused variants (statistics, GroupNorm backward, residual) are
+// runtime branches of ONE epilogue, and a kernel that carries all of them shares one register allocation between them
+// (168 registers, 13+ spilled in the CTA-pair halo conv).  Forcing the flags a launch cannot have to constants lets
+// the compiler drop the other variants' code and registers from that instantiation.
+enum : int { kEpiAny = -1, kEpiLean = 0, kEpiRes = 1, kEpiStats = 2, kEpiGnBwd = 3 };
+template <int MODE>
+__device__ __forceinline__ EpiParams epi_specialize(EpiParams e) {
+  if (MODE == kEpiLean || MODE == kEpiRes) {      // no fused reduction
+    e.gsums = nullptr; e.gstats = 0; e.gx0 = nullptr; e.gx1 = nullptr; e.gcoef = nullptr; e.gsilu = 0;
+  }
+  if (MODE == kEpiLean) { e.res = nullptr; e.split = 0; }
+  if (MODE == kEpiStats) { e.gstats = 1; e.gx0 = nullptr; e.gx1 = nullptr; e.gcoef = nullptr; e.gsilu = 0; }
+  if (MODE == kEpiGnBwd) e.gstats = 0;
+  return e;
+}
+// host side: the specialisation a launch with these parameters may use
+inline int epi_mode_of(const EpiParams& e) {
+  if (e.gsums == nullptr) return (e.res != nullptr || e.split) ? kEpiRes : kEpiLean;
+  return e.gstats ? kEpiStats : kEpiGnBwd;
+}
+
 struct EpiX {
   uint32_t w[16];   // 32 bf16 channels at this thread's pixel: the GroupNorm input (backward fusion) or the residual
 };
@@ -159,7 +211,7 @@ __device__ __forceinline__ void epi_prefetch_side(const EpiParams& e, bool valid
 
 // Per-thread column partials of the fused reductions, accumulated over the row blocks that share a 32-column chunk and
 // reduced across the warp ONCE (epi_reduce): GroupNorm-backward fusion a[j] = dz, b[j] = dz * x per column;
-// forward statistics a[k] = sum, b[k] = sum of squares per 4-channel granule (k < 8).
+// forward statistics a[2k] + a[2k+1] = sum, b[2k] + b[2k+1] = sum of squares per 4-channel granule (k < 8).
 struct EpiAcc {
   float a[32];
   float b[32];
@@ -183,7 +235,8 @@ __device__ __forceinline__ void epi_math(const EpiParams& e, float (&v)[32], boo
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = *reinterpret_cast<const float4*>(e.bias + col + j);
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        epi_add2(v[j], v[j + 1], b.x, b.y);
+        epi_add2(v[j + 2], v[j + 3], b.z, b.w);
       }
     }
     if (e.temb) {
@@ -191,33 +244,25 @@ __device__ __forceinline__ void epi_math(const EpiParams& e, float (&v)[32], boo
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = *reinterpret_cast<const float4*>(t + j);
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        epi_add2(v[j], v[j + 1], b.x, b.y);
+        epi_add2(v[j + 2], v[j + 3], b.z, b.w);
       }
     }
     if (e.res) {
       if (PREF && !epi_slot_is_gn(e)) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v[2 * j] += bf16lo_f(xin.w[j]);
-          v[2 * j + 1] += bf16hi_f(xin.w[j]);
-        }
+        for (int j = 0; j < 16; ++j) epi_add2(v[2 * j], v[2 * j + 1], bf16lo_f(xin.w[j]), bf16hi_f(xin.w[j]));
       } else {
         uint32_t rw[16];
         ld64B(e.res + pix * e.ldr + col, rw, e.wide != 0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v[2 * j] += bf16lo_f(rw[j]);
-          v[2 * j + 1] += bf16hi_f(rw[j]);
-        }
+        for (int j = 0; j < 16; ++j) epi_add2(v[2 * j], v[2 * j + 1], bf16lo_f(rw[j]), bf16hi_f(rw[j]));
       }
       if (e.split) {      // low halves of the split residual
         uint32_t rw[16];
         ld64B(e.res + pix * e.ldr + e.Cout + col, rw, e.wide != 0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v[2 * j] += bf16lo_f(rw[j]);
-          v[2 * j + 1] += bf16hi_f(rw[j]);
-        }
+        for (int j = 0; j < 16; ++j) epi_add2(v[2 * j], v[2 * j + 1], bf16lo_f(rw[j]), bf16hi_f(rw[j]));
       }
     }
   }
@@ -234,10 +279,18 @@ __device__ __forceinline__ void epi_math(const EpiParams& e, float (&v)[32], boo
         const float2 p0 = make_float2(bf16lo_f(w0), bf16hi_f(w0));
         const float2 p1 = make_float2(bf16lo_f(w1), bf16hi_f(w1));
         v[4 * k] = p0.x; v[4 * k + 1] = p0.y; v[4 * k + 2] = p1.x; v[4 * k + 3] = p1.y;
+#if EPI_CSUM_PAIRS
+        // per-granule partials stay PAIRS (a[2k], a[2k+1]) until epi_reduce folds them once per chunk
+        const float2 sa = __fadd2_rn(__fadd2_rn(p0, p1), make_float2(acc.a[2 * k], acc.a[2 * k + 1]));
+        const float2 sq = __ffma2_rn(p1, p1, __ffma2_rn(p0, p0, make_float2(acc.b[2 * k], acc.b[2 * k + 1])));
+        acc.a[2 * k] = sa.x; acc.a[2 * k + 1] = sa.y;
+        acc.b[2 * k] = sq.x; acc.b[2 * k + 1] = sq.y;
+#else
         const float2 sa = __fadd2_rn(p0, p1);
         const float2 sq = __ffma2_rn(p1, p1, __fmul2_rn(p0, p0));
-        acc.a[k] += sa.x + sa.y;
-        acc.b[k] += sq.x + sq.y;
+        acc.a[2 * k] += sa.x + sa.y;
+        acc.b[2 * k] += sq.x + sq.y;
+#endif
       }
     }
   } else if (GN && e.gsums != nullptr) {
@@ -254,22 +307,45 @@ __device__ __forceinline__ void epi_math(const EpiParams& e, float (&v)[32], boo
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const float4 c4 = cf[j / 2];   // (ka_j, ka_j+1, kb_j, kb_j+1), warp-uniform address
+          // silu'(z) = s + z s (1 - s), s = (1 + t) / 2, t = tanh(z / 2)  =>  silu'(z) = (1 + t + (z/2)(1 - t^2)) / 2:
+          // 6 packed instructions + 2 MUFU per channel pair (the sigmoid form took 7 + 2)
           const float2 z = __ffma2_rn(make_float2(x[j], x[j + 1]), make_float2(c4.x, c4.y), make_float2(c4.z, c4.w));
           const float2 h = __fmul2_rn(z, make_float2(0.5f, 0.5f));
+#if EPI_SILU_FORM2
+          const float2 t = make_float2(epi_tanh(h.x), epi_tanh(h.y));
+          const float2 w = __ffma2_rn(make_float2(-t.x, -t.y), t, make_float2(1.f, 1.f));
+          const float2 r = __ffma2_rn(h, w, t);
+          const float2 vh = __fmul2_rn(make_float2(v[j], v[j + 1]), make_float2(0.5f, 0.5f));
+          const float2 dz = __ffma2_rn(vh, r, vh);
+#else
           const float2 sg = __ffma2_rn(make_float2(epi_tanh(h.x), epi_tanh(h.y)), make_float2(0.5f, 0.5f),
                                        make_float2(0.5f, 0.5f));
           const float2 om = __ffma2_rn(sg, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
           const float2 u = __ffma2_rn(z, om, make_float2(1.f, 1.f));
           const float2 dz = __fmul2_rn(__fmul2_rn(make_float2(v[j], v[j + 1]), sg), u);
+#endif
           v[j] = dz.x;
           v[j + 1] = dz.y;
         }
       }
+#if EPI_PACKED_GNACC
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float2 ra = __fadd2_rn(make_float2(acc.a[j], acc.a[j + 1]), make_float2(v[j], v[j + 1]));
+        acc.a[j] = ra.x;
+        acc.a[j + 1] = ra.y;
+        const float2 r = __ffma2_rn(make_float2(v[j], v[j + 1]), make_float2(x[j], x[j + 1]),
+                                    make_float2(acc.b[j], acc.b[j + 1]));
+        acc.b[j] = r.x;
+        acc.b[j + 1] = r.y;
+      }
+#else
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         acc.a[j] += v[j];
         acc.b[j] = fmaf(v[j], x[j], acc.b[j]);
       }
+#endif
     }
   }
 }
@@ -304,7 +380,7 @@ __device__ __forceinline__ void epi_reduce(const EpiParams& e, int lane, EpiAcc&
   if (e.gstats) {
     float g1[8], g2[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { g1[k] = acc.a[k]; g2[k] = acc.b[k]; }
+    for (int k = 0; k < 8; ++k) { g1[k] = acc.a[2 * k] + acc.a[2 * k + 1]; g2[k] = acc.b[2 * k] + acc.b[2 * k + 1]; }
     t1 += warp_granule_sums(g1, lane);
     t2 += warp_granule_sums(g2, lane);
   } else {

@@ -344,6 +344,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // (the peer's TMA signals them through their shared::cluster address); "empty" barriers live in both CTAs and are
 // released by multicast tcgen05.commit; the accumulator-empty barrier of the leader collects both epilogues.
 // =====================================================================================================
+template <int MODE>      // epilogue specialisation (conv_epilogue.cuh::epi_specialize); kEpiAny = all variants at run time
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloPairThreads, 1)
 conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ HaloParams p) {
@@ -564,6 +565,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   } else {
     setmaxnreg_inc<224>();
     // ---------------- epilogue (8 warps per CTA; each CTA drains its own TMEM = its own image) ----------------
+    const EpiParams epi = epi_specialize<MODE>(p.epi);
     const int q = warp & 3;
     const int half = warp >> 2;
     uint32_t acc = 0, aph = 0;
@@ -585,15 +587,15 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       {
         int col, u; bool valid; long long pix;
         geom(0, col, valid, pix, u);
-        epi_load_x(p.epi, valid, pix, col, x0);
+        epi_load_x(epi, valid, pix, col, x0);
         geom(1, col, valid, pix, u);
-        epi_load_x(p.epi, valid, pix, col, x1);
+        epi_load_x(epi, valid, pix, col, x1);
         geom(2, col, valid, pix, u);
-        epi_load_x(p.epi, valid, pix, col, x2);
+        epi_load_x(epi, valid, pix, col, x2);
         geom(3, col, valid, pix, u);
-        epi_load_x(p.epi, valid, pix, col, x3);
+        epi_load_x(epi, valid, pix, col, x3);
       }
-      const int pt_next = (p.epi.res != nullptr || epi_slot_is_gn(p.epi)) ? feed.peek() : -1;
+      const int pt_next = (epi.res != nullptr || epi_slot_is_gn(epi)) ? feed.peek() : -1;
       if (pt_next >= 0) {
         // side input of the NEXT tile of this CTA -> L2, one whole tile ahead of its first use
         int img2, xs2, q02, nt2; bool ok2;
@@ -602,7 +604,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         for (int u2 = 0; u2 < 2; ++u2) {
           const int slot = q02 + u2 * 128 + q * 32 + lane;
           const int h2 = slot / p.Wp, w2 = slot - h2 * p.Wp - 1;
-          epi_prefetch_side(p.epi, ok2 && (w2 >= 0) && (w2 < p.Ws) && (h2 < p.H),
+          epi_prefetch_side(epi, ok2 && (w2 >= 0) && (w2 < p.Ws) && (h2 < p.H),
                             (static_cast<long long>(img2) * p.H + h2) * p.W + xs2 + w2, nt2 * 128 + half * 64, 64);
         }
       }
@@ -625,12 +627,12 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epi_math<true, true>(p.epi, v, valid, img, pix, col, u == 0 ? x0 : x1, racc);
-          epi_store(p.epi, v, valid, pix, col);
+          epi_math<true, true>(epi, v, valid, img, pix, col, u == 0 ? x0 : x1, racc);
+          epi_store(epi, v, valid, pix, col);
         }
         float t1 = 0.f, t2 = 0.f;
-        epi_reduce<true>(p.epi, lane, racc, t1, t2);
-        epi_flush_sums(p.epi, img_ok ? img : -1, col, lane, t1, t2);
+        epi_reduce<true>(epi, lane, racc, t1, t2);
+        epi_flush_sums(epi, img_ok ? img : -1, col, lane, t1, t2);
         x0 = x2;
         x1 = x3;
       }
@@ -745,10 +747,16 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
     pp.total_tiles = ((p.units + 1) / 2) * p.tiles_per_img * p.n_tiles;
     const size_t psmem = fixed + static_cast<size_t>(pst) * (kHaloBBytes / 2);
     if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 64)) return e;
-    static size_t pconfigured = 0;
-    if (psmem > pconfigured) {
-      DDPM_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-      pconfigured = psmem;
+    // one instantiation per epilogue variant (DDPM_HALO_SPECIALIZE=0: the all-variants kernel for every launch)
+    using PairFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const HaloParams);
+    static const PairFn fns[5] = {conv_halo_pair_kernel<kEpiAny>, conv_halo_pair_kernel<kEpiLean>,
+                                  conv_halo_pair_kernel<kEpiRes>, conv_halo_pair_kernel<kEpiStats>,
+                                  conv_halo_pair_kernel<kEpiGnBwd>};
+    const int fi = env_int("DDPM_HALO_SPECIALIZE", 1) != 0 ? 1 + epi_mode_of(pp.epi) : 0;
+    static size_t pconfigured[5] = {0, 0, 0, 0, 0};
+    if (psmem > pconfigured[fi]) {
+      DDPM_CUDA(cudaFuncSetAttribute(fns[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      pconfigured[fi] = psmem;
     }
     int pgrid = 2 * pp.total_tiles < kNumSMs ? 2 * pp.total_tiles : (kNumSMs / 2) * 2;
     pp.sched_ctr = nullptr;
@@ -760,7 +768,7 @@ int launch_conv_halo(const ::ddpm_conv_args* a, cudaStream_t stream) {
       if (pool == nullptr) DDPM_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&pool), g_halo_tile_ctr));
       pp.sched_ctr = pool + (seq.fetch_add(1) % kTileCtrPool);
     }
-    conv_halo_pair_kernel<<<pgrid, kHaloPairThreads, psmem, stream>>>(ma0, ma1, mb, pp);
+    fns[fi]<<<pgrid, kHaloPairThreads, psmem, stream>>>(ma0, ma1, mb, pp);
     return check_launch("conv_halo_pair_kernel");
   }
   if (int e = make_wgt_map(&mb, a->wgt, k_total, a->ldw, a->cout, 128)) return e;
