@@ -755,3 +755,56 @@ def test_fp32_faithful_inference_program_matches_fp32_oracle(emu_backend):
         m.inference_precision = "bf16"
         with torch.no_grad():
             assert ((m(x, t).sample - want).norm() / want.norm()).item() < 1e-3     # emulation runs the bf16 path in fp32
+
+
+def test_zero_pool_hands_out_disjoint_zero_slices_and_grows():
+    """unet._ZeroPool: one fill per pass; slices are zero, 128-byte aligned and disjoint; a pass that needs more than the
+    previous one gets fresh zero tensors and the next pass a larger buffer; buffers of earlier passes are never reused
+    (gradients of an accumulating loop may still alias them)."""
+    from polyp_image_generator_b200.unet import _ZeroPool
+    dev = torch.device("cpu")
+    zp = _ZeroPool().begin(dev)
+    a, b = zp.take((3, 5), dev), zp.take((7,), dev)          # first pass: nothing learned yet -> plain zero tensors
+    assert a.shape == (3, 5) and b.shape == (7,) and not a.any() and not b.any()
+    a.fill_(1.0)
+    zp.begin(dev)
+    assert zp.need == 2 * _ZeroPool.ALIGN
+    c, d = zp.take((3, 5), dev), zp.take((7,), dev)
+    assert c.untyped_storage().data_ptr() == d.untyped_storage().data_ptr() == zp.buf.untyped_storage().data_ptr()
+    assert (d.data_ptr() - c.data_ptr()) == 4 * _ZeroPool.ALIGN and not c.any() and not d.any()
+    c.fill_(2.0)
+    assert not d.any()
+    e = zp.take((100,), dev)                                  # more than the pass had last time: own tensor
+    assert e.untyped_storage().data_ptr() != zp.buf.untyped_storage().data_ptr() and not e.any()
+    old = zp.buf
+    zp.begin(dev)
+    assert zp.buf is not old and zp.buf.numel() >= 2 * _ZeroPool.ALIGN + 100 and not zp.buf.any()
+    assert (c == 2.0).all()                                   # the previous pass's slices are left alone
+
+
+def test_bias_gradient_fusion_equals_separate_reductions(emu_backend, monkeypatch):
+    """unet._colsum_target: the bias gradient of the conv that consumes a block's result rides on the block's last
+    GroupNorm-backward pass (out_c).  Same gradients as the separate column reductions, and fewer reduce_hw launches."""
+    from polyp_image_generator_b200 import UNet2DModel
+
+    def grads(fusion):
+        monkeypatch.setenv("DDPM_BIAS_FUSION", fusion)
+        torch.manual_seed(11)
+        m = UNet2DModel(**_small_cfg(32))
+        x, t = torch.randn(2, 3, 32, 32), torch.tensor([5, 700])
+        calls = {"n": 0}
+        real = emu_backend.reduce_hw
+
+        def counted(*a, **k):
+            calls["n"] += 1
+            return real(*a, **k)
+        monkeypatch.setattr(emu_backend, "reduce_hw", counted)
+        m(x, t).sample.square().mean().backward()
+        monkeypatch.setattr(emu_backend, "reduce_hw", real)
+        return {n: p.grad.clone() for n, p in m.named_parameters()}, calls["n"]
+
+    g1, n1 = grads("1")
+    g0, n0 = grads("0")
+    assert n1 < n0, (n1, n0)
+    for k in g0:
+        assert torch.allclose(g1[k], g0[k], rtol=1e-4, atol=1e-6), k

@@ -622,3 +622,33 @@ def test_full_size_properties_128(dev):
     assert torch.isfinite(y).all() and y.shape == x.shape
     assert rel(y, y2) < 1.5e-2        # see test_unet_forward_backward_vs_oracle: bf16-noise level, not bit-exact
     assert rel(y_sub, y[2:5]) < 1.5e-2
+
+
+def test_bias_gradient_fusion_on_off_agree_on_the_full_model(dev, monkeypatch):
+    """The bias gradient of a conv = pixel sums of the gradient entering it.  With DDPM_BIAS_FUSION=1 (default) the
+    GroupNorm-backward pass that PRODUCES that gradient accumulates the sums (gn_bwd_apply out_c); with 0 a separate
+    column reduction reads the stored tensor again.  Full polyp model at 64x64: every bias gradient and the whole
+    gradient agree to the run-to-run noise of the bf16 path."""
+    from polyp_image_generator_b200 import UNet2DModel
+    from polyp_image_generator_b200.training import mse_loss
+    torch.manual_seed(21)
+    m = UNet2DModel(**oracle.polyp_unet_config(64)).to(dev).train()
+    x = torch.randn(4, 3, 64, 64, device=dev)
+    noise = torch.randn_like(x)
+    t = torch.randint(0, 1000, (4,), device=dev)
+
+    def grads(flag):
+        monkeypatch.setenv("DDPM_BIAS_FUSION", flag)
+        m.zero_grad(set_to_none=True)
+        mse_loss(m(x, t, return_dict=False)[0], noise).backward()
+        return {n: p.grad.detach().float().clone() for n, p in m.named_parameters()}
+
+    g1, g0, g1b = grads("1"), grads("0"), grads("1")
+    flat = lambda g: torch.cat([v.reshape(-1) for v in g.values()])
+    noise_floor = rel(flat(g1b), flat(g1))
+    assert rel(flat(g0), flat(g1)) < max(3 * noise_floor, 2e-3), (rel(flat(g0), flat(g1)), noise_floor)
+    worst = 0.0
+    for n in g1:
+        if n.endswith(".bias") and ("conv" in n) and g1[n].norm() > 1e-3 * flat(g1).norm():
+            worst = max(worst, rel(g0[n], g1[n]))
+    assert worst < 2e-2, worst
