@@ -754,7 +754,9 @@ class UNet2DModel(nn.Module):
 
         # ---- conv_in ----
         patches = ops.im2col3(x)                                   # [N, H, W, 64] bf16, one k-block
-        h = ops.conv_gemm(patches, None, taps_1x1(), self._cin_wf, c0, (N, H, W), bias=self._aview(P.cin_b, (c0,)))
+        cs = self._csum_for(st, (N, H, W), c0, generic=True)
+        h = self._tag(ops.conv_gemm(patches, None, taps_1x1(), self._cin_wf, c0, (N, H, W),
+                                    bias=self._aview(P.cin_b, (c0,)), csum=cs), cs)
         skips = [h]
 
         # ---- down ----
@@ -962,9 +964,18 @@ class UNet2DModel(nn.Module):
     # GroupNorm statistics ride on the epilogue of the 3x3 conv that PRODUCES the tensor (per-(sample, channel) moments,
     # conv_gemm(csum=...)); the GroupNorm forward is then one streaming pass instead of the two-phase team kernel.
     # (Not for conv_in / the stride-2 convs: they run on the generic kernel, where the reductions are exposed.)
-    def _csum_for(self, st, grid, cout):
+    def _csum_for(self, st, grid, cout, generic=False):
+        """generic: the producing conv runs on the generic kernel (conv_in, stride-2 convs), where the reductions are not
+        hidden behind the next tile's mainloop -- taken only for memory-bound producers at >= 64x64, whose consumers then
+        run the single-pass GroupNorm instead of the two-phase team kernel (in-process A/B: training step -0.8 %, sampling
+        forward -0.5 %; DDPM_GN_STATS_GENERIC=0 switches it off)."""
         ops = st.ops
-        if os.environ.get("DDPM_GN_STATS_FUSION", "1") == "0" or not ops.gn_stats_fusable(grid):
+        if generic:
+            if os.environ.get("DDPM_GN_STATS_GENERIC", "1") == "0" or grid[1] * grid[2] < 4096:
+                return None
+            if os.environ.get("DDPM_GN_STATS_FUSION", "1") == "0":
+                return None
+        elif os.environ.get("DDPM_GN_STATS_FUSION", "1") == "0" or not ops.gn_stats_fusable(grid):
             return None
         # the statistics are kept per 4-channel granule: usable when the consuming GroupNorm's groups are whole granules,
         # which holds whenever every concatenated source is a multiple of 4 * norm_num_groups channels (128 here)
@@ -1051,7 +1062,9 @@ class UNet2DModel(nn.Module):
         N, H, W, C = x.shape
         s2d = ops.space_to_depth(x)
         grid = (N, H // 2, W // 2)
-        out = ops.conv_gemm(s2d, None, taps_s2d(C, N, d.pad), d.conv.wf, C, grid, bias=self._bias(d.conv), src_n=4 * N)
+        cs = self._csum_for(st, grid, C, generic=True)
+        out = self._tag(ops.conv_gemm(s2d, None, taps_s2d(C, N, d.pad), d.conv.wf, C, grid, bias=self._bias(d.conv),
+                                      src_n=4 * N, csum=cs), cs)
         if st.tape is not None:
             st.tape.add(("down", d, SimpleNamespace(s2d=s2d, in_skip=in_skip, shape=(N, H, W, C), grid=grid)))
         return out
