@@ -197,7 +197,7 @@ def run_reference(args, rank):
 LORA_BWD_FRACTION = 0.741      # dgrad only downstream of down_blocks.4.attentions.0, wgrad only LoRA
 
 
-def run_lora_finetune(args, dev, world, rank, barrier):
+def run_lora_finetune(args, dev, world, rank, barrier, batch=None):
     """train_with_lora_all_classes.py:120-180 over the drop-in objects: celebahq-architecture UNet (1 head x 512,
     downsample_padding 0), r=8 / alpha=8 / dropout 0.3 adapters on to_q, to_k, to_v, to_out.0, everything else frozen;
     add_noise -> forward -> MSE -> backward (LoRA gradients only) -> all-reduce -> clip 1.0 -> AdamW, graph-replayed."""
@@ -205,7 +205,7 @@ def run_lora_finetune(args, dev, world, rank, barrier):
     from polyp_image_generator_b200 import DDPMScheduler, LoraConfig, UNet2DModel
     from polyp_image_generator_b200.graphs import GraphedTrainStep
     from polyp_image_generator_b200.model import celebahq_unet_config
-    S, B = args.lora_size, args.lora_batch
+    S, B = args.lora_size, (batch or args.lora_batch)
     torch.manual_seed(1)
     model = UNet2DModel(**celebahq_unet_config(S)).to(dev)
     model.add_adapter(LoraConfig(r=8, lora_alpha=8, target_modules=["to_q", "to_k", "to_v", "to_out.0"],
@@ -540,8 +540,11 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_lora:
         try:
             lora = run_lora_finetune(args, dev, world, rank, barrier)
+            if args.lora_batch2 > 0:     # "B = 8/GPU (reference train_batch_size) plus a B = 32 point"
+                lora["batch_%d_point" % args.lora_batch2] = run_lora_finetune(args, dev, world, rank, barrier,
+                                                                              batch=args.lora_batch2)
         except Exception as e:  # noqa: BLE001 -- a secondary section must not take the headline line down with it
-            lora = {"error": repr(e)[:300]}
+            lora = {"error": repr(e)[:300]} if lora is None else dict(lora, batch2_error=repr(e)[:300])
 
     # ---- optional per-op breakdown (after the timed regions; CUDA events around every C-ABI op) ----
     if args.breakdown:       # all ranks step together (DDP collectives); rank 0 reports
@@ -712,6 +715,7 @@ def main():
     ap.add_argument("--no-lora", action="store_true", help="skip the secondary LoRA fine-tune measurement")
     ap.add_argument("--lora-batch", type=int, default=8, help="per-GPU batch of the LoRA measurement "
                     "(config_diffusion.py:7 train_batch_size = 8)")
+    ap.add_argument("--lora-batch2", type=int, default=32, help="second per-GPU batch of the LoRA measurement (0: skip)")
     ap.add_argument("--lora-size", type=int, default=256)
     ap.add_argument("--no-sampling", action="store_true", help="skip the secondary sampling measurement")
     ap.add_argument("--sampling-batch", type=int, default=32, help="images per GPU in the sampling measurement")
