@@ -216,16 +216,22 @@ class GemmLora:
             self.at_ext = torch.zeros((self.cin, LORA_K), device=dev, dtype=dt)
             self.bt_ext = torch.zeros((LORA_K, self.cout), device=dev, dtype=dt)
         with torch.no_grad():
-            gobj.wf[:, k:].zero_()
-            self.a_ext.zero_()
-            self.bt_ext.zero_()
+            # the regions no active slot writes stay zero from one step to the next: clear only when the set of active
+            # slots (or the buffers) changed -- merge_adapter / unmerge_adapter, a new device
+            layout = (gobj.wf.data_ptr(), self.a_ext.data_ptr(), tuple(m.merged for _, m, _ in self.slots))
+            if layout != getattr(self, "_layout", None):
+                gobj.wf[:, k:].zero_()
+                self.a_ext.zero_()
+                self.bt_ext.zero_()
+                self._layout = layout
             for i, m, off in self.slots:
                 if m.merged:
                     continue
-                sB = (m.B.detach() * m.scaling).to(dt)
-                gobj.wf[i * self.ce:(i + 1) * self.ce, k + off:k + off + m.r] = sB
-                self.bt_ext[off:off + m.r, i * self.ce:(i + 1) * self.ce] = sB.t()
-                self.a_ext[off:off + m.r] = m.A.detach().to(dt)
+                B = m.B.detach()
+                # one launch each: fp32 product, rounded once on the store into the (strided) bf16 operand view
+                torch.mul(B, m.scaling, out=gobj.wf[i * self.ce:(i + 1) * self.ce, k + off:k + off + m.r])
+                torch.mul(B.t(), m.scaling, out=self.bt_ext[off:off + m.r, i * self.ce:(i + 1) * self.ce])
+                self.a_ext[off:off + m.r].copy_(m.A.detach())
             self.at_ext.copy_(self.a_ext.t())
 
     def forward_extra(self, ops, x2: torch.Tensor, training: bool, tick: Optional[torch.Tensor] = None):
