@@ -92,7 +92,10 @@ def add_adapter(model: nn.Module, cfg: LoraConfig, adapter_name: str = "default"
     if any(isinstance(m, LoraLinear) for m in model.modules()):
         raise ValueError(f"Adapter with name {adapter_name} already exists. Please use a different name.")
     targets = [cfg.target_modules] if isinstance(cfg.target_modules, str) else list(cfg.target_modules)
-    supported = ("to_q", "to_k", "to_v", "to_out.0")
+    # attention projections (folded into the projection GEMMs, GemmLora) and the per-block time-embedding projections
+    # (fp32 side computation on the [batch, channels] vectors, unet.UNet2DModel._temb_lora_*): the targets of
+    # config_diffusion.py:34-37 that exist in a UNet2DModel
+    supported = ("to_q", "to_k", "to_v", "to_out.0", "time_emb_proj")
     wrapped = []
     for name, module in list(model.named_modules()):
         if not isinstance(module, nn.Linear) or not _matches(name, targets):

@@ -436,6 +436,7 @@ class UNet2DModel(nn.Module):
                 if r.conv_shortcut is not None else None
             rec.temb_off = temb_off[0]
             temb_off[0] += r.out_channels
+            rec.temb_lora = r.time_emb_proj if hasattr(r.time_emb_proj, "base_layer") else None   # lora.LoraLinear
             P.resnets.append(rec)
             return rec
 
@@ -742,6 +743,7 @@ class UNet2DModel(nn.Module):
         e1 = ops.linear_f32(t_emb, w1, b1, False)
         emb = ops.linear_f32(e1, w2, b2, True)
         temb_all = ops.linear_f32(emb, wt, bt, True)           # [N, sum C] fp32
+        temb_lora = self._temb_lora_fwd(ops, emb, temb_all, training)
         st = SimpleNamespace(temb_all=temb_all, N=N, tape=tape, ops=ops,
                              d_temb_all=None, rng_tick=None, zeros=self._zero_pool("fwd", training, x.device))
         if training and any(g.lora is not None and g.lora.active and g.lora.p > 0.0 for g in P.gemms):
@@ -795,7 +797,7 @@ class UNet2DModel(nn.Module):
         out = ops.nhwc_to_nchw_f32(o32, cfg.out_channels)
         if training:
             tape.head = SimpleNamespace(patches=patches, t_emb=t_emb, e1=e1, emb=emb, h_last=h, stats=stats, a=a,
-                                        coef=coef_out)
+                                        coef=coef_out, temb_lora=temb_lora)
         self.last_launches = ops.launches - l0
         return out
 
@@ -879,6 +881,7 @@ class UNet2DModel(nn.Module):
         emb = ops.linear_f32(e1, self._aview(P.te.w2, (ted, ted)), self._aview(P.te.b2, (ted,)), True)
         temb_all = ops.linear_f32(emb, self._aview(P.temb_w_off, (P.temb_total, ted)),
                                   self._aview(P.temb_b_off, (P.temb_total,)), True)
+        self._temb_lora_fwd(ops, emb, temb_all, False)
 
         def conv(xs, gobj, taps_fn, cout, grid, **kw):
             """xs: split tensor [.., 2*cin]; one GEMM over [hi | lo | hi] against the layer's split operand."""
@@ -955,6 +958,43 @@ class UNet2DModel(nn.Module):
         out = ops.nhwc_to_nchw_f32(o32, cfg.out_channels)
         self.last_launches = ops.launches - l0
         return out
+
+    # ---- LoRA on time_emb_proj (config_diffusion.py:37 lists it among the candidate targets) ---------------------
+    # y_r += (alpha / r) * B_r (A_r dropout(SiLU(emb))) on the [batch, 512] embedding: fp32 side computation with the
+    # tiled SIMT linears, per adapter (each has its own dropout mask, drawn by torch's capture-safe Philox).
+    def _temb_lora_fwd(self, ops, emb, temb_all, training: bool):
+        recs = [r for r in self._plan.resnets if r.temb_lora is not None and not r.temb_lora.merged]
+        if not recs:
+            return None
+        xs = torch.nn.functional.silu(emb)
+        saved = []
+        for r in recs:
+            m = r.temb_lora
+            xd = torch.nn.functional.dropout(xs, m.p, True) if (training and m.p > 0.0) else xs
+            u = ops.linear_f32(xd, m.A.detach(), None, False)                   # [N, rank]
+            y = ops.linear_f32(u, m.B.detach(), None, False)                    # [N, cout]
+            temb_all[:, r.temb_off:r.temb_off + r.cout].add_(y, alpha=m.scaling)
+            saved.append((r, xd, u))
+        return saved if training else None
+
+    def _temb_lora_bwd(self, ops, saved, d_temb_all, zeros):
+        """dA / dB of every time_emb_proj adapter from the per-sample sums of d_h1 (d_temb_all) -> {id(param): grad}."""
+        grads = {}
+        for r, xd, u in saved:
+            m = r.temb_lora
+            g = d_temb_all[:, r.temb_off:r.temb_off + r.cout].contiguous()
+            dB = zeros((r.cout, m.r), g.device)
+            ops.linear_f32_wgrad(u, g, dB, None, False)
+            dU = ops.linear_f32_dgrad(g, m.B.detach(), None, False)              # [N, rank], still without alpha / r
+            dU.mul_(m.scaling)
+            dA = zeros((m.r, xd.shape[1]), g.device)
+            ops.linear_f32_wgrad(xd, dU, dA, None, False)
+            grads[id(m.A)] = dA
+            grads[id(m.B)] = dB.mul_(m.scaling)
+        return grads
+
+    def _temb_lora_active(self):
+        return any(r.temb_lora is not None and not r.temb_lora.merged for r in self._plan.resnets)
 
     # ---- blocks: forward (each records its backward closure on the tape) -------------------------------------
     def _norm_params(self, nobj: _Norm):
@@ -1185,6 +1225,13 @@ class UNet2DModel(nn.Module):
                 self._gview(G, P.cin_w, (c0, 9 * cfg.in_channels)).add_(R[:, :9 * cfg.in_channels])
         if st.wg_stream is not None:      # d_temb_all and every weight gradient are complete from here on
             torch.cuda.current_stream().wait_stream(st.wg_stream)
+        # ---- time_emb_proj adapters ----
+        st.temb_lora_grads = {}
+        if hd.temb_lora:
+            if self.time_embedding.linear_1.weight.requires_grad:
+                raise NotImplementedError("LoRA on time_emb_proj together with a trainable time-embedding MLP: the "
+                                          "adapters' contribution to d_emb is not implemented")
+            st.temb_lora_grads = self._temb_lora_bwd(ops, hd.temb_lora, d_temb_all, zp.take)
         # ---- time-embedding MLP ----
         if self._temb_trainable() or self.time_embedding.linear_1.weight.requires_grad:
             wt = self._aview(P.temb_w_off, (P.temb_total, ted))
@@ -1260,7 +1307,7 @@ class UNet2DModel(nn.Module):
 
     def _head_trainable(self):
         return self.conv_in.weight.requires_grad or self.time_embedding.linear_1.weight.requires_grad or \
-            self._temb_trainable()
+            self._temb_trainable() or self._temb_lora_active()
 
     def _temb_trainable(self):
         return any(self._base(r.mod.time_emb_proj).weight.requires_grad for r in self._plan.resnets)
@@ -1268,7 +1315,8 @@ class UNet2DModel(nn.Module):
     def _step_trainable(self, kind, rec):
         if kind == "resnet":
             gl = [rec.conv1, rec.conv2] + ([rec.short] if rec.short else [])
-            return any(x.trainable or x.bias_trainable for x in gl) or rec.norm1.trainable or rec.norm2.trainable
+            return any(x.trainable or x.bias_trainable for x in gl) or rec.norm1.trainable or rec.norm2.trainable or \
+                (rec.temb_lora is not None and not rec.temb_lora.merged)
         if kind == "attn":
             return any(x.trainable or x.bias_trainable or x.lora is not None for x in (rec.qkv, rec.out)) or \
                 rec.norm.trainable
@@ -1437,6 +1485,7 @@ class UNet2DModel(nn.Module):
         for gobj in self._plan.gemms:
             if gobj.lora is not None:
                 out.update(gobj.lora.grads)
+        out.update(getattr(st, "temb_lora_grads", {}))
         return out
 
 
@@ -1457,7 +1506,8 @@ class _UNetFunction(torch.autograd.Function):
         views = model._grad_views(G, st)
         hook = getattr(model, "_grad_ready_hook", None)
         if hook is not None:              # DDP: all-reduce the flat gradient arena (+ LoRA grads)
-            hook(G, [g for gobj in model._plan.gemms if gobj.lora is not None for g in gobj.lora.grads.values()])
+            hook(G, [g for gobj in model._plan.gemms if gobj.lora is not None for g in gobj.lora.grads.values()] +
+                 list(getattr(st, "temb_lora_grads", {}).values()))
         grads = tuple(views.get(id(p)) for p in ctx.params)
         ctx.tape = None
         return (None, None, None, None) + grads

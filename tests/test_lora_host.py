@@ -53,7 +53,7 @@ def test_unknown_targets_raise(emu_backend):
     with pytest.raises(ValueError, match="not found"):
         m.add_adapter(LoraConfig(target_modules=["proj_in"]))
     with pytest.raises(NotImplementedError):
-        m.add_adapter(LoraConfig(target_modules=["time_emb_proj"]))
+        m.add_adapter(LoraConfig(target_modules=["linear_1"]))       # time-embedding MLP linears: not a supported target
 
 
 @pytest.mark.parametrize("targets", [("to_q", "to_k", "to_v", "to_out.0"), ("to_q", "to_v")])
@@ -253,3 +253,69 @@ def test_polyp_generator_model_wrapper_lora_plus_unfreezing(emu_backend, capsys)
         else:
             assert p.grad is None, n
     assert seen == 48 + 6
+
+
+@pytest.mark.parametrize("targets", [("time_emb_proj",), ("to_q", "to_k", "to_v", "to_out.0", "time_emb_proj")])
+def test_lora_on_time_emb_proj_matches_oracle(emu_backend, targets):
+    """config_diffusion.py:37 lists time_emb_proj among the candidate LoRA targets: the adapters on the 32 per-block
+    time-embedding projections (fp32 side computation on the [batch, 512] embedding) against the oracle's peft
+    restatement -- keys, forward, every adapter gradient, merge, and the fp32-faithful inference program."""
+    from polyp_image_generator_b200.lora import merge_adapter, unmerge_adapter
+    m, om = _pair(targets=targets)
+    assert list(m.state_dict().keys()) == list(om.state_dict().keys())
+    n_res = sum(1 for n, _ in om.named_modules() if n.endswith("time_emb_proj"))
+    m.train()
+    om.train()
+    x, t = torch.randn(2, 3, 32, 32), torch.tensor([3, 600])
+    y, yo = m(x, t).sample, om(x, t).sample
+    assert ((y - yo).norm() / yo.norm()).item() < 1e-5
+    tgt = torch.randn_like(y)
+    torch.nn.functional.mse_loss(y, tgt).backward()
+    torch.nn.functional.mse_loss(yo, tgt).backward()
+    og = dict(om.named_parameters())
+    tot = sum(p.grad.norm() ** 2 for p in om.parameters() if p.grad is not None) ** 0.5
+    n_temb = 0
+    for n, p in m.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None, n
+            continue
+        g = og[n].grad
+        assert ((p.grad - g).norm() / (g.norm() + 1e-4 * tot)).item() < 2e-3, n
+        n_temb += "time_emb_proj" in n
+    assert n_temb == 2 * n_res and n_res >= 20
+    # fp32-faithful inference program carries the adapters too
+    m.eval()
+    om.eval()
+    m.inference_precision = "fp32"
+    with torch.no_grad():
+        assert ((m(x, t).sample - om(x, t).sample).norm() / yo.norm()).item() < 1e-4
+    m.inference_precision = "bf16"
+    # merge: weights within 1e-5 of the oracle's, forward unchanged, unmerge restores
+    with torch.no_grad():
+        y_un = m(x, t).sample
+    merge_adapter(m)
+    oracle.merge_adapter(om)
+    for (n, p), (_, po) in zip(m.named_parameters(), om.named_parameters()):
+        assert torch.allclose(p, po, rtol=0, atol=1e-5), n
+    with torch.no_grad():
+        assert ((m(x, t).sample - y_un).norm() / y_un.norm()).item() < 1e-5
+    unmerge_adapter(m)
+    with torch.no_grad():
+        assert ((m(x, t).sample - y_un).norm() / y_un.norm()).item() < 1e-5
+
+
+def test_lora_on_time_emb_proj_dropout_trains_and_is_off_in_eval(emu_backend):
+    m, _ = _pair(dropout=0.3, targets=("time_emb_proj",))
+    x, t = torch.randn(2, 3, 32, 32), torch.tensor([3, 600])
+    m.eval()
+    with torch.no_grad():
+        a, b = m(x, t).sample, m(x, t).sample
+    assert torch.equal(a, b)                       # no dropout outside training
+    m.train()
+    torch.manual_seed(1)
+    y1 = m(x, t).sample
+    y2 = m(x, t).sample
+    assert not torch.equal(y1, y2)                 # fresh masks per forward
+    y2.square().mean().backward()
+    gs = [p.grad for n, p in m.named_parameters() if "lora_" in n]
+    assert gs and all(g is not None and torch.isfinite(g).all() for g in gs)

@@ -652,3 +652,51 @@ def test_bias_gradient_fusion_on_off_agree_on_the_full_model(dev, monkeypatch):
         if n.endswith(".bias") and ("conv" in n) and g1[n].norm() > 1e-3 * flat(g1).norm():
             worst = max(worst, rel(g0[n], g1[n]))
     assert worst < 2e-2, worst
+
+
+def test_lora_on_time_emb_proj_vs_oracle_and_self_consistency(dev):
+    """LoRA on the per-block time-embedding projections (config_diffusion.py:37 candidate target; fp32 side computation
+    on the tiled SIMT linears): forward against the oracle, and -- with the base projections also trainable -- the
+    identities dB = s dW A^T, dA = s B^T dW between the adapter gradients and the base weight gradient of the SAME
+    backward pass (common-mode bf16 noise of the UNet cancels; the LoRA arithmetic itself is fp32)."""
+    from polyp_image_generator_b200 import LoraConfig, UNet2DModel
+    from polyp_image_generator_b200.training import mse_loss
+    cfg = _small_cfg(64)
+    torch.manual_seed(9)
+    om = oracle.UNet2DModel(**cfg)
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(om.state_dict())
+    tg = ["to_q", "to_v", "time_emb_proj"]
+    oracle.add_adapter(om, oracle.LoraConfig(r=8, lora_alpha=16, target_modules=tg, init_lora_weights="gaussian"))
+    m.add_adapter(LoraConfig(r=8, lora_alpha=16, target_modules=tg, init_lora_weights="gaussian"))
+    sd = {k: torch.randn_like(v) * 0.05 for k, v in oracle.lora_state_dict(om).items()}
+    om.load_state_dict(sd, strict=False)
+    m.load_state_dict(sd, strict=False)
+    assert list(m.state_dict().keys()) == list(om.state_dict().keys())
+    m.to(dev).train()
+    x, t, nz = torch.randn(3, 3, 64, 64), torch.tensor([4, 400, 900]), torch.randn(3, 3, 64, 64)
+    pred = m(x.to(dev), t.to(dev)).sample
+    assert rel(pred, om(x, t).sample) < 2e-2
+    for n, p in m.named_parameters():
+        if n.endswith("time_emb_proj.base_layer.weight"):
+            p.requires_grad_(True)
+    pred = m(x.to(dev), t.to(dev)).sample
+    mse_loss(pred, nz.to(dev)).backward()
+    named = dict(m.named_parameters())
+    checked = 0
+    for n, p in named.items():
+        if ".time_emb_proj.lora_A." not in n:
+            continue
+        base = n.split(".lora_A.")[0]
+        dW = named[base + ".base_layer.weight"].grad.float()
+        A, Bm = named[base + ".lora_A.default.weight"], named[base + ".lora_B.default.weight"]
+        s = 16 / 8
+        assert rel(Bm.grad, s * dW @ A.detach().t()) < 1e-4, base
+        assert rel(A.grad, s * Bm.detach().t() @ dW) < 1e-4, base
+        checked += 1
+    assert checked >= 20
+    m.eval()
+    m.inference_precision = "fp32"
+    om.eval()
+    with torch.no_grad():
+        assert rel(m(x.to(dev), t.to(dev)).sample, om(x, t).sample) < 1e-4
