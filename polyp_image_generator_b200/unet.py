@@ -970,17 +970,21 @@ class UNet2DModel(nn.Module):
         saved = []
         for r in recs:
             m = r.temb_lora
-            xd = torch.nn.functional.dropout(xs, m.p, True) if (training and m.p > 0.0) else xs
+            keep = None
+            if training and m.p > 0.0:      # nn.Dropout: keep with probability 1 - p, scale the kept by 1 / (1 - p)
+                keep = (torch.rand_like(xs) >= m.p).to(xs.dtype).mul_(1.0 / (1.0 - m.p))
+            xd = xs * keep if keep is not None else xs
             u = ops.linear_f32(xd, m.A.detach(), None, False)                   # [N, rank]
             y = ops.linear_f32(u, m.B.detach(), None, False)                    # [N, cout]
             temb_all[:, r.temb_off:r.temb_off + r.cout].add_(y, alpha=m.scaling)
-            saved.append((r, xd, u))
+            saved.append((r, xd, u, keep))
         return saved if training else None
 
-    def _temb_lora_bwd(self, ops, saved, d_temb_all, zeros):
-        """dA / dB of every time_emb_proj adapter from the per-sample sums of d_h1 (d_temb_all) -> {id(param): grad}."""
-        grads = {}
-        for r, xd, u in saved:
+    def _temb_lora_bwd(self, ops, saved, d_temb_all, zeros, need_dx: bool):
+        """dA / dB of every time_emb_proj adapter from the per-sample sums of d_h1 (d_temb_all) -> ({id(param): grad},
+        d_xs): d_xs = the adapters' gradient w.r.t. SiLU(emb) (None unless need_dx: a trainable time-embedding MLP)."""
+        grads, d_xs = {}, None
+        for r, xd, u, keep in saved:
             m = r.temb_lora
             g = d_temb_all[:, r.temb_off:r.temb_off + r.cout].contiguous()
             dB = zeros((r.cout, m.r), g.device)
@@ -991,7 +995,12 @@ class UNet2DModel(nn.Module):
             ops.linear_f32_wgrad(xd, dU, dA, None, False)
             grads[id(m.A)] = dA
             grads[id(m.B)] = dB.mul_(m.scaling)
-        return grads
+            if need_dx:
+                dx = ops.linear_f32_dgrad(dU, m.A.detach(), None, False)         # [N, 512]
+                if keep is not None:
+                    dx.mul_(keep)
+                d_xs = dx if d_xs is None else d_xs.add_(dx)
+        return grads, d_xs
 
     def _temb_lora_active(self):
         return any(r.temb_lora is not None and not r.temb_lora.merged for r in self._plan.resnets)
@@ -1226,12 +1235,10 @@ class UNet2DModel(nn.Module):
         if st.wg_stream is not None:      # d_temb_all and every weight gradient are complete from here on
             torch.cuda.current_stream().wait_stream(st.wg_stream)
         # ---- time_emb_proj adapters ----
-        st.temb_lora_grads = {}
+        st.temb_lora_grads, d_xs_lora = {}, None
         if hd.temb_lora:
-            if self.time_embedding.linear_1.weight.requires_grad:
-                raise NotImplementedError("LoRA on time_emb_proj together with a trainable time-embedding MLP: the "
-                                          "adapters' contribution to d_emb is not implemented")
-            st.temb_lora_grads = self._temb_lora_bwd(ops, hd.temb_lora, d_temb_all, zp.take)
+            st.temb_lora_grads, d_xs_lora = self._temb_lora_bwd(
+                ops, hd.temb_lora, d_temb_all, zp.take, self.time_embedding.linear_1.weight.requires_grad)
         # ---- time-embedding MLP ----
         if self._temb_trainable() or self.time_embedding.linear_1.weight.requires_grad:
             wt = self._aview(P.temb_w_off, (P.temb_total, ted))
@@ -1241,6 +1248,9 @@ class UNet2DModel(nn.Module):
                                      self._gview(G, P.temb_b_off, (P.temb_total,)), True)
             if self.time_embedding.linear_1.weight.requires_grad:
                 d_emb = ops.linear_f32_dgrad(d_temb_all, wt, hd.emb, True)
+                if d_xs_lora is not None:       # the adapters read SiLU(emb) too: d_emb += d_xs * silu'(emb)
+                    sg = torch.sigmoid(hd.emb)
+                    d_emb.add_(d_xs_lora * (sg * (1.0 + hd.emb * (1.0 - sg))))
                 ops.linear_f32_wgrad(hd.e1, d_emb, self._gview(G, P.te.w2, (ted, ted)), self._gview(G, P.te.b2, (ted,)),
                                      True)
                 d_e1 = ops.linear_f32_dgrad(d_emb, w2, hd.e1, True)

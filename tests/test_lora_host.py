@@ -319,3 +319,28 @@ def test_lora_on_time_emb_proj_dropout_trains_and_is_off_in_eval(emu_backend):
     y2.square().mean().backward()
     gs = [p.grad for n, p in m.named_parameters() if "lora_" in n]
     assert gs and all(g is not None and torch.isfinite(g).all() for g in gs)
+
+
+def test_lora_on_time_emb_proj_with_a_trainable_time_embedding_mlp(emu_backend):
+    """PolypGeneratorModel.unfreeze_layers (PolypGeneratorModel.py:61-64) can make the time-embedding MLP trainable next
+    to the adapters: the adapters' path contributes to d_emb (they read SiLU(emb) as well)."""
+    m, om = _pair(targets=("time_emb_proj", "to_q"))
+    for mod in (m, om):
+        for n, p in mod.named_parameters():
+            if n.startswith("time_embedding."):
+                p.requires_grad_(True)
+        mod.train()
+    x, t = torch.randn(2, 3, 32, 32), torch.tensor([3, 600])
+    y, yo = m(x, t).sample, om(x, t).sample
+    tgt = torch.randn_like(y)
+    torch.nn.functional.mse_loss(y, tgt).backward()
+    torch.nn.functional.mse_loss(yo, tgt).backward()
+    og = dict(om.named_parameters())
+    tot = sum(p.grad.norm() ** 2 for p in om.parameters() if p.grad is not None) ** 0.5
+    seen = 0
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            g = og[n].grad
+            assert ((p.grad - g).norm() / (g.norm() + 1e-4 * tot)).item() < 2e-3, n
+            seen += n.startswith("time_embedding.")
+    assert seen == 4
