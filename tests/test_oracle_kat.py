@@ -244,3 +244,26 @@ def test_resize_golden_from_pillow():
     t = opre.transform(img, gold["size"], True)
     assert t.double().sum().item() == pytest.approx(gold["transform_flipped_sum"], abs=1e-9)
     assert torch.equal(t[0, 0], torch.tensor(gold["transform_flipped_first_row"]))
+
+
+def test_oracle_attention_block_equals_torch_multihead_attention():
+    """An INDEPENDENT implementation that is present in this image: torch.nn.MultiheadAttention splits the embedding
+    into heads the way diffusers' Attention does (head h = channels [h*d, (h+1)*d)), scales by d^-1/2 and applies the
+    output projection -- so the oracle's attention block (GroupNorm -> q/k/v -> SDPA -> to_out.0 -> + residual) must
+    equal x + MHA(GroupNorm(x)) with the same weights.  Pins the head split / scale / token order of oracle/unet2d.py."""
+    from oracle.unet2d import Attention
+    torch.manual_seed(0)
+    for C, d, hw in ((64, 8, (4, 4)), (128, 8, (7, 7)), (64, 64, (8, 8))):
+        heads = C // d
+        att = Attention(C, heads, d, norm_num_groups=32).double()
+        mha = torch.nn.MultiheadAttention(C, heads, bias=True, batch_first=True).double()
+        with torch.no_grad():
+            mha.in_proj_weight.copy_(torch.cat([att.to_q.weight, att.to_k.weight, att.to_v.weight], 0))
+            mha.in_proj_bias.copy_(torch.cat([att.to_q.bias, att.to_k.bias, att.to_v.bias], 0))
+            mha.out_proj.weight.copy_(att.to_out[0].weight)
+            mha.out_proj.bias.copy_(att.to_out[0].bias)
+        x = torch.randn(2, C, *hw, dtype=torch.float64)
+        tok = att.group_norm(x).flatten(2).transpose(1, 2)                  # [B, T, C], token = h * W + w
+        want = x + mha(tok, tok, tok, need_weights=False)[0].transpose(1, 2).reshape(x.shape)
+        got = att(x)
+        assert torch.allclose(got, want, rtol=1e-10, atol=1e-10), (C, d)
